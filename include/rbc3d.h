@@ -1,0 +1,139 @@
+/*
+ * rbc3d.h -- C ABI of librbc3d_b200.so: the B200-native (sm_100a, FP64) Ewald boundary-integral operator of
+ * comp-physics/RBC3D.  This is the drop-in boundary: the reference has no FFI layer, its boundary is the
+ * set of Fortran module procedures of ModPME, ModEwaldFunc, ModIntOnRbcs, ModIntOnWalls (+ the list modules
+ * ModSourceList / ModTargetList / ModHashTable they read).  Every entry point below names the reference
+ * procedure it replaces (paths relative to the reference's common/).  fortran/*.F90 holds the ISO_C_BINDING
+ * shims that re-export the reference names; INTEGRATION.md shows how they are wired.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all floating point is double (real(WP)), integers are int32 (default
+ *    Fortran integer); host arrays stay owned by the caller, the library keeps device mirrors.
+ *  - "SoA(3,N)" = three contiguous planes of length N = Fortran x(N,3).
+ *  - cell point index p = cell*nlat*nlon + (ilon-1)*nlat + (ilat-1)      (ModSourceList.F90:110-121)
+ *  - spline of a cell with nvar variables: [4 (u,u1,u2,u12)][nvar][nlon][2*nlat], theta index fastest
+ *    = the four t_spline component arrays of ModDataStruct.F90:37-43 back to back.
+ *  - velocities are ACCUMULATED into v (callers zero it, ModVelSolver.F90:473,571), rows of inactive
+ *    targets are left untouched (ModTargetList.F90:196-197).
+ *  - every function returns 0 on success, a negative RBC3D_E* code otherwise (the reference `stop`s).
+ *  - not re-entrant per context (the reference is single-threaded module state); one context per GPU.
+ */
+#ifndef RBC3D_H
+#define RBC3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbc3d_ctx rbc3d_ctx;
+
+enum {
+  RBC3D_OK = 0,
+  RBC3D_EINVAL = -1,    /* bad argument / call order */
+  RBC3D_ECUDA = -2,     /* CUDA runtime / cuFFT / NCCL failure (see rbc3d_last_error) */
+  RBC3D_ENOMEM = -3,
+  RBC3D_ESTATE = -4,    /* required state not set (e.g. PME_Transform before PME_Distrib_Source) */
+  RBC3D_EOVERFLOW = -5  /* neighbour-cell list exceeded 32 entries (ModRbcSingInt.F90:319) */
+};
+
+/* target list kinds (which t_TargetList of ModData.F90:48-49 an operator call refers to) */
+enum { RBC3D_TL_CELLS = 0, RBC3D_TL_RAW = 1, RBC3D_TL_WALLS = 2 };
+
+/* stage ids for rbc3d_get_timings (milliseconds of the last operator application, CUDA events) */
+enum {
+  RBC3D_T_PAIR = 0, RBC3D_T_SING, RBC3D_T_NEARSING, RBC3D_T_LINEAR, RBC3D_T_SPREAD, RBC3D_T_FFT,
+  RBC3D_T_KSPACE, RBC3D_T_FFT_INV, RBC3D_T_INTERP, RBC3D_T_COMBINE, RBC3D_T_WALL, RBC3D_T_COMM, RBC3D_T_H2D,
+  RBC3D_T_D2H, RBC3D_T_COUNT
+};
+
+const char *rbc3d_last_error(void);
+int rbc3d_version(void);
+
+/* ---- parameters: ModConf.F90:348-408 SetEwaldPrms (host arithmetic, no GPU needed) ---- */
+int rbc3d_set_ewald_prms(const double Lb[3], double alpha, double eps, int P, int nranks, double *rc,
+                         int Nb[3]);
+
+/* ---- context: replaces the module state of ModConf/ModData/ModPME.  PME_Init / PME_Finalize
+ *      (ModPME.F90:252-338, 342-350) happen inside create/destroy. device < 0 = current device. ---- */
+int rbc3d_ctx_create(rbc3d_ctx **ctx, const double Lb[3], double alpha, double eps, int P, double rc,
+                     const int Nb[3], int device);
+int rbc3d_ctx_destroy(rbc3d_ctx *ctx);
+
+/* Multi-GPU: z-slab decomposition of ModConf.F90:412-437 DomainDecomp, one context per rank; the 128-byte
+ * NCCL unique id is created on rank 0 and distributed by the host program (MPI_Bcast in the Fortran driver,
+ * torch.distributed in the Python harness). */
+int rbc3d_comm_unique_id(void *id128);
+int rbc3d_ctx_attach_comm(rbc3d_ctx *ctx, int nranks, int rank, const void *id128);
+
+/* ---- ModEwaldFunc.F90:13-16 (host scalars, the table versions use the context's alpha, rc) ---- */
+int rbc3d_ewald_coeff_sl_exact(double r, double alpha, double *A, double *B);
+int rbc3d_ewald_coeff_dl_exact(double r, double alpha, double *A);
+int rbc3d_ewald_coeff_sl(const rbc3d_ctx *ctx, double r, double *A, double *B);
+int rbc3d_ewald_coeff_dl(const rbc3d_ctx *ctx, double r, double *A);
+
+/* ---- cells ----
+ * rbc3d_cells_set_mesh: mesh shared by all cells (RBC_Create, ModRbc.F90:44-110) + the shared polar patch
+ *   (RbcPolarPatch_Create, ModPolarPatch.F90:27-76; TimeInt_Init, ModTimeInt.F90:62).
+ * rbc3d_cells_set_geometry: SourceList_UpdateCoord + TargetList_Update for tlist_rbc (ModSourceList.F90:
+ *   92-151, ModTargetList.F90:95-135) incl. the cell list build (HashTable_Build, ModHashTable.F90:23-58), and
+ *   the geometry splines written by Rbc_BuildSurfaceSource(xFlag) (ModRbc.F90:736-762).  active may be NULL
+ *   (all targets active; SetActiveFlag, ModTargetList.F90:205-233).
+ * rbc3d_cells_set_density: SourceList_UpdateDensity (ModSourceList.F90:160-187; f, g already multiplied by
+ *   detJ*w) + the density splines of Rbc_BuildSurfaceSource(fFlag/gFlag).  NULL = unchanged.             */
+int rbc3d_cells_set_mesh(rbc3d_ctx *ctx, int ncell, int nlat, int nlon, const double *th, const double *phi,
+                         const double *w);
+int rbc3d_cells_set_geometry(rbc3d_ctx *ctx, const double *x, const double *a3, const double *Acoef_cell,
+                             const double *Bcoef_cell, const double *area, const double *meshSize,
+                             const double *spx, const double *spa3, const double *spdetj,
+                             const int32_t *active);
+int rbc3d_cells_set_density(rbc3d_ctx *ctx, const double *f, const double *g, const double *spF,
+                            const double *spG);
+
+/* TargetList_CreateFromRaw (ModTargetList.F90:139-169): arbitrary points, Acoef = 2, indx = -1 */
+int rbc3d_targets_set_raw(rbc3d_ctx *ctx, int n, const double *x, const int32_t *active);
+
+/* ---- operator pieces, same names and call protocol as the reference ----
+ * AddIntOnRbcs(c1,c2,tlist,v)      ModIntOnRbcs.F90:25-158 (pair sum, singular, near-singular, linear term)
+ * PME_Distrib_Source(c1,c2,cells,walls) ModPME.F90:58-133; PME_Transform :137-222; PME_Add_Interp_Vel :228-248
+ * v: host SoA(3,n) of the chosen target list, accumulated into.                                          */
+int rbc3d_add_int_on_rbcs(rbc3d_ctx *ctx, double c1, double c2, int tlist, double *v);
+int rbc3d_pme_distrib_source(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls);
+int rbc3d_pme_transform(rbc3d_ctx *ctx);
+int rbc3d_pme_add_interp_vel(rbc3d_ctx *ctx, int tlist, double *v);
+
+/* Fused operator application (what MyMatMult / Compute_Rhs do between zeroing v and CollectArray,
+ * ModVelSolver.F90:473-493, 568-584): v += AddIntOnRbcs [+ AddIntOnWalls] + PME.  Host v. */
+int rbc3d_apply(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist, double *v);
+/* Same with everything resident: result written (not accumulated) to the context's device velocity buffer;
+ * rbc3d_get_velocity copies it out.  Used by the benchmark's device-resident timing. */
+int rbc3d_apply_resident(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist);
+int rbc3d_get_velocity(rbc3d_ctx *ctx, int tlist, double *v);
+/* bit mask to skip parts of AddIntOnRbcs (testing / profiling): 1 singular, 2 near-singular, 4 linear, 8 pairs */
+int rbc3d_set_skip_flags(rbc3d_ctx *ctx, int flags);
+
+/* ---- introspection (tests, profiling) ---- */
+/* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,
+ * ascending index inside a cell), start[Nc1*Nc2*Nc3+1]; any pointer may be NULL */
+int rbc3d_cell_list_get(rbc3d_ctx *ctx, int32_t Nc[3], int32_t *cid, int32_t *order, int32_t *start);
+/* per cell target: number of sources within rc and an order-independent checksum of their indices */
+int rbc3d_neighbor_signature(rbc3d_ctx *ctx, int tlist, int32_t *count, uint64_t *sig);
+/* near-singular entries found at geometry time: n entries (target, source cell, active flag, th0, phi0, dist) */
+int rbc3d_nearsing_get(rbc3d_ctx *ctx, int tlist, int *n, int32_t *target, int32_t *cell, int32_t *flag,
+                       double *th0, double *phi0, double *dist, int cap);
+int rbc3d_pme_get_grid(rbc3d_ctx *ctx, double *vv /* [3][Nz][Ny][Nx] */);
+int rbc3d_get_timings(rbc3d_ctx *ctx, float ms[RBC3D_T_COUNT]);
+int rbc3d_get_launch_count(rbc3d_ctx *ctx, long long *launches);
+/* Pin caller-owned host arrays that are passed repeatedly (the Fortran driver allocates its arrays once for the
+ * whole run), so host<->device copies run at full PCIe rate.  Optional; unregistered memory works, slower. */
+int rbc3d_host_register(void *ptr, size_t bytes);
+int rbc3d_host_unregister(void *ptr);
+/* measured FP64 FMA throughput of this GPU in TFLOP/s (register-resident DFMA chains) */
+int rbc3d_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

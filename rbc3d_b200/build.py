@@ -1,0 +1,98 @@
+"""Build librbc3d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m rbc3d_b200.build [--force]
+
+The shared library is the product: hand-written CUDA kernels + the C ABI of include/rbc3d.h, linked against cuFFT
+(the one library call on the path) and, when present, NCCL (multi-GPU transposes / halos).
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librbc3d_b200.so")
+OBJDIR = os.path.join(HERE, "csrc", "_obj")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-extended-lambda", "--expt-relaxed-constexpr",
+              "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _nccl_paths():
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            base = list(spec.submodule_search_locations)[0]
+            inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+            if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(os.path.join(lib, "libnccl.so.2")):
+                return inc, lib
+    except Exception:
+        pass
+    return None, None
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(HERE, "..", "include", "rbc3d.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(OBJDIR, exist_ok=True)
+    inc, libdir = _nccl_paths()
+    defs = []
+    link = ["-lcufft"]
+    if inc:
+        defs += ["-DRBC3D_WITH_NCCL", "-I", inc]
+        link += ["-L", libdir, "-l:libnccl.so.2", "-Xlinker", "-rpath," + libdir]
+    objs = []
+    procs = []
+    log = []
+    for src in sources():
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {os.path.basename(src)}\n{out}")
+        if p.returncode != 0:
+            failed = True
+    with open(os.path.join(OBJDIR, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if failed:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + link + ["-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

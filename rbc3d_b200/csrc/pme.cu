@@ -1,0 +1,557 @@
+// pme.cu -- smooth particle-mesh Ewald long-range part: PME_Init / PME_Distrib_Source / PME_Transform /
+// PME_Add_Interp_Vel (ModPME.F90:58-338, 405-489) with the slab FFT of ModPFFTW.F90 replaced by cuFFT.
+//
+// Mesh layout in HBM: real meshes [comp][Nz][Ny][Nx] (x fastest), spectra [comp][Nz][Ny][Nx/2+1] (cuFFT D2Z).
+// Components: 0..2 single-layer force density, 3..8 the SYMMETRIC part of the double-layer tensor
+// (xx,yy,zz,xy,xz,yz): the k-space multiplier (ModPME.F90:193-202) only sees q tr(T) + q^T T + T q = q tr(S) + 2 S q
+// and q^T T q = q^T S q, so 6 transforms replace the reference's 9.
+//
+// FFT conventions (ModPFFTW.F90:110-114): the reference transforms (x,y) with exp(-i..) and z with exp(+i..) and
+// stores q = (i/L1, jhat/L2, -khat/L3).  With a standard all-negative D2Z the coefficient the reference keeps at z
+// index k sits at (Nz-k) mod Nz, which turns its wave vector into q3 = +k/L3 for k <= Nz/2 and (k-Nz)/L3 above, while
+// q2 keeps "index >= Ny/2 is negative".  FFTW's c2r ignores the imaginary part of the x = 0 and x = Nx/2 bins after the
+// y/z transforms; the scaling kernel reproduces that by Hermitian-symmetrising those two planes.
+#include <cmath>
+#include <complex>
+
+#include "device_math.cuh"
+#include "rbc3d_internal.h"
+
+namespace rbc3d {
+
+constexpr int PME_BLK = 4;   // edge of a PME block in mesh cells
+constexpr int PME_PMAX = 8;  // largest supported B-spline support (PBspln_Ewd = 8 in every example)
+constexpr int SPREAD_CHUNK = 32;
+
+int pme_block_edge() { return PME_BLK; }
+
+void t_begin(rbc3d_ctx *c, int s) {
+  cudaEventRecord(c->ev[2 * s], c->stream);
+  c->ev_used[s] = true;
+}
+void t_end(rbc3d_ctx *c, int s) { cudaEventRecord(c->ev[2 * s + 1], c->stream); }
+
+int pme_init(rbc3d_ctx *c) {
+  Pme &pm = c->pme;
+  const Params &p = c->prm;
+  if (p.P < 2 || p.P > PME_PMAX) {
+    set_error("PBspln = %d unsupported (2..%d)", p.P, PME_PMAX);
+    return RBC3D_EINVAL;
+  }
+  pm.Nx = p.Nb[0];
+  pm.Ny = p.Nb[1];
+  pm.Nz = p.Nb[2];
+  pm.Nxh = pm.Nx / 2 + 1;
+  pm.G = (size_t)pm.Nx * pm.Ny * pm.Nz;
+  pm.M = (size_t)pm.Nxh * pm.Ny * pm.Nz;
+  for (int d = 0; d < 3; d++) pm.nblk[d] = (p.Nb[d] + PME_BLK - 1) / PME_BLK;
+  RBC_TRY(pm.src.resize(9 * pm.G));
+  RBC_TRY(pm.srcC.resize(9 * pm.M));
+  RBC_TRY(pm.vvC.resize(3 * pm.M));
+  RBC_TRY(pm.vv.resize(3 * pm.G));
+  // B-spline modulus factors, ModPME.F90:310-336
+  double MP[64];
+  int imin;
+  h_bspline_func((double)p.P + 2.220446049250313e-16, p.P, &imin, MP);
+  const int cnt[3] = {pm.Nxh, pm.Ny, pm.Nz};
+  dbuf<double> *dst[3] = {&pm.bx, &pm.by, &pm.bz};
+  for (int ii = 0; ii < 3; ii++) {
+    std::vector<double> b(cnt[ii]);
+    for (int k = 0; k < cnt[ii]; k++) {
+      std::complex<double> s(0.0, 0.0);
+      for (int m = 0; m <= p.P - 2; m++) {
+        double ang = 2 * 3.14159265358979323846 * k * m / (double)p.Nb[ii];
+        s += MP[m] * std::complex<double>(cos(ang), sin(ang));
+      }
+      double ang = 2 * 3.14159265358979323846 * k * (p.P - 1.) / (double)p.Nb[ii];
+      std::complex<double> r = std::complex<double>(cos(ang), sin(ang)) / s;
+      double a = std::abs(r);
+      b[k] = a * a;
+    }
+    RBC_TRY(dst[ii]->resize(cnt[ii]));
+    CUDA_TRY(cudaMemcpy(dst[ii]->p, b.data(), sizeof(double) * cnt[ii], cudaMemcpyHostToDevice));
+  }
+  return RBC3D_OK;
+}
+
+void pme_destroy(rbc3d_ctx *c) {
+  Pme &pm = c->pme;
+  for (int i = 0; i < 3; i++)
+    if (pm.planF_ok[i]) cufftDestroy(pm.planF[i]);
+  if (pm.planB_ok) cufftDestroy(pm.planB);
+  pm.src.release();
+  pm.srcC.release();
+  pm.vvC.release();
+  pm.vv.release();
+  pm.bx.release();
+  pm.by.release();
+  pm.bz.release();
+}
+
+static int get_plan_fwd(rbc3d_ctx *c, int batch, cufftHandle *out) {
+  Pme &pm = c->pme;
+  const int slot = batch / 3 - 1;
+  if (!pm.planF_ok[slot]) {
+    int n[3] = {pm.Nz, pm.Ny, pm.Nx};
+    CUFFT_TRY(cufftPlanMany(&pm.planF[slot], 3, n, nullptr, 1, (int)pm.G, nullptr, 1, (int)pm.M, CUFFT_D2Z, batch));
+    CUFFT_TRY(cufftSetStream(pm.planF[slot], c->stream));
+    pm.planF_ok[slot] = true;
+  }
+  *out = pm.planF[slot];
+  return RBC3D_OK;
+}
+
+static int get_plan_bwd(rbc3d_ctx *c, cufftHandle *out) {
+  Pme &pm = c->pme;
+  if (!pm.planB_ok) {
+    int n[3] = {pm.Nz, pm.Ny, pm.Nx};
+    CUFFT_TRY(cufftPlanMany(&pm.planB, 3, n, nullptr, 1, (int)pm.M, nullptr, 1, (int)pm.G, CUFFT_Z2D, 3));
+    CUFFT_TRY(cufftSetStream(pm.planB, c->stream));
+    pm.planB_ok = true;
+  }
+  *out = pm.planB;
+  return RBC3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Spreading (Distrib_Source, ModPME.F90:405-443).  One CTA per PME block of PME_BLK^3 mesh cells; the sources of
+// the block (sorted by block) are accumulated into a shared-memory tile of (PME_BLK+P-1)^3 mesh points with
+// plain read-modify-write (thread = one point of the P^3 support, one source at a time), then the tile is flushed
+// to the mesh with native FP64 global reductions (halo points are shared with neighbouring blocks).
+struct SpreadArgs {
+  Params prm;
+  int n;                 // number of points in the source list
+  const int *start;      // block offsets
+  const int *order;      // sorted position -> source index
+  const double *x;       // SoA(3,n)
+  const double *f;       // SoA(3,n) or null
+  const double *g;       // SoA(3,n) or null
+  const double *a3;      // SoA(3,n)
+  const double *Bcell;   // per cell
+  int npc;
+  double c1, c2;
+  int ncomp, comp0;      // components written: [comp0, comp0+ncomp)
+  int nbx, nby, nbz;
+  double *mesh;          // [9][G]
+  size_t G;
+};
+
+template <int NCOMP>
+__global__ void __launch_bounds__(512) k_spread(SpreadArgs a) {
+  extern __shared__ double sm[];
+  const int P = a.prm.P;
+  const int T = PME_BLK + P - 1, T3 = T * T * T;
+  double *tile = sm;                                   // [NCOMP][T3]
+  double *sw = tile + (size_t)NCOMP * T3;              // [CHUNK][3][PMAX]
+  double *sstr = sw + SPREAD_CHUNK * 3 * PME_PMAX;     // [CHUNK][NCOMP]
+  int *srel = (int *)(sstr + SPREAD_CHUNK * NCOMP);    // [CHUNK][3]
+  const int blk = blockIdx.x;
+  const int sb = a.start[blk], se = a.start[blk + 1];
+  if (sb == se) return;
+  const int bx = blk % a.nbx, by = (blk / a.nbx) % a.nby, bz = blk / (a.nbx * a.nby);
+  for (int i = threadIdx.x; i < NCOMP * T3; i += blockDim.x) tile[i] = 0.0;
+  const int tid = threadIdx.x;
+  const int i0 = tid % P, j0 = (tid / P) % P, k0 = tid / (P * P);
+  const bool worker = k0 < P;
+  for (int cb = sb; cb < se; cb += SPREAD_CHUNK) {
+    const int nch = min(SPREAD_CHUNK, se - cb);
+    __syncthreads();
+    if (tid < nch * 3) {
+      const int s = tid / 3, ax = tid - 3 * s;
+      const int p = a.order[cb + s];
+      const double u = __dmul_rn(a.x[(size_t)ax * a.n + p], a.prm.ih[ax]);  // ic = x*ih, ModPME.F90:420
+      int imin;
+      double w[PME_PMAX];
+      bspline_func<PME_PMAX>(u, P, imin, w);
+      const int mcell = imodulo(imin + (P - 1), a.prm.Nb[ax]);
+      const int b = (ax == 0) ? bx : (ax == 1) ? by : bz;
+      srel[s * 3 + ax] = mcell - b * PME_BLK;
+      for (int q = 0; q < P; q++) sw[(s * 3 + ax) * PME_PMAX + q] = w[q];
+    }
+    for (int t = tid; t < nch * NCOMP; t += blockDim.x) {
+      const int s = t / NCOMP, cc = t - s * NCOMP;
+      const int p = a.order[cb + s];
+      const size_t n = a.n;
+      double v;
+      int comp = a.comp0 + cc;
+      if (comp < 3) {
+        v = a.c1 * a.f[comp * n + p];
+      } else {
+        const double B = a.Bcell[p / a.npc];
+        const double g0 = a.g[p], g1 = a.g[n + p], g2 = a.g[2 * n + p];
+        const double n0 = a.a3[p] * B, n1 = a.a3[n + p] * B, n2 = a.a3[2 * n + p] * B;
+        switch (comp) {
+          case 3: v = g0 * n0; break;
+          case 4: v = g1 * n1; break;
+          case 5: v = g2 * n2; break;
+          case 6: v = 0.5 * (g0 * n1 + g1 * n0); break;
+          case 7: v = 0.5 * (g0 * n2 + g2 * n0); break;
+          default: v = 0.5 * (g1 * n2 + g2 * n1); break;
+        }
+        v *= a.c2;
+      }
+      sstr[s * NCOMP + cc] = v;
+    }
+    __syncthreads();
+    for (int s = 0; s < nch; s++) {
+      if (worker) {
+        const double w = sw[(s * 3 + 0) * PME_PMAX + i0] * sw[(s * 3 + 1) * PME_PMAX + j0] *
+                         sw[(s * 3 + 2) * PME_PMAX + k0];
+        const int addr = ((srel[s * 3 + 2] + k0) * T + (srel[s * 3 + 1] + j0)) * T + srel[s * 3 + 0] + i0;
+#pragma unroll
+        for (int cc = 0; cc < NCOMP; cc++) tile[cc * T3 + addr] += w * sstr[s * NCOMP + cc];
+      }
+      __syncthreads();
+    }
+  }
+  // flush
+  const int ox = bx * PME_BLK - (P - 1), oy = by * PME_BLK - (P - 1), oz = bz * PME_BLK - (P - 1);
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  for (int i = threadIdx.x; i < T3; i += blockDim.x) {
+    const int lx = i % T, ly = (i / T) % T, lz = i / (T * T);
+    const int gx = imodulo(ox + lx, Nx), gy = imodulo(oy + ly, Ny), gz = imodulo(oz + lz, Nz);
+    const size_t gi = ((size_t)gz * Ny + gy) * Nx + gx;
+#pragma unroll
+    for (int cc = 0; cc < NCOMP; cc++) {
+      const double v = tile[cc * T3 + i];
+      if (v != 0.0) atomicAdd(a.mesh + (size_t)(a.comp0 + cc) * a.G + gi, v);
+    }
+  }
+}
+
+int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls) {
+  Pme &pm = c->pme;
+  Cells &C = c->cells;
+  pm.flag_sl = fabs(c1) > 1.e-10;  // ModPME.F90:71-72
+  pm.flag_dl = fabs(c2) > 1.e-10;
+  pm.transformed = false;
+  if (pm.flag_sl) CUDA_TRY(cudaMemsetAsync(pm.src.p, 0, sizeof(double) * 3 * pm.G, c->stream));
+  if (pm.flag_dl) CUDA_TRY(cudaMemsetAsync(pm.src.p + 3 * pm.G, 0, sizeof(double) * 6 * pm.G, c->stream));
+  if (use_cells && C.Np > 0 && (pm.flag_sl || pm.flag_dl)) {
+    if (pm.flag_sl && !C.f_set) {
+      set_error("PME_Distrib_Source: c1 != 0 but no single-layer density set");
+      return RBC3D_ESTATE;
+    }
+    if (pm.flag_dl && !C.g_set) {
+      set_error("PME_Distrib_Source: c2 != 0 but no double-layer density set");
+      return RBC3D_ESTATE;
+    }
+    SpreadArgs a;
+    a.prm = c->prm;
+    a.n = C.Np;
+    a.start = C.pl.start.p;
+    a.order = C.pl.order.p;
+    a.x = C.x.p;
+    a.f = C.f.p;
+    a.g = C.g.p;
+    a.a3 = C.a3.p;
+    a.Bcell = C.B.p;
+    a.npc = C.npc;
+    a.c1 = c1;
+    a.c2 = c2;
+    a.nbx = pm.nblk[0];
+    a.nby = pm.nblk[1];
+    a.nbz = pm.nblk[2];
+    a.mesh = pm.src.p;
+    a.G = pm.G;
+    const int nblocks = a.nbx * a.nby * a.nbz;
+    const int T = PME_BLK + c->prm.P - 1;
+    auto smem = [&](int nc) {
+      return sizeof(double) * ((size_t)nc * T * T * T + SPREAD_CHUNK * 3 * PME_PMAX + SPREAD_CHUNK * nc) +
+             sizeof(int) * SPREAD_CHUNK * 3;
+    };
+    if (pm.flag_sl && pm.flag_dl) {
+      a.comp0 = 0;
+      a.ncomp = 9;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(9)));
+      k_spread<9><<<nblocks, 512, smem(9), c->stream>>>(a);
+    } else if (pm.flag_sl) {
+      a.comp0 = 0;
+      a.ncomp = 3;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(3)));
+      k_spread<3><<<nblocks, 512, smem(3), c->stream>>>(a);
+    } else {
+      a.comp0 = 3;
+      a.ncomp = 6;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(6)));
+      k_spread<6><<<nblocks, 512, smem(6), c->stream>>>(a);
+    }
+    KERNEL_CHECK();
+    c->launches++;
+  }
+  (void)use_walls;  // wall centroid sources: see walls.cu (PME_Distrib_Source walls branch, ModPME.F90:105-131)
+  pm.distributed = true;
+  return RBC3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k-space multiply (ModPME.F90:165-210), fused with the B-spline modulus and the Hermitian symmetrisation of the
+// x = 0 and x = Nx/2 planes.  One thread per retained mode.
+struct KArgs {
+  Params prm;
+  int Nx, Ny, Nz, Nxh;
+  size_t M;
+  const cufftDoubleComplex *srcC;  // [9][M]
+  cufftDoubleComplex *vvC;         // [3][M]
+  const double *bx, *by, *bz;
+  int sl, dl;
+  double vol;
+};
+
+template <bool SL, bool DL>
+__device__ __forceinline__ void kspace_mode(const KArgs &a, int i, int j, int k, double vr[3], double vi[3]) {
+  vr[0] = vr[1] = vr[2] = vi[0] = vi[1] = vi[2] = 0.0;
+  if (i == 0 && j == 0 && k == 0) return;
+  const size_t idx = ((size_t)k * a.Ny + j) * a.Nxh + i;
+  const double q0 = (double)i * a.prm.iLb[0];
+  const double q1 = (double)(j < a.Ny / 2 ? j : j - a.Ny) * a.prm.iLb[1];
+  const double q2 = (double)(k <= a.Nz / 2 ? k : k - a.Nz) * a.prm.iLb[2];
+  const double alpha = a.prm.alpha;
+  const double qq = q0 * q0 + q1 * q1 + q2 * q2;
+  const double q2t = RBC_PI * alpha * qq;
+  const double e = exp(-q2t);
+  const double phi0 = e / q2t;
+  const double phi1 = (e + phi0) / q2t;
+  const double q[3] = {q0, q1, q2};
+  if (SL) {
+    double fr[3], fi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const cufftDoubleComplex z = a.srcC[(size_t)d * a.M + idx];
+      fr[d] = z.x;
+      fi[d] = z.y;
+    }
+    // 2 alpha/V phi1 (q2t F - qt (qt.F)), qt = sqrt(pi alpha) q  => qt(qt.F) = pi alpha q (q.F)
+    const double pa = RBC_PI * alpha;
+    const double dr = q0 * fr[0] + q1 * fr[1] + q2 * fr[2], di = q0 * fi[0] + q1 * fi[1] + q2 * fi[2];
+    const double cf = 2.0 * alpha / a.vol * phi1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      vr[d] += cf * (q2t * fr[d] - pa * q[d] * dr);
+      vi[d] += cf * (q2t * fi[d] - pa * q[d] * di);
+    }
+  }
+  if (DL) {
+    double sr[6], si[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+      const cufftDoubleComplex z = a.srcC[(size_t)(3 + d) * a.M + idx];
+      sr[d] = z.x;
+      si[d] = z.y;
+    }
+    // S = [[0,3,4],[3,1,5],[4,5,2]]
+    const double trr = sr[0] + sr[1] + sr[2], tri = si[0] + si[1] + si[2];
+    const double Sqr[3] = {sr[0] * q0 + sr[3] * q1 + sr[4] * q2, sr[3] * q0 + sr[1] * q1 + sr[5] * q2,
+                           sr[4] * q0 + sr[5] * q1 + sr[2] * q2};
+    const double Sqi[3] = {si[0] * q0 + si[3] * q1 + si[4] * q2, si[3] * q0 + si[1] * q1 + si[5] * q2,
+                           si[4] * q0 + si[5] * q1 + si[2] * q2};
+    const double qSqr = q0 * Sqr[0] + q1 * Sqr[1] + q2 * Sqr[2];
+    const double qSqi = q0 * Sqi[0] + q1 * Sqi[1] + q2 * Sqi[2];
+    const double ca = 4.0 * RBC_PI * alpha / a.vol * phi0;
+    const double cb = 8.0 * RBC_PI * RBC_PI * alpha * alpha / a.vol * phi1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      // t = i*[ca (q tr + 2 S q) - cb (q.Sq) q];  V -= t ;  i*(x+iy) = -y + ix
+      const double wr = ca * (q[d] * trr + 2.0 * Sqr[d]) - cb * qSqr * q[d];
+      const double wi = ca * (q[d] * tri + 2.0 * Sqi[d]) - cb * qSqi * q[d];
+      vr[d] -= -wi;
+      vi[d] -= wr;
+    }
+  }
+  const double b = a.bx[i] * a.by[j] * a.bz[k];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    vr[d] *= b;
+    vi[d] *= b;
+  }
+}
+
+template <bool SL, bool DL>
+__global__ void __launch_bounds__(256) k_kspace(KArgs a) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.M) return;
+  const int i = (int)(idx % a.Nxh);
+  const int j = (int)((idx / a.Nxh) % a.Ny);
+  const int k = (int)(idx / ((size_t)a.Nxh * a.Ny));
+  double vr[3], vi[3];
+  kspace_mode<SL, DL>(a, i, j, k, vr, vi);
+  if (i == 0 || i == a.Nx / 2) {
+    double wr[3], wi[3];
+    kspace_mode<SL, DL>(a, i, (a.Ny - j) % a.Ny, (a.Nz - k) % a.Nz, wr, wi);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      vr[d] = 0.5 * (vr[d] + wr[d]);
+      vi[d] = 0.5 * (vi[d] - wi[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) a.vvC[(size_t)d * a.M + idx] = make_cuDoubleComplex(vr[d], vi[d]);
+}
+
+int pme_transform(rbc3d_ctx *c) {
+  Pme &pm = c->pme;
+  if (!pm.distributed) {
+    set_error("PME_Transform called before PME_Distrib_Source");
+    return RBC3D_ESTATE;
+  }
+  const Params &p = c->prm;
+  if (!pm.flag_sl && !pm.flag_dl) {
+    CUDA_TRY(cudaMemsetAsync(pm.vv.p, 0, sizeof(double) * 3 * pm.G, c->stream));
+    pm.transformed = true;
+    return RBC3D_OK;
+  }
+  t_begin(c, RBC3D_T_FFT);
+  cufftHandle plan;
+  if (pm.flag_sl && pm.flag_dl) {
+    RBC_TRY(get_plan_fwd(c, 9, &plan));
+    CUFFT_TRY(cufftExecD2Z(plan, pm.src.p, pm.srcC.p));
+  } else if (pm.flag_sl) {
+    RBC_TRY(get_plan_fwd(c, 3, &plan));
+    CUFFT_TRY(cufftExecD2Z(plan, pm.src.p, pm.srcC.p));
+  } else {
+    RBC_TRY(get_plan_fwd(c, 6, &plan));
+    CUFFT_TRY(cufftExecD2Z(plan, pm.src.p + 3 * pm.G, pm.srcC.p + 3 * pm.M));
+  }
+  t_end(c, RBC3D_T_FFT);
+  t_begin(c, RBC3D_T_KSPACE);
+  KArgs a;
+  a.prm = p;
+  a.Nx = pm.Nx;
+  a.Ny = pm.Ny;
+  a.Nz = pm.Nz;
+  a.Nxh = pm.Nxh;
+  a.M = pm.M;
+  a.srcC = pm.srcC.p;
+  a.vvC = pm.vvC.p;
+  a.bx = pm.bx.p;
+  a.by = pm.by.p;
+  a.bz = pm.bz.p;
+  a.vol = p.Lb[0] * p.Lb[1] * p.Lb[2];
+  const int grid = (int)((pm.M + 255) / 256);
+  if (pm.flag_sl && pm.flag_dl)
+    k_kspace<true, true><<<grid, 256, 0, c->stream>>>(a);
+  else if (pm.flag_sl)
+    k_kspace<true, false><<<grid, 256, 0, c->stream>>>(a);
+  else
+    k_kspace<false, true><<<grid, 256, 0, c->stream>>>(a);
+  KERNEL_CHECK();
+  t_end(c, RBC3D_T_KSPACE);
+  cufftHandle planb;
+  RBC_TRY(get_plan_bwd(c, &planb));
+  t_begin(c, RBC3D_T_FFT_INV);
+  CUFFT_TRY(cufftExecZ2D(planb, pm.vvC.p, pm.vv.p));
+  t_end(c, RBC3D_T_FFT_INV);
+  c->launches += 3;
+  pm.transformed = true;
+  return RBC3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Interpolation (Interp_Vel, ModPME.F90:450-489): one CTA per PME block of targets, the (PME_BLK+P-1)^3 x 3
+// velocity tile is staged in shared memory (coalesced rows), one warp per target gathers its P^3 support.
+struct InterpArgs {
+  Params prm;
+  int n;
+  const int *start, *order;
+  const double *x;   // targets SoA(3,n)
+  const double *vv;  // [3][G]
+  size_t G;
+  int nbx, nby, nbz;
+  double *acc;       // SoA(3,n)
+};
+
+constexpr int INTERP_WARPS = 8;
+
+__global__ void __launch_bounds__(INTERP_WARPS * 32) k_interp(InterpArgs a) {
+  extern __shared__ double sm[];
+  const int P = a.prm.P;
+  const int T = PME_BLK + P - 1, T3 = T * T * T;
+  double *tile = sm;            // [3][T3]
+  double *sw = tile + 3 * T3;   // [WARPS][3][PMAX]
+  const int blk = blockIdx.x;
+  const int sb = a.start[blk], se = a.start[blk + 1];
+  if (sb == se) return;
+  const int bx = blk % a.nbx, by = (blk / a.nbx) % a.nby, bz = blk / (a.nbx * a.nby);
+  const int ox = bx * PME_BLK - (P - 1), oy = by * PME_BLK - (P - 1), oz = bz * PME_BLK - (P - 1);
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  for (int i = threadIdx.x; i < T3; i += blockDim.x) {
+    const int lx = i % T, ly = (i / T) % T, lz = i / (T * T);
+    const int gx = imodulo(ox + lx, Nx), gy = imodulo(oy + ly, Ny), gz = imodulo(oz + lz, Nz);
+    const size_t gi = ((size_t)gz * Ny + gy) * Nx + gx;
+    tile[i] = a.vv[gi];
+    tile[T3 + i] = a.vv[a.G + gi];
+    tile[2 * T3 + i] = a.vv[2 * a.G + gi];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w = sw + warp * 3 * PME_PMAX;
+  for (int s = sb + warp; s < se; s += INTERP_WARPS) {
+    const int p = a.order[s];
+    int rel = 0;
+    __syncwarp();
+    if (lane < 3) {
+      const double u = __dmul_rn(a.x[(size_t)lane * a.n + p], a.prm.ih[lane]);
+      int imin;
+      double ww[PME_PMAX];
+      bspline_func<PME_PMAX>(u, P, imin, ww);
+      const int mcell = imodulo(imin + (P - 1), a.prm.Nb[lane]);
+      const int b = (lane == 0) ? bx : (lane == 1) ? by : bz;
+      rel = mcell - b * PME_BLK;
+      for (int q = 0; q < P; q++) w[lane * PME_PMAX + q] = ww[q];
+    }
+    __syncwarp();
+    const int rx = __shfl_sync(FULL_MASK, rel, 0), ry = __shfl_sync(FULL_MASK, rel, 1),
+              rz = __shfl_sync(FULL_MASK, rel, 2);
+    double d0 = 0, d1 = 0, d2 = 0;
+    for (int pr = lane; pr < P * P; pr += 32) {
+      const int j0 = pr % P, k0 = pr / P;
+      const double wyz = w[PME_PMAX + j0] * w[2 * PME_PMAX + k0];
+      const int base = ((rz + k0) * T + (ry + j0)) * T + rx;
+      for (int i0 = 0; i0 < P; i0++) {
+        const double wt = w[i0] * wyz;
+        d0 += wt * tile[base + i0];
+        d1 += wt * tile[T3 + base + i0];
+        d2 += wt * tile[2 * T3 + base + i0];
+      }
+    }
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (lane == 0) {
+      a.acc[p] += d0;
+      a.acc[(size_t)a.n + p] += d1;
+      a.acc[2 * (size_t)a.n + p] += d2;
+    }
+  }
+}
+
+int pme_interp(rbc3d_ctx *c, TargetList &t) {
+  Pme &pm = c->pme;
+  if (!pm.transformed) {
+    set_error("PME_Add_Interp_Vel called before PME_Transform");
+    return RBC3D_ESTATE;
+  }
+  if (t.n == 0) return RBC3D_OK;
+  CellList &pl = t.pl;
+  InterpArgs a;
+  a.prm = c->prm;
+  a.n = t.n;
+  a.start = pl.start.p;
+  a.order = pl.order.p;
+  a.x = t.x.p;
+  a.vv = pm.vv.p;
+  a.G = pm.G;
+  a.nbx = pm.nblk[0];
+  a.nby = pm.nblk[1];
+  a.nbz = pm.nblk[2];
+  a.acc = t.acc.p;
+  const int T = PME_BLK + c->prm.P - 1;
+  const size_t smem = sizeof(double) * (3 * (size_t)T * T * T + INTERP_WARPS * 3 * PME_PMAX);
+  CUDA_TRY(cudaFuncSetAttribute(k_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_interp<<<a.nbx * a.nby * a.nbz, INTERP_WARPS * 32, smem, c->stream>>>(a);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
+}
+
+}  // namespace rbc3d

@@ -1,0 +1,222 @@
+// rbc3d_internal.h -- internal declarations of librbc3d_b200.so (sm_100a, FP64).
+// The public surface is include/rbc3d.h.  No CPU fallback exists: every operator entry point launches CUDA
+// kernels and fails with RBC3D_ECUDA when no device is present.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rbc3d.h"
+
+#define RBC3D_NTAB 8192
+#define RBC3D_NBR_MAX 32
+
+namespace rbc3d {
+
+void set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      rbc3d::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return RBC3D_ECUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+#define CUFFT_TRY(expr)                                                              \
+  do {                                                                               \
+    cufftResult r__ = (expr);                                                        \
+    if (r__ != CUFFT_SUCCESS) {                                                      \
+      rbc3d::set_error("%s:%d: %s -> cufft %d", __FILE__, __LINE__, #expr, (int)r__); \
+      return RBC3D_ECUDA;                                                            \
+    }                                                                                \
+  } while (0)
+#define RBC_TRY(expr)           \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != RBC3D_OK) return r__; \
+  } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+template <class T>
+struct dbuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int resize(size_t m) {  // grow-only
+    if (m <= n && p) return RBC3D_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (m == 0) return RBC3D_OK;
+    cudaError_t e = cudaMalloc((void **)&p, m * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", m * sizeof(T), cudaGetErrorString(e));
+      return RBC3D_ENOMEM;
+    }
+    n = m;
+    return RBC3D_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// Constants every kernel needs (passed by value).
+struct Params {
+  double Lb[3], iLb[3];
+  double alpha, eps, rc;
+  double rc2_thr;   // largest double t with sqrt(t) <= rc  (exact replacement of "sqrt(r2) > rc")
+  double r_eps;     // 1e-3 * sqrt(alpha/pi)    (ModEwaldFunc.F90:105)
+  double tab_scale; // NTAB / rc
+  int P;
+  int Nb[3];
+  int Nc[3];        // cell list blocks (ModHashTable.F90:99-126)
+  double iLbNc[3];
+  double ih[3];     // Nb / Lb  (ModPME.F90:418)
+  // z-slab decomposition (ModConf.F90:412-437); single rank: [0, Nb3)
+  int nranks, rank;
+};
+
+// Sorted-by-cell view of a point set (cell list = "sort by cell + prefix-scan offsets").
+struct CellList {
+  int n = 0;            // number of points
+  int n_sorted = 0;     // number of points that received a valid cell (active ones)
+  dbuf<int> cid;        // [n] cell id (0-based, i1 fastest), -> ncells for inactive points
+  dbuf<int> order;      // [n] point indices sorted by cell, ascending index inside a cell
+  dbuf<int> start;      // [ncells + 2]
+  dbuf<int> keys_tmp, vals_tmp;
+  dbuf<char> cub_tmp;
+};
+
+struct NearSing {      // geometry-time products of the neighbour scan + Spline_FindProjection
+  int n = 0;           // entries (target, other cell within rc)
+  int n_active = 0;    // entries that pass the distance check of ModRbcSingInt.F90:122-125
+  dbuf<int> cnt, off;  // per sorted target
+  dbuf<int> target, cell, pt;  // [n] original target index, source cell, closest mesh point (ilon*nlat+ilat)
+  dbuf<double> th0, phi0, dist, x0, a30, xi;  // x0,a30,xi SoA(3,n)
+  dbuf<int> flag;      // 1 = active
+  dbuf<double> dv;     // SoA(3,n) per-entry corrections of the current application
+  dbuf<int> overflow;  // device flag
+};
+
+struct TargetList {
+  int kind = RBC3D_TL_RAW;
+  int n = 0;
+  bool valid = false;
+  dbuf<double> x;       // SoA(3,n)
+  dbuf<double> Acoef;   // [n]
+  dbuf<int> active;     // [n]
+  dbuf<int> surf;       // [n] cell index (0-based) of a cell target, -1 otherwise
+  CellList cl;          // sorted by real-space cell
+  CellList pl;          // sorted by PME block (interpolation)
+  dbuf<int2> tiles;     // (cell, first sorted position) per warp tile
+  int ntiles = 0;
+  NearSing ns;
+  dbuf<double> acc;     // SoA(3,n) un-normalised sums of the current application
+  dbuf<double> v;       // SoA(3,n) result of rbc3d_apply_resident
+  dbuf<double> host_io; // staging for host v
+};
+
+struct Cells {
+  int ncell = 0, nlat = 0, nlon = 0, npc = 0, Np = 0;
+  bool mesh_set = false, geom_set = false, f_set = false, g_set = false;
+  std::vector<double> h_th, h_phi, h_w, h_A, h_B, h_area, h_mesh;
+  dbuf<double> th, phi, w, A, B, area, meshSize;
+  dbuf<double> x, a3, f, g;          // SoA(3,Np), original order (f, g already * detJ*w)
+  dbuf<double> spx, spa3, spdetj, spF, spG;  // ABI layout
+  // polar patch
+  double radius = 0;
+  int nrad = 0, nazm = 0;
+  dbuf<double> thG, phiG, pw;        // [ilon][ilat][iazm][irad], [nrad]
+  dbuf<double> omm;                  // one-minus-mask table [ilat_i][ilat_j][dlon]
+  dbuf<int> dlonmax;                 // [ilat_i][ilat_j] largest cyclic |dlon| with mask != 0, -1 if none
+  // sorted (by real-space cell) copies used by the pair kernel
+  CellList cl;
+  dbuf<double> sx, sa3, sf, sgB;     // SoA(3,Np) in sorted order; sgB = g * Bcoef(cell)
+  CellList pl;                       // sorted by PME block (spreading)
+  dbuf<double> xvint_part;           // partial sums of the linear term
+  dbuf<double> sing_xi;              // SoA(3,Np) spline-evaluated target positions (ModRbcSingInt.F90:58)
+};
+
+struct Pme {
+  int Nx = 0, Ny = 0, Nz = 0, Nxh = 0;
+  size_t G = 0, M = 0;
+  dbuf<double> src;                 // [9][Nz][Ny][Nx] spread densities (3 SL + 6 symmetric DL)
+  dbuf<cufftDoubleComplex> srcC;    // [9][Nz][Ny][Nxh]
+  dbuf<cufftDoubleComplex> vvC;     // [3][Nz][Ny][Nxh]
+  dbuf<double> vv;                  // [3][Nz][Ny][Nx]
+  dbuf<double> bx, by, bz;          // B-spline modulus factors per axis (ModPME.F90:318-325)
+  cufftHandle planF[3] = {0, 0, 0}; // batch 3, 6, 9
+  bool planF_ok[3] = {false, false, false};
+  cufftHandle planB = 0;
+  bool planB_ok = false;
+  dbuf<char> work;
+  bool flag_sl = false, flag_dl = false;
+  bool distributed = false, transformed = false;
+  int nblk[3] = {0, 0, 0};          // PME blocks of PME_BLK^3 mesh cells
+};
+
+}  // namespace rbc3d
+
+struct rbc3d_ctx {
+  int device = 0;
+  rbc3d::Params prm;
+  cudaStream_t stream = nullptr;
+  // lookup tables (device): interleaved SL (c1,c2) pairs, DL, mask
+  rbc3d::dbuf<double> tab_sl, tab_dl, tab_mask;
+  std::vector<double> h_tab_sl1, h_tab_sl2, h_tab_dl, h_tab_mask;
+  rbc3d::Cells cells;
+  rbc3d::TargetList tl[3];
+  rbc3d::Pme pme;
+  int skip_flags = 0;
+  cudaEvent_t ev[2 * RBC3D_T_COUNT];
+  bool ev_used[RBC3D_T_COUNT];
+  float ms[RBC3D_T_COUNT];
+  long long launches = 0;
+  int sm_count = 148;
+};
+
+namespace rbc3d {
+
+// ---- host helpers (host_math.cpp part of capi.cu) ----
+void h_bspline_func(double xc, int P, int *imin, double *w);
+double h_mask_func_exact(double x);
+void h_gauleg(double x1, double x2, int n, double *x, double *w);
+
+// ---- cell list (celllist.cu) ----
+int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
+int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
+int tiles_build(rbc3d_ctx *c, TargetList &t);
+
+// ---- real-space operator (pairsum.cu, singular.cu, nearsing.cu) ----
+int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g);
+int pair_sum(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int neighbor_signature(rbc3d_ctx *c, TargetList &t, int *count, unsigned long long *sig);
+int nearsing_scan(rbc3d_ctx *c, TargetList &t, bool fill);
+int nearsing_prepare(rbc3d_ctx *c, TargetList &t);
+int nearsing_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int singular_prepare(rbc3d_ctx *c);
+int singular_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int linear_term(rbc3d_ctx *c, TargetList &t, double c2);
+int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate);
+
+// ---- PME (pme.cu) ----
+int pme_block_edge();
+int pme_init(rbc3d_ctx *c);
+void pme_destroy(rbc3d_ctx *c);
+int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls);
+int pme_transform(rbc3d_ctx *c);
+int pme_interp(rbc3d_ctx *c, TargetList &t);
+
+// timing helpers
+void t_begin(rbc3d_ctx *c, int stage);
+void t_end(rbc3d_ctx *c, int stage);
+
+}  // namespace rbc3d

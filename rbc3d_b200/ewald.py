@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's operator interface for the Ewald boundary-integral path.
+
+The method names and the call protocol are the reference's module procedures:
+
+    ModConf      SetEwaldPrms
+    ModEwaldFunc EwaldCoeff_SL / EwaldCoeff_DL / EwaldCoeff_SL_Exact / EwaldCoeff_DL_Exact
+    ModSourceList / ModTargetList   SourceList_UpdateCoord, SourceList_UpdateDensity, TargetList_CreateFromRaw
+    ModIntOnRbcs AddIntOnRbcs(c1, c2, tlist, v)
+    ModPME       PME_Distrib_Source(c1, c2, cells, walls) -> PME_Transform() -> PME_Add_Interp_Vel(tlist, v)
+
+plus the fused ``apply`` the GMRES callbacks amount to (ModVelSolver.F90:568-584).  Everything forwards to
+librbc3d_b200.so through the C ABI (rbc3d_b200.capi); v arrays are SoA (3, n) NumPy arrays, accumulated into like
+the Fortran ``v(:, :)`` arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import TL_CELLS, TL_RAW, TL_WALLS, check, dp, f64, i32, ip
+
+
+def SetEwaldPrms(Lb, alpha=0.44, eps=1e-3, P=8, nranks=1):
+    """ModConf.F90:348-408 -> (rc, Nb)."""
+    lib = capi.load()
+    Lb3 = (C.c_double * 3)(*[float(v) for v in Lb])
+    rc = C.c_double()
+    Nb = (C.c_int32 * 3)()
+    check(lib.rbc3d_set_ewald_prms(Lb3, alpha, eps, P, nranks, C.byref(rc), Nb), "rbc3d_set_ewald_prms")
+    return rc.value, [int(v) for v in Nb]
+
+
+def EwaldCoeff_SL_Exact(r, alpha):
+    a, b = C.c_double(), C.c_double()
+    check(capi.load().rbc3d_ewald_coeff_sl_exact(r, alpha, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def EwaldCoeff_DL_Exact(r, alpha):
+    a = C.c_double()
+    check(capi.load().rbc3d_ewald_coeff_dl_exact(r, alpha, C.byref(a)))
+    return a.value
+
+
+class EwaldOperator:
+    """One context per GPU: the module state of ModConf / ModData / ModPME behind the drop-in boundary."""
+
+    def __init__(self, Lb, alpha=0.44, eps=1e-3, P=8, rc=None, Nb=None, device=-1, nranks=1):
+        self.lib = capi.load()
+        self.Lb = np.asarray(Lb, dtype=np.float64)
+        self.alpha, self.eps, self.P = float(alpha), float(eps), int(P)
+        rc0, Nb0 = SetEwaldPrms(self.Lb, alpha, eps, P, nranks)
+        self.rc = rc0 if rc is None else float(rc)
+        self.Nb = Nb0 if Nb is None else [int(v) for v in Nb]
+        self._h = C.c_void_p()
+        Lb3 = (C.c_double * 3)(*self.Lb)
+        Nb3 = (C.c_int32 * 3)(*self.Nb)
+        check(self.lib.rbc3d_ctx_create(C.byref(self._h), Lb3, self.alpha, self.eps, self.P, self.rc, Nb3, device),
+              "rbc3d_ctx_create (PME_Init)")
+        self.ncell = self.npoint = 0
+        self.n_raw = 0
+        self._keep = {}
+
+    # -- lifetime ---------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.rbc3d_ctx_destroy(self._h)  # PME_Finalize
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- ModEwaldFunc -----------------------------------------------------------------------------------
+    def EwaldCoeff_SL(self, r):
+        a, b = C.c_double(), C.c_double()
+        check(self.lib.rbc3d_ewald_coeff_sl(self._h, r, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def EwaldCoeff_DL(self, r):
+        a = C.c_double()
+        check(self.lib.rbc3d_ewald_coeff_dl(self._h, r, C.byref(a)))
+        return a.value
+
+    # -- cells ------------------------------------------------------------------------------------------
+    def set_mesh(self, ncell, nlat, nlon, th, phi, w):
+        th, phi, w = f64(th), f64(phi), f64(w)
+        check(self.lib.rbc3d_cells_set_mesh(self._h, ncell, nlat, nlon, dp(th), dp(phi), dp(w)), "rbc3d_cells_set_mesh")
+        self.ncell, self.nlat, self.nlon = ncell, nlat, nlon
+        self.npoint = ncell * nlat * nlon
+
+    def SourceList_UpdateCoord(self, x, a3, Acoef, Bcoef, area, meshSize, spx, spa3, spdetj, active=None):
+        """SourceList_UpdateCoord + TargetList_Update for the cell lists (rebuilds the cell list)."""
+        arrs = [f64(a) for a in (x, a3, Acoef, Bcoef, area, meshSize, spx, spa3, spdetj)]
+        act = i32(active)
+        check(self.lib.rbc3d_cells_set_geometry(self._h, *[dp(a) for a in arrs], ip(act)), "rbc3d_cells_set_geometry")
+
+    def SourceList_UpdateDensity(self, f=None, g=None, spF=None, spG=None):
+        """f, g: slist%f / slist%g (densities * detJ * w); spF, spG: splines of f*detJ, g*detJ."""
+        f, g, spF, spG = f64(f), f64(g), f64(spF), f64(spG)
+        check(self.lib.rbc3d_cells_set_density(self._h, dp(f), dp(g), dp(spF), dp(spG)), "rbc3d_cells_set_density")
+
+    def set_suspension(self, sus, active=None, with_f=True, with_g=True):
+        """Convenience: load a rbc3d_b200.synth.Suspension."""
+        self.set_mesh(sus.ncell, sus.nlat, sus.nlon, sus.th, sus.phi, sus.w)
+        self.SourceList_UpdateCoord(sus.x, sus.a3, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize, sus.spx, sus.spa3,
+                                    sus.spdetj, active)
+        f = sus.weighted(sus.f) if (with_f and sus.f is not None) else None
+        g = sus.weighted(sus.g) if (with_g and sus.g is not None) else None
+        self.SourceList_UpdateDensity(f, g, sus.spF if f is not None else None, sus.spG if g is not None else None)
+
+    def TargetList_CreateFromRaw(self, x, active=None):
+        x = f64(x)
+        act = i32(active)
+        self.n_raw = x.shape[1]
+        check(self.lib.rbc3d_targets_set_raw(self._h, self.n_raw, dp(x), ip(act)), "rbc3d_targets_set_raw")
+
+    def _n(self, tlist):
+        return self.npoint if tlist == TL_CELLS else self.n_raw
+
+    def _v(self, tlist, v):
+        if v is None:
+            return np.zeros((3, self._n(tlist)))
+        assert v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (3, self._n(tlist))
+        return v
+
+    # -- operator pieces (reference names) ----------------------------------------------------------------
+    def AddIntOnRbcs(self, c1, c2, tlist=TL_CELLS, v=None):
+        v = self._v(tlist, v)
+        check(self.lib.rbc3d_add_int_on_rbcs(self._h, c1, c2, tlist, dp(v)), "AddIntOnRbcs")
+        return v
+
+    def PME_Distrib_Source(self, c1, c2, cells=True, walls=False):
+        check(self.lib.rbc3d_pme_distrib_source(self._h, c1, c2, int(cells), int(walls)), "PME_Distrib_Source")
+
+    def PME_Transform(self):
+        check(self.lib.rbc3d_pme_transform(self._h), "PME_Transform")
+
+    def PME_Add_Interp_Vel(self, tlist=TL_CELLS, v=None):
+        v = self._v(tlist, v)
+        check(self.lib.rbc3d_pme_add_interp_vel(self._h, tlist, dp(v)), "PME_Add_Interp_Vel")
+        return v
+
+    def apply(self, c1, c2, tlist=TL_CELLS, v=None, cells=True, walls=False):
+        v = self._v(tlist, v)
+        check(self.lib.rbc3d_apply(self._h, c1, c2, int(cells), int(walls), tlist, dp(v)), "rbc3d_apply")
+        return v
+
+    def apply_resident(self, c1, c2, tlist=TL_CELLS, cells=True, walls=False):
+        check(self.lib.rbc3d_apply_resident(self._h, c1, c2, int(cells), int(walls), tlist), "rbc3d_apply_resident")
+
+    def get_velocity(self, tlist=TL_CELLS):
+        v = np.zeros((3, self._n(tlist)))
+        check(self.lib.rbc3d_get_velocity(self._h, tlist, dp(v)), "rbc3d_get_velocity")
+        return v
+
+    def set_skip_flags(self, flags):
+        check(self.lib.rbc3d_set_skip_flags(self._h, flags))
+
+    # -- introspection ------------------------------------------------------------------------------------
+    def cell_list(self):
+        Nc = (C.c_int32 * 3)()
+        check(self.lib.rbc3d_cell_list_get(self._h, Nc, None, None, None))
+        ncells = Nc[0] * Nc[1] * Nc[2]
+        cid = np.zeros(self.npoint, dtype=np.int32)
+        order = np.zeros(self.npoint, dtype=np.int32)
+        start = np.zeros(ncells + 1, dtype=np.int32)
+        check(self.lib.rbc3d_cell_list_get(self._h, Nc, ip(cid), ip(order), ip(start)))
+        return [int(v) for v in Nc], cid, order, start
+
+    def neighbor_signature(self, tlist=TL_CELLS):
+        n = self._n(tlist)
+        cnt = np.zeros(n, dtype=np.int32)
+        sig = np.zeros(n, dtype=np.uint64)
+        check(self.lib.rbc3d_neighbor_signature(self._h, tlist, ip(cnt), sig.ctypes.data_as(capi.c_up)))
+        return cnt, sig
+
+    def nearsing_entries(self, tlist=TL_CELLS):
+        n = C.c_int()
+        check(self.lib.rbc3d_nearsing_get(self._h, tlist, C.byref(n), None, None, None, None, None, None, 0))
+        m = n.value
+        out = dict(target=np.zeros(m, np.int32), cell=np.zeros(m, np.int32), flag=np.zeros(m, np.int32),
+                   th0=np.zeros(m), phi0=np.zeros(m), dist=np.zeros(m))
+        if m:
+            check(self.lib.rbc3d_nearsing_get(self._h, tlist, C.byref(n), ip(out["target"]), ip(out["cell"]),
+                                              ip(out["flag"]), dp(out["th0"]), dp(out["phi0"]), dp(out["dist"]), m))
+        return out
+
+    def pme_grid(self):
+        Nx, Ny, Nz = self.Nb
+        vv = np.zeros((3, Nz, Ny, Nx))
+        check(self.lib.rbc3d_pme_get_grid(self._h, dp(vv)))
+        return vv
+
+    def timings(self):
+        ms = (C.c_float * len(capi.STAGES))()
+        check(self.lib.rbc3d_get_timings(self._h, ms))
+        return {k: float(ms[i]) for i, k in enumerate(capi.STAGES)}
+
+    def launch_count(self):
+        n = C.c_longlong()
+        check(self.lib.rbc3d_get_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+def measure_fp64_peak(device=-1):
+    t = C.c_double()
+    check(capi.load().rbc3d_measure_fp64_peak(device, C.byref(t)), "rbc3d_measure_fp64_peak")
+    return t.value

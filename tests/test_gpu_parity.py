@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA path behind the C ABI against the CPU oracle on the same seeded inputs.
+
+Tolerance: relative L2 error of the velocity over all targets <= 1e-10 in FP64 (BASELINE.json north_star);
+cell ids and in-range neighbour sets bit-exact."""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import C1_RHS, C2_MATVEC, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def sus8():
+    return util.small_suspension(2)
+
+
+@pytest.fixture(scope="module")
+def pair8(sus8, oracle_lib):
+    from rbc3d_b200.ewald import EwaldOperator
+    op = EwaldOperator(sus8.Lb)
+    op.set_suspension(sus8)
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
+    yield op, orc
+    op.close()
+
+
+def test_parameters_match(pair8):
+    op, orc = pair8
+    assert op.rc == orc.rc
+    assert op.Nb == orc.Nb
+
+
+def test_cell_list_bit_exact(pair8, sus8):
+    op, orc = pair8
+    Nc, cid, order, start = op.cell_list()
+    assert Nc == orc.Nc
+    ref = orc.cell_ids(sus8.x)
+    assert np.array_equal(cid, ref)
+    # sorted by cell, ascending index inside a cell, offsets = prefix sums of the histogram
+    assert np.array_equal(order, np.argsort(ref, kind="stable").astype(np.int32))
+    assert np.array_equal(start, np.concatenate([[0], np.cumsum(np.bincount(ref, minlength=len(start) - 1))]))
+
+
+def test_neighbor_sets_bit_exact(pair8, sus8):
+    op, orc = pair8
+    cnt, sig = op.neighbor_signature()
+    rcnt, rsig = orc.neighbor_signature(sus8.x, sus8.x)
+    assert np.array_equal(cnt, rcnt)
+    assert np.array_equal(sig, rsig)
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)])
+def test_pair_sum(pair8, c1, c2):
+    op, orc = pair8
+    op.set_skip_flags(1 | 2 | 4)
+    v = op.AddIntOnRbcs(c1, c2)
+    op.set_skip_flags(0)
+    ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
+    assert rel_l2(v, ref) < TOL
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0)])
+def test_singular(pair8, c1, c2):
+    op, orc = pair8
+    op.set_skip_flags(2 | 4 | 8)
+    v = op.AddIntOnRbcs(c1, c2)
+    op.set_skip_flags(0)
+    ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_PAIRS | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
+    assert rel_l2(v, ref) < TOL
+
+
+def test_linear_term(pair8):
+    op, orc = pair8
+    op.set_skip_flags(1 | 2 | 8)
+    v = op.AddIntOnRbcs(0.0, C2_MATVEC)
+    op.set_skip_flags(0)
+    ref = orc.add_int_on_rbcs(0.0, C2_MATVEC, orc.cell_targets(), flags=orc.FLAG_NO_PAIRS | orc.FLAG_NO_NEARSING | orc.FLAG_NO_SING)
+    assert rel_l2(v, ref) < TOL
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0)])
+def test_add_int_on_rbcs_full(pair8, c1, c2):
+    op, orc = pair8
+    v = op.AddIntOnRbcs(c1, c2)
+    ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets())
+    assert rel_l2(v, ref) < TOL
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)])
+def test_pme_triple(pair8, sus8, c1, c2):
+    """PME_Distrib_Source -> PME_Transform -> PME_Add_Interp_Vel: mesh velocities and target velocities."""
+    op, orc = pair8
+    op.PME_Distrib_Source(c1, c2, cells=True)
+    op.PME_Transform()
+    v = op.PME_Add_Interp_Vel()
+    npc = sus8.nlat * sus8.nlon
+    orc.pme_distrib(c1, c2, sus8.x, sus8.weighted(sus8.f), sus8.weighted(sus8.g), sus8.a3, np.repeat(sus8.Bcoef, npc))
+    orc.pme_transform()
+    ref = orc.pme_interp(orc.cell_targets())
+    assert rel_l2(op.pme_grid(), orc.pme_vv()) < TOL
+    assert rel_l2(v, ref) < TOL
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0)])
+def test_apply_matches_oracle(pair8, c1, c2):
+    """the whole operator as the GMRES callbacks use it (ModVelSolver.F90:473-489, 568-582)."""
+    op, orc = pair8
+    v = op.apply(c1, c2)
+    ref = orc.apply_cells(c1, c2, orc.cell_targets())
+    assert rel_l2(v, ref) < TOL
+    # resident path returns the same numbers, and accumulation into a non-zero v works
+    op.apply_resident(c1, c2)
+    assert rel_l2(op.get_velocity(), ref) < TOL
+    v2 = op.apply(c1, c2, v=np.ones_like(ref))
+    assert rel_l2(v2 - 1.0, ref) < 1e-9
+
+
+def test_raw_targets(pair8, sus8):
+    """CalcVelocityField-style targets (ModPostProcess.F90:40-59): indx = -1, Acoef = 2, no self mask."""
+    op, orc = pair8
+    rng = np.random.default_rng(3)
+    xt = rng.uniform(0, sus8.Lb[0], size=(3, 500))
+    # a few points outside the box and a few hugging a membrane
+    xt[:, :5] -= sus8.Lb[0]
+    xt[:, 5:25] = sus8.x[:, 100:2100:100] + 0.05 * sus8.a3[:, 100:2100:100]
+    # inside the |dist| < 0.01*sizePat band on both sides of a membrane (jump-condition interpolation branch)
+    xt[:, 25:35] = sus8.x[:, 3000:4000:100] + 0.003 * sus8.a3[:, 3000:4000:100]
+    xt[:, 35:45] = sus8.x[:, 5000:6000:100] - 0.002 * sus8.a3[:, 5000:6000:100]
+    xt[:, 45:50] = sus8.x[:, 7000:7500:100] - 0.2 * sus8.a3[:, 7000:7500:100]
+    op.TargetList_CreateFromRaw(xt)
+    from rbc3d_b200.ewald import TL_RAW
+    v = op.apply(C1_RHS, C1_RHS, tlist=TL_RAW)
+    ref = orc.apply_cells(C1_RHS, C1_RHS, orc.make_targets(xt))
+    assert rel_l2(v, ref) < TOL
+
+
+def test_inactive_targets_untouched(sus8, oracle_lib):
+    from rbc3d_b200.ewald import EwaldOperator
+    act = (np.arange(sus8.npoint) % 3 == 0).astype(np.int32)
+    op = EwaldOperator(sus8.Lb)
+    op.set_suspension(sus8, active=act)
+    v = op.apply(0.0, C2_MATVEC, v=np.full((3, sus8.npoint), 7.0))
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
+    ref = orc.apply_cells(0.0, C2_MATVEC, orc.cell_targets(active=act), v=np.full((3, sus8.npoint), 7.0))
+    assert np.all(v[:, act == 0] == 7.0)
+    assert rel_l2(v - 7.0, ref - 7.0) < TOL
+    op.close()
+
+
+@pytest.mark.parametrize("gap", [0.15, 0.03])
+def test_near_singular_pairs(gap, oracle_lib):
+    """cells almost in contact: projection, distance check, subtract, sinh re-add and the jump interpolation."""
+    from rbc3d_b200.ewald import EwaldOperator
+    sus = util.close_pair_suspension(gap=gap, extra=1)
+    op = EwaldOperator(sus.Lb)
+    op.set_suspension(sus)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    ent = op.nearsing_entries()
+    assert ent["flag"].sum() > 0, "test configuration does not trigger the near-singular path"
+    for c1, c2 in [(0.0, C2_MATVEC), (C1_RHS, 0.0)]:
+        op.set_skip_flags(1 | 4 | 8)
+        v = op.AddIntOnRbcs(c1, c2)
+        op.set_skip_flags(0)
+        ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_PAIRS | orc.FLAG_NO_SING | orc.FLAG_NO_LINEAR)
+        assert rel_l2(v, ref) < 1e-9, (c1, c2)
+        v = op.apply(c1, c2)
+        ref = orc.apply_cells(c1, c2, orc.cell_targets())
+        assert rel_l2(v, ref) < TOL, (c1, c2)
+    op.close()
+
+
+def test_noncubic_box_small_cells(oracle_lib):
+    """non-cubic box (minicase-like 10.5 x 10.5 x 8), different Nb per axis, fewer modes (nlat0 = 6)."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    rng = np.random.default_rng(5)
+    Lb = np.array([10.5, 10.5, 8.0])
+    centers = np.array([[3.0, 3.0, 2.0], [7.0, 6.5, 5.5], [3.5, 7.5, 6.0]])
+    sus = synth.make_suspension(1, nlat0=6, centers=centers, L=1.0, seed=11)
+    sus.Lb = Lb
+    op = EwaldOperator(Lb)
+    op.set_suspension(sus)
+    orc = oracle_lib.Oracle(Lb).set_cells(sus)
+    assert op.Nb == orc.Nb == [48, 48, 36]
+    v = op.apply(C1_RHS, C1_RHS)
+    ref = orc.apply_cells(C1_RHS, C1_RHS, orc.cell_targets())
+    assert rel_l2(v, ref) < TOL
+    op.close()
+
+
+def test_timings_and_launch_count(pair8):
+    op, _ = pair8
+    n0 = op.launch_count()
+    op.apply_resident(0.0, C2_MATVEC)
+    t = op.timings()
+    assert op.launch_count() > n0
+    assert t["pair"] > 0 and t["sing"] > 0 and t["spread"] > 0 and t["fft"] > 0 and t["interp"] > 0
