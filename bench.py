@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- Ewald boundary-integral matvecs/s on the synthetic periodic suspension of BASELINE.json configs[2].
+
+One "step" = one application of the cell double-layer operator that every GMRES iteration of ModVelSolver
+evaluates (MyMatMult, ModVelSolver.F90:523-601: c1 = 0, c2 = -1/(4 pi), cell sources -> cell targets):
+SourceList_UpdateDensity(g) + AddIntOnRbcs (pair sum, singular, near-singular, linear term) + PME_Distrib_Source +
+PME_Transform + PME_Add_Interp_Vel [+ TargetList_CollectArray when N > 1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells 4096] [--impl reference]
+
+* value  = matvecs/s with g / spline(g) already resident in HBM (rbc3d_apply_resident), device time (CUDA events
+           recorded by the library on its own stream), max over ranks.
+* e2e    = the same metric through the reference-facing C ABI with HOST buffers: rbc3d_cells_set_density(g, spG)
+           + rbc3d_apply(v) -- host->device copies of g, spline(g*detJ), v and the device->host copy of v are
+           inside the timed region (wall clock around the synchronous calls).
+* roofline / kernels = per-kernel algorithmic work / CUDA-event time / measured peak.
+* cpu_baseline = the CPU restatement of the reference operator (oracle/, "port": the Fortran reference cannot be
+           built in this image) on the host cores of the GPU box, on a bounded sample of the same workload.
+* --impl reference = that CPU operator alone (no GPU), same metric/config.
+
+Inputs are larger than L2 (>= 8.8 GB of spline data + 1.2 GB of meshes at 4096 cells), so no explicit L2 flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C2_MATVEC = -1.0 / (4.0 * np.pi)
+FLOPS_DL_PAIR = 54.0      # flops per in-range double-layer pair (FMA = 2)
+FLOPS_SPLINE3 = 155.0     # one bicubic interpolation of 3 variables
+FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
+
+
+def n_side_of(cells: int) -> int:
+    n = round(cells ** (1.0 / 3.0))
+    if n ** 3 != cells:
+        raise SystemExit(f"--cells must be a cube (64, 512, 4096); got {cells}")
+    return n
+
+
+def workload_name(cells, Nb):
+    return f"synthetic periodic box, {cells} RBCs, SH order 12 (36x72 pts/cell), PME grid {Nb[0]}x{Nb[1]}x{Nb[2]}"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([s.strip() for s in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("hbm_gbs", 6650.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_operator_sample(sus, sample_cells: int, spread_stride: int = 1, threads: int | None = None):
+    """Time the CPU restatement on a bounded sample of the workload: ALL cells are sources of the real-space sum,
+    the PME transform runs in full, the PME spread covers every ``spread_stride``-th cell (linear in sources),
+    real-space sums and interpolation only the targets of the first ``sample_cells`` cells (exactly how a
+    reference MPI rank works on its slab); both are extrapolated linearly.
+    Returns (seconds per full matvec, detail dict)."""
+    from oracle import oracle  # the one place bench.py runs oracle/: cpu_baseline and --impl reference
+    if threads:
+        oracle.lib().orc_set_num_threads(int(threads))
+    cores = int(oracle.lib().orc_num_threads())
+    orc = oracle.Oracle(sus.Lb).set_cells(sus)
+    npc = sus.nlat * sus.nlon
+    ns = min(sample_cells, sus.ncell)
+    act = np.zeros(sus.npoint, np.int32)
+    # a compact block of cells (neighbouring lattice sites) so that the sample sees typical neighbourhoods
+    act[:ns * npc] = 1
+    tl = orc.cell_targets(active=act)
+    t0 = time.perf_counter()
+    orc.add_int_on_rbcs(0.0, C2_MATVEC, tl)
+    t_real = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    gw, Bp = sus.weighted(sus.g), np.repeat(sus.Bcoef, npc)
+    sel = slice(None)
+    if spread_stride > 1:
+        sel = (np.arange(sus.npoint) // npc) % spread_stride == 0
+    xs, gs, a3s, Bs = (np.ascontiguousarray(a[..., sel]) for a in (sus.x, gw, sus.a3, Bp))
+    t0 = time.perf_counter()
+    orc.pme_distrib(0.0, C2_MATVEC, xs, None, gs, a3s, Bs)
+    t_spread = (time.perf_counter() - t0) * (sus.npoint / xs.shape[1])
+    t0 = time.perf_counter()
+    orc.pme_transform()
+    t_fft = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.pme_interp(tl)
+    t_interp = time.perf_counter() - t0
+    scale = sus.ncell / ns
+    total = (t_real + t_interp) * scale + t_spread + t_fft
+    detail = {"cores": cores, "sample_cells": ns, "spread_stride": spread_stride, "t_realspace_sample_s": t_real, "t_interp_sample_s": t_interp,
+              "t_spread_full_s": t_spread, "t_transform_full_s": t_fft, "extrapolated_matvec_s": total}
+    return total, detail
+
+
+def sample_text(d, ncell):
+    cpu_s = (d["t_realspace_sample_s"] + d["t_interp_sample_s"] + d["t_spread_full_s"] / d["spread_stride"] +
+             d["t_transform_full_s"])
+    return (f"all {ncell} cells as real-space sources, PME FFT+scaling in full, PME spread of every "
+            f"{d['spread_stride']}-th cell (x{d['spread_stride']}), real-space sums + interpolation for the targets of "
+            f"{d['sample_cells']} cells (x{ncell / d['sample_cells']:.0f}); {cpu_s:.1f} s of CPU work per sample")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import SetEwaldPrms
+    n_side = n_side_of(args.cells)
+    sus = synth.make_suspension(n_side, seed=args.seed, with_f=False)
+    _, Nb = SetEwaldPrms(sus.Lb)
+    times = []
+    detail = None
+    for it in range(args.warmup + args.steps):
+        t, detail = cpu_operator_sample(sus, args.ref_sample_cells, args.ref_spread_stride)
+        if it >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    cb = {"value": val, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
+          "sample": sample_text(detail, sus.ncell), "detail": detail}
+    out = {"impl": "reference", "metric": "Ewald BI matvecs/s", "value": val, "unit": "matvecs/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(sus.ncell, Nb), "cells": sus.ncell, "points": sus.npoint,
+                      "seed": args.seed},
+           "cpu_baseline": cb,
+           "e2e": {"value": val, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def kernel_table(op, sus, ms, npairs, peaks):
+    """Algorithmic work per application (DESIGN.md "Kernels") / CUDA-event time -> roofline fractions."""
+    hbm_peak, fp64_peak = peaks
+    N = sus.npoint
+    P3 = op.P ** 3
+    Nx, Ny, Nz = op.Nb
+    G = Nx * Ny * Nz
+    M = (Nx // 2 + 1) * Ny * Nz
+    npatch = op.nrad * op.nazm
+    rows = []
+
+    def add(name, t_ms, flops=None, bytes_=None, bound="fp64"):
+        if t_ms <= 0:
+            return
+        r = {"kernel": name, "ms": t_ms, "bound": bound}
+        if flops is not None:
+            r["tflops"] = flops / (t_ms * 1e-3) / 1e12
+            r["frac_fp64"] = r["tflops"] / fp64_peak if fp64_peak else None
+        if bytes_ is not None:
+            r["gbs"] = bytes_ / (t_ms * 1e-3) / 1e9
+            r["frac_hbm"] = r["gbs"] / hbm_peak
+        rows.append(r)
+
+    add("pair_sum(DL)", ms["pair"], flops=npairs * FLOPS_DL_PAIR)
+    add("singular(DL)", ms["sing"], flops=N * npatch * (3 * FLOPS_SPLINE3 + FLOPS_PATCH_EXTRA))
+    add("near_singular", ms["nearsing"])
+    add("spread(DL,6 sym comps)", ms["spread"], flops=N * P3 * (2 + 2 * 6), bytes_=80.0 * N + 2 * 6 * 8.0 * G)
+    add("fft_fwd(cuFFT D2Z x6)", ms["fft"], bytes_=6 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
+    add("kspace_scale", ms["kspace"], bytes_=(6 + 3) * 16.0 * M, bound="hbm")
+    add("fft_inv(cuFFT Z2D x3)", ms["fft_inv"], bytes_=3 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
+    add("interp", ms["interp"], flops=N * P3 * 8.0, bytes_=3 * 8.0 * G + 56.0 * N)
+    add("density_gather", ms["density"], bytes_=(3 * 8 * 2 + 4 + 8) * N, bound="hbm")
+    add("combine", ms["combine"], bytes_=(3 * 8 * 2 + 12) * N, bound="hbm")
+    return rows
+
+
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rbc3d_b200 import capi, synth
+    from rbc3d_b200.ewald import EwaldOperator, measure_fp64_peak
+
+    n_side = n_side_of(args.cells)
+    t0 = time.perf_counter()
+    sus = synth.make_suspension(n_side, seed=args.seed, with_f=False)
+    t_synth = time.perf_counter() - t0
+    op = EwaldOperator(sus.Lb, device=local, nranks=1)
+    if world > 1:
+        op.attach_comm(world, rank, dist)
+    t0 = time.perf_counter()
+    active = op.ownership_mask(sus, world, rank) if world > 1 else None
+    op.set_suspension(sus, active=active, with_f=False)
+    t_setup = time.perf_counter() - t0
+    N = sus.npoint
+    g_host = np.ascontiguousarray(sus.weighted(sus.g))
+    spG_host = np.ascontiguousarray(sus.spG)
+    v_host = np.zeros((3, N))
+    lib = capi.load()
+    for a in (g_host, spG_host, v_host):
+        capi.check(lib.rbc3d_host_register(a.ctypes.data, a.nbytes), "rbc3d_host_register")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident timing -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        op.apply_resident(0.0, C2_MATVEC)
+    l0 = op.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    stage_ms = {k: 0.0 for k in capi.STAGES}
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        op.apply_resident(0.0, C2_MATVEC)
+        t = op.timings()
+        for k in stage_ms:
+            stage_ms[k] += t[k]
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = op.launch_count() - l0
+    dev_ms = stage_ms["total"] / args.steps
+    ms_rank = torch.tensor([dev_ms, wall * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms_rank, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(ms_rank[0]), float(ms_rank[1])
+    for k in stage_ms:
+        stage_ms[k] /= args.steps
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    e2e_steps = 1 if args.profile else max(1, min(args.steps, args.e2e_steps))
+    for _ in range(0 if args.profile else min(2, args.warmup)):
+        op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
+        v_host[:] = 0.0
+        op.apply(0.0, C2_MATVEC, v=v_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
+        op.apply(0.0, C2_MATVEC, v=v_host)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t[0])
+    clocks = sampler.stop()
+    h2d = g_host.nbytes + spG_host.nbytes + v_host.nbytes
+    d2h = v_host.nbytes
+
+    if rank != 0:
+        op.close()
+        return 0
+
+    hbm_peak, peak_src = measured_peaks()
+    fp64_peak = measure_fp64_peak(local)
+    cnt, _ = op.neighbor_signature()
+    npairs = float(cnt.astype(np.float64).sum())
+    rows = kernel_table(op, sus, stage_ms, npairs, (hbm_peak, fp64_peak))
+    dom = max(rows, key=lambda r: r["ms"])
+    if dom.get("tflops") is not None and dom["bound"] == "fp64":
+        roof = {"kernel": dom["kernel"], "bound": "fp64", "achieved": dom["tflops"], "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": dom["tflops"] / fp64_peak, "traffic": None,
+                "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)"}
+    else:
+        roof = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom.get("gbs"), "peak": hbm_peak, "unit": "GB/s",
+                "frac": (dom.get("gbs") or 0.0) / hbm_peak, "traffic": None, "peak_source": peak_src}
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        tcpu, detail = cpu_operator_sample(sus, args.cpu_sample_cells)
+        cb = {"value": 1.0 / tcpu, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
+              "sample": sample_text(detail, sus.ncell), "detail": detail}
+
+    out = {"metric": "Ewald BI matvecs/s", "value": world_value(1e3 / dev_ms), "unit": "matvecs/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+           "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(sus.ncell, op.Nb), "cells": sus.ncell, "points": N,
+                      "alpha": op.alpha, "eps": op.eps, "P": op.P, "rc": op.rc, "Nc": op.cell_list_dims(),
+                      "visc_ratio": 5.0, "seed": args.seed, "in_range_pairs": npairs,
+                      "l2": "inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
+                      "partition": "targets by owned cell, sources replicated" if world > 1 else "single GPU"},
+           "clocks": clocks,
+           "e2e": {"value": 1.0 / e2e_s, "unit": "matvecs/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches),
+           "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
+           "roofline": roof, "kernels": rows,
+           "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "fp64_tflops": fp64_peak,
+                     "fp64_source": "in-process DFMA micro-benchmark"},
+           "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
+    if cb is not None:
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    op.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def world_value(v):
+    return float(v)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=161269)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-cells", type=int, default=32)
+    ap.add_argument("--ref-sample-cells", type=int, default=8, help="--impl reference: target cells per step")
+    ap.add_argument("--ref-spread-stride", type=int, default=8, help="--impl reference: spread every n-th cell")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: exact --warmup, no CPU leg, 1 e2e step")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not args.profile:
+        args.warmup = 3   # timing hygiene: at least 3 warm-up steps
+    if args.profile:
+        args.no_cpu_baseline = True
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -570,6 +570,7 @@ static int realspace_cells(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
 
 static int begin_apply(rbc3d_ctx *c, TargetList &t) {
   for (int i = 0; i < RBC3D_T_COUNT; i++) c->ev_used[i] = false;
+  t_begin(c, RBC3D_T_TOTAL);
   CUDA_TRY(cudaMemsetAsync(t.acc.p, 0, sizeof(double) * 3 * (size_t)(t.n > 0 ? t.n : 1), c->stream));
   return RBC3D_OK;
 }
@@ -585,6 +586,7 @@ static int v_roundtrip_end(rbc3d_ctx *c, TargetList &t, double *v) {
   t_begin(c, RBC3D_T_D2H);
   if (t.n) CUDA_TRY(cudaMemcpyAsync(v, t.host_io.p, sizeof(double) * 3 * t.n, cudaMemcpyDeviceToHost, c->stream));
   t_end(c, RBC3D_T_D2H);
+  t_end(c, RBC3D_T_TOTAL);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -674,10 +676,16 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   TargetList *t;
   RBC_TRY(get_tl(c, tlist, &t));
   RBC_TRY(begin_apply(c, *t));
+  // density-dependent part of SourceList_UpdateDensity (ModSourceList.F90:160-187) redone from the resident
+  // f / g so that a resident step does the same per-matvec work as ModVelSolver.F90:560-565
+  t_begin(c, RBC3D_T_DENSITY);
+  if (use_cells) RBC_TRY(cells_gather_sorted(c, false, c1 != 0 && c->cells.f_set, c2 != 0 && c->cells.g_set));
+  t_end(c, RBC3D_T_DENSITY);
   RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
   t_begin(c, RBC3D_T_COMBINE);
   RBC_TRY(combine(c, *t, t->v.p, false));
   t_end(c, RBC3D_T_COMBINE);
+  t_end(c, RBC3D_T_TOTAL);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }

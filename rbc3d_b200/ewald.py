@@ -92,6 +92,9 @@ class EwaldOperator:
         check(self.lib.rbc3d_cells_set_mesh(self._h, ncell, nlat, nlon, dp(th), dp(phi), dp(w)), "rbc3d_cells_set_mesh")
         self.ncell, self.nlat, self.nlon = ncell, nlat, nlon
         self.npoint = ncell * nlat * nlon
+        # shared polar patch size, RbcPolarPatch_Create (ModPolarPatch.F90:42-45)
+        self.nrad = 2 * int(round((np.pi / np.sqrt(nlat)) / (np.pi / nlat)))
+        self.nazm = 2 * self.nrad
 
     def SourceList_UpdateCoord(self, x, a3, Acoef, Bcoef, area, meshSize, spx, spa3, spdetj, active=None):
         """SourceList_UpdateCoord + TargetList_Update for the cell lists (rebuilds the cell list)."""
@@ -171,6 +174,11 @@ class EwaldOperator:
         start = np.zeros(ncells + 1, dtype=np.int32)
         check(self.lib.rbc3d_cell_list_get(self._h, Nc, ip(cid), ip(order), ip(start)))
         return [int(v) for v in Nc], cid, order, start
+
+    def cell_list_dims(self):
+        Nc = (C.c_int32 * 3)()
+        check(self.lib.rbc3d_cell_list_get(self._h, Nc, None, None, None))
+        return [int(v) for v in Nc]
 
     def neighbor_signature(self, tlist=TL_CELLS):
         n = self._n(tlist)

@@ -1,0 +1,313 @@
+"""CPU tests of the oracle itself.  The reference ships no tests or golden vectors for this path
+(PARITY UNPINNED), so the C restatement under oracle/ is pinned by (a) an independent NumPy/SciPy restatement of
+the closed-form pieces written here from the formulas of the reference, and (b) physics identities that only hold
+if kernels, signs, FFT conventions, quadratures and the Ewald split are mutually consistent."""
+import numpy as np
+import pytest
+from scipy.special import erfc
+
+from rbc3d_b200 import synth
+from tests import util
+from tests.util import C1_RHS, C2_MATVEC
+
+PI = np.pi
+
+
+# ---- independent NumPy restatement of the closed forms -------------------------------------------------
+def sl_exact(r, alpha):  # ModEwaldFunc.F90:25-52
+    rt = np.sqrt(PI / alpha) * r
+    c1, c2 = erfc(rt), 2 / np.sqrt(alpha) * np.exp(-rt * rt)
+    return c1 / r ** 3 + c2 / r ** 2, c1 / r - c2
+
+
+def dl_exact(r, alpha):  # ModEwaldFunc.F90:59-79
+    rt = np.sqrt(PI / alpha) * r
+    a = np.exp(-rt * rt) * (1.5 * rt + rt ** 3) + 0.75 * np.sqrt(PI) * erfc(rt)
+    return -8 / np.sqrt(PI) * a / r ** 5
+
+
+def real_space_points(x, Lb, alpha, rcut, f=None, T=None, nimg=1):
+    """direct O(n^2 * images) real-space Ewald sum at the source points themselves; xx = x_src - x_tgt."""
+    n = x.shape[1]
+    v = np.zeros((3, n))
+    shifts = [np.array([a, b, c]) * Lb for a in range(-nimg, nimg + 1) for b in range(-nimg, nimg + 1)
+              for c in range(-nimg, nimg + 1)]
+    for i in range(n):
+        for s in shifts:
+            xx = x + s[:, None] - x[:, i:i + 1]
+            r = np.sqrt((xx ** 2).sum(0))
+            ok = (r > 1e-12) & (r < rcut)
+            xo, ro = xx[:, ok], r[ok]
+            if f is not None:
+                A, B = sl_exact(ro, alpha)
+                fo = f[:, ok]
+                v[:, i] += (A * xo * (xo * fo).sum(0) + B * fo).sum(1)
+            if T is not None:  # T[j] = g_j (x) n_j
+                A = dl_exact(ro, alpha)
+                To = T[:, :, ok]
+                v[:, i] += (A * xo * np.einsum("an,abn,bn->n", xo, To, xo)).sum(1)
+    return v
+
+
+def kspace_direct(x, Lb, alpha, kmax, f=None, T=None):
+    """direct k-space sum with exact structure factors, multipliers of ModPME.F90:165-206."""
+    V = np.prod(Lb)
+    n = x.shape[1]
+    v = np.zeros((3, n))
+    rng_ = [np.arange(-kmax[d], kmax[d] + 1) for d in range(3)]
+    K = np.stack(np.meshgrid(*rng_, indexing="ij"), -1).reshape(-1, 3)
+    K = K[(K != 0).any(1)]
+    q = K / Lb[None, :]                                  # (nq, 3)
+    ph = np.exp(-2j * PI * (q @ x))                      # (nq, n)  e^{-2 pi i q.x_j}
+    q2t = PI * alpha * (q ** 2).sum(1)
+    e = np.exp(-q2t)
+    phi0 = e / q2t
+    phi1 = (e + phi0) / q2t
+    Vq = np.zeros((len(q), 3), complex)
+    if f is not None:
+        F = ph @ f.T                                      # (nq, 3)
+        qt = np.sqrt(PI * alpha) * q
+        Vq += (2 * alpha / V * phi1)[:, None] * (q2t[:, None] * F - qt * (qt * F).sum(1)[:, None])
+    if T is not None:
+        Tq = np.einsum("qn,abn->qab", ph, T)              # (nq, 3, 3)
+        tr = np.trace(Tq, axis1=1, axis2=2)
+        t = 1j * (4 * PI * alpha / V * phi0)[:, None] * (q * tr[:, None] + np.einsum("qa,qab->qb", q, Tq) +
+                                                         np.einsum("qab,qb->qa", Tq, q))
+        t -= 1j * (8 * PI ** 2 * alpha ** 2 / V * phi1 * np.einsum("qa,qab,qb->q", q, Tq, q))[:, None] * q
+        Vq -= t
+    v = np.real(np.einsum("qa,qn->an", Vq, np.conj(ph)))  # sum_q V e^{+2 pi i q.x}
+    return v
+
+
+@pytest.fixture(scope="module")
+def orc_mod(oracle_lib):
+    return oracle_lib
+
+
+# ---- A.6 (1): tables vs closed forms; C closed forms vs NumPy -------------------------------------------
+def test_ewald_tables_and_exact(orc_mod):
+    orc = orc_mod.Oracle([10.5, 10.5, 8.0])
+    assert abs(orc.rc - 1.19861) < 1e-5 and orc.Nb == [48, 48, 36] and orc.Nc == [8, 8, 6]
+    rs = np.linspace(0.02, orc.rc * 0.9999, 400)
+    for r in rs:
+        A, B = orc.ewald_sl(r)
+        Ae, Be = sl_exact(r, orc.alpha)
+        Ac, Bc = orc.ewald_sl_exact(r, orc.alpha)
+        assert abs(Ac - Ae) <= 1e-13 * abs(Ae) + 1e-300 and abs(Bc - Be) <= 1e-12 * (abs(Be) + 1)
+        assert abs(A - Ae) <= 2e-7 * abs(Ae) + 1e-7 and abs(B - Be) <= 2e-7 * (abs(Be) + 1)
+        D, De = orc.ewald_dl(r), dl_exact(r, orc.alpha)
+        assert abs(orc.ewald_dl_exact(r, orc.alpha) - De) <= 1e-12 * abs(De)
+        assert abs(D - De) <= 2e-7 * abs(De) + 1e-7
+    # cut-offs: zero below r_eps and at/after rc (ModEwaldFunc.F90:109-118)
+    assert orc.ewald_sl(1e-6) == (0.0, 0.0) and orc.ewald_dl(1e-6) == 0.0
+    assert orc.ewald_sl(orc.rc * 1.0000001) == (0.0, 0.0) and orc.ewald_dl(orc.rc) == 0.0
+
+
+def test_mask_function(orc_mod):
+    orc = orc_mod.Oracle([9.0, 9.0, 9.0])
+    assert orc.mask(0.0) == 1.0 and orc.mask(1.0) == 0.0 and orc.mask(1.7) == 0.0
+    for t in np.linspace(0.05, 0.95, 50):
+        ex = np.exp(2 * np.exp(-1 / t) / (t - 1))
+        assert abs(orc.mask(t) - ex) < 1e-7 and abs(orc.mask(-t) - ex) < 1e-7
+
+
+# ---- A.6 (2): B-spline partition of unity, cardinal values, modulus at k = 0 ----------------------------
+def test_bspline(orc_mod):
+    rng = np.random.default_rng(0)
+    for P in (4, 6, 8):
+        for xc in rng.uniform(-20, 20, 50):
+            imin, w = orc_mod.Oracle.bspline(xc, P)
+            assert imin == int(np.floor(xc)) - (P - 1)
+            assert abs(w.sum() - 1.0) < 1e-14 and (w >= 0).all()
+    # cubic cardinal B-spline at integers: 1/6, 4/6, 1/6
+    _, w = orc_mod.Oracle.bspline(5.0, 4)
+    assert np.allclose(w, [1 / 6, 4 / 6, 1 / 6, 0], atol=1e-15)
+    orc = orc_mod.Oracle([3.0, 3.0, 3.0])
+    bb = orc.pme_bb()
+    assert bb[0, 0, 0] == 0.0                     # ModPME.F90: bb(0,0,0) = 0
+    assert abs(bb[0, 0, 1] / bb[0, 1, 0] - 1.0) < 1e-13   # cubic box: symmetric
+
+
+def test_fft_conventions_vs_numpy(orc_mod):
+    """forward = (x,y) with e^{-i}, z with e^{+i}; backward the opposite; both unnormalised (ModPFFTW.F90:110-114)."""
+    orc = orc_mod.Oracle([3.0, 2.5, 2.0])
+    Nx, Ny, Nz = orc.Nb
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(Nz, Ny, Nx))
+    F = orc.fft_forward(a)
+    ref = np.fft.ifft(np.fft.rfft2(a, axes=(1, 2)), axis=0) * Nz
+    assert np.allclose(F, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+    back = orc.fft_backward(F)
+    assert np.allclose(back, a * (Nx * Ny * Nz), rtol=0, atol=1e-9 * Nx * Ny * Nz)
+
+
+# ---- A.6 (3): PME vs the direct k-space sum (B-spline error only, made small by a fine mesh) ----------
+@pytest.mark.parametrize("kind", ["sl", "dl"])
+def test_pme_matches_direct_kspace_sum(orc_mod, kind):
+    Lb = np.array([2.0, 2.6, 1.8])
+    alpha = 0.06
+    rng = np.random.default_rng(2)
+    n = 24
+    x = rng.uniform(0, 1, size=(3, n)) * Lb[:, None]
+    f = rng.normal(size=(3, n))
+    f -= f.mean(1, keepdims=True)
+    g, nrm, B = rng.normal(size=(3, n)), rng.normal(size=(3, n)), rng.uniform(0.5, 1.5, n)
+    Nb = [40, 52, 36]    # e^{-pi alpha q^2} at the Nyquist wave number ~ 1e-8: aliasing/truncation negligible
+    orc = orc_mod.Oracle(Lb, alpha=alpha, eps=1e-3, P=8, Nb=Nb, rc=0.55)
+    tl = orc.make_targets(x)
+    if kind == "sl":
+        orc.pme_distrib(1.0, 0.0, x, f=f)
+        ref = kspace_direct(x, Lb, alpha, [20, 26, 18], f=f)
+    else:
+        orc.pme_distrib(0.0, 1.0, x, g=g, a3=nrm, Bcoef=B)
+        T = np.einsum("an,bn->abn", g, nrm * B)
+        ref = kspace_direct(x, Lb, alpha, [20, 26, 18], T=T)
+    orc.pme_transform()
+    v = orc.pme_interp(tl) * 2.0   # raw targets: Acoef = 2
+    assert util.rel_l2(v, ref) < 2e-6
+
+
+# ---- A.6 (4): real + Fourier is independent of the splitting parameter ---------------------------------
+@pytest.mark.parametrize("kind", ["sl", "dl"])
+def test_alpha_independence_point_sources(orc_mod, kind):
+    Lb = np.array([2.0, 2.6, 1.8])
+    rng = np.random.default_rng(3)
+    n = 16
+    x = rng.uniform(0, 1, size=(3, n)) * Lb[:, None]
+    f = rng.normal(size=(3, n))
+    f -= f.mean(1, keepdims=True)
+    g, nrm = rng.normal(size=(3, n)), rng.normal(size=(3, n))
+    T = np.einsum("an,bn->abn", g, nrm)
+    tot = []
+    for alpha in (0.05, 0.08):
+        kw = dict(f=f) if kind == "sl" else dict(T=T)
+        vr = real_space_points(x, Lb, alpha, rcut=2.5, nimg=2, **kw)
+        vk = kspace_direct(x, Lb, alpha, [22, 28, 20], **kw)
+        tot.append(vr + vk)
+    # the SL self term (B(r->0) limit) is alpha dependent but identical for all components of f_i: remove it
+    if kind == "sl":
+        for k, alpha in enumerate((0.05, 0.08)):
+            tot[k] = tot[k] - (-4.0 / np.sqrt(alpha)) * f   # lim_{r->0} [B(r) - 1/r] = -4/sqrt(alpha)
+    assert util.rel_l2(tot[0], tot[1]) < 1e-7
+
+
+# ---- cell list ------------------------------------------------------------------------------------------
+def test_hash_index_and_neighbor_sets_vs_bruteforce(orc_mod):
+    sus = util.small_suspension(2)
+    orc = orc_mod.Oracle(sus.Lb)
+    x = sus.x[:, ::7]
+    cid = orc.cell_ids(x)
+    Nc = np.array(orc.Nc)
+    ijk = np.floor(x * (Nc / sus.Lb)[:, None]).astype(int) % Nc[:, None]
+    assert np.array_equal(cid, ijk[0] + Nc[0] * (ijk[1] + Nc[1] * ijk[2]))
+    cnt, _ = orc.neighbor_signature(x, x)
+    d = x[:, :, None] - x[:, None, :]
+    d -= np.rint(d / sus.Lb[:, None, None]) * sus.Lb[:, None, None]
+    r = np.sqrt((d ** 2).sum(0))
+    assert np.array_equal(cnt, (r <= orc.rc).sum(0).astype(np.int32))
+
+
+# ---- A.6 (6): uniform pressure on a closed membrane moves nothing --------------------------------------
+def test_single_layer_of_normal_is_zero(orc_mod):
+    sus = util.small_suspension(2)
+    v_rand = None
+    orc = orc_mod.Oracle(sus.Lb).set_cells(sus)
+    act = np.zeros(sus.npoint, np.int32)
+    act[::5] = 1
+    v_rand = orc.apply_cells(C1_RHS, 0.0, orc.cell_targets(active=act))
+    sus2 = util.small_suspension(2)
+    sus2.f = sus2.a3.copy()
+    synth.build_splines(sus2, sus2._builder, which=("F",))
+    orc2 = orc_mod.Oracle(sus2.Lb).set_cells(sus2)
+    v = orc2.apply_cells(C1_RHS, 0.0, orc2.cell_targets(active=act))
+    # scale: the same operator on an O(1) random traction
+    assert np.abs(v).max() < 5e-3 * np.abs(v_rand).max()
+
+
+# ---- A.6 (7): double layer of a constant density: 0 outside, -8 pi c2 B g inside, half way on the surface
+def test_double_layer_constant_density_jump(orc_mod):
+    L = 6.0
+    sus = synth.make_suspension(1, L=L, centers=np.array([[3.1, 2.9, 3.0]]), seed=5)
+    g0 = np.array([0.3, -0.7, 0.5])
+    sus.g = np.repeat(g0[:, None], sus.npoint, axis=1)
+    synth.build_splines(sus, sus._builder, which=("G",))
+    orc = orc_mod.Oracle(sus.Lb).set_cells(sus)
+    c2 = C2_MATVEC
+    B, A = sus.Bcoef[0], sus.Acoef[0]
+    ctr = sus.centers[0]
+    idx = np.arange(50, sus.npoint, 397)
+    x_out = sus.x[:, idx] + 0.4 * sus.a3[:, idx]
+    x_in = sus.x[:, idx] - 0.12 * sus.a3[:, idx]
+    far = np.array([[0.3, 0.4, 0.2], [5.5, 0.5, 3.0]]).T
+    jump = 8 * PI * c2 * B * g0
+    v_out = orc.apply_cells(0.0, c2, orc.make_targets(np.hstack([x_out, far]))) * 2.0   # raw targets: Acoef = 2
+    assert np.abs(v_out).max() < 2e-3 * np.abs(jump).max()
+    v_in = orc.apply_cells(0.0, c2, orc.make_targets(np.hstack([x_in, ctr[:, None]]))) * 2.0
+    assert np.abs(v_in + jump[:, None]).max() < 3e-3 * np.abs(jump).max()
+    act = np.zeros(sus.npoint, np.int32)
+    act[idx] = 1
+    v_on = orc.apply_cells(0.0, c2, orc.cell_targets(active=act))[:, idx] * A
+    assert np.abs(v_on + 0.5 * jump[:, None]).max() < 3e-3 * np.abs(jump).max()
+
+
+# ---- A.6 (5): invariance under a lattice translation of one cell and under a global shift --------------
+def test_periodic_shift_invariance(orc_mod):
+    sus = util.small_suspension(2)
+    orc = orc_mod.Oracle(sus.Lb).set_cells(sus)
+    act = np.zeros(sus.npoint, np.int32)
+    act[::11] = 1
+    v0 = orc.apply_cells(0.0, C2_MATVEC, orc.cell_targets(active=act))
+    import copy
+    sus2 = copy.copy(sus)
+    npc = sus.nlat * sus.nlon
+    x2 = sus.x.copy()
+    x2[0, 3 * npc:4 * npc] += sus.Lb[0]          # cell 3 moved by one period in x
+    x2[2, 5 * npc:6 * npc] -= sus.Lb[2]          # cell 5 moved by one period in -z
+    sus2.x = x2
+    spx = sus.spx.copy()
+    spx[3, 0, 0] += sus.Lb[0]
+    spx[5, 0, 2] -= sus.Lb[2]
+    sus2.spx = spx
+    orc2 = orc_mod.Oracle(sus.Lb).set_cells(sus2)
+    v1 = orc2.apply_cells(0.0, C2_MATVEC, orc2.cell_targets(active=act))
+    # the linear term (AddLinearInt) is NOT translation invariant cell by cell (x enters explicitly): compare without
+    a = orc.add_int_on_rbcs(0.0, C2_MATVEC, orc.cell_targets(active=act), flags=1 | 2 | 8)
+    b = orc2.add_int_on_rbcs(0.0, C2_MATVEC, orc2.cell_targets(active=act), flags=1 | 2 | 8)
+    assert util.rel_l2((v1 - b), (v0 - a)) < 1e-9
+
+
+# ---- small numerical helpers ---------------------------------------------------------------------------
+def test_gauss_legendre_and_sinh_rule(orc_mod):
+    x, w = orc_mod.Oracle.gauleg(0.0, 2.0, 12)
+    xr, wr = np.polynomial.legendre.leggauss(12)
+    assert np.allclose(x, xr + 1.0, atol=1e-13) and np.allclose(w, wr, atol=1e-13)
+    xs, ws = orc_mod.Oracle.gauleg_sinh(0.0, 0.5, 0.0, 0.01, 16)
+    # integrates a function with a near-singularity at distance b from a: int_0^.5 dx / sqrt(x^2 + b^2)
+    exact = np.arcsinh(0.5 / 0.01)
+    assert abs((ws / np.sqrt(xs ** 2 + 0.01 ** 2)).sum() - exact) < 1e-9 * exact
+
+
+def test_quadfit_and_projection(orc_mod):
+    rng = np.random.default_rng(4)
+    xy = rng.normal(size=(17, 2))
+    c = np.array([0.3, -1.0, 0.5, 2.0, 0.4, 1.5])
+    fvals = c[0] + c[1] * xy[:, 0] + c[2] * xy[:, 1] + c[3] * xy[:, 0] ** 2 + c[4] * xy[:, 0] * xy[:, 1] + c[5] * xy[:, 1] ** 2
+    info, cc = orc_mod.Oracle.quadfit_2d(xy.T.copy() if False else xy, fvals)
+    assert info == 0
+    sus = synth.make_suspension(1, L=6.0, centers=np.array([[3.0, 3.0, 3.0]]), seed=1)
+    # projection of a point 0.1 above the surface lands below it
+    p = 900
+    xt = sus.x[:, p] + 0.1 * sus.a3[:, p]
+    ilat, ilon = p % sus.nlat, p // sus.nlat
+    th0, phi0, x0 = orc_mod.Oracle.find_projection(sus.spx[0], xt, sus.th[min(ilat + 1, sus.nlat - 1)], sus.phi[ilon])
+    assert np.linalg.norm(x0 - sus.x[:, p]) < 5e-3
+    assert abs(np.linalg.norm(xt - x0) - 0.1) < 1e-4
+
+
+def test_spline_interp_reproduces_mesh(orc_mod):
+    sus = synth.make_suspension(1, L=6.0, centers=np.array([[3.0, 3.0, 3.0]]), seed=1)
+    for p in (0, 17, 1000, 2591):
+        ilat, ilon = p % sus.nlat, p // sus.nlat
+        xs = orc_mod.Oracle.spline_interp(sus.spx[0], sus.th[ilat], sus.phi[ilon])
+        # band-limited shape: the spline (built from the SH-filtered surface) passes close to the mesh point
+        assert np.linalg.norm(xs - sus.x[:, p]) < 2e-3
