@@ -113,6 +113,11 @@ int rbc3d_apply_resident(rbc3d_ctx *ctx, double c1, double c2, int use_cells, in
 int rbc3d_get_velocity(rbc3d_ctx *ctx, int tlist, double *v);
 /* bit mask to skip parts of AddIntOnRbcs (testing / profiling): 1 singular, 2 near-singular, 4 linear, 8 pairs */
 int rbc3d_set_skip_flags(rbc3d_ctx *ctx, int flags);
+/* Singular double-layer patch integrals (RBC_SingInt, ModRbcSingInt.F90:29-90): mode 1 (default) caches the
+ * density-independent factors of every patch point at geometry time (32 B per point, 8.5 MB per 36x72 cell) when
+ * device memory allows, so that GMRES matvecs only interpolate the density; mode 0 always evaluates directly.
+ * Takes effect at the next rbc3d_cells_set_geometry. */
+int rbc3d_set_sing_cache(rbc3d_ctx *ctx, int mode);
 
 /* ---- introspection (tests, profiling) ---- */
 /* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,

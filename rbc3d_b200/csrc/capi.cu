@@ -330,6 +330,13 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
                           &C.sgB, &C.xvint_part, &C.sing_xi, &c->tab_sl, &c->tab_dl, &c->tab_mask})
     b->release();
   C.dlonmax.release();
+  C.sg_tile_tgt.release();
+  C.sg_tile_win.release();
+  C.sg_idx.release();
+  C.sg_cell_active.release();
+  C.sg_st.release();
+  C.spGi.release();
+  C.sg_cache.release();
   rel_cl(C.cl);
   rel_cl(C.pl);
   for (int k = 0; k < 3; k++) {
@@ -364,6 +371,16 @@ int rbc3d_host_register(void *ptr, size_t bytes) {
 }
 int rbc3d_host_unregister(void *ptr) {
   CUDA_TRY(cudaHostUnregister(ptr));
+  return RBC3D_OK;
+}
+
+int rbc3d_set_sing_cache(rbc3d_ctx *c, int mode) {
+  if (!c) return RBC3D_EINVAL;
+  c->sing_cache_mode = mode;
+  if (mode == 0) {
+    c->cells.sg_cache_ok = false;
+    c->cells.sg_cache.release();
+  }
   return RBC3D_OK;
 }
 
@@ -432,6 +449,7 @@ int rbc3d_cells_set_mesh(rbc3d_ctx *c, int ncell, int nlat, int nlon, const doub
   RBC_TRY(upload(C.omm, omm.data(), omm.size(), c->stream));
   RBC_TRY(upload(C.dlonmax, dmax.data(), dmax.size(), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  RBC_TRY(singular_mesh_prepare(c, thG.data(), phiG.data()));
   C.mesh_set = true;
   C.geom_set = C.f_set = C.g_set = false;
   c->launches = 0;
@@ -502,7 +520,9 @@ int rbc3d_cells_set_density(rbc3d_ctx *c, const double *f, const double *g, cons
   t_end(c, RBC3D_T_H2D);
   if (f) C.f_set = true;
   if (g) C.g_set = true;
+  if (spG) C.spGi_valid = false;
   RBC_TRY(cells_gather_sorted(c, false, f != nullptr, g != nullptr));
+  if (spG) RBC_TRY(singular_density_prepare(c));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -679,7 +699,10 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   // density-dependent part of SourceList_UpdateDensity (ModSourceList.F90:160-187) redone from the resident
   // f / g so that a resident step does the same per-matvec work as ModVelSolver.F90:560-565
   t_begin(c, RBC3D_T_DENSITY);
-  if (use_cells) RBC_TRY(cells_gather_sorted(c, false, c1 != 0 && c->cells.f_set, c2 != 0 && c->cells.g_set));
+  if (use_cells) {
+    RBC_TRY(cells_gather_sorted(c, false, c1 != 0 && c->cells.f_set, c2 != 0 && c->cells.g_set));
+    if (c2 != 0 && c1 == 0 && t->kind == RBC3D_TL_CELLS) RBC_TRY(singular_density_prepare(c));
+  }
   t_end(c, RBC3D_T_DENSITY);
   RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
   t_begin(c, RBC3D_T_COMBINE);

@@ -143,6 +143,13 @@ struct Cells {
   CellList pl;                       // sorted by PME block (spreading)
   dbuf<double> xvint_part;           // partial sums of the linear term
   dbuf<double> sing_xi;              // SoA(3,Np) spline-evaluated target positions (ModRbcSingInt.F90:58)
+  // cached double-layer singular path (singular.cu): cell-independent tile tables, per-geometry cache
+  bool sg_ok = false, sg_cache_ok = false, spGi_valid = false;
+  int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
+  dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active;
+  dbuf<double> sg_st;                // (s, t) pairs
+  dbuf<double> spGi;                 // node-interleaved spline(g detJ): [cell][2][nlon][2 nlat][6]
+  dbuf<double4> sg_cache;            // [cell][tile][K][8][32] (xx, w EA (xx.a3))
 };
 
 struct Pme {
@@ -176,6 +183,7 @@ struct rbc3d_ctx {
   rbc3d::TargetList tl[3];
   rbc3d::Pme pme;
   int skip_flags = 0;
+  int sing_cache_mode = 1;  // 0: never cache the singular double-layer integrand, 1: when memory allows
   cudaEvent_t ev[2 * RBC3D_T_COUNT];
   bool ev_used[RBC3D_T_COUNT];
   float ms[RBC3D_T_COUNT];
@@ -202,7 +210,9 @@ int neighbor_signature(rbc3d_ctx *c, TargetList &t, int *count, unsigned long lo
 int nearsing_scan(rbc3d_ctx *c, TargetList &t, bool fill);
 int nearsing_prepare(rbc3d_ctx *c, TargetList &t);
 int nearsing_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG);
 int singular_prepare(rbc3d_ctx *c);
+int singular_density_prepare(rbc3d_ctx *c);
 int singular_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
 int linear_term(rbc3d_ctx *c, TargetList &t, double c2);
 int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate);
