@@ -337,6 +337,9 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.sg_st.release();
   C.spGi.release();
   C.sg_cache.release();
+  C.ps_warp_tgt.release();
+  C.ps_maskbits.release();
+  C.ps_compact.release();
   rel_cl(C.cl);
   rel_cl(C.pl);
   for (int k = 0; k < 3; k++) {
@@ -381,6 +384,12 @@ int rbc3d_set_sing_cache(rbc3d_ctx *c, int mode) {
     c->cells.sg_cache_ok = false;
     c->cells.sg_cache.release();
   }
+  return RBC3D_OK;
+}
+
+int rbc3d_set_pair_self(rbc3d_ctx *c, int mode) {
+  if (!c) return RBC3D_EINVAL;
+  c->pair_self_mode = mode;
   return RBC3D_OK;
 }
 
@@ -450,6 +459,7 @@ int rbc3d_cells_set_mesh(rbc3d_ctx *c, int ncell, int nlat, int nlon, const doub
   RBC_TRY(upload(C.dlonmax, dmax.data(), dmax.size(), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   RBC_TRY(singular_mesh_prepare(c, thG.data(), phiG.data()));
+  RBC_TRY(pairself_mesh_prepare(c, omm));
   C.mesh_set = true;
   C.geom_set = C.f_set = C.g_set = false;
   c->launches = 0;
@@ -498,6 +508,8 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
     KERNEL_CHECK();
   }
   RBC_TRY(target_list_finish(c, t));
+  RBC_TRY(cells_active_flags(c));
+  RBC_TRY(pairself_geometry_prepare(c));
   RBC_TRY(singular_prepare(c));
   // other target lists depend on the cell geometry through their near-singular entries
   for (int k = 1; k < 3; k++)

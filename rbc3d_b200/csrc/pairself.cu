@@ -1,0 +1,319 @@
+// pairself.cu -- the same-surface part of the real-space pair loop of AddIntOnRbcs (ModIntOnRbcs.F90:63-112,
+// branch surfId_i == surfId_j): every target of a cell against every mesh point of the SAME cell, weighted by
+// 1 - MaskFunc(DistOnSphere / patch radius).
+//
+// At the reference's cut-off (rc ~ 1.2 cell radii) ~43 % of a cell's own 2592 points are within range of each of its
+// points, and in a suspension at physiological spacing those same-cell pairs are > 99 % of all in-range pairs.  The
+// hashed cell list is the wrong tool for them (it returns the whole cell plus its neighbours as candidates), so they
+// are evaluated as a dense block per cell:
+//   * one CTA per (cell, third of its targets); the cell's sources (x, g*B, a3 or x, f) are staged chunk-wise in shared
+//     memory as 80-byte records and read with warp-wide broadcast LDS.128;
+//   * warp = a compact 4 lat x 8 lon patch of targets, so whole sources out of range of the patch are skipped
+//     warp-uniformly; lane = one target, accumulators in registers;
+//   * Ewald lookup table(s) in shared memory (lerp on 8192 intervals like EwaldCoeff_DL/SL, ModEwaldFunc.F90:86-178);
+//   * the mask is non-zero for ~9 % of the pairs only: a 64-bit set per (lat_i, |dlon|) says for which lat_j the
+//     one-minus-mask table has to be consulted;
+//   * the range test uses the reference's arithmetic (no FMA contraction); the minimum-image step is skipped for
+//     cells whose extent is below half a box (nint(xx/L) = 0 exactly), which is decided per cell at geometry time.
+// Cross-surface pairs stay with the cell-list kernel (pairsum.cu), which now skips same-surface sources.
+#include <algorithm>
+#include <vector>
+
+#include "device_math.cuh"
+#include "rbc3d_internal.h"
+
+namespace rbc3d {
+
+constexpr int PS_WARPS = 27;          // 864 targets per CTA
+constexpr int PS_REC = 10;            // doubles per staged source record (80 B)
+constexpr int PS_CHUNK_MAX = 1296;    // sources per staged chunk
+
+struct SelfArgs {
+  Params prm;
+  int ncell, npc, nlat, nlon, Np;
+  const double *x, *a3, *f, *g;   // SoA(3,Np), original order; f, g weighted by detJ*w
+  const double *Bcell;
+  const int *warp_tgt;            // [nwarps_cell][32] mesh point of (warp, lane) or -1
+  int nwarps_cell, ctas_per_cell;
+  const unsigned long long *maskbits;  // [nlat][nlon/2+1]
+  const double *omm;                    // [nlat][nlat][nlon/2+1]
+  const double *tab_sl, *tab_dl;
+  const int *active, *cell_active;
+  const unsigned char *cell_compact;
+  double c1, c2;
+  double *acc;
+  int chunk_cols;                 // longitude columns per staged chunk
+};
+
+template <bool SL>
+__global__ void __launch_bounds__(PS_WARPS * 32, 1) k_pair_self(SelfArgs a) {
+  extern __shared__ double smem[];
+  // [table: DL 8193 | SL 2*8193][maskbits nlat*nlonh (as double-sized words)][records chunk*10]
+  const int nlonh = a.nlon / 2 + 1;
+  double *s_tab = smem;
+  const int ntab = SL ? 2 * (RBC3D_NTAB + 1) : (RBC3D_NTAB + 1) + 1;   // keep 16-byte alignment of what follows
+  unsigned long long *s_bits = reinterpret_cast<unsigned long long *>(smem + ntab);
+  const int nbits = (a.nlat * nlonh + 1) & ~1;
+  double *s_rec = smem + ntab + nbits;
+  const int cell = blockIdx.x / a.ctas_per_cell, part = blockIdx.x - cell * a.ctas_per_cell;
+  if (!a.cell_active[cell]) return;
+  for (int i = threadIdx.x; i <= RBC3D_NTAB; i += blockDim.x) {
+    if (SL) {
+      s_tab[2 * i] = a.tab_sl[2 * i];
+      s_tab[2 * i + 1] = a.tab_sl[2 * i + 1];
+    } else {
+      s_tab[i] = a.tab_dl[i];
+    }
+  }
+  for (int i = threadIdx.x; i < a.nlat * nlonh; i += blockDim.x) s_bits[i] = a.maskbits[i];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wcell = part * PS_WARPS + warp;  // warp index inside the cell
+  int p = -1;
+  if (wcell < a.nwarps_cell) p = a.warp_tgt[wcell * 32 + lane];
+  const size_t base = (size_t)cell * a.npc, Np = a.Np;
+  bool valid = p >= 0;
+  if (valid) valid = a.active[base + p] != 0;
+  double xi = 0, yi = 0, zi = 0;
+  int lat_i = 0, lon_i = 0;
+  if (p >= 0) {
+    lon_i = p / a.nlat;
+    lat_i = p - lon_i * a.nlat;
+    xi = a.x[base + p];
+    yi = a.x[Np + base + p];
+    zi = a.x[2 * Np + base + p];
+  }
+  const bool compact = a.cell_compact[cell] != 0;
+  const double Bc = a.Bcell[cell];
+  const double r_eps2 = a.prm.r_eps * a.prm.r_eps;
+  const double rc2 = a.prm.rc2_thr, tab_scale = a.prm.tab_scale;
+  double ax = 0, ay = 0, az = 0;
+  const int chunk = a.chunk_cols * a.nlat;
+
+  for (int col0 = 0; col0 < a.nlon; col0 += a.chunk_cols) {
+    const int ncol = min(a.chunk_cols, a.nlon - col0), nsrc = ncol * a.nlat;
+    __syncthreads();
+    for (int jj = threadIdx.x; jj < nsrc; jj += blockDim.x) {
+      const size_t j = base + (size_t)col0 * a.nlat + jj;
+      double *r = s_rec + (size_t)jj * PS_REC;
+      r[0] = a.x[j];
+      r[1] = a.x[Np + j];
+      r[2] = a.x[2 * Np + j];
+      if (SL) {
+        r[3] = a.f[j];
+        r[4] = a.f[Np + j];
+        r[5] = a.f[2 * Np + j];
+      } else {
+        r[3] = a.g[j] * Bc;   // slist%Bcoef(j) * slist%g(j,:), ModIntOnRbcs.F90:102-105
+        r[4] = a.g[Np + j] * Bc;
+        r[5] = a.g[2 * Np + j] * Bc;
+        r[6] = a.a3[j];
+        r[7] = a.a3[Np + j];
+        r[8] = a.a3[2 * Np + j];
+      }
+    }
+    __syncthreads();
+    (void)chunk;
+    for (int c = 0; c < ncol; c++) {
+      const int lon_j = col0 + c;
+      int dl = abs(lon_i - lon_j);
+      dl = min(dl, a.nlon - dl);
+      const unsigned long long bits = s_bits[lat_i * nlonh + dl];
+      const double2 *rec = reinterpret_cast<const double2 *>(s_rec + (size_t)c * a.nlat * PS_REC);
+#pragma unroll 2
+      for (int lat_j = 0; lat_j < a.nlat; lat_j++, rec += PS_REC / 2) {
+        const double2 q0 = rec[0], q1 = rec[1];  // (x, y), (z, d0)
+        double xx = __dsub_rn(q0.x, xi), yy = __dsub_rn(q0.y, yi), zz = __dsub_rn(q1.x, zi);
+        if (!compact) {
+          xx = min_image(xx, a.prm.iLb[0], a.prm.Lb[0]);
+          yy = min_image(yy, a.prm.iLb[1], a.prm.Lb[1]);
+          zz = min_image(zz, a.prm.iLb[2], a.prm.Lb[2]);
+        }
+        const double r2 = norm2_exact(xx, yy, zz);
+        const bool in = valid && !(r2 > rc2) && r2 >= r_eps2;
+        if (!__any_sync(FULL_MASK, in)) continue;
+        const double2 q2 = rec[2];  // (d1, d2)
+        if (in) {
+          const double rinv = rsqrt(r2);
+          const double s = r2 * rinv * tab_scale;
+          const int i = (int)s;
+          if (i < RBC3D_NTAB) {
+            double om = 1.0;  // 1 - mask
+            if ((bits >> lat_j) & 1ull) om = __ldg(a.omm + ((size_t)(lat_i * a.nlat + lat_j)) * nlonh + dl);
+            const double fr = s - (double)i;
+            const double ir2 = rinv * rinv;
+            if (SL) {
+              const double t10 = s_tab[2 * i], t20 = s_tab[2 * i + 1], t11 = s_tab[2 * i + 2], t21 = s_tab[2 * i + 3];
+              const double e1 = fma(fr, t11 - t10, t10), e2 = fma(fr, t21 - t20, t20);
+              const double EA = e1 * rinv * ir2 + e2 * ir2;  // ModEwaldFunc.F90:126-127
+              const double EB = e1 * rinv - e2;
+              const double fx = q1.y, fy = q2.x, fz = q2.y;
+              const double xf = EA * (xx * fx + yy * fy + zz * fz);
+              ax += om * (xf * xx + EB * fx);
+              ay += om * (xf * yy + EB * fy);
+              az += om * (xf * zz + EB * fz);
+            } else {
+              const double2 q3 = rec[3], q4 = rec[4];  // (n0, n1), (n2, -)
+              const double t0 = s_tab[i], t1 = s_tab[i + 1];
+              const double e = fma(fr, t1 - t0, t0);
+              const double EA = e * ir2 * ir2 * rinv;  // c1 / r^5, ModEwaldFunc.F90:174
+              const double qd = om * EA * (xx * q1.y + yy * q2.x + zz * q2.y) * (xx * q3.x + yy * q3.y + zz * q4.x);
+              ax += qd * xx;
+              ay += qd * yy;
+              az += qd * zz;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    const double cc = SL ? a.c1 : a.c2;
+    const size_t ti = base + p;
+    a.acc[ti] += cc * ax;
+    a.acc[Np + ti] += cc * ay;
+    a.acc[2 * Np + ti] += cc * az;
+  }
+}
+
+// per cell: is the extent of the cell below half a box in every direction (then nint((xj-xi)/L) = 0 exactly)?
+__global__ void __launch_bounds__(256) k_cell_compact(int npc, int Np, const double *__restrict__ x, Params prm,
+                                                      unsigned char *__restrict__ compact) {
+  const int cell = blockIdx.x;
+  __shared__ double s_mn[3][8], s_mx[3][8];
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = threadIdx.x; i < npc; i += blockDim.x)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const double v = x[(size_t)d * Np + (size_t)cell * npc + i];
+      mn[d] = fmin(mn[d], v);
+      mx[d] = fmax(mx[d], v);
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fmin(mn[d], __shfl_xor_sync(FULL_MASK, mn[d], o));
+      mx[d] = fmax(mx[d], __shfl_xor_sync(FULL_MASK, mx[d], o));
+    }
+    if (lane == 0) {
+      s_mn[d][warp] = mn[d];
+      s_mx[d][warp] = mx[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    for (int d = 0; d < 3; d++) {
+      double a = s_mn[d][0], b = s_mx[d][0];
+      for (int w = 1; w < 8; w++) {
+        a = fmin(a, s_mn[d][w]);
+        b = fmax(b, s_mx[d][w]);
+      }
+      ok = ok && ((b - a) * prm.iLb[d] < 0.49);
+    }
+    compact[cell] = ok ? 1 : 0;
+  }
+}
+
+// cell-independent tables (rbc3d_cells_set_mesh): target -> (warp, lane) map and the mask bit sets
+int pairself_mesh_prepare(rbc3d_ctx *c, const std::vector<double> &omm) {
+  Cells &C = c->cells;
+  C.ps_ok = false;
+  const int nlat = C.nlat, nlon = C.nlon, nlonh = nlon / 2 + 1;
+  if (nlat > 64) return RBC3D_OK;  // bit sets are 64 wide; the cell-list kernel handles such meshes
+  // warps = compact blocks of 4 lat x 8 lon targets
+  const int nbl = (nlat + 3) / 4, nbn = (nlon + 7) / 8;
+  std::vector<int> wt((size_t)nbl * nbn * 32, -1);
+  for (int bl = 0; bl < nbl; bl++)
+    for (int bn = 0; bn < nbn; bn++)
+      for (int lane = 0; lane < 32; lane++) {
+        const int ilat = bl * 4 + (lane & 3), ilon = bn * 8 + (lane >> 2);
+        if (ilat < nlat && ilon < nlon) wt[((size_t)bl * nbn + bn) * 32 + lane] = ilon * nlat + ilat;
+      }
+  std::vector<unsigned long long> bits((size_t)nlat * nlonh, 0ull);
+  for (int i = 0; i < nlat; i++)
+    for (int j = 0; j < nlat; j++)
+      for (int dl = 0; dl < nlonh; dl++)
+        if (omm[((size_t)i * nlat + j) * nlonh + dl] != 1.0) bits[(size_t)i * nlonh + dl] |= 1ull << j;
+  C.ps_nwarps = nbl * nbn;
+  RBC_TRY(C.ps_warp_tgt.resize(wt.size()));
+  RBC_TRY(C.ps_maskbits.resize(bits.size()));
+  CUDA_TRY(cudaMemcpyAsync(C.ps_warp_tgt.p, wt.data(), sizeof(int) * wt.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.ps_maskbits.p, bits.data(), sizeof(unsigned long long) * bits.size(),
+                           cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  C.ps_ok = true;
+  return RBC3D_OK;
+}
+
+// geometry time
+int pairself_geometry_prepare(rbc3d_ctx *c) {
+  Cells &C = c->cells;
+  if (C.ncell == 0) return RBC3D_OK;
+  RBC_TRY(C.ps_compact.resize(C.ncell));
+  k_cell_compact<<<C.ncell, 256, 0, c->stream>>>(C.npc, C.Np, C.x.p, c->prm, C.ps_compact.p);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
+}
+
+bool pairself_available(rbc3d_ctx *c, const TargetList &t) {
+  return c->cells.ps_ok && t.kind == RBC3D_TL_CELLS && c->pair_self_mode != 0;
+}
+
+int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
+  Cells &C = c->cells;
+  SelfArgs a;
+  a.prm = c->prm;
+  a.ncell = C.ncell;
+  a.npc = C.npc;
+  a.nlat = C.nlat;
+  a.nlon = C.nlon;
+  a.Np = C.Np;
+  a.x = C.x.p;
+  a.a3 = C.a3.p;
+  a.f = C.f.p;
+  a.g = C.g.p;
+  a.Bcell = C.B.p;
+  a.warp_tgt = C.ps_warp_tgt.p;
+  a.nwarps_cell = C.ps_nwarps;
+  a.ctas_per_cell = (C.ps_nwarps + PS_WARPS - 1) / PS_WARPS;
+  a.maskbits = C.ps_maskbits.p;
+  a.omm = C.omm.p;
+  a.tab_sl = c->tab_sl.p;
+  a.tab_dl = c->tab_dl.p;
+  a.active = t.active.p;
+  a.cell_active = C.sg_cell_active.p;
+  a.cell_compact = C.ps_compact.p;
+  a.c1 = c1;
+  a.c2 = c2;
+  a.acc = t.acc.p;
+  const int nlonh = C.nlon / 2 + 1;
+  const int nbits = (C.nlat * nlonh + 1) & ~1;
+  const int grid = C.ncell * a.ctas_per_cell;
+  for (int pass = 0; pass < 2; pass++) {
+    const bool sl = pass == 0;
+    if (sl ? (c1 == 0) : (c2 == 0)) continue;
+    const int ntab = sl ? 2 * (RBC3D_NTAB + 1) : (RBC3D_NTAB + 1) + 1;
+    const size_t fixed = sizeof(double) * ((size_t)ntab + nbits);
+    const size_t budget = 224 * 1024 - fixed;
+    int cols = (int)(budget / (sizeof(double) * PS_REC * C.nlat));
+    cols = std::min(cols, std::min(C.nlon, PS_CHUNK_MAX / C.nlat > 0 ? PS_CHUNK_MAX / C.nlat : 1));
+    if (cols < 1) cols = 1;
+    a.chunk_cols = cols;
+    const size_t smem = fixed + sizeof(double) * PS_REC * (size_t)cols * C.nlat;
+    if (sl) {
+      CUDA_TRY(cudaFuncSetAttribute(k_pair_self<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_pair_self<true><<<grid, PS_WARPS * 32, smem, c->stream>>>(a);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(k_pair_self<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_pair_self<false><<<grid, PS_WARPS * 32, smem, c->stream>>>(a);
+    }
+    KERNEL_CHECK();
+    c->launches++;
+  }
+  return RBC3D_OK;
+}
+
+}  // namespace rbc3d

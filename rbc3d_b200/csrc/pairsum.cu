@@ -41,16 +41,20 @@ struct PairArgs {
   double *acc;  // SoA(3,nt), += result
 };
 
-// Walk all sources in the 27 neighbour cells of cell c; calls body(j, xx, yy, zz, r2, in_range) warp-uniformly
-// for every source for which at least one lane is in range.
+// Walk all sources in the 27 neighbour cells of cell c; calls body(j, pj, xx, yy, zz, r2, in_range) warp-uniformly
+// for every source for which at least one lane is in range.  Sources are fetched 32 at a time with coalesced loads
+// (lane = source) and handed round with shuffles (lane = target); sources of surface `excl_cell` (warp-uniform,
+// -2 = none) are dropped before the distance test -- the same-surface pairs of cell targets belong to pairself.cu.
 template <class Body>
 __device__ __forceinline__ void walk_neighbours(const Params &prm, const int *__restrict__ sstart,
-                                                const double *__restrict__ sx, int Np, int c, bool valid,
-                                                double xi, double yi, double zi, Body body) {
+                                                const double *__restrict__ sx, const int *__restrict__ sorder, int Np,
+                                                int npc, int c, bool valid, double xi, double yi, double zi,
+                                                int excl_cell, Body body) {
   const int Nc1 = prm.Nc[0], Nc2 = prm.Nc[1], Nc3 = prm.Nc[2];
   const int c1 = c % Nc1, c2 = (c / Nc1) % Nc2, c3 = c / (Nc1 * Nc2);
   const double *__restrict__ sy = sx + Np;
   const double *__restrict__ sz = sx + 2 * (size_t)Np;
+  const int lane = threadIdx.x & 31;
   for (int d3 = -1; d3 <= 1; d3++) {
     int n3 = c3 + d3;
     n3 = n3 < 0 ? n3 + Nc3 : (n3 >= Nc3 ? n3 - Nc3 : n3);
@@ -62,20 +66,36 @@ __device__ __forceinline__ void walk_neighbours(const Params &prm, const int *__
         n1 = n1 < 0 ? n1 + Nc1 : (n1 >= Nc1 ? n1 - Nc1 : n1);
         const int nc = n1 + Nc1 * (n2 + Nc2 * n3);
         const int jb = sstart[nc], je = sstart[nc + 1];
-        for (int j = jb; j < je; j++) {
-          double xx = min_image(__dsub_rn(__ldg(sx + j), xi), prm.iLb[0], prm.Lb[0]);
-          double yy = min_image(__dsub_rn(__ldg(sy + j), yi), prm.iLb[1], prm.Lb[1]);
-          double zz = min_image(__dsub_rn(__ldg(sz + j), zi), prm.iLb[2], prm.Lb[2]);
-          double r2 = norm2_exact(xx, yy, zz);
-          bool in = valid && !(r2 > prm.rc2_thr);
-          if (__any_sync(FULL_MASK, in)) body(j, xx, yy, zz, r2, in);
+        for (int j0 = jb; j0 < je; j0 += 32) {
+          const int jl = j0 + lane;
+          const bool have = jl < je;
+          double xs = 0, ys = 0, zs = 0;
+          int pjl = -1;
+          if (have) {
+            xs = __ldg(sx + jl);
+            ys = __ldg(sy + jl);
+            zs = __ldg(sz + jl);
+            pjl = __ldg(sorder + jl);
+          }
+          unsigned m = __ballot_sync(FULL_MASK, have && (pjl / npc) != excl_cell);
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int pj = __shfl_sync(FULL_MASK, pjl, b);
+            double xx = min_image(__dsub_rn(__shfl_sync(FULL_MASK, xs, b), xi), prm.iLb[0], prm.Lb[0]);
+            double yy = min_image(__dsub_rn(__shfl_sync(FULL_MASK, ys, b), yi), prm.iLb[1], prm.Lb[1]);
+            double zz = min_image(__dsub_rn(__shfl_sync(FULL_MASK, zs, b), zi), prm.iLb[2], prm.Lb[2]);
+            double r2 = norm2_exact(xx, yy, zz);
+            bool in = valid && !(r2 > prm.rc2_thr);
+            if (__any_sync(FULL_MASK, in)) body(j0 + b, pj, xx, yy, zz, r2, in);
+          }
         }
       }
     }
   }
 }
 
-template <bool SL, bool DL>
+template <bool SL, bool DL, bool EXCL>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(PairArgs a) {
   extern __shared__ double smem[];
   // tables in shared memory: DL 8193, SL 2*8193
@@ -117,13 +137,19 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(PairArgs a) {
   const int nlonh = a.nlon / 2 + 1;
   const size_t Np = a.Np;
 
-  walk_neighbours(a.prm, a.sstart, a.sx, a.Np, c, valid, xi, yi, zi,
-                  [&](int j, double xx, double yy, double zz, double r2, bool in) {
-    const int pj = __ldg(a.sorder + j);
+  // same-surface sources are excluded (EXCL: pairself.cu owns them): warp-uniformly when the whole tile belongs to
+  // one surface, per lane otherwise
+  int excl = -2;
+  if (EXCL) {
+    const int c0 = __shfl_sync(FULL_MASK, my_cell, __ffs(__ballot_sync(FULL_MASK, valid)) - 1);
+    if (__all_sync(FULL_MASK, !valid || my_cell == c0)) excl = c0;
+  }
+  walk_neighbours(a.prm, a.sstart, a.sx, a.sorder, a.Np, a.npc, c, valid, xi, yi, zi, excl,
+                  [&](int j, int pj, double xx, double yy, double zz, double r2, bool in) {
     const int cj = pj / a.npc;
-    if (in && r2 >= r_eps2) {
+    if (in && r2 >= r_eps2 && !(EXCL && cj == my_cell)) {
       double om = 1.0;  // 1 - mask
-      if (cj == my_cell) {
+      if (!EXCL && cj == my_cell) {
         int rem = pj - cj * a.npc;
         int lon_j = rem / a.nlat, lat_j = rem - lon_j * a.nlat;
         int dl = abs(my_lon - lon_j);
@@ -213,18 +239,23 @@ int pair_sum(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
   if (!sl && !dl) return RBC3D_OK;
   const int grid = (t.ntiles + PAIR_WARPS - 1) / PAIR_WARPS;
   const size_t sm = sizeof(double) * (RBC3D_NTAB + 1) * ((dl ? 1 : 0) + (sl ? 2 : 0));
+  const bool excl = pairself_available(c, t);  // same-surface pairs: dense per-cell kernel (pairself.cu)
+#define LAUNCH_PAIR(SL_, DL_, EX_)                                                                              \
+  do {                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(k_pair<SL_, DL_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_pair<SL_, DL_, EX_><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a);                                        \
+  } while (0)
   if (sl && dl) {
-    CUDA_TRY(cudaFuncSetAttribute(k_pair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pair<true, true><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a);
+    if (excl) LAUNCH_PAIR(true, true, true); else LAUNCH_PAIR(true, true, false);
   } else if (sl) {
-    CUDA_TRY(cudaFuncSetAttribute(k_pair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pair<true, false><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a);
+    if (excl) LAUNCH_PAIR(true, false, true); else LAUNCH_PAIR(true, false, false);
   } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_pair<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pair<false, true><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a);
+    if (excl) LAUNCH_PAIR(false, true, true); else LAUNCH_PAIR(false, true, false);
   }
+#undef LAUNCH_PAIR
   KERNEL_CHECK();
   c->launches++;
+  if (excl) RBC_TRY(pairself_apply(c, t, c1, c2));
   return RBC3D_OK;
 }
 
@@ -255,11 +286,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_signature(PairArgs a, int *
   }
   int cnt = 0;
   unsigned long long s = 0;
-  walk_neighbours(a.prm, a.sstart, a.sx, a.Np, c, valid, xi, yi, zi,
-                  [&](int j, double, double, double, double, bool in) {
+  walk_neighbours(a.prm, a.sstart, a.sx, a.sorder, a.Np, a.npc, c, valid, xi, yi, zi, -2,
+                  [&](int, int pj, double, double, double, double, bool in) {
                     if (in) {
                       cnt++;
-                      s += mix64((unsigned long long)__ldg(a.sorder + j));
+                      s += mix64((unsigned long long)pj);
                     }
                   });
   if (valid) {
@@ -318,9 +349,13 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_nbr_scan(PairArgs a, int *_
   int l_cell[RBC3D_NBR_MAX], l_pt[RBC3D_NBR_MAX];
   double l_r2[RBC3D_NBR_MAX];
   bool ovf = false;
-  walk_neighbours(a.prm, a.sstart, a.sx, a.Np, c, valid, xi, yi, zi,
-                  [&](int j, double, double, double, double r2, bool in) {
-                    const int pj = __ldg(a.sorder + j);
+  int excl = -2;  // cell targets: the own surface never enters the neighbour list
+  {
+    const int c0 = __shfl_sync(FULL_MASK, my_cell, __ffs(__ballot_sync(FULL_MASK, valid)) - 1);
+    if (c0 >= 0 && __all_sync(FULL_MASK, !valid || my_cell == c0)) excl = c0;
+  }
+  walk_neighbours(a.prm, a.sstart, a.sx, a.sorder, a.Np, a.npc, c, valid, xi, yi, zi, excl,
+                  [&](int, int pj, double, double, double, double r2, bool in) {
                     const int cj = pj / a.npc;
                     if (in && cj != my_cell) {
                       int q = 0;

@@ -150,6 +150,12 @@ struct Cells {
   dbuf<double> sg_st;                // (s, t) pairs
   dbuf<double> spGi;                 // node-interleaved spline(g detJ): [cell][2][nlon][2 nlat][6]
   dbuf<double4> sg_cache;            // [cell][tile][K][8][32] (xx, w EA (xx.a3))
+  // dense same-surface pair kernel (pairself.cu)
+  bool ps_ok = false;
+  int ps_nwarps = 0;
+  dbuf<int> ps_warp_tgt;
+  dbuf<unsigned long long> ps_maskbits;
+  dbuf<unsigned char> ps_compact;
 };
 
 struct Pme {
@@ -183,6 +189,7 @@ struct rbc3d_ctx {
   rbc3d::TargetList tl[3];
   rbc3d::Pme pme;
   int skip_flags = 0;
+  int pair_self_mode = 1;   // 0: same-surface pairs through the cell list (old path), 1: dense per-cell kernel
   int sing_cache_mode = 1;  // 0: never cache the singular double-layer integrand, 1: when memory allows
   cudaEvent_t ev[2 * RBC3D_T_COUNT];
   bool ev_used[RBC3D_T_COUNT];
@@ -206,6 +213,11 @@ int tiles_build(rbc3d_ctx *c, TargetList &t);
 // ---- real-space operator (pairsum.cu, singular.cu, nearsing.cu) ----
 int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g);
 int pair_sum(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int pairself_mesh_prepare(rbc3d_ctx *c, const std::vector<double> &omm);
+int pairself_geometry_prepare(rbc3d_ctx *c);
+bool pairself_available(rbc3d_ctx *c, const TargetList &t);
+int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
+int cells_active_flags(rbc3d_ctx *c);
 int neighbor_signature(rbc3d_ctx *c, TargetList &t, int *count, unsigned long long *sig);
 int nearsing_scan(rbc3d_ctx *c, TargetList &t, bool fill);
 int nearsing_prepare(rbc3d_ctx *c, TargetList &t);

@@ -426,16 +426,24 @@ __global__ void k_cell_active(int Np, int npc, const int *__restrict__ active, i
   if (i < Np && active[i]) cell_active[i / npc] = 1;
 }
 
+// per cell: does it own any active target (z-slab / cell ownership of multi-GPU runs, SetActiveFlag)
+int cells_active_flags(rbc3d_ctx *c) {
+  Cells &C = c->cells;
+  TargetList &t = c->tl[RBC3D_TL_CELLS];
+  RBC_TRY(C.sg_cell_active.resize(C.ncell > 0 ? C.ncell : 1));
+  if (C.Np == 0) return RBC3D_OK;
+  CUDA_TRY(cudaMemsetAsync(C.sg_cell_active.p, 0, sizeof(int) * C.ncell, c->stream));
+  k_cell_active<<<(C.Np + 255) / 256, 256, 0, c->stream>>>(C.Np, C.npc, t.active.p, C.sg_cell_active.p);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
+}
+
 // geometry time (SourceList_UpdateCoord): density-independent cache of the double-layer patch integrand
 int singular_prepare(rbc3d_ctx *c) {
   Cells &C = c->cells;
   C.sg_cache_ok = false;
   if (!C.sg_ok || C.Np == 0 || c->sing_cache_mode == 0) return RBC3D_OK;
-  TargetList &t = c->tl[RBC3D_TL_CELLS];
-  RBC_TRY(C.sg_cell_active.resize(C.ncell));
-  CUDA_TRY(cudaMemsetAsync(C.sg_cell_active.p, 0, sizeof(int) * C.ncell, c->stream));
-  k_cell_active<<<(C.Np + 255) / 256, 256, 0, c->stream>>>(C.Np, C.npc, t.active.p, C.sg_cell_active.p);
-  KERNEL_CHECK();
   const size_t per_cell = (size_t)C.sg_ntiles * C.sg_K * SG_T * 32;
   const size_t need = per_cell * C.ncell * sizeof(double4);
   if (C.sg_cache.n < per_cell * C.ncell) {
@@ -478,6 +486,7 @@ int singular_prepare(rbc3d_ctx *c) {
     c->launches++;
   }
   C.sg_cache_ok = true;
+  if (C.g_set && !C.spGi_valid) RBC_TRY(singular_density_prepare(c));
   return RBC3D_OK;
 }
 

@@ -164,6 +164,9 @@ class EwaldOperator:
     def set_skip_flags(self, flags):
         check(self.lib.rbc3d_set_skip_flags(self._h, flags))
 
+    def set_pair_self(self, mode):
+        check(self.lib.rbc3d_set_pair_self(self._h, int(mode)))
+
     def set_sing_cache(self, mode):
         check(self.lib.rbc3d_set_sing_cache(self._h, int(mode)))
 

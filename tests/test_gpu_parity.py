@@ -220,3 +220,44 @@ def test_singular_direct_and_cached_paths_agree(sus8, oracle_lib):
         op.close()
     assert rel_l2(out[0], ref) < TOL and rel_l2(out[1], ref) < TOL
     assert rel_l2(out[0], out[1]) < 1e-12
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)])
+def test_pair_sum_dense_self_kernel_vs_cell_list(sus8, oracle_lib, c1, c2):
+    """same-surface pairs through the dense per-cell kernel (default) and through the hashed cell list."""
+    from rbc3d_b200.ewald import EwaldOperator
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
+    ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
+    out = []
+    for mode in (1, 0):
+        op = EwaldOperator(sus8.Lb)
+        op.set_pair_self(mode)
+        op.set_suspension(sus8)
+        op.set_skip_flags(1 | 2 | 4)
+        out.append(op.AddIntOnRbcs(c1, c2))
+        op.close()
+    assert rel_l2(out[0], ref) < TOL and rel_l2(out[1], ref) < TOL
+
+
+def test_cell_straddling_the_periodic_boundary(oracle_lib):
+    """a cell whose points are wrapped into the box individually (extent ~ L: the non-compact branch with the
+    minimum-image step) and a cell shifted by a lattice vector give the same velocities as the oracle."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    L = 8.0
+    centers = np.array([[0.3, 4.0, 7.9], [4.2, 3.6, 4.1]])
+    sus = synth.make_suspension(1, L=L, centers=centers, seed=3)
+    npc = sus.nlat * sus.nlon
+    x = sus.x.copy()
+    x[:, :npc] = np.mod(x[:, :npc], L)            # wrap every point of cell 0 into [0, L)
+    sus.x = x
+    op = EwaldOperator(sus.Lb)
+    op.set_suspension(sus)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    for c1, c2 in [(0.0, C2_MATVEC), (C1_RHS, 0.0)]:
+        op.set_skip_flags(1 | 2 | 4)
+        v = op.AddIntOnRbcs(c1, c2)
+        op.set_skip_flags(0)
+        ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
+        assert rel_l2(v, ref) < TOL
+    op.close()
