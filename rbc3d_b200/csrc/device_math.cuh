@@ -39,10 +39,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// 1/sqrt(x) to full double precision: hardware seed + two Newton steps (x > 0, normal)
-__device__ __forceinline__ double rsqrt_full(double x) {
-  double y = rsqrt(x);
-  return y;
+// 1/sqrt(x) for normal positive x: the hardware seed (MUFU.RSQ64H) and one third-order correction -- the same
+// arithmetic as CUDA's rsqrt() without its special-case branch (callers guarantee r_eps^2 <= x <= rc^2).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double h = fma(x, -(y0 * y0), 1.0);
+  const double p = fma(h, 0.375, 0.5);
+  return fma(p, y0 * h, y0);
 }
 
 // ModEwaldFunc.F90:120-121,173: linear interpolation in an 8193-entry table indexed by s = N*r/rc

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) k_pair_self(SelfArgs a) {
         if (!__any_sync(FULL_MASK, in)) continue;
         const double2 q2 = rec[2];  // (d1, d2)
         if (in) {
-          const double rinv = rsqrt(r2);
+          const double rinv = rsqrt_pos(r2);
           const double s = r2 * rinv * tab_scale;
           const int i = (int)s;
           if (i < RBC3D_NTAB) {

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(PairArgs a) {
         int pair = my_lat * a.nlat + lat_j;
         if (dl <= __ldg(a.dlonmax + pair)) om = __ldg(a.omm + (size_t)pair * nlonh + dl);
       }
-      const double rinv = rsqrt(r2);
+      const double rinv = rsqrt_pos(r2);
       const double r = r2 * rinv;
       const double s = r * a.prm.tab_scale;
       const int i = (int)s;
