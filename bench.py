@@ -40,6 +40,7 @@ C2_MATVEC = -1.0 / (4.0 * np.pi)
 FLOPS_DL_PAIR = 54.0      # flops per in-range double-layer pair (FMA = 2)
 FLOPS_SPLINE3 = 155.0     # one bicubic interpolation of 3 variables
 FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
+FLOPS_PATCH_CACHED = 110.0  # cached matvec path: one 3-variable bicubic (96) + 7 FMAs per patch point
 
 
 def n_side_of(cells: int) -> int:
@@ -193,10 +194,10 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def kernel_table(op, sus, ms, npairs, peaks):
+def kernel_table(op, sus, ms, npairs, peaks, world=1):
     """Algorithmic work per application (DESIGN.md "Kernels") / CUDA-event time -> roofline fractions."""
     hbm_peak, fp64_peak = peaks
-    N = sus.npoint
+    N = sus.npoint / world      # every rank owns 1/world of the cells (targets, singular integrals, spreading)
     P3 = op.P ** 3
     Nx, Ny, Nz = op.Nb
     G = Nx * Ny * Nz
@@ -217,9 +218,11 @@ def kernel_table(op, sus, ms, npairs, peaks):
         rows.append(r)
 
     add("pair_sum(DL)", ms["pair"], flops=npairs * FLOPS_DL_PAIR)
-    add("singular(DL)", ms["sing"], flops=N * npatch * (3 * FLOPS_SPLINE3 + FLOPS_PATCH_EXTRA))
+    add("singular(DL, cached geometry)", ms["sing"], flops=N * npatch * FLOPS_PATCH_CACHED,
+        bytes_=N * npatch * 32.0)
     add("near_singular", ms["nearsing"])
     add("spread(DL,6 sym comps)", ms["spread"], flops=N * P3 * (2 + 2 * 6), bytes_=80.0 * N + 2 * 6 * 8.0 * G)
+    add("mesh_allreduce+velocity_allreduce(NCCL)", ms["comm"], bound="nvlink")
     add("fft_fwd(cuFFT D2Z x6)", ms["fft"], bytes_=6 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
     add("kspace_scale", ms["kspace"], bytes_=(6 + 3) * 16.0 * M, bound="hbm")
     add("fft_inv(cuFFT Z2D x3)", ms["fft_inv"], bytes_=3 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
@@ -301,11 +304,16 @@ def run_gpu(args):
         op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
         v_host[:] = 0.0
         op.apply(0.0, C2_MATVEC, v=v_host)
+        if world > 1:
+            op.TargetList_CollectArray(v_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
+        v_host[:] = 0.0                                   # callers zero v (ModVelSolver.F90:571)
         op.apply(0.0, C2_MATVEC, v=v_host)
+        if world > 1:
+            op.TargetList_CollectArray(v_host)            # ModVelSolver.F90:584
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -324,7 +332,7 @@ def run_gpu(args):
     fp64_peak = measure_fp64_peak(local)
     cnt, _ = op.neighbor_signature()
     npairs = float(cnt.astype(np.float64).sum())
-    rows = kernel_table(op, sus, stage_ms, npairs, (hbm_peak, fp64_peak))
+    rows = kernel_table(op, sus, stage_ms, npairs, (hbm_peak, fp64_peak), world)
     dom = max(rows, key=lambda r: r["ms"])
     if dom.get("tflops") is not None and dom["bound"] == "fp64":
         roof = {"kernel": dom["kernel"], "bound": "fp64", "achieved": dom["tflops"], "peak": fp64_peak,
@@ -348,7 +356,8 @@ def run_gpu(args):
                       "alpha": op.alpha, "eps": op.eps, "P": op.P, "rc": op.rc, "Nc": op.cell_list_dims(),
                       "visc_ratio": 5.0, "seed": args.seed, "in_range_pairs": npairs,
                       "l2": "inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
-                      "partition": "targets by owned cell, sources replicated" if world > 1 else "single GPU"},
+                      "partition": ("targets and PME spreading by owned cell block, sources replicated, meshes and velocities "
+                                    "summed with ncclAllReduce") if world > 1 else "single GPU"},
            "clocks": clocks,
            "e2e": {"value": 1.0 / e2e_s, "unit": "matvecs/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -67,6 +67,10 @@ int rbc3d_ctx_destroy(rbc3d_ctx *ctx);
  * torch.distributed in the Python harness). */
 int rbc3d_comm_unique_id(void *id128);
 int rbc3d_ctx_attach_comm(rbc3d_ctx *ctx, int nranks, int rank, const void *id128);
+/* TargetList_CollectArray(tlist, 3, v, MPI_COMM_WORLD) (ModTargetList.F90:172-202): v <- sum over ranks of the
+ * per-rank arrays (each rank holds only the rows of its active targets); host SoA(3,n).  No-op on one rank.
+ * rbc3d_apply_resident includes this step. */
+int rbc3d_collect_array(rbc3d_ctx *ctx, int tlist, double *v);
 
 /* ---- ModEwaldFunc.F90:13-16 (host scalars, the table versions use the context's alpha, rc) ---- */
 int rbc3d_ewald_coeff_sl_exact(double r, double alpha, double *A, double *B);

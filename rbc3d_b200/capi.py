@@ -30,6 +30,7 @@ SIGNATURES = {
     "rbc3d_ctx_destroy": (C.c_int, [C.c_void_p]),
     "rbc3d_comm_unique_id": (C.c_int, [C.c_void_p]),
     "rbc3d_ctx_attach_comm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbc3d_collect_array": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_ewald_coeff_sl_exact": (C.c_int, [C.c_double, C.c_double, c_dp, c_dp]),
     "rbc3d_ewald_coeff_dl_exact": (C.c_int, [C.c_double, C.c_double, c_dp]),
     "rbc3d_ewald_coeff_sl": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),

@@ -111,6 +111,10 @@ __global__ void k_fill_int(int n, int *p, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+__global__ void k_fill_range(int n, int *p, int lo, int hi) {  // p[i] = lo <= i < hi
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (i >= lo && i < hi) ? 1 : 0;
+}
 __global__ void k_cell_target_meta(int n, int npc, const double *__restrict__ Acell, int *__restrict__ surf,
                                    double *__restrict__ A) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,6 +317,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   pme_destroy(c);
+  comm_destroy(c);
   for (int i = 0; i < 2 * RBC3D_T_COUNT; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   // device buffers are released with the context's allocations
@@ -340,6 +345,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.ps_warp_tgt.release();
   C.ps_maskbits.release();
   C.ps_compact.release();
+  C.src_own.release();
   rel_cl(C.cl);
   rel_cl(C.pl);
   for (int k = 0; k < 3; k++) {
@@ -356,16 +362,6 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   }
   delete c;
   return RBC3D_OK;
-}
-
-int rbc3d_comm_unique_id(void *) {
-  set_error("multi-GPU communicator not built into this library version");
-  return RBC3D_EINVAL;
-}
-int rbc3d_ctx_attach_comm(rbc3d_ctx *, int nranks, int, const void *) {
-  if (nranks == 1) return RBC3D_OK;
-  set_error("multi-GPU communicator not built into this library version");
-  return RBC3D_EINVAL;
 }
 
 int rbc3d_host_register(void *ptr, size_t bytes) {
@@ -486,7 +482,17 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
   RBC_TRY(upload(C.spdetj, spdetj, sp1 * nc, c->stream));
   // source cell lists: real-space cells (HashTable_Build) and PME blocks
   RBC_TRY(celllist_build_realspace(c, C.cl, (int)Np, C.x.p, nullptr));
-  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, nullptr));
+  // PME sources: with several ranks every rank spreads a contiguous block of cells (comm.cu)
+  const int *src_own = nullptr;
+  if (c->prm.nranks > 1 && Np > 0) {
+    RBC_TRY(C.src_own.resize(Np));
+    const int c_lo = (int)((long long)C.ncell * c->prm.rank / c->prm.nranks);
+    const int c_hi = (int)((long long)C.ncell * (c->prm.rank + 1) / c->prm.nranks);
+    k_fill_range<<<(int)((Np + 255) / 256), 256, 0, c->stream>>>((int)Np, C.src_own.p, c_lo * C.npc, c_hi * C.npc);
+    KERNEL_CHECK();
+    src_own = C.src_own.p;
+  }
+  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own));
   C.geom_set = true;
   RBC_TRY(cells_gather_sorted(c, true, false, false));
   // tlist_rbc: TargetList_Update, ModTargetList.F90:95-135
@@ -720,6 +726,11 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   t_begin(c, RBC3D_T_COMBINE);
   RBC_TRY(combine(c, *t, t->v.p, false));
   t_end(c, RBC3D_T_COMBINE);
+  if (c->prm.nranks > 1) {  // TargetList_CollectArray
+    t_begin(c, RBC3D_T_COMM);
+    RBC_TRY(comm_allreduce_sum(c, t->v.p, 3 * (size_t)t->n));
+    t_end(c, RBC3D_T_COMM);
+  }
   t_end(c, RBC3D_T_TOTAL);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;

@@ -1,0 +1,115 @@
+// comm.cu -- multi-GPU plumbing of the operator (one context per GPU, NCCL over NVLink / NVSwitch).
+//
+// The reference replicates all surface state on every MPI rank, gives every rank the targets of its z-slab
+// (SetActiveFlag, ModTargetList.F90:205-233) and sums the per-rank velocity arrays with TargetList_CollectArray
+// (ModTargetList.F90:172-202 -> CollectArray, ModConf.F90:531-597: AllGatherV + scatter-add).  Here:
+//   * targets: the caller's `active` flags (by owned cell in the Python harness) select each rank's rows;
+//   * PME sources: cells are split into nranks contiguous index blocks, each rank spreads its block on a full
+//     mesh and the meshes are summed with one ncclAllReduce (the reference's slab-wise spreading + halo
+//     exchange, ModPME.F90:354-396, becomes an in-switch reduction); transforms are then rank-local;
+//   * results: rbc3d_collect_array / the resident path sum the velocity rows with ncclAllReduce (rows of
+//     inactive targets are zero), which is CollectArray's MPI_SUM semantics without the index traffic.
+#include "rbc3d_internal.h"
+
+#ifdef RBC3D_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace rbc3d {
+
+#ifdef RBC3D_WITH_NCCL
+#define NCCL_TRY(expr)                                                                       \
+  do {                                                                                       \
+    ncclResult_t r__ = (expr);                                                               \
+    if (r__ != ncclSuccess) {                                                                \
+      rbc3d::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(r__)); \
+      return RBC3D_ECUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+#endif
+
+int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n) {
+  if (c->prm.nranks <= 1 || n == 0) return RBC3D_OK;
+#ifdef RBC3D_WITH_NCCL
+  NCCL_TRY(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
+void comm_destroy(rbc3d_ctx *c) {
+#ifdef RBC3D_WITH_NCCL
+  if (c->nccl_comm) ncclCommDestroy((ncclComm_t)c->nccl_comm);
+#endif
+  c->nccl_comm = nullptr;
+}
+
+}  // namespace rbc3d
+
+using namespace rbc3d;
+
+extern "C" {
+
+int rbc3d_comm_unique_id(void *id128) {
+  if (!id128) return RBC3D_EINVAL;
+#ifdef RBC3D_WITH_NCCL
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
+int rbc3d_ctx_attach_comm(rbc3d_ctx *c, int nranks, int rank, const void *id128) {
+  if (!c || nranks < 1 || rank < 0 || rank >= nranks) return RBC3D_EINVAL;
+  if (c->cells.geom_set) {
+    set_error("rbc3d_ctx_attach_comm must precede rbc3d_cells_set_geometry");
+    return RBC3D_ESTATE;
+  }
+  if (nranks == 1) {
+    c->prm.nranks = 1;
+    c->prm.rank = 0;
+    return RBC3D_OK;
+  }
+#ifdef RBC3D_WITH_NCCL
+  if (!id128) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t comm;
+  NCCL_TRY(ncclCommInitRank(&comm, nranks, id, rank));
+  c->nccl_comm = comm;
+  c->prm.nranks = nranks;
+  c->prm.rank = rank;
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
+// TargetList_CollectArray (ModTargetList.F90:172-202): v <- sum over ranks, host SoA(3,n)
+int rbc3d_collect_array(rbc3d_ctx *c, int tlist, double *v) {
+  if (!c || tlist < 0 || tlist > 2 || !v) return RBC3D_EINVAL;
+  TargetList &t = c->tl[tlist];
+  if (!t.valid) return RBC3D_ESTATE;
+  if (c->prm.nranks <= 1 || t.n == 0) return RBC3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t n3 = 3 * (size_t)t.n;
+  RBC_TRY(t.host_io.resize(n3));
+  t_begin(c, RBC3D_T_COMM);
+  CUDA_TRY(cudaMemcpyAsync(t.host_io.p, v, sizeof(double) * n3, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(comm_allreduce_sum(c, t.host_io.p, n3));
+  CUDA_TRY(cudaMemcpyAsync(v, t.host_io.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->stream));
+  t_end(c, RBC3D_T_COMM);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+}  // extern "C"

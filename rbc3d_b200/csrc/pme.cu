@@ -279,6 +279,12 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     KERNEL_CHECK();
     c->launches++;
   }
+  if (c->prm.nranks > 1 && (pm.flag_sl || pm.flag_dl)) {
+    // every rank spread its block of cells: sum the meshes over the ranks (one in-switch reduction)
+    double *base = pm.src.p + (pm.flag_sl ? 0 : 3 * pm.G);
+    const size_t ncomp = (pm.flag_sl ? 3 : 0) + (pm.flag_dl ? 6 : 0);
+    RBC_TRY(comm_allreduce_sum(c, base, ncomp * pm.G));
+  }
   (void)use_walls;  // wall centroid sources: see walls.cu (PME_Distrib_Source walls branch, ModPME.F90:105-131)
   pm.distributed = true;
   return RBC3D_OK;

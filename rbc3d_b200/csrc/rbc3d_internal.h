@@ -156,6 +156,7 @@ struct Cells {
   dbuf<int> ps_warp_tgt;
   dbuf<unsigned long long> ps_maskbits;
   dbuf<unsigned char> ps_compact;
+  dbuf<int> src_own;                 // multi-GPU: 1 for the points of the cells this rank spreads
 };
 
 struct Pme {
@@ -196,6 +197,7 @@ struct rbc3d_ctx {
   float ms[RBC3D_T_COUNT];
   long long launches = 0;
   int sm_count = 148;
+  void *nccl_comm = nullptr;
 };
 
 namespace rbc3d {
@@ -236,6 +238,10 @@ void pme_destroy(rbc3d_ctx *c);
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls);
 int pme_transform(rbc3d_ctx *c);
 int pme_interp(rbc3d_ctx *c, TargetList &t);
+
+// ---- multi-GPU (comm.cu) ----
+int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);
+void comm_destroy(rbc3d_ctx *c);
 
 // timing helpers
 void t_begin(rbc3d_ctx *c, int stage);

@@ -60,6 +60,7 @@ class EwaldOperator:
         check(self.lib.rbc3d_ctx_create(C.byref(self._h), Lb3, self.alpha, self.eps, self.P, self.rc, Nb3, device),
               "rbc3d_ctx_create (PME_Init)")
         self.ncell = self.npoint = 0
+        self.nranks, self.rank = 1, 0
         self.n_raw = 0
         self._keep = {}
 
@@ -74,6 +75,32 @@ class EwaldOperator:
             self.close()
         except Exception:
             pass
+
+    # -- multi-GPU --------------------------------------------------------------------------------------
+    def attach_comm(self, nranks, rank, dist=None, unique_id: bytes | None = None):
+        """Join the NCCL communicator of the run (before any geometry is set).  The 128-byte unique id is made on
+        rank 0 and handed round by the host program: torch.distributed here, MPI_Bcast in the Fortran driver."""
+        self.nranks, self.rank = int(nranks), int(rank)
+        if nranks == 1:
+            return
+        if unique_id is None:
+            buf = C.create_string_buffer(128)
+            if rank == 0:
+                check(self.lib.rbc3d_comm_unique_id(buf), "rbc3d_comm_unique_id")
+            obj = [bytes(buf.raw) if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            unique_id = obj[0]
+        idbuf = C.create_string_buffer(unique_id, 128)
+        check(self.lib.rbc3d_ctx_attach_comm(self._h, nranks, rank, idbuf), "rbc3d_ctx_attach_comm")
+
+    def ownership_mask(self, sus, nranks, rank):
+        from . import partition
+        return partition.ownership_mask(sus.ncell, sus.nlat * sus.nlon, nranks, rank)
+
+    def TargetList_CollectArray(self, v, tlist=TL_CELLS):
+        """v <- sum over ranks (ModTargetList.F90:172-202)."""
+        check(self.lib.rbc3d_collect_array(self._h, tlist, dp(v)), "TargetList_CollectArray")
+        return v
 
     # -- ModEwaldFunc -----------------------------------------------------------------------------------
     def EwaldCoeff_SL(self, r):

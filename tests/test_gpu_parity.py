@@ -261,3 +261,19 @@ def test_cell_straddling_the_periodic_boundary(oracle_lib):
         ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
         assert rel_l2(v, ref) < TOL
     op.close()
+
+
+def test_multi_gpu_parity_when_several_gpus_are_visible():
+    """2-rank NCCL run of tests/run_multi_gpu.py (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "run_multi_gpu.py")], capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

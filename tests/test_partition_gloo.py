@@ -1,0 +1,73 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes, each evaluating its share of the targets with the oracle
+as the operator, summed like TargetList_CollectArray; the partition helpers are the ones bench.py and the GPU
+path use."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rbc3d_b200 import partition
+
+
+def test_cell_blocks_are_a_partition():
+    for ncell in (1, 2, 7, 8, 64, 4096):
+        for nranks in (1, 2, 3, 4, 8):
+            covered = np.zeros(ncell, int)
+            for r in range(nranks):
+                lo, hi = partition.cell_block(ncell, nranks, r)
+                covered[lo:hi] += 1
+            assert (covered == 1).all()
+    m = [partition.ownership_mask(8, 10, 4, r) for r in range(4)]
+    assert (np.sum(m, axis=0) == 1).all()
+
+
+def test_zslab_active_is_a_partition():
+    rng = np.random.default_rng(0)
+    Lb = np.array([10.5, 10.5, 8.0])
+    x = rng.uniform(-3, 12, size=(3, 1000))         # points outside the box wrap like Fortran modulo
+    for nranks in (1, 2, 3, 8):
+        tot = sum(partition.zslab_active(x, Lb, nranks, r) for r in range(nranks))
+        assert (tot == 1).all()
+
+
+def _worker(rank, world, port, mode, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    from tests import util
+    oracle.lib().orc_set_num_threads(2)
+    sus = util.small_suspension(2)
+    npc = sus.nlat * sus.nlon
+    if mode == "cells":
+        act = partition.ownership_mask(sus.ncell, npc, world, rank)
+    else:
+        act = partition.zslab_active(sus.x, sus.Lb, world, rank)
+    act = act * (np.arange(sus.npoint) % 7 == 0)    # a subset of the targets keeps the CPU test short
+    orc = oracle.Oracle(sus.Lb).set_cells(sus)
+    v = orc.apply_cells(0.0, util.C2_MATVEC, orc.cell_targets(active=act.astype(np.int32)))
+    t = torch.from_numpy(v)
+    dist.all_reduce(t)                               # TargetList_CollectArray
+    if rank == 0:
+        np.save(out, t.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["cells", "zslab"])
+def test_two_rank_sum_equals_single_rank(tmp_path, oracle_lib, mode):
+    from tests import util
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "v.npy")
+    mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
+    v2 = np.load(out)
+    sus = util.small_suspension(2)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    act = (np.arange(sus.npoint) % 7 == 0).astype(np.int32)
+    ref = orc.apply_cells(0.0, util.C2_MATVEC, orc.cell_targets(active=act))
+    assert util.rel_l2(v2, ref) < 1e-13
