@@ -28,7 +28,8 @@ __global__ void k_cid_realspace(int n, const double *__restrict__ x, const int *
 // PME block of a point: mesh cell floor(x*Nb/Lb) (the product rounded like ModPME.F90:420-427), wrapped into
 // [0,Nb), divided by the block edge.
 __global__ void k_cid_pme(int n, const double *__restrict__ x, const int *__restrict__ active, Params prm,
-                          int blk, int nbx, int nby, int nbz, int *__restrict__ cid, int *__restrict__ count) {
+                          int bx, int by, int bz, int nbx, int nby, int nbz, int *__restrict__ cid,
+                          int *__restrict__ count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = nbx * nby * nbz;
@@ -36,7 +37,7 @@ __global__ void k_cid_pme(int n, const double *__restrict__ x, const int *__rest
     int m0 = imodulo((int)floor(__dmul_rn(x[i], prm.ih[0])), prm.Nb[0]);
     int m1 = imodulo((int)floor(__dmul_rn(x[(size_t)n + i], prm.ih[1])), prm.Nb[1]);
     int m2 = imodulo((int)floor(__dmul_rn(x[2 * (size_t)n + i], prm.ih[2])), prm.Nb[2]);
-    c = (m0 / blk) + nbx * ((m1 / blk) + nby * (m2 / blk));
+    c = (m0 / bx) + nbx * ((m1 / by) + nby * (m2 / bz));
   }
   cid[i] = c;
   atomicAdd(&count[c], 1);
@@ -98,18 +99,19 @@ int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x,
   return sort_by_cell(c, cl, n, ncells);
 }
 
-int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active) {
+int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3]) {
   const Params &p = c->prm;
-  const Pme &pm = c->pme;
-  int ncells = pm.nblk[0] * pm.nblk[1] * pm.nblk[2];
+  int nb[3];
+  for (int d = 0; d < 3; d++) nb[d] = (p.Nb[d] + blk[d] - 1) / blk[d];
+  int ncells = nb[0] * nb[1] * nb[2];
   RBC_TRY(alloc_list(cl, n > 0 ? n : 1, ncells));
   CUDA_TRY(cudaMemsetAsync(cl.start.p, 0, sizeof(int) * ((size_t)ncells + 2), c->stream));
   if (n == 0) {
     cl.n = cl.n_sorted = 0;
     return RBC3D_OK;
   }
-  k_cid_pme<<<(n + 255) / 256, 256, 0, c->stream>>>(n, x, active, p, pme_block_edge(), pm.nblk[0], pm.nblk[1],
-                                                    pm.nblk[2], cl.cid.p, cl.start.p);
+  k_cid_pme<<<(n + 255) / 256, 256, 0, c->stream>>>(n, x, active, p, blk[0], blk[1], blk[2], nb[0], nb[1], nb[2],
+                                                    cl.cid.p, cl.start.p);
   KERNEL_CHECK();
   c->launches++;
   return sort_by_cell(c, cl, n, ncells);

@@ -19,7 +19,8 @@
 
 namespace rbc3d {
 
-constexpr int PME_BLK = 4;   // edge of a PME block in mesh cells
+constexpr int PME_BLK = 4;   // edge of a PME block in mesh cells (y, z; and x for the P != 8 kernels)
+constexpr int SPR_BX = 8, SPR_BY = 4, SPR_BZ = 4;  // source blocks of the P = 8 spreading kernel
 constexpr int PME_PMAX = 8;  // largest supported B-spline support (PBspln_Ewd = 8 in every example)
 constexpr int SPREAD_CHUNK = 32;
 
@@ -44,7 +45,13 @@ int pme_init(rbc3d_ctx *c) {
   pm.Nxh = pm.Nx / 2 + 1;
   pm.G = (size_t)pm.Nx * pm.Ny * pm.Nz;
   pm.M = (size_t)pm.Nxh * pm.Ny * pm.Nz;
-  for (int d = 0; d < 3; d++) pm.nblk[d] = (p.Nb[d] + PME_BLK - 1) / PME_BLK;
+  const int sb[3] = {SPR_BX, SPR_BY, SPR_BZ};
+  for (int d = 0; d < 3; d++) {
+    pm.iblk[d] = PME_BLK;
+    pm.nblk[d] = (p.Nb[d] + PME_BLK - 1) / PME_BLK;
+    pm.sblk[d] = (p.P == 8) ? sb[d] : PME_BLK;
+    pm.nsblk[d] = (p.Nb[d] + pm.sblk[d] - 1) / pm.sblk[d];
+  }
   RBC_TRY(pm.src.resize(9 * pm.G));
   RBC_TRY(pm.srcC.resize(9 * pm.M));
   RBC_TRY(pm.vvC.resize(3 * pm.M));
@@ -219,6 +226,141 @@ __global__ void __launch_bounds__(512) k_spread(SpreadArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// P = 8 spreading, v2: register accumulation, no shared-memory read-modify-write and no barrier per source.
+// One CTA per source block of 8 x 4 x 4 mesh cells; its sources touch a tile of 15 x 11 x 11 mesh points.  Thread =
+// one (y, z) column of the tile, holding the 15 x-points x NCOMP components of that column in registers.  Per
+// source: w_y w_z from zero-padded weight rows (no branch), then 8 x (1 + NCOMP) FMAs into the 8 x-points the
+// source touches; the x offset is warp-uniform, so a switch selects one of 8 fully unrolled bodies (static register
+// indices).  Weights / strengths of 32 sources at a time are prepared cooperatively in shared memory.  The tile is
+// flushed component by component through a 15 x 11 x 11 shared buffer with coalesced FP64 reductions.
+constexpr int SPR_TX = SPR_BX + 7, SPR_TY = SPR_BY + 7, SPR_TZ = SPR_BZ + 7;
+constexpr int SPR_COLS = SPR_TY * SPR_TZ;  // 121
+constexpr int SPR_THREADS = 128;
+constexpr int SPR_PADW = 8 + 2 * 3 + 2;    // zero-padded weight row: index (t - rel + 3), t - rel in [-3, 10]
+
+template <int NCOMP, int R>
+__device__ __forceinline__ void spread_update(double (&acc)[SPR_TX][NCOMP], const double wyz,
+                                              const double *__restrict__ wx, const double *__restrict__ st) {
+  double sv[NCOMP];
+#pragma unroll
+  for (int cc = 0; cc < NCOMP; cc++) sv[cc] = st[cc];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const double w = wyz * wx[i];
+#pragma unroll
+    for (int cc = 0; cc < NCOMP; cc++) acc[R + i][cc] = fma(w, sv[cc], acc[R + i][cc]);
+  }
+}
+
+template <int NCOMP>
+__global__ void __launch_bounds__(SPR_THREADS) k_spread8(SpreadArgs a) {
+  __shared__ __align__(16) double s_wx[SPREAD_CHUNK][8];
+  __shared__ __align__(16) double s_wy[SPREAD_CHUNK][SPR_PADW];
+  __shared__ __align__(16) double s_wz[SPREAD_CHUNK][SPR_PADW];
+  __shared__ __align__(16) double s_str[SPREAD_CHUNK][NCOMP + (NCOMP & 1)];
+  __shared__ int s_rel[SPREAD_CHUNK][4];
+  __shared__ double s_out[SPR_TZ * SPR_TY * SPR_TX];
+  const int blk = blockIdx.x;
+  const int sb = a.start[blk], se = a.start[blk + 1];
+  if (sb == se) return;
+  const int bx = blk % a.nbx, by = (blk / a.nbx) % a.nby, bz = blk / (a.nbx * a.nby);
+  const int tid = threadIdx.x;
+  const bool col = tid < SPR_COLS;
+  const int ty = tid % SPR_TY, tz = col ? tid / SPR_TY : 0;
+  double acc[SPR_TX][NCOMP];
+#pragma unroll
+  for (int i = 0; i < SPR_TX; i++)
+#pragma unroll
+    for (int cc = 0; cc < NCOMP; cc++) acc[i][cc] = 0.0;
+  for (int i = tid; i < SPREAD_CHUNK * SPR_PADW; i += SPR_THREADS) {
+    (&s_wy[0][0])[i] = 0.0;
+    (&s_wz[0][0])[i] = 0.0;
+  }
+  for (int cb = sb; cb < se; cb += SPREAD_CHUNK) {
+    const int nch = min(SPREAD_CHUNK, se - cb);
+    __syncthreads();
+    if (tid < nch * 3) {
+      const int s = tid / 3, ax = tid - 3 * s;
+      const int p = a.order[cb + s];
+      const double u = __dmul_rn(a.x[(size_t)ax * a.n + p], a.prm.ih[ax]);  // ic = x*ih, ModPME.F90:420
+      int imin;
+      double w[PME_PMAX];
+      bspline_func<PME_PMAX>(u, 8, imin, w);
+      const int mcell = imodulo(imin + 7, a.prm.Nb[ax]);
+      const int b = (ax == 0) ? bx * SPR_BX : (ax == 1) ? by * SPR_BY : bz * SPR_BZ;
+      s_rel[s][ax] = mcell - b;
+      double *dst = (ax == 0) ? &s_wx[s][0] : (ax == 1) ? &s_wy[s][3] : &s_wz[s][3];
+#pragma unroll
+      for (int q = 0; q < 8; q++) dst[q] = w[q];
+    }
+    for (int t = tid; t < nch * NCOMP; t += SPR_THREADS) {
+      const int s = t / NCOMP, cc = t - s * NCOMP;
+      const int p = a.order[cb + s];
+      const size_t n = a.n;
+      double v;
+      const int comp = a.comp0 + cc;
+      if (comp < 3) {
+        v = a.c1 * a.f[comp * n + p];
+      } else {
+        const double B = a.Bcell[p / a.npc];
+        const double g0 = a.g[p], g1 = a.g[n + p], g2 = a.g[2 * n + p];
+        const double n0 = a.a3[p] * B, n1 = a.a3[n + p] * B, n2 = a.a3[2 * n + p] * B;
+        switch (comp) {
+          case 3: v = g0 * n0; break;
+          case 4: v = g1 * n1; break;
+          case 5: v = g2 * n2; break;
+          case 6: v = 0.5 * (g0 * n1 + g1 * n0); break;
+          case 7: v = 0.5 * (g0 * n2 + g2 * n0); break;
+          default: v = 0.5 * (g1 * n2 + g2 * n1); break;
+        }
+        v *= a.c2;
+      }
+      s_str[s][cc] = v;
+    }
+    __syncthreads();
+    if (col) {
+      for (int s = 0; s < nch; s++) {
+        const int rx = s_rel[s][0], ry = s_rel[s][1], rz = s_rel[s][2];
+        const double wyz = s_wy[s][ty - ry + 3] * s_wz[s][tz - rz + 3];
+        const double *wx = s_wx[s], *st = s_str[s];
+        switch (rx) {
+          case 0: spread_update<NCOMP, 0>(acc, wyz, wx, st); break;
+          case 1: spread_update<NCOMP, 1>(acc, wyz, wx, st); break;
+          case 2: spread_update<NCOMP, 2>(acc, wyz, wx, st); break;
+          case 3: spread_update<NCOMP, 3>(acc, wyz, wx, st); break;
+          case 4: spread_update<NCOMP, 4>(acc, wyz, wx, st); break;
+          case 5: spread_update<NCOMP, 5>(acc, wyz, wx, st); break;
+          case 6: spread_update<NCOMP, 6>(acc, wyz, wx, st); break;
+          default: spread_update<NCOMP, 7>(acc, wyz, wx, st); break;
+        }
+      }
+    }
+  }
+  // flush: component by component through shared memory, then coalesced reductions into the mesh
+  const int ox = bx * SPR_BX - 7, oy = by * SPR_BY - 7, oz = bz * SPR_BZ - 7;
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+#pragma unroll
+  for (int cc = 0; cc < NCOMP; cc++) {
+    __syncthreads();
+    if (col) {
+#pragma unroll
+      for (int i = 0; i < SPR_TX; i++) s_out[(tz * SPR_TY + ty) * SPR_TX + i] = acc[i][cc];
+    }
+    __syncthreads();
+    double *mesh = a.mesh + (size_t)(a.comp0 + cc) * a.G;
+    for (int i = tid; i < SPR_TZ * SPR_TY * SPR_TX; i += SPR_THREADS) {
+      const double v = s_out[i];
+      if (v != 0.0) {
+        const int lx = i % SPR_TX, ly = (i / SPR_TX) % SPR_TY, lz = i / (SPR_TX * SPR_TY);
+        const int gx = imodulo(ox + lx, Nx), gy = imodulo(oy + ly, Ny), gz = imodulo(oz + lz, Nz);
+        atomicAdd(mesh + ((size_t)gz * Ny + gy) * Nx + gx, v);
+      }
+    }
+  }
+}
+
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls) {
   Pme &pm = c->pme;
   Cells &C = c->cells;
@@ -249,12 +391,27 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     a.npc = C.npc;
     a.c1 = c1;
     a.c2 = c2;
-    a.nbx = pm.nblk[0];
-    a.nby = pm.nblk[1];
-    a.nbz = pm.nblk[2];
+    a.nbx = pm.nsblk[0];
+    a.nby = pm.nsblk[1];
+    a.nbz = pm.nsblk[2];
     a.mesh = pm.src.p;
     a.G = pm.G;
     const int nblocks = a.nbx * a.nby * a.nbz;
+    if (c->prm.P == 8) {
+      if (pm.flag_sl) {
+        a.comp0 = 0;
+        a.ncomp = 3;
+        k_spread8<3><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+      }
+      if (pm.flag_dl) {
+        a.comp0 = 3;
+        a.ncomp = 6;
+        k_spread8<6><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+      }
+      KERNEL_CHECK();
+    } else {
     const int T = PME_BLK + c->prm.P - 1;
     auto smem = [&](int nc) {
       return sizeof(double) * ((size_t)nc * T * T * T + SPREAD_CHUNK * 3 * PME_PMAX + SPREAD_CHUNK * nc) +
@@ -278,6 +435,7 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     }
     KERNEL_CHECK();
     c->launches++;
+    }
   }
   if (c->prm.nranks > 1 && (pm.flag_sl || pm.flag_dl)) {
     // every rank spread its block of cells: sum the meshes over the ranks (one in-switch reduction)

@@ -174,7 +174,10 @@ struct Pme {
   dbuf<char> work;
   bool flag_sl = false, flag_dl = false;
   bool distributed = false, transformed = false;
-  int nblk[3] = {0, 0, 0};          // PME blocks of PME_BLK^3 mesh cells
+  int nblk[3] = {0, 0, 0};          // PME blocks of PME_BLK^3 mesh cells (interpolation)
+  int iblk[3] = {4, 4, 4};          // their edges
+  int sblk[3] = {4, 4, 4};          // edges of the source blocks of the spreading kernel
+  int nsblk[3] = {0, 0, 0};
 };
 
 }  // namespace rbc3d
@@ -209,7 +212,7 @@ void h_gauleg(double x1, double x2, int n, double *x, double *w);
 
 // ---- cell list (celllist.cu) ----
 int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
-int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
+int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3]);
 int tiles_build(rbc3d_ctx *c, TargetList &t);
 
 // ---- real-space operator (pairsum.cu, singular.cu, nearsing.cu) ----
