@@ -345,6 +345,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.ps_warp_tgt.release();
   C.ps_maskbits.release();
   C.ps_compact.release();
+  C.ps_needmask.release();
   C.src_own.release();
   rel_cl(C.cl);
   rel_cl(C.pl);

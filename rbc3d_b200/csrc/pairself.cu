@@ -176,6 +176,239 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) k_pair_self(SelfArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v3: symmetric evaluation.  The pairs (i <- j) and (j <- i) share the distance, the range test, the table lookup and
+// the mask, so the cell's targets are grouped into compact patches of 32 (the same 4 lat x 8 lon patches) and the
+// unordered patch pairs (I <= J) are the work units: lane l owns target i_l of patch I in registers and, at step k,
+// meets source j_{(l+k) mod 32} of patch J, whose record it reads from a per-warp shared-memory slot (80-byte
+// records, conflict-free LDS.128 under rotation).  The contribution to i_l stays in lane l; the contribution to
+// j_{l+k} travels in an accumulator that is rotated one lane per step, so after the last step every lane holds the
+// sum for its own j.  Patch pairs farther apart than rc + r_I + r_J (bounding spheres) are skipped, the mask table is
+// consulted only for patch pairs whose reference-sphere patches can overlap a mask support (cell-independent
+// table), and both sides are flushed with FP64 reductions.  Warps draw patches I from a shared counter, largest first.
+constexpr int P3_WARPS = 16;
+
+struct Self3Args {
+  SelfArgs s;
+  const unsigned char *needmask;  // [G][G], cell independent
+};
+
+template <bool SL>
+__global__ void __launch_bounds__(P3_WARPS * 32, 1) k_pair_self3(Self3Args aa) {
+  const SelfArgs &a = aa.s;
+  extern __shared__ double smem[];
+  const int G = a.nwarps_cell;
+  const int ntab = SL ? 2 * (RBC3D_NTAB + 1) : (RBC3D_NTAB + 1) + 1;
+  double *s_tab = smem;
+  double *s_bs = smem + ntab;                        // [G][4] centre, radius
+  double *s_rec = s_bs + 4 * ((G + 1) & ~1);         // [P3_WARPS][32][PS_REC]
+  __shared__ int s_next;
+  const int cell = blockIdx.x;
+  if (!a.cell_active[cell]) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = (size_t)cell * a.npc, Np = a.Np;
+  const int nlonh = a.nlon / 2 + 1;
+  for (int i = threadIdx.x; i <= RBC3D_NTAB; i += blockDim.x) {
+    if (SL) {
+      s_tab[2 * i] = a.tab_sl[2 * i];
+      s_tab[2 * i + 1] = a.tab_sl[2 * i + 1];
+    } else {
+      s_tab[i] = a.tab_dl[i];
+    }
+  }
+  const bool compact = a.cell_compact[cell] != 0;
+  // bounding spheres of the patches (actual, deformed geometry)
+  for (int g = warp; g < G; g += P3_WARPS) {
+    const int p = a.warp_tgt[g * 32 + lane];
+    double x = 0, y = 0, z = 0;
+    if (p >= 0) {
+      x = a.x[base + p];
+      y = a.x[Np + base + p];
+      z = a.x[2 * Np + base + p];
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, p >= 0);
+    const double inv = 1.0 / (double)max(__popc(m), 1);
+    const double cx = warp_sum(x) * inv, cy = warp_sum(y) * inv, cz = warp_sum(z) * inv;
+    double d2 = p >= 0 ? (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(FULL_MASK, d2, o));
+    if (lane == 0) {
+      s_bs[4 * g] = cx;
+      s_bs[4 * g + 1] = cy;
+      s_bs[4 * g + 2] = cz;
+      s_bs[4 * g + 3] = compact ? sqrt(d2) * (1.0 + 1e-12) + 1e-12 : 1e300;  // no culling across periodic wraps
+    }
+  }
+  if (threadIdx.x == 0) s_next = 0;
+  __syncthreads();
+  const double r_eps2 = a.prm.r_eps * a.prm.r_eps;
+  const double rc = a.prm.rc, rc2 = a.prm.rc2_thr, tab_scale = a.prm.tab_scale;
+  const double *src_d = SL ? a.f : a.g;
+  const double Bc = SL ? 1.0 : a.Bcell[cell];
+  double *rec = s_rec + (size_t)warp * 32 * PS_REC;
+
+  for (;;) {
+    int I = 0;
+    if (lane == 0) I = atomicAdd(&s_next, 1);
+    I = __shfl_sync(FULL_MASK, I, 0);
+    if (I >= G) break;
+    const int p_i = a.warp_tgt[I * 32 + lane];
+    const bool valid_i = p_i >= 0;
+    double xi = 0, yi = 0, zi = 0, d0 = 0, d1 = 0, d2i = 0, n0 = 0, n1 = 0, n2 = 0;
+    int lat_i = 0, lon_i = 0;
+    if (valid_i) {
+      const size_t q = base + p_i;
+      xi = a.x[q];
+      yi = a.x[Np + q];
+      zi = a.x[2 * Np + q];
+      d0 = src_d[q] * Bc;
+      d1 = src_d[Np + q] * Bc;
+      d2i = src_d[2 * Np + q] * Bc;
+      if (!SL) {
+        n0 = a.a3[q];
+        n1 = a.a3[Np + q];
+        n2 = a.a3[2 * Np + q];
+      }
+      lon_i = p_i / a.nlat;
+      lat_i = p_i - lon_i * a.nlat;
+    }
+    const double cIx = s_bs[4 * I], cIy = s_bs[4 * I + 1], cIz = s_bs[4 * I + 2], rI = s_bs[4 * I + 3];
+    double ax = 0, ay = 0, az = 0;
+    for (int J = I; J < G; J++) {
+      {
+        const double ex = s_bs[4 * J] - cIx, ey = s_bs[4 * J + 1] - cIy, ez = s_bs[4 * J + 2] - cIz;
+        const double reach = rc + rI + s_bs[4 * J + 3];
+        if (ex * ex + ey * ey + ez * ez > reach * reach) continue;  // warp-uniform
+      }
+      // stage patch J: lane -> its own record
+      __syncwarp();
+      {
+        const int p_j = a.warp_tgt[J * 32 + lane];
+        double *r = rec + lane * PS_REC;
+        int meta = -1;
+        if (p_j >= 0) {
+          const size_t q = base + p_j;
+          r[0] = a.x[q];
+          r[1] = a.x[Np + q];
+          r[2] = a.x[2 * Np + q];
+          r[3] = src_d[q] * Bc;
+          r[4] = src_d[Np + q] * Bc;
+          r[5] = src_d[2 * Np + q] * Bc;
+          if (!SL) {
+            r[6] = a.a3[q];
+            r[7] = a.a3[Np + q];
+            r[8] = a.a3[2 * Np + q];
+          }
+          const int lon_j = p_j / a.nlat;
+          meta = (p_j - lon_j * a.nlat) | (lon_j << 8);
+        }
+        r[9] = __longlong_as_double((long long)meta);
+      }
+      __syncwarp();
+      const bool diag = (I == J);
+      const bool nm = aa.needmask[I * G + J] != 0;
+      const int kbeg = diag ? 1 : 0, kend = diag ? 17 : 32;
+      double bx = 0, by = 0, bz = 0;  // travelling accumulator for j_{lane + k}
+      for (int k = kbeg; k < kend; k++) {
+        const int jl = (lane + k) & 31;
+        const double2 *rj = reinterpret_cast<const double2 *>(rec + jl * PS_REC);
+        const double2 q0 = rj[0], q1 = rj[1], q4 = rj[4];  // (x, y), (z, d0), (n2 | -, meta)
+        const int meta = (int)__double_as_longlong(q4.y);
+        double xx = __dsub_rn(q0.x, xi), yy = __dsub_rn(q0.y, yi), zz = __dsub_rn(q1.x, zi);
+        if (!compact) {
+          xx = min_image(xx, a.prm.iLb[0], a.prm.Lb[0]);
+          yy = min_image(yy, a.prm.iLb[1], a.prm.Lb[1]);
+          zz = min_image(zz, a.prm.iLb[2], a.prm.Lb[2]);
+        }
+        const double r2 = norm2_exact(xx, yy, zz);
+        bool in = valid_i && meta >= 0 && !(r2 > rc2) && r2 >= r_eps2;
+        if (diag && k == 16 && lane >= 16) in = false;  // {l, l+16} is met from both ends
+        if (__any_sync(FULL_MASK, in)) {
+          const double2 q2 = rj[2];  // (d1, d2)
+          double cxi = 0, cyi = 0, czi = 0, cxj = 0, cyj = 0, czj = 0;
+          if (in) {
+            const double rinv = rsqrt_pos(r2);
+            const double s = r2 * rinv * tab_scale;
+            const int it = (int)s;
+            if (it < RBC3D_NTAB) {
+              double om = 1.0;
+              if (nm) {
+                const int lat_j = meta & 0xff, lon_j = meta >> 8;
+                int dl = abs(lon_i - lon_j);
+                dl = min(dl, a.nlon - dl);
+                om = __ldg(a.omm + ((size_t)(lat_i * a.nlat + lat_j)) * nlonh + dl);
+              }
+              const double fr = s - (double)it;
+              const double ir2 = rinv * rinv;
+              if (SL) {
+                const double t10 = s_tab[2 * it], t20 = s_tab[2 * it + 1], t11 = s_tab[2 * it + 2],
+                             t21 = s_tab[2 * it + 3];
+                const double e1 = fma(fr, t11 - t10, t10), e2 = fma(fr, t21 - t20, t20);
+                const double EA = om * (e1 * rinv * ir2 + e2 * ir2), EB = om * (e1 * rinv - e2);
+                const double xfj = EA * (xx * q1.y + yy * q2.x + zz * q2.y);
+                const double xfi = EA * (xx * d0 + yy * d1 + zz * d2i);
+                cxi = xfj * xx + EB * q1.y;
+                cyi = xfj * yy + EB * q2.x;
+                czi = xfj * zz + EB * q2.y;
+                cxj = xfi * xx + EB * d0;
+                cyj = xfi * yy + EB * d1;
+                czj = xfi * zz + EB * d2i;
+              } else {
+                const double2 q3 = rj[3];  // (n0, n1)
+                const double t0 = s_tab[it], t1 = s_tab[it + 1];
+                const double e = fma(fr, t1 - t0, t0);
+                const double EA = om * e * ir2 * ir2 * rinv;
+                const double qj = EA * (xx * q1.y + yy * q2.x + zz * q2.y) * (xx * q3.x + yy * q3.y + zz * q4.x);
+                const double qi = -EA * (xx * d0 + yy * d1 + zz * d2i) * (xx * n0 + yy * n1 + zz * n2);
+                cxi = qj * xx;
+                cyi = qj * yy;
+                czi = qj * zz;
+                cxj = qi * xx;
+                cyj = qi * yy;
+                czj = qi * zz;
+              }
+            }
+          }
+          ax += cxi;
+          ay += cyi;
+          az += czi;
+          bx += cxj;
+          by += cyj;
+          bz += czj;
+        }
+        if (k + 1 < kend) {  // hand the travelling accumulator to the lane that meets the same j next
+          const int from = (lane + 1) & 31;
+          bx = __shfl_sync(FULL_MASK, bx, from);
+          by = __shfl_sync(FULL_MASK, by, from);
+          bz = __shfl_sync(FULL_MASK, bz, from);
+        }
+      }
+      // after the last step lane l holds the sum for j_{(l + kend - 1) mod 32}: deliver and flush
+      {
+        const int from = (lane - (kend - 1)) & 31;
+        bx = __shfl_sync(FULL_MASK, bx, from);
+        by = __shfl_sync(FULL_MASK, by, from);
+        bz = __shfl_sync(FULL_MASK, bz, from);
+        const int p_j = a.warp_tgt[J * 32 + lane];
+        if (p_j >= 0 && a.active[base + p_j]) {
+          const double cc = SL ? a.c1 : a.c2;
+          const size_t tj = base + p_j;
+          atomicAdd(a.acc + tj, cc * bx);
+          atomicAdd(a.acc + Np + tj, cc * by);
+          atomicAdd(a.acc + 2 * Np + tj, cc * bz);
+        }
+      }
+    }
+    if (valid_i && a.active[base + p_i]) {
+      const double cc = SL ? a.c1 : a.c2;
+      const size_t ti = base + p_i;
+      atomicAdd(a.acc + ti, cc * ax);
+      atomicAdd(a.acc + Np + ti, cc * ay);
+      atomicAdd(a.acc + 2 * Np + ti, cc * az);
+    }
+  }
+}
+
 // per cell: is the extent of the cell below half a box in every direction (then nint((xj-xi)/L) = 0 exactly)?
 __global__ void __launch_bounds__(256) k_cell_compact(int npc, int Np, const double *__restrict__ x, Params prm,
                                                       unsigned char *__restrict__ compact) {
@@ -237,6 +470,27 @@ int pairself_mesh_prepare(rbc3d_ctx *c, const std::vector<double> &omm) {
       for (int dl = 0; dl < nlonh; dl++)
         if (omm[((size_t)i * nlat + j) * nlonh + dl] != 1.0) bits[(size_t)i * nlonh + dl] |= 1ull << j;
   C.ps_nwarps = nbl * nbn;
+  // patch pairs whose mask supports can overlap
+  const int G = nbl * nbn;
+  std::vector<unsigned char> nm((size_t)G * G, 0);
+  for (int I = 0; I < G; I++)
+    for (int J = 0; J < G; J++) {
+      bool any = false;
+      for (int li = 0; li < 32 && !any; li++) {
+        const int pi = wt[(size_t)I * 32 + li];
+        if (pi < 0) continue;
+        for (int lj = 0; lj < 32 && !any; lj++) {
+          const int pj = wt[(size_t)J * 32 + lj];
+          if (pj < 0) continue;
+          int dl = abs(pi / nlat - pj / nlat);
+          dl = std::min(dl, nlon - dl);
+          any = omm[((size_t)(pi % nlat) * nlat + (pj % nlat)) * nlonh + dl] != 1.0;
+        }
+      }
+      nm[(size_t)I * G + J] = any ? 1 : 0;
+    }
+  RBC_TRY(C.ps_needmask.resize(nm.size()));
+  CUDA_TRY(cudaMemcpyAsync(C.ps_needmask.p, nm.data(), nm.size(), cudaMemcpyHostToDevice, c->stream));
   RBC_TRY(C.ps_warp_tgt.resize(wt.size()));
   RBC_TRY(C.ps_maskbits.resize(bits.size()));
   CUDA_TRY(cudaMemcpyAsync(C.ps_warp_tgt.p, wt.data(), sizeof(int) * wt.size(), cudaMemcpyHostToDevice, c->stream));
@@ -292,6 +546,27 @@ int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
   const int nlonh = C.nlon / 2 + 1;
   const int nbits = (C.nlat * nlonh + 1) & ~1;
   const int grid = C.ncell * a.ctas_per_cell;
+  if (c->pair_self_mode == 1) {  // symmetric patch-pair kernel
+    Self3Args aa;
+    aa.s = a;
+    aa.needmask = C.ps_needmask.p;
+    for (int pass = 0; pass < 2; pass++) {
+      const bool sl = pass == 0;
+      if (sl ? (c1 == 0) : (c2 == 0)) continue;
+      const int ntab = sl ? 2 * (RBC3D_NTAB + 1) : (RBC3D_NTAB + 1) + 1;
+      const size_t smem = sizeof(double) * ((size_t)ntab + 4 * ((C.ps_nwarps + 1) & ~1) + (size_t)P3_WARPS * 32 * PS_REC);
+      if (sl) {
+        CUDA_TRY(cudaFuncSetAttribute(k_pair_self3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pair_self3<true><<<C.ncell, P3_WARPS * 32, smem, c->stream>>>(aa);
+      } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_pair_self3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pair_self3<false><<<C.ncell, P3_WARPS * 32, smem, c->stream>>>(aa);
+      }
+      KERNEL_CHECK();
+      c->launches++;
+    }
+    return RBC3D_OK;
+  }
   for (int pass = 0; pass < 2; pass++) {
     const bool sl = pass == 0;
     if (sl ? (c1 == 0) : (c2 == 0)) continue;

@@ -156,6 +156,7 @@ struct Cells {
   dbuf<int> ps_warp_tgt;
   dbuf<unsigned long long> ps_maskbits;
   dbuf<unsigned char> ps_compact;
+  dbuf<unsigned char> ps_needmask;   // [patch][patch]: mask table needed for this patch pair
   dbuf<int> src_own;                 // multi-GPU: 1 for the points of the cells this rank spreads
 };
 
@@ -193,7 +194,7 @@ struct rbc3d_ctx {
   rbc3d::TargetList tl[3];
   rbc3d::Pme pme;
   int skip_flags = 0;
-  int pair_self_mode = 1;   // 0: same-surface pairs through the cell list (old path), 1: dense per-cell kernel
+  int pair_self_mode = 1;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel
   int sing_cache_mode = 1;  // 0: never cache the singular double-layer integrand, 1: when memory allows
   cudaEvent_t ev[2 * RBC3D_T_COUNT];
   bool ev_used[RBC3D_T_COUNT];

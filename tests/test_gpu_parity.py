@@ -229,14 +229,14 @@ def test_pair_sum_dense_self_kernel_vs_cell_list(sus8, oracle_lib, c1, c2):
     orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
     ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
     out = []
-    for mode in (1, 0):
+    for mode in (1, 2, 0):   # symmetric patch pairs, dense per cell, hashed cell list
         op = EwaldOperator(sus8.Lb)
         op.set_pair_self(mode)
         op.set_suspension(sus8)
         op.set_skip_flags(1 | 2 | 4)
         out.append(op.AddIntOnRbcs(c1, c2))
         op.close()
-    assert rel_l2(out[0], ref) < TOL and rel_l2(out[1], ref) < TOL
+    assert rel_l2(out[0], ref) < TOL and rel_l2(out[1], ref) < TOL and rel_l2(out[2], ref) < TOL
 
 
 def test_cell_straddling_the_periodic_boundary(oracle_lib):
