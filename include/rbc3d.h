@@ -96,6 +96,33 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *ctx, const double *x, const double *a3, 
 int rbc3d_cells_set_density(rbc3d_ctx *ctx, const double *f, const double *g, const double *spF,
                             const double *spG);
 
+/* ---- walls ----
+ * rbc3d_walls_set: SourceList_UpdateCoord(slist_wall, walls) (element centroids + cell list, ModSourceList.F90:
+ *   127-146) and TargetList_Update(tlist_wall, walls) (all wall vertices, Acoef = 2, ModTargetList.F90:122-131).
+ *   x: SoA(3,NV), the vertices of all walls back to back (= tlist_wall%x); e2v: SoA(3,NE) = wall%e2v of every wall
+ *   back to back, 1-based vertex numbers local to the wall; area, epsDist [NE] from Wall_ComputeGeometry
+ *   (ModWall.F90:118-145); active [NV] or NULL = SetActiveFlag of the wall target list.
+ * rbc3d_walls_set_traction: wall%f of all walls, SoA(3,NV).
+ * rbc3d_wall_prepare_sing: PrepareSingIntOnWall (ModIntOnWalls.F90:181-308) for every wall: the sparse
+ *   self-interaction matrix t_Wall%lhs is assembled in HBM (rows of active vertices only, :199-203).
+ * rbc3d_sing_int_on_wall: SingIntOnWall(c1, wall, v) (:136-172): v = c1 * lhs * f, v host SoA(3,nvert(iwall)),
+ *   iwall 0-based.
+ * rbc3d_add_int_on_walls: AddIntOnWalls(c1, tlist, v) (:33-130): self-interactions through lhs when tlist is the
+ *   wall list, the direct Duffy / 7-point loop over all other (target, element) pairs within rc.           */
+int rbc3d_walls_set(rbc3d_ctx *ctx, int nwall, const int32_t *nvert, const int32_t *nele, const double *x,
+                    const int32_t *e2v, const double *area, const double *epsDist, const int32_t *active);
+int rbc3d_walls_set_traction(rbc3d_ctx *ctx, const double *f);
+int rbc3d_wall_prepare_sing(rbc3d_ctx *ctx);
+int rbc3d_sing_int_on_wall(rbc3d_ctx *ctx, double c1, int iwall, double *v);
+int rbc3d_add_int_on_walls(rbc3d_ctx *ctx, double c1, int tlist, double *v);
+/* MinDistToTri (:480-577), Tri_Int_Regular (:319-363), Tri_Int_Duffy (:373-465) for n independent
+ * (target, triangle) pairs, evaluated on the device.  xtar SoA(3,n); xtri, ftri [n][3 corners][3]; s0 = t0 = NULL
+ * selects the regular rule; rhs [n][3] and/or lhs [n][3 corners][3][3] (either may be NULL). */
+int rbc3d_min_dist_to_tri(rbc3d_ctx *ctx, int n, const double *xtar, const double *xtri, double *dist, double *s0,
+                          double *t0);
+int rbc3d_tri_int(rbc3d_ctx *ctx, int n, const double *xtri, const double *ftri, const double *xtar,
+                  const double *s0, const double *t0, double *rhs, double *lhs);
+
 /* TargetList_CreateFromRaw (ModTargetList.F90:139-169): arbitrary points, Acoef = 2, indx = -1 */
 int rbc3d_targets_set_raw(rbc3d_ctx *ctx, int n, const double *x, const int32_t *active);
 
@@ -136,6 +163,13 @@ int rbc3d_neighbor_signature(rbc3d_ctx *ctx, int tlist, int32_t *count, uint64_t
 /* near-singular entries found at geometry time: n entries (target, source cell, active flag, th0, phi0, dist) */
 int rbc3d_nearsing_get(rbc3d_ctx *ctx, int tlist, int *n, int32_t *target, int32_t *cell, int32_t *flag,
                        double *th0, double *phi0, double *dist, int cap);
+/* wall self-interaction matrix as block rows over the NV vertices: rowptr[NV+1], col[nblk] (global vertex),
+ * val[nblk][3][3] (target component, source component) */
+int rbc3d_wall_matrix_get(rbc3d_ctx *ctx, int32_t *nblk, int32_t *rowptr, int32_t *col, double *val, int cap);
+/* per target of a list: number of wall elements within rc (MinDistToTri), checksum of their indices, how many take
+ * the Duffy rule; self_skip = 1 applies the same-surface exclusion of AddIntOnWalls (:92) */
+int rbc3d_wall_neighbor_signature(rbc3d_ctx *ctx, int tlist, int self_skip, int32_t *count, uint64_t *sig,
+                                  int32_t *nduffy);
 int rbc3d_pme_get_grid(rbc3d_ctx *ctx, double *vv /* [3][Nz][Ny][Nx] */);
 int rbc3d_get_timings(rbc3d_ctx *ctx, float ms[RBC3D_T_COUNT]);
 int rbc3d_get_launch_count(rbc3d_ctx *ctx, long long *launches);

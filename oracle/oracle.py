@@ -43,6 +43,11 @@ class Cells(C.Structure):
                 ("thG", c_dp), ("phiG", c_dp), ("patch_w", c_dp)]
 
 
+class WallsStruct(C.Structure):
+    _fields_ = [("nwall", C.c_int), ("nvert", c_ip), ("nele", c_ip), ("id0", C.c_int), ("x", c_dp), ("f", c_dp),
+                ("e2v", c_ip), ("area", c_dp), ("epsDist", c_dp)]
+
+
 class Targets(C.Structure):
     _fields_ = [("n", C.c_int), ("x", c_dp), ("Acoef", c_dp), ("indx", c_ip), ("active", c_ip)]
 
@@ -74,6 +79,9 @@ def lib():
         L.orc_mask_func_exact.restype = C.c_double
         L.orc_dist_on_sphere.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
+        L.orc_min_dist_to_tri.restype = C.c_double
+        L.orc_prepare_sing_int_on_wall.restype = C.c_void_p
+        L.orc_wallmat_nblk.restype = C.c_int
         _lib = L
     return _lib
 
@@ -315,7 +323,145 @@ class Oracle:
                               C.c_double(c1), C.c_double(c2), C.byref(tl), _dp(v), C.c_int(flags))
         return v
 
+    # ---- walls (rbc3d_oracle_walls.c) -----------------------------------------------
+    def set_walls(self, W, ncell=None):
+        """W: rbc3d_b200.synth.Walls.  Surface ids: cells 1..ncell, walls ncell+1.. (ModData: walls(1)%ID)."""
+        if ncell is None:
+            ncell = self.sus.ncell if self.cells is not None else 0
+        keep = dict(nvert=np.ascontiguousarray(W.nvert, np.int32), nele=np.ascontiguousarray(W.nele, np.int32),
+                    x=_f64(W.x), f=_f64(W.f), e2v=np.ascontiguousarray(W.e2v, np.int32), area=_f64(W.area),
+                    epsDist=_f64(W.epsDist))
+        w = WallsStruct()
+        w.nwall, w.id0 = W.nwall, ncell + 1
+        w.nvert, w.nele, w.e2v = _ip(keep["nvert"]), _ip(keep["nele"]), _ip(keep["e2v"])
+        w.x, w.f, w.area, w.epsDist = _dp(keep["x"]), _dp(keep["f"]), _dp(keep["area"]), _dp(keep["epsDist"])
+        self._walls_keep, self.walls, self.W = keep, w, W
+        self.wall_mats = None
+        return self
+
+    def set_wall_traction(self, f):
+        self._walls_keep["f"] = _f64(f).copy()
+        self.walls.f = _dp(self._walls_keep["f"])
+
+    def wall_targets(self, active=None):
+        """tlist_wall: all wall vertices, Acoef = 2, indx(:,0) = wall id (ModTargetList.F90:122-131)."""
+        W = self.W
+        n = W.NV
+        indx = np.full((3, n), -1, dtype=np.int32)
+        indx[0] = self.walls.id0 + np.repeat(np.arange(W.nwall), W.nvert)
+        return self.make_targets(W.x, np.full(n, 2.0), indx, active)
+
+    def wall_compute_geometry(self):
+        area, eps = np.zeros(self.W.NE), np.zeros(self.W.NE)
+        lib().orc_wall_compute_geometry(C.byref(self.walls), _dp(area), _dp(eps))
+        return area, eps
+
+    def wall_centroids(self):
+        xc = np.zeros((3, self.W.NE))
+        lib().orc_wall_centroids(C.byref(self.prm), C.byref(self.walls), _dp(xc))
+        return xc
+
+    @staticmethod
+    def min_dist_to_tri(xtar, xtri):
+        """xtri: (3 corners, 3 comps).  Returns dist, s0, t0, x0."""
+        xt, tri = _f64(xtar), _f64(xtri)
+        s0, t0 = C.c_double(), C.c_double()
+        x0 = np.zeros(3)
+        d = lib().orc_min_dist_to_tri(_dp(xt), _dp(tri), C.byref(s0), C.byref(t0), _dp(x0))
+        return d, s0.value, t0.value, x0
+
+    def tri_int(self, xtri, ftri, xtar, s0=None, t0=None, want_lhs=True):
+        """Tri_Int_Regular (s0 is None) or Tri_Int_Duffy.  Returns rhs(3), lhs(3 corners,3,3)."""
+        tri, f, xt = _f64(xtri), _f64(ftri), _f64(xtar)
+        rhs, lhs = np.zeros(3), np.zeros((3, 3, 3))
+        if s0 is None:
+            lib().orc_tri_int_regular(C.byref(self.prm), _dp(tri), _dp(f), _dp(xt), _dp(rhs), _dp(lhs) if want_lhs else None)
+        else:
+            lib().orc_tri_int_duffy(C.byref(self.prm), _dp(tri), _dp(f), _dp(xt), C.c_double(s0), C.c_double(t0),
+                                    _dp(rhs), _dp(lhs) if want_lhs else None)
+        return rhs, lhs
+
+    def prepare_sing_int_on_walls(self, active=None):
+        """PrepareSingIntOnWall for every wall; active: per wall-vertex flags of the wall target list or None."""
+        self.free_wall_mats()
+        vo = self.W.voff()
+        mats = []
+        for w in range(self.W.nwall):
+            act = None if active is None else np.ascontiguousarray(active[vo[w]:vo[w + 1]], dtype=np.int32)
+            mats.append(C.c_void_p(lib().orc_prepare_sing_int_on_wall(C.byref(self.prm), C.byref(self.walls), C.c_int(w), _ip(act))))
+        self.wall_mats = mats
+        return self
+
+    def free_wall_mats(self):
+        for m in getattr(self, "wall_mats", None) or []:
+            lib().orc_wallmat_free(m)
+        self.wall_mats = None
+
+    def wall_matrix(self, iwall):
+        """(rowptr, col, val[nblk,3,3]) of wall iwall's self-interaction matrix."""
+        m = self.wall_mats[iwall]
+        nblk = lib().orc_wallmat_nblk(m)
+        rowptr = np.zeros(int(self.W.nvert[iwall]) + 1, np.int32)
+        col = np.zeros(max(nblk, 1), np.int32)
+        val = np.zeros((max(nblk, 1), 3, 3))
+        lib().orc_wallmat_get(m, _ip(rowptr), _ip(col), _dp(val))
+        return rowptr, col[:nblk], val[:nblk]
+
+    def sing_int_on_wall(self, c1, iwall, f=None):
+        vo = self.W.voff()
+        fw = _f64(self._walls_keep["f"][:, vo[iwall]:vo[iwall + 1]] if f is None else f)
+        v = np.zeros_like(fw)
+        lib().orc_sing_int_on_wall(self.wall_mats[iwall], C.c_double(c1), _dp(fw), _dp(v))
+        return v
+
+    def add_int_on_walls(self, c1, tl, v=None):
+        if v is None:
+            v = np.zeros((3, tl.n))
+        mats = None
+        if self.wall_mats is not None:
+            mats = (C.c_void_p * len(self.wall_mats))(*[m.value for m in self.wall_mats])
+        lib().orc_add_int_on_walls(C.byref(self.prm), C.byref(self.walls), C.c_double(c1), C.byref(tl), _dp(v), mats)
+        return v
+
+    def wall_neighbor_signature(self, tl, self_skip=True):
+        cnt = np.zeros(tl.n, np.int32)
+        nd = np.zeros(tl.n, np.int32)
+        sig = np.zeros(tl.n, np.uint64)
+        lib().orc_wall_neighbor_signature(C.byref(self.prm), C.byref(self.walls), C.byref(tl), C.c_int(1 if self_skip else 0),
+                                          _ip(cnt), sig.ctypes.data_as(C.POINTER(C.c_ulonglong)), _ip(nd))
+        return cnt, sig, nd
+
+    def pme_distrib_walls(self, c1, c2=0.0, accumulate=False):
+        lib().orc_pme_distrib_walls(self.pme(), C.byref(self.prm), C.c_double(c1), C.c_double(c2), C.byref(self.walls),
+                                    C.c_int(1 if accumulate else 0))
+
+    def apply(self, c1, c2, tl, cells=True, walls=False, v=None):
+        """v += AddIntOnRbcs + AddIntOnWalls + PME over the chosen source sets (the composition of
+        ModVelSolver.F90:473-493 / ModNoSlip.F90:172-191, 284-299)."""
+        if v is None:
+            v = np.zeros((3, tl.n))
+        if cells:
+            self.add_int_on_rbcs(c1, c2, tl, v)
+        if walls:
+            self.add_int_on_walls(c1, tl, v)
+        first = True
+        if cells:
+            sus = self.sus
+            npc = sus.nlat * sus.nlon
+            self.pme_distrib(c1, c2, sus.x, sus.weighted(sus.f) if abs(c1) > 1e-10 else None,
+                             sus.weighted(sus.g) if abs(c2) > 1e-10 else None, sus.a3, np.repeat(sus.Bcoef, npc))
+            first = False
+        if walls:
+            self.pme_distrib_walls(c1, c2, accumulate=not first)
+        self.pme_transform()
+        self.pme_interp(tl, v)
+        return v
+
     def __del__(self):
+        try:
+            self.free_wall_mats()
+        except Exception:
+            pass
         try:
             if self._pme is not None:
                 lib().orc_pme_finalize(self._pme)

@@ -11,8 +11,8 @@
  * this path and cannot be compiled in this image (no
  * Fortran compiler, MPI, PETSc, FFTW).  The restatement is validated by physics
  * identities (tests/test_oracle_identities.py) and by an independent NumPy mirror
- * of the closed-form pieces (oracle/np_mirror.py); nothing here was checked
- * against an execution of the reference binary.
+ * of the closed-form pieces inside the tests; nothing here was checked against an
+ * execution of the reference binary.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/common/).  Index conventions follow the Fortran (1-based
@@ -145,6 +145,41 @@ void orc_fft_backward(const orc_params *prm, const double *cplx_in, double *real
 /* whole cell operator: v += AddIntOnRbcs + PME (ModVelSolver.F90:568-582 pattern) */
 void orc_apply_cells(const orc_params *prm, const orc_cells *cells, orc_pme *pme, double c1,
                      double c2, const orc_targets *tl, double *v, int flags);
+
+
+/* ---- walls (rbc3d_oracle_walls.c): ModIntOnWalls.F90, wall branches of ModSourceList/ModPME ---- */
+typedef struct {
+  int nwall;
+  const int *nvert, *nele; /* [nwall] */
+  int id0;                 /* walls(1)%ID: surface id of the first wall (cells are 1..ncell) */
+  const double *x;         /* SoA(3,NV): vertices of all walls back to back (= tlist_wall%x) */
+  const double *f;         /* SoA(3,NV) tractions wall%f, or NULL */
+  const int *e2v;          /* SoA(3,NE): wall%e2v, 1-based vertex numbers local to the wall */
+  const double *area, *epsDist; /* [NE] (Wall_ComputeGeometry, ModWall.F90:118-145) */
+} orc_walls;
+typedef struct orc_wallmat orc_wallmat; /* t_Wall%lhs */
+
+void orc_gq_tri7(double *rs /* [7][2] */, double *w);
+void orc_wall_compute_geometry(const orc_walls *W, double *area, double *epsDist);
+void orc_wall_centroids(const orc_params *prm, const orc_walls *W, double *xc /* SoA(3,NE) */);
+/* x: [l*3+d] = x(l+1,d+1) */
+double orc_min_dist_to_tri(const double xTar[3], const double *x, double *s0, double *t0, double *x0);
+/* lhs[(l*3+ii)*3+jj] = lhs(l+1,ii+1,jj+1) or NULL */
+void orc_tri_int_regular(const orc_params *prm, const double *x, const double *f, const double xtar[3],
+                         double rhs[3], double *lhs);
+void orc_tri_int_duffy(const orc_params *prm, const double *x, const double *f, const double xtar[3], double s0,
+                       double t0, double rhs[3], double *lhs);
+orc_wallmat *orc_prepare_sing_int_on_wall(const orc_params *prm, const orc_walls *W, int iwall, const int *active);
+void orc_wallmat_free(orc_wallmat *M);
+int orc_wallmat_nblk(const orc_wallmat *M);
+void orc_wallmat_get(const orc_wallmat *M, int *rowptr, int *col, double *val /* [nblk][3][3] */);
+void orc_sing_int_on_wall(const orc_wallmat *M, double c1, const double *f, double *v);
+void orc_add_int_on_walls(const orc_params *prm, const orc_walls *W, double c1, const orc_targets *tl, double *v,
+                          orc_wallmat *const *mats);
+void orc_wall_neighbor_signature(const orc_params *prm, const orc_walls *W, const orc_targets *tl, int self_skip,
+                                 int *count, unsigned long long *sig, int *nduffy);
+void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, double c2, const orc_walls *W,
+                           int accumulate);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

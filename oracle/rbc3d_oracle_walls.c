@@ -513,7 +513,8 @@ void orc_wall_neighbor_signature(const orc_params *prm, const orc_walls *W, cons
 }
 
 /* ModPME.F90:105-129: wall sources of the PME spread = element centroid, THRD*sum(fele)*area */
-void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, const orc_walls *W, int accumulate) {
+void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, double c2, const orc_walls *W,
+                           int accumulate) {
   wall_lists L;
   wall_lists_init(prm, W, &L);
   const int NE = L.NE, NV = L.NV;
@@ -526,8 +527,8 @@ void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, const
       ft[(size_t)d * NE + e] = THRD * (fe[0] + fe[1] + fe[2]) * W->area[e];
     }
   }
-  /* flag_sing_lay = |c1| > 1e-10: with it off ftmp = 0 and the call only zeroes the grids */
-  orc_pme_distrib_source(pme, c1, 0., NE, L.xc, ft, NULL, NULL, NULL, accumulate);
+  /* ttmp = 0: no double-layer density on walls (:124); c2 only keeps flag_doub_lay of the same call */
+  orc_pme_distrib_source(pme, c1, c2, NE, L.xc, ft, NULL, NULL, NULL, accumulate);
   free(ft);
   wall_lists_free(&L);
 }

@@ -38,6 +38,15 @@ SIGNATURES = {
     "rbc3d_cells_set_mesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "rbc3d_cells_set_geometry": (C.c_int, [C.c_void_p] + [c_dp] * 9 + [c_ip]),
     "rbc3d_cells_set_density": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp]),
+    "rbc3d_walls_set": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip, c_dp, c_ip, c_dp, c_dp, c_ip]),
+    "rbc3d_walls_set_traction": (C.c_int, [C.c_void_p, c_dp]),
+    "rbc3d_wall_prepare_sing": (C.c_int, [C.c_void_p]),
+    "rbc3d_sing_int_on_wall": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_dp]),
+    "rbc3d_add_int_on_walls": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_dp]),
+    "rbc3d_min_dist_to_tri": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "rbc3d_tri_int": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "rbc3d_wall_matrix_get": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_dp, C.c_int]),
+    "rbc3d_wall_neighbor_signature": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_ip, c_up, c_ip]),
     "rbc3d_targets_set_raw": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip]),
     "rbc3d_add_int_on_rbcs": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, c_dp]),
     "rbc3d_pme_distrib_source": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]),

@@ -139,6 +139,8 @@ static int target_list_finish(rbc3d_ctx *c, TargetList &t) {
   RBC_TRY(t.v.resize(3 * (size_t)(t.n > 0 ? t.n : 1)));
   if (c->cells.geom_set) RBC_TRY(nearsing_prepare(c, t));
   t.valid = true;
+  t.version++;
+  t.wp.valid = false;
   return RBC3D_OK;
 }
 
@@ -318,6 +320,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   cudaStreamSynchronize(c->stream);
   pme_destroy(c);
   comm_destroy(c);
+  walls_release(c);
   for (int i = 0; i < 2 * RBC3D_T_COUNT; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   // device buffers are released with the context's allocations
@@ -572,6 +575,100 @@ int rbc3d_targets_set_raw(rbc3d_ctx *c, int n, const double *x, const int32_t *a
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// walls: SourceList_UpdateCoord(slist_wall) + TargetList_Update(tlist_wall) (ModSourceList.F90:127-146,
+// ModTargetList.F90:122-131)
+int rbc3d_walls_set(rbc3d_ctx *c, int nwall, const int32_t *nvert, const int32_t *nele, const double *x,
+                    const int32_t *e2v, const double *area, const double *epsDist, const int32_t *active) {
+  if (!c || nwall < 0 || (nwall > 0 && (!nvert || !nele || !x || !e2v || !area || !epsDist))) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  RBC_TRY(walls_set_geometry(c, nwall, nvert, nele, x, e2v, area, epsDist));
+  Walls &W = c->walls;
+  TargetList &t = c->tl[RBC3D_TL_WALLS];
+  t.kind = RBC3D_TL_WALLS;
+  t.n = W.NV;
+  const size_t n1 = W.NV > 0 ? W.NV : 1;
+  RBC_TRY(t.x.resize(3 * n1));
+  RBC_TRY(t.Acoef.resize(n1));
+  RBC_TRY(t.surf.resize(n1));
+  RBC_TRY(t.active.resize(n1));
+  if (W.NV > 0) {
+    CUDA_TRY(cudaMemcpyAsync(t.x.p, W.x.p, sizeof(double) * 3 * W.NV, cudaMemcpyDeviceToDevice, c->stream));
+    RBC_TRY(walls_target_meta(c, t));
+    if (active)
+      CUDA_TRY(cudaMemcpyAsync(t.active.p, active, sizeof(int) * W.NV, cudaMemcpyHostToDevice, c->stream));
+    else
+      k_fill_int<<<(W.NV + 255) / 256, 256, 0, c->stream>>>(W.NV, t.active.p, 1);
+    KERNEL_CHECK();
+  }
+  RBC_TRY(target_list_finish(c, t));
+  for (int k = 0; k < 3; k++) c->tl[k].wp.valid = false;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int rbc3d_walls_set_traction(rbc3d_ctx *c, const double *f) {
+  if (!c || !f) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  RBC_TRY(walls_set_traction(c, f));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int rbc3d_wall_prepare_sing(rbc3d_ctx *c) {  // PrepareSingIntOnWall, ModIntOnWalls.F90:181-308, every wall
+  if (!c) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return walls_prepare_sing(c);
+}
+
+int rbc3d_sing_int_on_wall(rbc3d_ctx *c, double c1, int iwall, double *v) {  // ModIntOnWalls.F90:136-172
+  if (!c || !v || iwall < 0 || iwall >= c->walls.nwall) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Walls &W = c->walls;
+  const int nv = W.h_nvert[iwall];
+  TargetList &t = c->tl[RBC3D_TL_WALLS];
+  RBC_TRY(t.host_io.resize(3 * (size_t)(t.n > 0 ? t.n : 1)));
+  RBC_TRY(walls_sing_int(c, c1, iwall, t.host_io.p));
+  if (nv > 0) CUDA_TRY(cudaMemcpyAsync(v, t.host_io.p, sizeof(double) * 3 * nv, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int rbc3d_wall_matrix_get(rbc3d_ctx *c, int32_t *nblk, int32_t *rowptr, int32_t *col, double *val, int cap) {
+  if (!c || !c->walls.mat_ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Walls &W = c->walls;
+  if (nblk) *nblk = W.nblk;
+  if (rowptr) CUDA_TRY(cudaMemcpy(rowptr, W.rowptr.p, sizeof(int) * (W.NV + 1), cudaMemcpyDeviceToHost));
+  const int m = W.nblk < cap ? W.nblk : cap;
+  if (m > 0 && col) CUDA_TRY(cudaMemcpy(col, W.col.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
+  if (m > 0 && val) CUDA_TRY(cudaMemcpy(val, W.val.p, sizeof(double) * 9 * m, cudaMemcpyDeviceToHost));
+  return RBC3D_OK;
+}
+
+int rbc3d_wall_neighbor_signature(rbc3d_ctx *c, int tlist, int self_skip, int32_t *count, uint64_t *sig,
+                                  int32_t *nduffy) {
+  if (!c || tlist < 0 || tlist > 2 || !c->tl[tlist].valid) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return walls_signature(c, c->tl[tlist], self_skip, count, (unsigned long long *)sig, nduffy);
+}
+
+int rbc3d_min_dist_to_tri(rbc3d_ctx *c, int n, const double *xtar, const double *xtri, double *dist, double *s0,
+                          double *t0) {
+  if (!c || n < 0 || !xtar || !xtri || !dist) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return walls_min_dist_batch(c, n, xtar, xtri, dist, s0, t0);
+}
+
+int rbc3d_tri_int(rbc3d_ctx *c, int n, const double *xtri, const double *ftri, const double *xtar, const double *s0,
+                  const double *t0, double *rhs, double *lhs) {
+  if (!c || n < 0 || !xtri || !xtar || (!rhs && !lhs) || ((s0 == nullptr) != (t0 == nullptr))) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (rhs) RBC_TRY(walls_tri_int_batch(c, n, xtri, ftri, xtar, s0, t0, rhs, nullptr));
+  if (lhs) RBC_TRY(walls_tri_int_batch(c, n, xtri, ftri, xtar, s0, t0, nullptr, lhs));
+  return RBC3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 static int check_density(rbc3d_ctx *c, double c1, double c2) {
   if (c1 != 0 && !c->cells.f_set) {
     set_error("c1 != 0 but no single-layer density (f, spF) was set");
@@ -653,6 +750,19 @@ int rbc3d_add_int_on_rbcs(rbc3d_ctx *c, double c1, double c2, int tlist, double 
   return v_roundtrip_end(c, *t, v);
 }
 
+int rbc3d_add_int_on_walls(rbc3d_ctx *c, double c1, int tlist, double *v) {  // ModIntOnWalls.F90:33-130
+  TargetList *t;
+  RBC_TRY(get_tl(c, tlist, &t));
+  RBC_TRY(begin_apply(c, *t));
+  RBC_TRY(v_roundtrip_begin(c, *t, v));
+  t_begin(c, RBC3D_T_WALL);
+  RBC_TRY(walls_add_int(c, *t, c1));
+  t_end(c, RBC3D_T_WALL);
+  RBC_TRY(linear_term(c, *t, 0.0));
+  RBC_TRY(combine(c, *t, t->host_io.p, true));
+  return v_roundtrip_end(c, *t, v);
+}
+
 int rbc3d_pme_distrib_source(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls) {
   if (!c) return RBC3D_EINVAL;
   CUDA_TRY(cudaSetDevice(c->device));
@@ -686,6 +796,11 @@ int rbc3d_pme_add_interp_vel(rbc3d_ctx *c, int tlist, double *v) {
 
 static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int use_cells, int use_walls) {
   if (use_cells) RBC_TRY(realspace_cells(c, t, c1, c2));
+  if (use_walls && c1 != 0) {
+    t_begin(c, RBC3D_T_WALL);
+    RBC_TRY(walls_add_int(c, t, c1));
+    t_end(c, RBC3D_T_WALL);
+  }
   t_begin(c, RBC3D_T_LINEAR);
   RBC_TRY(linear_term(c, t, (use_cells && !(c->skip_flags & 4)) ? c2 : 0.0));
   t_end(c, RBC3D_T_LINEAR);

@@ -361,6 +361,58 @@ __global__ void __launch_bounds__(SPR_THREADS) k_spread8(SpreadArgs a) {
   }
 }
 
+// launch the spreading kernel(s) for one source list (cells or wall centroids); the meshes are accumulated into
+static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
+  Pme &pm = c->pme;
+  struct { bool flag_sl, flag_dl; } pmf = {sl, dl};
+    a.nbx = pm.nsblk[0];
+    a.nby = pm.nsblk[1];
+    a.nbz = pm.nsblk[2];
+    a.mesh = pm.src.p;
+    a.G = pm.G;
+    const int nblocks = a.nbx * a.nby * a.nbz;
+    if (c->prm.P == 8) {
+      if (pmf.flag_sl) {
+        a.comp0 = 0;
+        a.ncomp = 3;
+        k_spread8<3><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+      }
+      if (pmf.flag_dl) {
+        a.comp0 = 3;
+        a.ncomp = 6;
+        k_spread8<6><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+      }
+      KERNEL_CHECK();
+    } else {
+    const int T = PME_BLK + c->prm.P - 1;
+    auto smem = [&](int nc) {
+      return sizeof(double) * ((size_t)nc * T * T * T + SPREAD_CHUNK * 3 * PME_PMAX + SPREAD_CHUNK * nc) +
+             sizeof(int) * SPREAD_CHUNK * 3;
+    };
+    if (pmf.flag_sl && pmf.flag_dl) {
+      a.comp0 = 0;
+      a.ncomp = 9;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(9)));
+      k_spread<9><<<nblocks, 512, smem(9), c->stream>>>(a);
+    } else if (pmf.flag_sl) {
+      a.comp0 = 0;
+      a.ncomp = 3;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(3)));
+      k_spread<3><<<nblocks, 512, smem(3), c->stream>>>(a);
+    } else {
+      a.comp0 = 3;
+      a.ncomp = 6;
+      CUDA_TRY(cudaFuncSetAttribute(k_spread<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(6)));
+      k_spread<6><<<nblocks, 512, smem(6), c->stream>>>(a);
+    }
+    KERNEL_CHECK();
+    c->launches++;
+    }
+  return RBC3D_OK;
+}
+
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls) {
   Pme &pm = c->pme;
   Cells &C = c->cells;
@@ -391,51 +443,29 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     a.npc = C.npc;
     a.c1 = c1;
     a.c2 = c2;
-    a.nbx = pm.nsblk[0];
-    a.nby = pm.nsblk[1];
-    a.nbz = pm.nsblk[2];
-    a.mesh = pm.src.p;
-    a.G = pm.G;
-    const int nblocks = a.nbx * a.nby * a.nbz;
-    if (c->prm.P == 8) {
-      if (pm.flag_sl) {
-        a.comp0 = 0;
-        a.ncomp = 3;
-        k_spread8<3><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
-        c->launches++;
-      }
-      if (pm.flag_dl) {
-        a.comp0 = 3;
-        a.ncomp = 6;
-        k_spread8<6><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
-        c->launches++;
-      }
-      KERNEL_CHECK();
-    } else {
-    const int T = PME_BLK + c->prm.P - 1;
-    auto smem = [&](int nc) {
-      return sizeof(double) * ((size_t)nc * T * T * T + SPREAD_CHUNK * 3 * PME_PMAX + SPREAD_CHUNK * nc) +
-             sizeof(int) * SPREAD_CHUNK * 3;
-    };
-    if (pm.flag_sl && pm.flag_dl) {
-      a.comp0 = 0;
-      a.ncomp = 9;
-      CUDA_TRY(cudaFuncSetAttribute(k_spread<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(9)));
-      k_spread<9><<<nblocks, 512, smem(9), c->stream>>>(a);
-    } else if (pm.flag_sl) {
-      a.comp0 = 0;
-      a.ncomp = 3;
-      CUDA_TRY(cudaFuncSetAttribute(k_spread<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(3)));
-      k_spread<3><<<nblocks, 512, smem(3), c->stream>>>(a);
-    } else {
-      a.comp0 = 3;
-      a.ncomp = 6;
-      CUDA_TRY(cudaFuncSetAttribute(k_spread<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(6)));
-      k_spread<6><<<nblocks, 512, smem(6), c->stream>>>(a);
+    RBC_TRY(spread_launch(c, a, pm.flag_sl, pm.flag_dl));
+  }
+  // wall sources: element centroids with THRD*sum(fele)*area, single layer only (ModPME.F90:105-129)
+  Walls &W = c->walls;
+  if (use_walls && W.NE > 0 && pm.flag_sl) {
+    if (!W.f_set) {
+      set_error("PME_Distrib_Source: wall tractions not set");
+      return RBC3D_ESTATE;
     }
-    KERNEL_CHECK();
-    c->launches++;
-    }
+    SpreadArgs a;
+    a.prm = c->prm;
+    a.n = W.NE;
+    a.start = W.pl.start.p;
+    a.order = W.pl.order.p;
+    a.x = W.xc.p;
+    a.f = W.ft.p;
+    a.g = nullptr;
+    a.a3 = nullptr;
+    a.Bcell = nullptr;
+    a.npc = 1;
+    a.c1 = c1;
+    a.c2 = 0.0;
+    RBC_TRY(spread_launch(c, a, true, false));
   }
   if (c->prm.nranks > 1 && (pm.flag_sl || pm.flag_dl)) {
     // every rank spread its block of cells: sum the meshes over the ranks (one in-switch reduction)
@@ -443,7 +473,6 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     const size_t ncomp = (pm.flag_sl ? 3 : 0) + (pm.flag_dl ? 6 : 0);
     RBC_TRY(comm_allreduce_sum(c, base, ncomp * pm.G));
   }
-  (void)use_walls;  // wall centroid sources: see walls.cu (PME_Distrib_Source walls branch, ModPME.F90:105-131)
   pm.distributed = true;
   return RBC3D_OK;
 }

@@ -106,6 +106,21 @@ struct NearSing {      // geometry-time products of the neighbour scan + Spline_
   dbuf<int> overflow;  // device flag
 };
 
+// (target, wall element) pairs within rc of a target list (AddIntOnWalls direct loop), built lazily per geometry
+struct WallPairs {
+  bool valid = false;
+  int npair = 0;
+  long long geom_version = -1, tl_version = -1;
+  dbuf<int> off, ele, kind, ptarget;  // off[n+1]; per pair: element, 1 = Duffy, target
+  dbuf<double> s0, t0, dv;            // closest-point coordinates; dv SoA(3,npair) of the current application
+  dbuf<char> tmp;
+  void release() {
+    off.release(), ele.release(), kind.release(), ptarget.release();
+    s0.release(), t0.release(), dv.release(), tmp.release();
+    valid = false;
+  }
+};
+
 struct TargetList {
   int kind = RBC3D_TL_RAW;
   int n = 0;
@@ -122,6 +137,27 @@ struct TargetList {
   dbuf<double> acc;     // SoA(3,n) un-normalised sums of the current application
   dbuf<double> v;       // SoA(3,n) result of rbc3d_apply_resident
   dbuf<double> host_io; // staging for host v
+  WallPairs wp;
+  long long version = 0; // bumped whenever the list is rebuilt
+};
+
+// walls (walls.cu): t_Wall arrays of all walls back to back + slist_wall + the self-interaction matrices
+struct Walls {
+  int nwall = 0, NV = 0, NE = 0;
+  bool geom_set = false, f_set = false, mat_ok = false;
+  long long geom_version = 0, mat_version = -1;
+  std::vector<int> h_nvert, h_nele, h_voff, h_eoff;
+  dbuf<double> x, f;            // SoA(3,NV)
+  dbuf<int> e2v;                // SoA(3,NE), global 0-based vertex numbers
+  dbuf<int> ewall, vwall;       // wall index of an element / a vertex
+  dbuf<double> area, epsDist;   // [NE]
+  dbuf<double> xc, ft;          // SoA(3,NE): centroids (slist_wall%x), PME strengths THRD*sum(fele)*area
+  CellList cl, pl;              // centroids by real-space cell / by PME source block
+  dbuf<int> src_own, minus1;
+  // t_Wall%lhs of every wall as one block-row matrix over the NV vertices (3x3 blocks, row-major)
+  int nblk = 0;
+  dbuf<int> rowptr, col;
+  dbuf<double> val;
 };
 
 struct Cells {
@@ -192,6 +228,7 @@ struct rbc3d_ctx {
   std::vector<double> h_tab_sl1, h_tab_sl2, h_tab_dl, h_tab_mask;
   rbc3d::Cells cells;
   rbc3d::TargetList tl[3];
+  rbc3d::Walls walls;
   rbc3d::Pme pme;
   int skip_flags = 0;
   int pair_self_mode = 1;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel
@@ -242,6 +279,21 @@ void pme_destroy(rbc3d_ctx *c);
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls);
 int pme_transform(rbc3d_ctx *c);
 int pme_interp(rbc3d_ctx *c, TargetList &t);
+
+// ---- walls (walls.cu) ----
+int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nele, const double *x, const int *e2v,
+                       const double *area, const double *epsDist);
+int walls_set_traction(rbc3d_ctx *c, const double *f_host);
+int walls_target_meta(rbc3d_ctx *c, TargetList &t);
+int walls_prepare_sing(rbc3d_ctx *c);
+int walls_sing_int(rbc3d_ctx *c, double c1, int iwall, double *v_dev);
+int walls_add_int(rbc3d_ctx *c, TargetList &t, double c1);
+int walls_signature(rbc3d_ctx *c, TargetList &t, int self_skip, int *count, unsigned long long *sig, int *nduffy);
+int walls_min_dist_batch(rbc3d_ctx *c, int n, const double *xtar, const double *xtri, double *dist, double *s0,
+                         double *t0);
+int walls_tri_int_batch(rbc3d_ctx *c, int n, const double *xtri, const double *ftri, const double *xtar,
+                        const double *s0, const double *t0, double *rhs, double *lhs);
+void walls_release(rbc3d_ctx *c);
 
 // ---- multi-GPU (comm.cu) ----
 int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);

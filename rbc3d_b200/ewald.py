@@ -150,7 +150,73 @@ class EwaldOperator:
         check(self.lib.rbc3d_targets_set_raw(self._h, self.n_raw, dp(x), ip(act)), "rbc3d_targets_set_raw")
 
     def _n(self, tlist):
-        return self.npoint if tlist == TL_CELLS else self.n_raw
+        return self.npoint if tlist == TL_CELLS else (self.n_raw if tlist == TL_RAW else self.n_wall_vert)
+
+    # -- walls (ModIntOnWalls, wall branches of ModSourceList / ModTargetList) --------------------------------
+    def set_walls(self, W, active=None, traction=True):
+        """W: rbc3d_b200.synth.Walls (or any object with nvert, nele, x, e2v, area, epsDist[, f]).
+        SourceList_UpdateCoord(slist_wall) + TargetList_Update(tlist_wall)."""
+        nv, ne = i32(W.nvert), i32(W.nele)
+        x, e2v, area, eps = f64(W.x), i32(W.e2v), f64(W.area), f64(W.epsDist)
+        act = i32(active)
+        self.n_wall_vert, self.n_wall_ele, self.wall_nvert = int(nv.sum()), int(ne.sum()), [int(v) for v in nv]
+        check(self.lib.rbc3d_walls_set(self._h, len(nv), ip(nv), ip(ne), dp(x), ip(e2v), dp(area), dp(eps), ip(act)),
+              "rbc3d_walls_set")
+        if traction and getattr(W, "f", None) is not None:
+            self.set_wall_traction(W.f)
+
+    def set_wall_traction(self, f):
+        f = f64(f)
+        assert f.shape == (3, self.n_wall_vert)
+        check(self.lib.rbc3d_walls_set_traction(self._h, dp(f)), "rbc3d_walls_set_traction")
+
+    def PrepareSingIntOnWall(self):
+        """All walls at once (the reference loops over walls, ModTimeInt / ModNoSlip callers)."""
+        check(self.lib.rbc3d_wall_prepare_sing(self._h), "PrepareSingIntOnWall")
+
+    def SingIntOnWall(self, c1, iwall):
+        v = np.zeros((3, self.wall_nvert[iwall]))
+        check(self.lib.rbc3d_sing_int_on_wall(self._h, c1, iwall, dp(v)), "SingIntOnWall")
+        return v
+
+    def AddIntOnWalls(self, c1, tlist=TL_CELLS, v=None):
+        v = self._v(tlist, v)
+        check(self.lib.rbc3d_add_int_on_walls(self._h, c1, tlist, dp(v)), "AddIntOnWalls")
+        return v
+
+    def MinDistToTri(self, xtar, xtri):
+        """xtar (3, n) SoA, xtri (n, 3 corners, 3).  Returns dist, s0, t0."""
+        xtar, xtri = f64(xtar), f64(xtri)
+        n = xtar.shape[1]
+        d, s0, t0 = np.zeros(n), np.zeros(n), np.zeros(n)
+        check(self.lib.rbc3d_min_dist_to_tri(self._h, n, dp(xtar), dp(xtri), dp(d), dp(s0), dp(t0)), "MinDistToTri")
+        return d, s0, t0
+
+    def Tri_Int(self, xtri, ftri, xtar, s0=None, t0=None, lhs=False):
+        """Tri_Int_Regular (s0 is None) / Tri_Int_Duffy for n triples: xtri, ftri (n,3,3); xtar (3,n) SoA.
+        Returns rhs (n,3) [, lhs (n,3,3,3)]."""
+        xtri, ftri, xtar, s0, t0 = f64(xtri), f64(ftri), f64(xtar), f64(s0), f64(t0)
+        n = xtar.shape[1]
+        rhs = np.zeros((n, 3))
+        L = np.zeros((n, 3, 3, 3)) if lhs else None
+        check(self.lib.rbc3d_tri_int(self._h, n, dp(xtri), dp(ftri), dp(xtar), dp(s0), dp(t0), dp(rhs), dp(L)), "Tri_Int")
+        return (rhs, L) if lhs else rhs
+
+    def wall_matrix(self):
+        nb = (C.c_int32 * 1)()
+        rowptr = np.zeros(self.n_wall_vert + 1, np.int32)
+        check(self.lib.rbc3d_wall_matrix_get(self._h, nb, ip(rowptr), None, None, 0))
+        col = np.zeros(max(nb[0], 1), np.int32)
+        val = np.zeros((max(nb[0], 1), 3, 3))
+        check(self.lib.rbc3d_wall_matrix_get(self._h, nb, ip(rowptr), ip(col), dp(val), nb[0]))
+        return rowptr, col[:nb[0]], val[:nb[0]]
+
+    def wall_neighbor_signature(self, tlist=TL_CELLS, self_skip=True):
+        n = self._n(tlist)
+        cnt, nd, sig = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint64)
+        check(self.lib.rbc3d_wall_neighbor_signature(self._h, tlist, int(self_skip), ip(cnt), sig.ctypes.data_as(capi.c_up),
+                                                     ip(nd)))
+        return cnt, sig, nd
 
     def _v(self, tlist, v):
         if v is None:

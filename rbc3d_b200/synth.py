@@ -107,10 +107,10 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
     th, phi, w = sphere.gauss_grid(nlat, nlon)
     if L is None:
         L = L_4096 * n_side / 16.0 * spacing_scale
-    Lb = np.array([L, L, L], dtype=float)
+    Lb = np.asarray(L, dtype=float) * np.ones(3)      # scalar (cubic box) or the three box lengths
     if centers is None:
         idx = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
-        centers = (idx + 0.5) * (L / n_side) + rng.uniform(-jitter, jitter, size=idx.shape)
+        centers = (idx + 0.5) * (Lb / n_side) + rng.uniform(-jitter, jitter, size=idx.shape)
     centers = np.asarray(centers, dtype=float)
     ncell = centers.shape[0]
     R = sphere.rotation_matrices(rng, ncell)
@@ -138,3 +138,110 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
     build_splines(sus, builder)
     sus._builder = builder
     return sus
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Walls: triangulated tubes like the vessel of examples/minicase and examples/case (a cylinder along z whose end
+# rings sit on z = 0 and z = Lb3 as duplicated vertices, the way the reference's Exodus meshes close the period).
+@dataclass
+class Walls:
+    nvert: np.ndarray         # (nwall,) int32
+    nele: np.ndarray          # (nwall,) int32
+    x: np.ndarray             # SoA (3, NV): vertices of all walls back to back (= tlist_wall%x)
+    e2v: np.ndarray           # SoA (3, NE) int32: wall%e2v, 1-based vertex numbers local to the wall
+    area: np.ndarray          # (NE,)  Wall_ComputeGeometry, ModWall.F90:118-145
+    epsDist: np.ndarray       # (NE,)  sqrt(area)
+    f: np.ndarray             # SoA (3, NV) tractions wall%f
+
+    @property
+    def nwall(self) -> int:
+        return len(self.nvert)
+
+    @property
+    def NV(self) -> int:
+        return int(self.nvert.sum())
+
+    @property
+    def NE(self) -> int:
+        return int(self.nele.sum())
+
+    def voff(self):
+        return np.concatenate([[0], np.cumsum(self.nvert)]).astype(np.int64)
+
+    def eoff(self):
+        return np.concatenate([[0], np.cumsum(self.nele)]).astype(np.int64)
+
+    def e2v_global(self) -> np.ndarray:
+        """(3, NE) 0-based indices into the concatenated vertex list."""
+        out = self.e2v.astype(np.int64) - 1
+        vo, eo = self.voff(), self.eoff()
+        for w in range(self.nwall):
+            out[:, eo[w]:eo[w + 1]] += vo[w]
+        return out
+
+
+def wall_geometry(x: np.ndarray, e2v_glb: np.ndarray):
+    """area and epsDist of every element with the arithmetic of Wall_ComputeGeometry (ModWall.F90:118-145)."""
+    xe = x[:, e2v_glb]                      # (3 comps, 3 corners, NE)
+    x12, x13 = xe[:, 1] - xe[:, 0], xe[:, 2] - xe[:, 0]
+    a3 = np.stack([x12[1] * x13[2] - x12[2] * x13[1], x12[2] * x13[0] - x12[0] * x13[2],
+                   x12[0] * x13[1] - x12[1] * x13[0]])
+    a3n = np.sqrt(a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2])
+    area = 0.5 * a3n
+    return area, np.sqrt(area)
+
+
+def tube_mesh(Lz: float, radius: float, ntheta: int, nz: int, center=(0.0, 0.0), z0: float = 0.0, wobble: float = 0.0,
+              rng=None):
+    """Vertices (3, (nz+1) ntheta) and 1-based e2v (3, 2 nz ntheta) of a cylinder along z, rings at z0 + k Lz/nz,
+    k = 0..nz (first and last ring are periodic duplicates)."""
+    k, j = np.meshgrid(np.arange(nz + 1), np.arange(ntheta), indexing="ij")
+    ang = 2 * np.pi * (j + 0.5 * (k % 2)) / ntheta
+    r = radius * np.ones_like(ang)
+    if wobble and rng is not None:
+        dr = wobble * rng.uniform(-1, 1, size=(nz, ntheta))
+        r[:nz] += dr
+        r[nz] = r[0]                        # the duplicated ring must coincide with ring 0 modulo the period
+    x = np.stack([center[0] + r * np.cos(ang), center[1] + r * np.sin(ang), z0 + Lz * k / nz]).reshape(3, -1)
+    # ring nz duplicates ring 0 only when nz is even (the half-cell stagger); force it
+    if nz % 2:
+        raise ValueError("nz must be even so that the staggered end rings coincide")
+    vid = lambda kk, jj: kk * ntheta + (jj % ntheta)  # noqa: E731
+    tri = []
+    for kk in range(nz):
+        for jj in range(ntheta):
+            a, b, c, d = vid(kk, jj), vid(kk, jj + 1), vid(kk + 1, jj), vid(kk + 1, jj + 1)
+            if kk % 2 == 0:
+                tri += [(a, b, c), (b, d, c)]
+            else:
+                tri += [(a, b, d), (a, d, c)]
+    e2v = np.array(tri, dtype=np.int32).T + 1
+    return x, np.ascontiguousarray(e2v)
+
+
+def make_walls(Lb, specs, seed: int = 161269, wobble: float = 0.0) -> Walls:
+    """specs: list of dicts(radius, ntheta, nz[, center]) -- one tube wall each, spanning the z period of the box.
+    Tractions: smooth random field (low-order trigonometric polynomial in angle and z) per wall."""
+    rng = np.random.default_rng(np.random.PCG64(seed + 1))
+    xs, es, nv, ne, fs = [], [], [], [], []
+    for s in specs:
+        x, e2v = tube_mesh(float(Lb[2]), s["radius"], s["ntheta"], s["nz"], center=s.get("center", (0.5 * Lb[0], 0.5 * Lb[1])),
+                           wobble=wobble, rng=rng)
+        xs.append(x)
+        es.append(e2v)
+        nv.append(x.shape[1])
+        ne.append(e2v.shape[1])
+        cx, cy = s.get("center", (0.5 * Lb[0], 0.5 * Lb[1]))
+        ang = np.arctan2(x[1] - cy, x[0] - cx)
+        zz = 2 * np.pi * x[2] / Lb[2]
+        f = np.zeros_like(x)
+        for d in range(3):
+            for m in range(3):
+                a, b, c, e = rng.uniform(-1, 1, 4)
+                f[d] += a * np.cos(m * ang) * np.cos(m * zz) + b * np.sin(m * ang) + c * np.sin(m * zz) + e * np.cos(m * ang + zz)
+        fs.append(f)
+    x = np.ascontiguousarray(np.concatenate(xs, axis=1))
+    e2v = np.ascontiguousarray(np.concatenate(es, axis=1))
+    W = Walls(np.array(nv, np.int32), np.array(ne, np.int32), x, e2v, None, None, np.ascontiguousarray(np.concatenate(fs, axis=1)))
+    W.area, W.epsDist = wall_geometry(x, W.e2v_global())
+    return W

@@ -1,0 +1,222 @@
+"""GPU parity tests of the wall part of the operator (walls.cu behind the C ABI) against the CPU oracle.
+
+Configurations follow BASELINE.json configs[0]/[1]/[4]: cells inside a triangulated tube wall in the minicase box
+(10.5 x 10.5 x 8), one wall (self-interaction matrix only) and two walls (matrix + direct wall-wall loop).
+Tolerance: relative L2 <= 1e-10 on velocities and matrix entries; in-range (target, element) sets, Duffy
+classification and the sparsity pattern bit-exact."""
+import numpy as np
+import pytest
+
+from rbc3d_b200 import synth
+from tests import util
+from tests.util import C1_RHS, C2_MATVEC, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+LB = np.array([10.5, 10.5, 8.0])
+
+
+def tube_suspension(seed=161269):
+    """examples/minicase-like: 2 cells on the axis of the tube, one pushed towards the wall"""
+    centers = np.array([[5.25, 5.25, 2.0], [8.4, 5.6, 6.0]])
+    return synth.make_suspension(1, L=LB, centers=centers, seed=seed)
+
+
+@pytest.fixture(scope="module")
+def one_wall(oracle_lib):
+    from rbc3d_b200.ewald import EwaldOperator
+    sus = tube_suspension()
+    W = synth.make_walls(LB, [dict(radius=4.4, ntheta=36, nz=12)], wobble=0.05)
+    op = EwaldOperator(LB)
+    op.set_suspension(sus)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc = oracle_lib.Oracle(LB).set_cells(sus)
+    orc.set_walls(W)
+    orc.prepare_sing_int_on_walls()
+    yield op, orc, sus, W
+    op.close()
+
+
+@pytest.fixture(scope="module")
+def two_walls(oracle_lib):
+    from rbc3d_b200.ewald import EwaldOperator
+    W = synth.make_walls(LB, [dict(radius=4.4, ntheta=28, nz=10), dict(radius=3.7, ntheta=24, nz=10)], wobble=0.03)
+    op = EwaldOperator(LB)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc = oracle_lib.Oracle(LB)
+    orc.set_walls(W, ncell=0)
+    orc.prepare_sing_int_on_walls()
+    yield op, orc, W
+    op.close()
+
+
+def test_min_dist_to_tri_batch(one_wall):
+    op, orc, _, _ = one_wall
+    rng = np.random.default_rng(1)
+    n = 4000
+    tri = rng.normal(size=(n, 3, 3))
+    xt = rng.normal(size=(3, n)) * 1.5
+    d, s0, t0 = op.MinDistToTri(xt, tri)
+    for i in range(0, n, 7):
+        rd, rs, rt, _ = orc.min_dist_to_tri(xt[:, i], tri[i])
+        assert d[i] == rd and s0[i] == rs and t0[i] == rt       # un-fused arithmetic: bit-exact
+
+
+def test_tri_int_regular_and_duffy(one_wall):
+    op, orc, _, _ = one_wall
+    rng = np.random.default_rng(2)
+    n = 300
+    tri = rng.normal(size=(n, 3, 3)) * 0.35
+    f = rng.normal(size=(n, 3, 3))
+    xt = (tri.mean(axis=1) + rng.normal(size=(n, 3)) * 0.3).T.copy()
+    d, s0, t0 = op.MinDistToTri(xt, tri)
+    rhs_r, lhs_r = op.Tri_Int(tri, f, xt, lhs=True)
+    rhs_d, lhs_d = op.Tri_Int(tri, f, xt, s0, t0, lhs=True)
+    ref = np.zeros((4, n, 27))
+    for i in range(n):
+        a, la = orc.tri_int(tri[i], f[i], xt[:, i])
+        b, lb = orc.tri_int(tri[i], f[i], xt[:, i], s0[i], t0[i])
+        ref[0, i, :3], ref[1, i], ref[2, i, :3], ref[3, i] = a, la.ravel(), b, lb.ravel()
+    assert rel_l2(rhs_r, ref[0, :, :3]) < TOL
+    assert rel_l2(lhs_r.reshape(n, 27), ref[1]) < TOL
+    assert rel_l2(rhs_d, ref[2, :, :3]) < TOL
+    assert rel_l2(lhs_d.reshape(n, 27), ref[3]) < TOL
+
+
+def test_wall_neighbor_sets_bit_exact(one_wall):
+    op, orc, sus, W = one_wall
+    from rbc3d_b200.capi import TL_CELLS, TL_WALLS
+    for tl_kind, tl in ((TL_CELLS, orc.cell_targets()), (TL_WALLS, orc.wall_targets())):
+        for skip in (True, False):
+            cnt, sig, nd = op.wall_neighbor_signature(tl_kind, self_skip=skip)
+            rcnt, rsig, rnd = orc.wall_neighbor_signature(tl, self_skip=skip)
+            assert np.array_equal(cnt, rcnt) and np.array_equal(sig, rsig) and np.array_equal(nd, rnd)
+    cnt, _, nd = op.wall_neighbor_signature(TL_CELLS)
+    assert cnt.sum() > 0 and nd.sum() > 0     # the displaced cell is close enough for the Duffy branch
+
+
+def test_wall_matrix(one_wall):
+    op, orc, _, W = one_wall
+    rowptr, col, val = op.wall_matrix()
+    rrow, rcol, rval = orc.wall_matrix(0)
+    assert np.array_equal(rowptr, rrow) and np.array_equal(col, rcol)        # sparsity pattern bit-exact
+    assert rel_l2(val, rval) < TOL
+    assert np.abs(val - rval).max() <= 1e-12 * np.abs(rval).max()
+
+
+def test_sing_int_on_wall(one_wall):
+    op, orc, _, W = one_wall
+    v = op.SingIntOnWall(C1_RHS, 0)
+    assert rel_l2(v, orc.sing_int_on_wall(C1_RHS, 0)) < TOL
+    rng = np.random.default_rng(4)
+    f2 = rng.normal(size=W.f.shape)
+    op.set_wall_traction(f2)
+    orc.set_wall_traction(f2)
+    assert rel_l2(op.SingIntOnWall(0.7, 0), orc.sing_int_on_wall(0.7, 0)) < TOL
+    op.set_wall_traction(W.f)
+    orc.set_wall_traction(W.f)
+
+
+def test_add_int_on_walls_cell_targets(one_wall):
+    """Compute_Rhs wall term (ModVelSolver.F90:481): every cell point against the wall elements within rc"""
+    op, orc, _, _ = one_wall
+    v = op.AddIntOnWalls(C1_RHS)
+    ref = orc.add_int_on_walls(C1_RHS, orc.cell_targets())
+    assert np.abs(ref).max() > 0
+    assert rel_l2(v, ref) < TOL
+
+
+def test_add_int_on_walls_raw_and_inactive_targets(one_wall):
+    op, orc, _, W = one_wall
+    from rbc3d_b200.capi import TL_RAW
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(0, 2 * np.pi, 500)
+    rad = rng.uniform(3.2, 4.6, 500)           # both sides of the wall, some within epsDist of it
+    x = np.stack([5.25 + rad * np.cos(ang), 5.25 + rad * np.sin(ang), rng.uniform(-3, 11, 500)])
+    active = (rng.uniform(size=500) < 0.8).astype(np.int32)
+    op.TargetList_CreateFromRaw(x, active)
+    v0 = rng.normal(size=(3, 500))
+    v = op.AddIntOnWalls(C1_RHS, TL_RAW, v0.copy())
+    ref = orc.add_int_on_walls(C1_RHS, orc.make_targets(x, active=active), v0.copy())
+    assert rel_l2(v, ref) < TOL
+    assert np.array_equal(v[:, active == 0], v0[:, active == 0])     # rows of inactive targets untouched
+
+
+def test_pme_wall_sources(one_wall):
+    op, orc, _, _ = one_wall
+    op.PME_Distrib_Source(C1_RHS, 0.0, cells=False, walls=True)
+    op.PME_Transform()
+    orc.pme_distrib_walls(C1_RHS)
+    orc.pme_transform()
+    assert rel_l2(op.pme_grid(), orc.pme_vv()) < TOL
+
+
+@pytest.mark.parametrize("tl_name", ["cells", "walls"])
+def test_full_operator_cells_and_walls(one_wall, tl_name):
+    """Compute_Rhs (cell targets, ModVelSolver.F90:465-493) and Compute_Wall_Residual_Vel (wall targets,
+    ModNoSlip.F90:172-191: c1 = c2 = 1/4pi, cells + walls)"""
+    op, orc, _, _ = one_wall
+    from rbc3d_b200.capi import TL_CELLS, TL_WALLS
+    if tl_name == "cells":
+        kind, tl, c1, c2 = TL_CELLS, orc.cell_targets(), C1_RHS, 0.0
+    else:
+        kind, tl, c1, c2 = TL_WALLS, orc.wall_targets(), C1_RHS, C1_RHS
+    v = op.apply(c1, c2, kind, cells=True, walls=True)
+    ref = orc.apply(c1, c2, tl, cells=True, walls=True)
+    assert rel_l2(v, ref) < TOL
+    op.apply_resident(c1, c2, kind, cells=True, walls=True)
+    assert rel_l2(op.get_velocity(kind), ref) < TOL
+
+
+def test_wall_matvec_two_walls(two_walls):
+    """wall GMRES matvec (ModNoSlip.F90:284-299): c1 = 1/4pi, wall sources -> wall vertices; with two walls the
+    self blocks go through lhs and the cross blocks through the direct loop"""
+    op, orc, W = two_walls
+    from rbc3d_b200.capi import TL_WALLS
+    rowptr, col, val = op.wall_matrix()
+    vo = W.voff()
+    for w in range(2):
+        rrow, rcol, rval = orc.wall_matrix(w)
+        lo, hi = rowptr[vo[w]], rowptr[vo[w + 1]]
+        assert np.array_equal(rowptr[vo[w]:vo[w + 1] + 1] - lo, rrow)
+        assert np.array_equal(col[lo:hi] - vo[w], rcol)
+        assert rel_l2(val[lo:hi], rval) < TOL
+    tl = orc.wall_targets()
+    v = op.AddIntOnWalls(C1_RHS, TL_WALLS)
+    ref = orc.add_int_on_walls(C1_RHS, tl)
+    assert rel_l2(v, ref) < TOL
+    v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+    ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+    assert rel_l2(v, ref) < TOL
+    # a second traction: only the density changes, pair lists and matrix are reused
+    rng = np.random.default_rng(6)
+    f2 = rng.normal(size=W.f.shape)
+    op.set_wall_traction(f2)
+    orc.set_wall_traction(f2)
+    v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+    ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+    assert rel_l2(v, ref) < TOL
+    op.set_wall_traction(W.f)
+    orc.set_wall_traction(W.f)
+
+
+def test_partial_active_rows(two_walls):
+    """PrepareSingIntOnWall only assembles the rows of active vertices (ModIntOnWalls.F90:199-203, 216)"""
+    op, orc, W = two_walls
+    from rbc3d_b200.capi import TL_WALLS
+    active = (W.x[2] < 0.5 * LB[2]).astype(np.int32)      # z-slab ownership of a 2-rank run (SetActiveFlag)
+    op.set_walls(W, active=active)
+    op.PrepareSingIntOnWall()
+    orc.prepare_sing_int_on_walls(active=active)
+    rowptr, col, val = op.wall_matrix()
+    assert np.all(np.diff(rowptr)[active == 0] == 0)
+    tl = orc.wall_targets(active=active)
+    v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+    ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+    assert rel_l2(v, ref) < TOL
+    assert np.all(v[:, active == 0] == 0)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc.prepare_sing_int_on_walls()
