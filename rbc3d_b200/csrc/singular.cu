@@ -17,9 +17,13 @@
 //      - geometry time, per cell: xx = x(patch point) - x(target) and s = w * EwaldCoeff_DL(|xx|) * (xx . a3) per
 //        patch point, 32 B each, streamed from HBM by the matvec (k_sing_cache_build);
 //      - per matvec: spline(g detJ) is re-laid out node-interleaved ([cell][half][phi][theta][6 doubles], 48 B
-//        node halves: conflict-free LDS.128 for neighbouring nodes), one CTA per (tile, cell group) stages the
-//        window of each cell in shared memory, one warp per target gathers 4 nodes x 12 doubles per patch point
-//        and reduces with shuffles.
+//        node halves), one CTA per (cell, tile row) stages the band of the spline the row's patches touch and walks
+//        over the row's tiles.  The 8 x 288 patch points of a tile are processed SORTED BY SPLINE CELL (a cell-independent permutation, so
+//        is the cache layout): the 32 lanes of a warp then read only 3-6 distinct spline cells per instruction
+//        and the LDS.128 node gathers are served as multicasts (5-12 patch points share a spline cell) instead of
+//        32 distinct 48-byte records.  Every point's contribution w EA (xx.a3)(xx.g) xx is written to a
+//        target-major shared buffer, which one warp per target then sums in the patch order of the reference
+//        (fixed order: deterministic).
 #include <algorithm>
 #include <cstdlib>
 
@@ -30,7 +34,7 @@ namespace rbc3d {
 
 constexpr int SING_WARPS = 8;
 constexpr int SG_TLAT = 4, SG_TLON = 2, SG_T = SG_TLAT * SG_TLON;  // targets per tile = warps per CTA
-constexpr size_t SG_SMEM_MAX = 110 * 1024;                          // two CTAs per SM
+constexpr size_t SG_SMEM_MAX = 226 * 1024;                          // one CTA per SM
 
 struct SingArgs {
   Params prm;
@@ -145,73 +149,96 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   C.sg_ok = false;
   C.sg_cache_ok = false;
   const int nlat = C.nlat, nlon = C.nlon, m = 2 * nlat, n = nlon, npatch = C.nrad * C.nazm;
-  const int ntl = (nlat + SG_TLAT - 1) / SG_TLAT, ntn = (nlon + SG_TLON - 1) / SG_TLON;
-  const int ntiles = ntl * ntn, K = (npatch + 31) / 32;
+  const int ntl = (nlat + SG_TLAT - 1) / SG_TLAT, ntn = nlon / SG_TLON;
+  const int K = (npatch + 31) / 32, NPT = K * SG_T * 32;
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   const double ihx = 1.0 / hx, ihy = 1.0 / hy;
-  std::vector<int> tile_tgt((size_t)ntiles * SG_T, -1), tile_win((size_t)ntiles * 4, 0);
-  std::vector<int> idx((size_t)ntiles * K * SG_T * 32, 0);
-  std::vector<double> st((size_t)ntiles * K * SG_T * 32 * 2, 0.0);
+  C.sg_ntl = ntl;
+  C.sg_ntn = ntn;
+  C.sg_ntiles = ntl * ntn;
+  C.sg_K = K;
+  if (nlon % SG_TLON != 0 || n > 1023 || NPT > 16383) return RBC3D_OK;  // direct kernel only
+  // Tables of tile column 0 of every tile row.  The patch of (ilat, ilon) is the patch of (ilat, 0) rotated by
+  // phi(ilon) about the polar axis (PolarPatch_Build, ModPolarPatch.F90:99-148: thG does not depend on phi0, phiG
+  // = atan2(..) + phi0), so tile column tn uses the same tables with the phi node index advanced by tn*SG_TLON.
+  std::vector<int> row_tgt((size_t)ntl * SG_T, -1), row_win((size_t)ntl * 2, 0);
+  std::vector<int> pk((size_t)ntl * NPT, 0), pos((size_t)ntl * NPT, 0);
+  std::vector<double> st((size_t)ntl * NPT * 2, 0.0);
   std::vector<int> ni1((size_t)SG_T * npatch), nj1((size_t)SG_T * npatch);
-  int win_max = 0;
-  for (int tl = 0; tl < ntl; tl++)
-    for (int tn = 0; tn < ntn; tn++) {
-      const int tile = tl * ntn + tn;
-      std::vector<char> ui(m, 0), uj(n, 0);
-      for (int w = 0; w < SG_T; w++) {
-        const int ilat = tl * SG_TLAT + (w % SG_TLAT), ilon = tn * SG_TLON + (w / SG_TLAT);
-        if (ilat >= nlat || ilon >= nlon) continue;
-        const int p = ilon * nlat + ilat;
-        tile_tgt[(size_t)tile * SG_T + w] = p;
-        for (int q = 0; q < npatch; q++) {
-          // same arithmetic as spline_interp (device_math.cuh)
-          const double xs = thG[(size_t)p * npatch + q] * ihx, ys = phiG[(size_t)p * npatch + q] * ihy;
-          const int i1 = (int)floor(xs), j1 = (int)floor(ys);
-          const double s = xs - (double)i1, t = ys - (double)j1;
-          const int i1m = ((i1 % m) + m) % m, j1m = ((j1 % n) + n) % n;
-          ni1[(size_t)w * npatch + q] = i1m;
-          nj1[(size_t)w * npatch + q] = j1m;
-          ui[i1m] = ui[(i1m + 1) % m] = 1;
-          uj[j1m] = uj[(j1m + 1) % n] = 1;
-          const int k = q / 32, lane = q % 32;
-          const size_t e = (((size_t)tile * K + k) * SG_T + w) * 32 + lane;
-          st[2 * e] = s;
-          st[2 * e + 1] = t;
-        }
-      }
-      int ilo, ni, jlo, nj;
-      cyclic_cover(ui, m, ilo, ni);
-      cyclic_cover(uj, n, jlo, nj);
-      // a full circle needs the first column/row once more so that node+1 stays inside the window
-      if (ni == m) ni = m + 1;
-      if (nj == n) nj = n + 1;
-      tile_win[(size_t)tile * 4 + 0] = ilo;
-      tile_win[(size_t)tile * 4 + 1] = ni;
-      tile_win[(size_t)tile * 4 + 2] = jlo;
-      tile_win[(size_t)tile * 4 + 3] = nj;
-      win_max = std::max(win_max, ni * nj);
-      for (int w = 0; w < SG_T; w++) {
-        if (tile_tgt[(size_t)tile * SG_T + w] < 0) continue;
-        for (int q = 0; q < npatch; q++) {
-          const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m, wj = (nj1[(size_t)w * npatch + q] - jlo + n) % n;
-          const int k = q / 32, lane = q % 32;
-          idx[(((size_t)tile * K + k) * SG_T + w) * 32 + lane] = wj * ni + wi;
-        }
+  std::vector<double> fs((size_t)SG_T * npatch), ft((size_t)SG_T * npatch);
+  std::vector<std::pair<long long, int>> keys(NPT);
+  int ni_max = 0;
+  for (int tl = 0; tl < ntl; tl++) {
+    std::vector<char> ui(m, 0);
+    for (int w = 0; w < SG_T; w++) {
+      const int ilat = tl * SG_TLAT + (w % SG_TLAT), ilon = w / SG_TLAT;
+      if (ilat >= nlat) continue;
+      const int p = ilon * nlat + ilat;
+      row_tgt[(size_t)tl * SG_T + w] = p;
+      for (int q = 0; q < npatch; q++) {
+        // same arithmetic as spline_interp (device_math.cuh)
+        const double xs = thG[(size_t)p * npatch + q] * ihx, ys = phiG[(size_t)p * npatch + q] * ihy;
+        const int i1 = (int)floor(xs), j1 = (int)floor(ys);
+        fs[(size_t)w * npatch + q] = xs - (double)i1;
+        ft[(size_t)w * npatch + q] = ys - (double)j1;
+        const int i1m = ((i1 % m) + m) % m, j1m = ((j1 % n) + n) % n;
+        ni1[(size_t)w * npatch + q] = i1m;
+        nj1[(size_t)w * npatch + q] = j1m;
+        ui[i1m] = ui[(i1m + 1) % m] = 1;
       }
     }
-  C.sg_ntiles = ntiles;
-  C.sg_K = K;
-  C.sg_win_max = win_max;
-  if ((size_t)win_max * 96 > SG_SMEM_MAX) return RBC3D_OK;  // direct kernel only
-  RBC_TRY(C.sg_tile_tgt.resize(tile_tgt.size()));
-  RBC_TRY(C.sg_tile_win.resize(tile_win.size()));
-  RBC_TRY(C.sg_idx.resize(idx.size()));
+    int ilo, ni;
+    cyclic_cover(ui, m, ilo, ni);
+    if (ni == m) ni = m + 1;  // a full circle needs the first row once more so that node+1 stays inside
+    row_win[(size_t)tl * 2 + 0] = ilo;
+    row_win[(size_t)tl * 2 + 1] = ni;
+    ni_max = std::max(ni_max, ni);
+    // sorted order of the tile's patch points: by spline cell (phi column, theta row), ties in target-major order
+    for (int k = 0; k < K; k++)
+      for (int w = 0; w < SG_T; w++)
+        for (int lane = 0; lane < 32; lane++) {
+          const int slot = (k * SG_T + w) * 32 + lane, q = k * 32 + lane;
+          const bool valid = row_tgt[(size_t)tl * SG_T + w] >= 0 && q < npatch;
+          long long key = 1LL << 40;
+          if (valid) {
+            const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
+            key = (long long)nj1[(size_t)w * npatch + q] * ni + wi;
+          }
+          keys[slot] = {key * (long long)NPT + (w * K * 32 + q), slot};
+        }
+    std::sort(keys.begin(), keys.end());
+    for (int sp = 0; sp < NPT; sp++) {
+      const int slot = keys[sp].second;
+      const int lane = slot % 32, w = (slot / 32) % SG_T, k = slot / (32 * SG_T), q = k * 32 + lane;
+      const int dest = w * K * 32 + q;
+      const bool valid = row_tgt[(size_t)tl * SG_T + w] >= 0 && q < npatch;
+      int wi = 0, j0 = 0;
+      if (valid) {
+        wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
+        j0 = nj1[(size_t)w * npatch + q];
+        st[2 * ((size_t)tl * NPT + sp)] = fs[(size_t)w * npatch + q];
+        st[2 * ((size_t)tl * NPT + sp) + 1] = ft[(size_t)w * npatch + q];
+      }
+      pk[(size_t)tl * NPT + sp] = wi | (j0 << 8) | (dest << 18);
+      pos[(size_t)tl * NPT + slot] = sp;
+    }
+  }
+  C.sg_ni_max = ni_max;
+  // shared memory: band of the spline (2 halves x (n+1) phi columns x ni theta rows x 48 B) + contribution buffer
+  const size_t smem = (size_t)12 * ni_max * (n + 1) * sizeof(double) + (size_t)3 * NPT * sizeof(double);
+  if (smem > SG_SMEM_MAX || ni_max > 255) return RBC3D_OK;  // direct kernel only
+  C.sg_smem = smem;
+  RBC_TRY(C.sg_tile_tgt.resize(row_tgt.size()));
+  RBC_TRY(C.sg_tile_win.resize(row_win.size()));
+  RBC_TRY(C.sg_idx.resize(pk.size()));
+  RBC_TRY(C.sg_pos.resize(pos.size()));
   RBC_TRY(C.sg_st.resize(st.size()));
-  CUDA_TRY(cudaMemcpyAsync(C.sg_tile_tgt.p, tile_tgt.data(), sizeof(int) * tile_tgt.size(), cudaMemcpyHostToDevice,
+  CUDA_TRY(cudaMemcpyAsync(C.sg_tile_tgt.p, row_tgt.data(), sizeof(int) * row_tgt.size(), cudaMemcpyHostToDevice,
                            c->stream));
-  CUDA_TRY(cudaMemcpyAsync(C.sg_tile_win.p, tile_win.data(), sizeof(int) * tile_win.size(), cudaMemcpyHostToDevice,
+  CUDA_TRY(cudaMemcpyAsync(C.sg_tile_win.p, row_win.data(), sizeof(int) * row_win.size(), cudaMemcpyHostToDevice,
                            c->stream));
-  CUDA_TRY(cudaMemcpyAsync(C.sg_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.sg_idx.p, pk.data(), sizeof(int) * pk.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.sg_pos.p, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(C.sg_st.p, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   C.sg_ok = true;
@@ -219,26 +246,32 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// geometry time: density-independent factors of every patch point (one warp per target)
+// geometry time: density-independent factors of every patch point (one warp per target), written in the sorted
+// order of the target's tile
 struct CacheArgs {
   Params prm;
-  int ncell, npc, nlat, nlon, npatch, nrad, ntiles, K;
+  int ncell, npc, nlat, nlon, npatch, nrad, ntn, K;
   const double *th, *phi, *thG, *phiG, *pw;
   const double *spx, *spa3;
-  const int *tile_tgt;
+  const int *row_tgt;
+  const int *pos;  // [tile row][K][T][32] -> position in the tile's sorted order
   const double *tab_dl;
-  double4 *cache;  // [cell][tile][K][T][32]
+  double4 *cache;  // [cell][tile][sorted position]
 };
 
 __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, cell = blockIdx.y;
-  const int pt = a.tile_tgt[tile * SG_T + w];
-  double4 *out = a.cache + ((size_t)cell * a.ntiles + tile) * a.K * SG_T * 32;
-  if (pt < 0) {
-    for (int k = 0; k < a.K; k++) out[((size_t)k * SG_T + w) * 32 + lane] = make_double4(0, 0, 0, 0);
+  const int tl = tile / a.ntn, tn = tile - tl * a.ntn;
+  const int pt0 = a.row_tgt[tl * SG_T + w];
+  const int NPT = a.K * SG_T * 32;
+  double4 *out = a.cache + ((size_t)cell * gridDim.x + tile) * NPT;
+  const int *pos = a.pos + (size_t)tl * NPT;
+  if (pt0 < 0) {
+    for (int k = 0; k < a.K; k++) out[pos[(k * SG_T + w) * 32 + lane]] = make_double4(0, 0, 0, 0);
     return;
   }
+  const int pt = pt0 + tn * SG_TLON * a.nlat;
   const int ilon0 = pt / a.nlat, ilat0 = pt - ilon0 * a.nlat;
   const int m = 2 * a.nlat, n = a.nlon;
   const size_t sp3 = (size_t)12 * m * n;
@@ -263,7 +296,7 @@ __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
         r = make_double4(xx, yy, zz, EA * wq * (xx * nj[0] + yy * nj[1] + zz * nj[2]));
       }
     }
-    out[((size_t)k * SG_T + w) * 32 + lane] = r;
+    out[pos[(k * SG_T + w) * 32 + lane]] = r;
   }
 }
 
@@ -289,12 +322,14 @@ __global__ void __launch_bounds__(256) k_spline_interleave(int ncell, int plane,
   }
 }
 
-struct CachedArgs {
-  int ncell, npc, nlat, nlon, ntiles, Np;
-  const int *tile_tgt, *tile_win, *idx;
-  const double2 *st;
+struct BandArgs {
+  int ncell, npc, nlat, nlon, ntl, ntn, Np, K;
+  const int *row_tgt;      // [tile row][T]: mesh point (ilon*nlat + ilat) of the targets of tile column 0, -1 = none
+  const int *row_win;      // [tile row][2]: first theta row of the band, number of rows
+  const int *pk;           // [tile row][sorted position]: theta row | phi column << 8 | target-major slot << 18
+  const double2 *st;       // [tile row][sorted position]: fractional coordinates in the spline cell
   const double *spGi;      // [cell][2][n][m][6]
-  const double4 *cache;    // [cell][tile][K][T][32]
+  const double4 *cache;    // [cell][tile][sorted position]
   const double *Bcell;
   const int *active;
   const int *cell_active;  // per cell: any active target
@@ -342,50 +377,58 @@ __device__ __forceinline__ void interp_window(const double *__restrict__ sA, con
   }
 }
 
-template <int KT>  // patch points per lane kept in registers (0: generic, tables re-read per cell)
-__global__ void __launch_bounds__(SG_T * 32, 2) k_sing_cached(CachedArgs a, int K) {
+// One CTA per (cell, tile row): the band of spline(g detJ) that the row's patches touch (all phi columns, ni theta
+// rows) is staged once and serves the ntn tiles of the row; the per-point tables live in registers for the whole
+// CTA (tile column tn only advances the phi column by tn*SG_TLON); the geometry cache of the NEXT tile is already in
+// flight (one register set, refilled as it is consumed) while the current tile is evaluated.
+template <int KT>  // patch points per thread (0: generic, tables and cache re-read per tile without the register set)
+__global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int ilo = a.tile_win[tile * 4 + 0], ni = a.tile_win[tile * 4 + 1], jlo = a.tile_win[tile * 4 + 2],
-            nj = a.tile_win[tile * 4 + 3];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int cell = blockIdx.x / a.ntl, tl = blockIdx.x - cell * a.ntl;
+  if (!a.cell_active[cell]) return;  // block-uniform
+  const int ilo = a.row_win[tl * 2 + 0], ni = a.row_win[tl * 2 + 1];
   const int m = 2 * a.nlat, n = a.nlon, plane = m * n;
-  double *sA = smem, *sB = smem + (size_t)6 * ni * nj;
-  const int pt = a.tile_tgt[tile * SG_T + w];
+  const int K = a.K, NPT = K * SG_T * 32;
+  double *sA = smem, *sB = smem + (size_t)6 * ni * (n + 1);
+  double *sC = sB + (size_t)6 * ni * (n + 1);  // [3][NPT] contributions, target-major
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   constexpr int KR = KT > 0 ? KT : 1;
-  int r_idx[KR];
+  int r_pk[KR];
   double2 r_st[KR];
-  const size_t ebase = (size_t)tile * K * SG_T * 32 + (size_t)w * 32 + lane;
+  double4 r_c[KR];
+  const size_t ebase = (size_t)tl * NPT + tid;
+  const double4 *cg = a.cache + ((size_t)cell * a.ntl * a.ntn + (size_t)tl * a.ntn) * NPT + tid;
   if (KT > 0) {
 #pragma unroll
     for (int k = 0; k < KR; k++) {
-      r_idx[k] = a.idx[ebase + (size_t)k * SG_T * 32];
+      r_c[k] = ld_stream4(cg + (size_t)k * SG_T * 32);
+      r_pk[k] = a.pk[ebase + (size_t)k * SG_T * 32];
       r_st[k] = a.st[ebase + (size_t)k * SG_T * 32];
     }
   }
-  for (int cell = blockIdx.y; cell < a.ncell; cell += gridDim.y) {
-    if (!a.cell_active[cell]) continue;  // block-uniform
-    __syncthreads();
-    // stage the window: rows = (half, phi column), each a cyclic run of ni nodes x 48 B
-    for (int row = w; row < 2 * nj; row += SG_T) {
-      const int h = row / nj, wj = row - h * nj;
-      int j = jlo + wj;
-      if (j >= n) j -= n;
-      const double2 *src = reinterpret_cast<const double2 *>(a.spGi + (((size_t)cell * 2 + h) * plane + (size_t)j * m) * 6);
-      double2 *dst = reinterpret_cast<double2 *>((h ? sB : sA) + (size_t)6 * wj * ni);
-      for (int u = lane; u < 3 * ni; u += 32) {
-        const int wi = u / 3, part = u - 3 * wi;
-        int i = ilo + wi;
-        if (i >= m) i -= m;
-        dst[u] = __ldg(src + 3 * i + part);
-      }
+  // stage the band: rows = (half, phi column 0..n with column n = column 0), each a cyclic run of ni nodes x 48 B
+  for (int row = w; row < 2 * (n + 1); row += SG_T) {
+    const int h = row / (n + 1), wj = row - h * (n + 1);
+    const int j = wj == n ? 0 : wj;
+    const double2 *src = reinterpret_cast<const double2 *>(a.spGi + (((size_t)cell * 2 + h) * plane + (size_t)j * m) * 6);
+    double2 *dst = reinterpret_cast<double2 *>((h ? sB : sA) + (size_t)6 * wj * ni);
+    for (int u = lane; u < 3 * ni; u += 32) {
+      const int wi = u / 3, part = u - 3 * wi;
+      int i = ilo + wi;
+      if (i >= m) i -= m;
+      dst[u] = __ldg(src + 3 * i + part);
     }
-    __syncthreads();
-    if (pt < 0) continue;
-    const double4 *cg = a.cache + ((size_t)cell * a.ntiles + tile) * K * SG_T * 32 + (size_t)w * 32 + lane;
-    double dvx = 0, dvy = 0, dvz = 0;
-    auto point = [&](int a11, double2 stv, double4 c4) {
+  }
+  __syncthreads();
+  const int pt0 = a.row_tgt[tl * SG_T + w];
+  const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
+  for (int tn = 0; tn < a.ntn; tn++) {
+    const int jshift = tn * SG_TLON;
+    auto point = [&](int pk, double2 stv, double4 c4) {
+      int j = ((pk >> 8) & 1023) + jshift;
+      if (j >= n) j -= n;
+      const int a11 = j * ni + (pk & 255), dest = pk >> 18;
       const double s = stv.x, t = stv.y;
       const double cx[4] = {1.0 + s * s * (-3.0 + 2.0 * s), s * s * (3.0 - 2.0 * s), hx * s * (1.0 + s * (-2.0 + s)),
                             hx * s * s * (-1.0 + s)};
@@ -394,30 +437,51 @@ __global__ void __launch_bounds__(SG_T * 32, 2) k_sing_cached(CachedArgs a, int 
       double g[3];
       interp_window(sA, sB, a11, ni, cx, cy, g);
       const double qd = c4.w * (c4.x * g[0] + c4.y * g[1] + c4.z * g[2]);
-      dvx += qd * c4.x;
-      dvy += qd * c4.y;
-      dvz += qd * c4.z;
+      sC[dest] = qd * c4.x;
+      sC[NPT + dest] = qd * c4.y;
+      sC[2 * NPT + dest] = qd * c4.z;
     };
+    const double4 *cgn = cg + (size_t)(tn + 1) * NPT;  // next tile of the row
+    const bool more = tn + 1 < a.ntn;
     if (KT > 0) {
 #pragma unroll
-      for (int k = 0; k < KR; k++) point(r_idx[k], r_st[k], ld_stream4(cg + (size_t)k * SG_T * 32));
+      for (int k = 0; k < KR; k++) {
+        const double4 c4 = r_c[k];
+        if (more) r_c[k] = ld_stream4(cgn + (size_t)k * SG_T * 32);
+        point(r_pk[k], r_st[k], c4);
+      }
     } else {
-      for (int k = 0; k < K; k++)
-        point(a.idx[ebase + (size_t)k * SG_T * 32], a.st[ebase + (size_t)k * SG_T * 32],
-              ld_stream4(cg + (size_t)k * SG_T * 32));
-    }
-    dvx = warp_sum(dvx);
-    dvy = warp_sum(dvy);
-    dvz = warp_sum(dvz);
-    if (lane == 0) {
-      const int ti = cell * a.npc + pt;
-      if (a.active[ti]) {
-        const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
-        a.acc[ti] += c2m * dvx;
-        a.acc[(size_t)a.Np + ti] += c2m * dvy;
-        a.acc[2 * (size_t)a.Np + ti] += c2m * dvz;
+      const double4 *cgc = cg + (size_t)tn * NPT;
+      double4 c_next = ld_stream4(cgc);
+      for (int k = 0; k < K; k++) {
+        const double4 c4 = c_next;
+        if (k + 1 < K) c_next = ld_stream4(cgc + (size_t)(k + 1) * SG_T * 32);
+        point(a.pk[ebase + (size_t)k * SG_T * 32], a.st[ebase + (size_t)k * SG_T * 32], c4);
       }
     }
+    __syncthreads();
+    // one warp per target: sum its patch in the reference's order (lane = point mod 32, then the shuffle tree)
+    if (pt0 >= 0) {
+      double dvx = 0, dvy = 0, dvz = 0;
+      const double *sc = sC + w * K * 32 + lane;
+      for (int k = 0; k < K; k++) {
+        dvx += sc[k * 32];
+        dvy += sc[NPT + k * 32];
+        dvz += sc[2 * NPT + k * 32];
+      }
+      dvx = warp_sum(dvx);
+      dvy = warp_sum(dvy);
+      dvz = warp_sum(dvz);
+      if (lane == 0) {
+        const int ti = cell * a.npc + pt0 + tn * SG_TLON * a.nlat;
+        if (a.active[ti]) {
+          a.acc[ti] += c2m * dvx;
+          a.acc[(size_t)a.Np + ti] += c2m * dvy;
+          a.acc[2 * (size_t)a.Np + ti] += c2m * dvz;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -462,7 +526,7 @@ int singular_prepare(rbc3d_ctx *c) {
   a.nlon = C.nlon;
   a.npatch = C.nrad * C.nazm;
   a.nrad = C.nrad;
-  a.ntiles = C.sg_ntiles;
+  a.ntn = C.sg_ntn;
   a.K = C.sg_K;
   a.th = C.th.p;
   a.phi = C.phi.p;
@@ -471,7 +535,8 @@ int singular_prepare(rbc3d_ctx *c) {
   a.pw = C.pw.p;
   a.spx = C.spx.p;
   a.spa3 = C.spa3.p;
-  a.tile_tgt = C.sg_tile_tgt.p;
+  a.row_tgt = C.sg_tile_tgt.p;
+  a.pos = C.sg_pos.p;
   a.tab_dl = c->tab_dl.p;
   a.cache = C.sg_cache.p;
   // 65535 limit of gridDim.y: chunk the cells
@@ -505,16 +570,18 @@ int singular_density_prepare(rbc3d_ctx *c) {
 
 static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   Cells &C = c->cells;
-  CachedArgs a;
+  BandArgs a;
   a.ncell = C.ncell;
   a.npc = C.npc;
   a.nlat = C.nlat;
   a.nlon = C.nlon;
-  a.ntiles = C.sg_ntiles;
+  a.ntl = C.sg_ntl;
+  a.ntn = C.sg_ntn;
   a.Np = C.Np;
-  a.tile_tgt = C.sg_tile_tgt.p;
-  a.tile_win = C.sg_tile_win.p;
-  a.idx = C.sg_idx.p;
+  a.K = C.sg_K;
+  a.row_tgt = C.sg_tile_tgt.p;
+  a.row_win = C.sg_tile_win.p;
+  a.pk = C.sg_idx.p;
   a.st = reinterpret_cast<const double2 *>(C.sg_st.p);
   a.spGi = C.spGi.p;
   a.cache = C.sg_cache.p;
@@ -523,21 +590,18 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   a.cell_active = C.sg_cell_active.p;
   a.c2 = c2;
   a.acc = t.acc.p;
-  const size_t smem = (size_t)C.sg_win_max * 96;
-  // cells are strided over gridDim.y groups; enough CTAs for ~8 waves of 2 CTAs per SM
-  int groups = (c->sm_count * 2 * 8 + C.sg_ntiles - 1) / C.sg_ntiles;
-  groups = std::max(1, std::min(groups, C.ncell));
-  dim3 grid(C.sg_ntiles, groups);
   static const bool generic = getenv("RBC3D_SING_GENERIC") != nullptr;
+  const int grid = C.ncell * C.sg_ntl;
+  const size_t smem = C.sg_smem;
   if (C.sg_K == 9 && !generic) {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_cached<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_cached<9><<<grid, SG_T * 32, smem, c->stream>>>(a, C.sg_K);
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sing_band<9><<<grid, SG_T * 32, smem, c->stream>>>(a);
   } else if (C.sg_K == 4 && !generic) {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_cached<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_cached<4><<<grid, SG_T * 32, smem, c->stream>>>(a, C.sg_K);
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sing_band<4><<<grid, SG_T * 32, smem, c->stream>>>(a);
   } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_cached<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_cached<0><<<grid, SG_T * 32, smem, c->stream>>>(a, C.sg_K);
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sing_band<0><<<grid, SG_T * 32, smem, c->stream>>>(a);
   }
   KERNEL_CHECK();
   c->launches++;
