@@ -183,10 +183,12 @@ struct Cells {
   bool sg_ok = false, sg_cache_ok = false, spGi_valid = false;
   int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
   dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active, sg_tile_list, sg_pos;
-  int sg_ntl = 0, sg_ntn = 0, sg_ni_max = 0;
+  int sg_ntl = 0, sg_ntn = 0, sg_ni_max = 0, sg_chunk_stride = 0;
+  dbuf<int> sg_rounds;
+  dbuf<int2> sg_chunk;
   size_t sg_smem = 0;
   dbuf<double> sg_st;                // (s, t) pairs
-  dbuf<double> spGi;                 // node-interleaved spline(g detJ): [cell][2][nlon][2 nlat][6]
+  dbuf<double> spGi;                 // spline(g detJ) as double2 planes: [cell][6][nlon][2 nlat][2]
   dbuf<double4> sg_cache;            // [cell][tile][sorted patch point] (xx, w EA (xx.a3))
   // dense same-surface pair kernel (pairself.cu)
   bool ps_ok = false;

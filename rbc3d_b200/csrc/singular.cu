@@ -34,7 +34,8 @@ namespace rbc3d {
 
 constexpr int SING_WARPS = 8;
 constexpr int SG_TLAT = 4, SG_TLON = 2, SG_T = SG_TLAT * SG_TLON;  // targets per tile = warps per CTA
-constexpr size_t SG_SMEM_MAX = 226 * 1024;                          // one CTA per SM
+constexpr size_t SG_SMEM_MAX = 227 * 1024;                          // one CTA per SM
+constexpr int SG_PC = 4;  // patch points of one spline cell evaluated per thread from one load of its 4 nodes
 
 struct SingArgs {
   Params prm;
@@ -161,13 +162,14 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   // Tables of tile column 0 of every tile row.  The patch of (ilat, ilon) is the patch of (ilat, 0) rotated by
   // phi(ilon) about the polar axis (PolarPatch_Build, ModPolarPatch.F90:99-148: thG does not depend on phi0, phiG
   // = atan2(..) + phi0), so tile column tn uses the same tables with the phi node index advanced by tn*SG_TLON.
-  std::vector<int> row_tgt((size_t)ntl * SG_T, -1), row_win((size_t)ntl * 2, 0);
-  std::vector<int> pk((size_t)ntl * NPT, 0), pos((size_t)ntl * NPT, 0);
+  std::vector<int> row_tgt((size_t)ntl * SG_T, -1), row_win((size_t)ntl * 2, 0), row_rounds(ntl, 0);
+  std::vector<int> pt_dest((size_t)ntl * NPT, 0), pos((size_t)ntl * NPT, -1);
   std::vector<double> st((size_t)ntl * NPT * 2, 0.0);
+  std::vector<std::vector<int2>> chunks(ntl);
   std::vector<int> ni1((size_t)SG_T * npatch), nj1((size_t)SG_T * npatch);
   std::vector<double> fs((size_t)SG_T * npatch), ft((size_t)SG_T * npatch);
-  std::vector<std::pair<long long, int>> keys(NPT);
-  int ni_max = 0;
+  std::vector<std::pair<long long, int>> keys;
+  int ni_max = 0, rounds_max = 0;
   for (int tl = 0; tl < ntl; tl++) {
     std::vector<char> ui(m, 0);
     for (int w = 0; w < SG_T; w++) {
@@ -193,53 +195,67 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
     row_win[(size_t)tl * 2 + 0] = ilo;
     row_win[(size_t)tl * 2 + 1] = ni;
     ni_max = std::max(ni_max, ni);
-    // sorted order of the tile's patch points: by spline cell (phi column, theta row), ties in target-major order
-    for (int k = 0; k < K; k++)
-      for (int w = 0; w < SG_T; w++)
-        for (int lane = 0; lane < 32; lane++) {
-          const int slot = (k * SG_T + w) * 32 + lane, q = k * 32 + lane;
-          const bool valid = row_tgt[(size_t)tl * SG_T + w] >= 0 && q < npatch;
-          long long key = 1LL << 40;
-          if (valid) {
-            const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
-            key = (long long)nj1[(size_t)w * npatch + q] * ni + wi;
-          }
-          keys[slot] = {key * (long long)NPT + (w * K * 32 + q), slot};
-        }
-    std::sort(keys.begin(), keys.end());
-    for (int sp = 0; sp < NPT; sp++) {
-      const int slot = keys[sp].second;
-      const int lane = slot % 32, w = (slot / 32) % SG_T, k = slot / (32 * SG_T), q = k * 32 + lane;
-      const int dest = w * K * 32 + q;
-      const bool valid = row_tgt[(size_t)tl * SG_T + w] >= 0 && q < npatch;
-      int wi = 0, j0 = 0;
-      if (valid) {
-        wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
-        j0 = nj1[(size_t)w * npatch + q];
-        st[2 * ((size_t)tl * NPT + sp)] = fs[(size_t)w * npatch + q];
-        st[2 * ((size_t)tl * NPT + sp) + 1] = ft[(size_t)w * npatch + q];
+    // the tile's valid patch points sorted by spline cell (phi column, theta row), ties in target-major order
+    keys.clear();
+    for (int w = 0; w < SG_T; w++) {
+      if (row_tgt[(size_t)tl * SG_T + w] < 0) continue;
+      for (int q = 0; q < npatch; q++) {
+        const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
+        const long long cellkey = (long long)nj1[(size_t)w * npatch + q] * ni + wi;
+        keys.push_back({cellkey * (long long)NPT + (w * K * 32 + q), w * npatch + q});
       }
-      pk[(size_t)tl * NPT + sp] = wi | (j0 << 8) | (dest << 18);
-      pos[(size_t)tl * NPT + slot] = sp;
     }
+    std::sort(keys.begin(), keys.end());
+    // chunks: runs of <= SG_PC consecutive points of one spline cell; a thread evaluates one chunk per round from
+    // node data it loads once
+    size_t sp = 0;
+    while (sp < keys.size()) {
+      const long long cellkey = keys[sp].first / NPT;
+      int cnt = 0;
+      while (sp + cnt < keys.size() && cnt < SG_PC && keys[sp + cnt].first / NPT == cellkey) cnt++;
+      const int wi = (int)(cellkey % ni), j0 = (int)(cellkey / ni);
+      chunks[tl].push_back(make_int2(wi | (j0 << 8) | (cnt << 18), (int)sp));
+      for (int u = 0; u < cnt; u++) {
+        const int wq = keys[sp + u].second, w = wq / npatch, q = wq - w * npatch;
+        pt_dest[(size_t)tl * NPT + sp + u] = w * K * 32 + q;
+        st[2 * ((size_t)tl * NPT + sp + u)] = fs[wq];
+        st[2 * ((size_t)tl * NPT + sp + u) + 1] = ft[wq];
+        const int k = q / 32, lane = q % 32;
+        pos[(size_t)tl * NPT + (k * SG_T + w) * 32 + lane] = (int)(sp + u);
+      }
+      sp += cnt;
+    }
+    row_rounds[tl] = (int)((chunks[tl].size() + SG_T * 32 - 1) / (SG_T * 32));
+    rounds_max = std::max(rounds_max, row_rounds[tl]);
   }
+  const int CH = rounds_max * SG_T * 32;  // chunk slots per tile row (empty chunks: cnt = 0)
+  std::vector<int2> chunk_tab((size_t)ntl * CH, make_int2(0, 0));
+  for (int tl = 0; tl < ntl; tl++)
+    for (size_t u = 0; u < chunks[tl].size(); u++) chunk_tab[(size_t)tl * CH + u] = chunks[tl][u];
   C.sg_ni_max = ni_max;
-  // shared memory: band of the spline (2 halves x (n+1) phi columns x ni theta rows x 48 B) + contribution buffer
+  C.sg_chunk_stride = CH;
+  // shared memory: band of the spline (6 double2 planes x (n+1) phi columns x ni theta rows) + contribution buffer
   const size_t smem = (size_t)12 * ni_max * (n + 1) * sizeof(double) + (size_t)3 * NPT * sizeof(double);
   if (smem > SG_SMEM_MAX || ni_max > 255) return RBC3D_OK;  // direct kernel only
   C.sg_smem = smem;
   RBC_TRY(C.sg_tile_tgt.resize(row_tgt.size()));
   RBC_TRY(C.sg_tile_win.resize(row_win.size()));
-  RBC_TRY(C.sg_idx.resize(pk.size()));
+  RBC_TRY(C.sg_rounds.resize(row_rounds.size()));
+  RBC_TRY(C.sg_idx.resize(pt_dest.size()));
   RBC_TRY(C.sg_pos.resize(pos.size()));
   RBC_TRY(C.sg_st.resize(st.size()));
+  RBC_TRY(C.sg_chunk.resize(chunk_tab.size()));
   CUDA_TRY(cudaMemcpyAsync(C.sg_tile_tgt.p, row_tgt.data(), sizeof(int) * row_tgt.size(), cudaMemcpyHostToDevice,
                            c->stream));
   CUDA_TRY(cudaMemcpyAsync(C.sg_tile_win.p, row_win.data(), sizeof(int) * row_win.size(), cudaMemcpyHostToDevice,
                            c->stream));
-  CUDA_TRY(cudaMemcpyAsync(C.sg_idx.p, pk.data(), sizeof(int) * pk.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.sg_rounds.p, row_rounds.data(), sizeof(int) * row_rounds.size(), cudaMemcpyHostToDevice,
+                           c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.sg_idx.p, pt_dest.data(), sizeof(int) * pt_dest.size(), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(C.sg_pos.p, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(C.sg_st.p, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(C.sg_chunk.p, chunk_tab.data(), sizeof(int2) * chunk_tab.size(), cudaMemcpyHostToDevice,
+                           c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   C.sg_ok = true;
   return RBC3D_OK;
@@ -267,10 +283,7 @@ __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
   const int NPT = a.K * SG_T * 32;
   double4 *out = a.cache + ((size_t)cell * gridDim.x + tile) * NPT;
   const int *pos = a.pos + (size_t)tl * NPT;
-  if (pt0 < 0) {
-    for (int k = 0; k < a.K; k++) out[pos[(k * SG_T + w) * 32 + lane]] = make_double4(0, 0, 0, 0);
-    return;
-  }
+  if (pt0 < 0) return;  // no target in this slot: its cache entries do not exist
   const int pt = pt0 + tn * SG_TLON * a.nlat;
   const int ilon0 = pt / a.nlat, ilat0 = pt - ilon0 * a.nlat;
   const int m = 2 * a.nlat, n = a.nlon;
@@ -296,39 +309,39 @@ __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
         r = make_double4(xx, yy, zz, EA * wq * (xx * nj[0] + yy * nj[1] + zz * nj[2]));
       }
     }
-    out[pos[(k * SG_T + w) * 32 + lane]] = r;
+    const int sp = pos[(k * SG_T + w) * 32 + lane];
+    if (sp >= 0) out[sp] = r;
   }
 }
 
-// spline re-layout: ABI [cell][4 (u,u1,u2,u12)][3][n][m] -> [cell][half][n][m][6], half 0 = (u[0..2], u1[0..2]),
-// half 1 = (u2[0..2], u12[0..2])
+// spline re-layout: ABI [cell][4 (u,u1,u2,u12)][3][n][m] -> [cell][6 planes][n][m] double2 with plane 2l = (u_l, u1_l)
+// and plane 2l+1 = (u2_l, u12_l): the four Hermite data of one variable at one node are two 16-byte loads, and
+// neighbouring nodes are neighbouring 16-byte words (conflict-free LDS.128 for lanes on neighbouring spline cells)
 __global__ void __launch_bounds__(256) k_spline_interleave(int ncell, int plane, const double *__restrict__ sp,
                                                            double *__restrict__ out) {
   const size_t total = (size_t)ncell * plane;
+  double2 *o2 = reinterpret_cast<double2 *>(out);
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t cell = e / plane, node = e - cell * plane;
     const double *src = sp + cell * 12 * (size_t)plane + node;
-    double v[12];
 #pragma unroll
-    for (int a = 0; a < 12; a++) v[a] = src[(size_t)a * plane];  // a = arr*3 + var
-    double2 *dA = reinterpret_cast<double2 *>(out + ((cell * 2 + 0) * plane + node) * 6);
-    double2 *dB = reinterpret_cast<double2 *>(out + ((cell * 2 + 1) * plane + node) * 6);
-    dA[0] = make_double2(v[0], v[1]);
-    dA[1] = make_double2(v[2], v[3]);
-    dA[2] = make_double2(v[4], v[5]);
-    dB[0] = make_double2(v[6], v[7]);
-    dB[1] = make_double2(v[8], v[9]);
-    dB[2] = make_double2(v[10], v[11]);
+    for (int l = 0; l < 3; l++) {
+      // a = arr*3 + var, arr = 0 (u), 1 (u1), 2 (u2), 3 (u12)
+      o2[(cell * 6 + 2 * l) * plane + node] = make_double2(src[(size_t)l * plane], src[(size_t)(3 + l) * plane]);
+      o2[(cell * 6 + 2 * l + 1) * plane + node] = make_double2(src[(size_t)(6 + l) * plane], src[(size_t)(9 + l) * plane]);
+    }
   }
 }
 
 struct BandArgs {
-  int ncell, npc, nlat, nlon, ntl, ntn, Np, K;
+  int ncell, npc, nlat, nlon, ntl, ntn, Np, K, chunk_stride;
   const int *row_tgt;      // [tile row][T]: mesh point (ilon*nlat + ilat) of the targets of tile column 0, -1 = none
   const int *row_win;      // [tile row][2]: first theta row of the band, number of rows
-  const int *pk;           // [tile row][sorted position]: theta row | phi column << 8 | target-major slot << 18
-  const double2 *st;       // [tile row][sorted position]: fractional coordinates in the spline cell
-  const double *spGi;      // [cell][2][n][m][6]
+  const int *row_rounds;   // [tile row]: chunk rounds (chunks / 256, rounded up)
+  const int2 *chunk;       // [tile row][chunk]: (theta row | phi column << 8 | points << 18, first sorted position)
+  const int *pt_dest;      // [tile row][sorted position]: target-major slot of the contribution buffer
+  const double2 *pt_st;    // [tile row][sorted position]: fractional coordinates in the spline cell
+  const double2 *spGp;     // [cell][6][n][m]
   const double4 *cache;    // [cell][tile][sorted position]
   const double *Bcell;
   const int *active;
@@ -339,49 +352,20 @@ struct BandArgs {
 
 // streaming (evict-first) 32-byte load: the cache is read exactly once per matvec
 __device__ __forceinline__ double4 ld_stream4(const double4 *p) {
-  const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p));
-  const double2 hi = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
-  return make_double4(lo.x, lo.y, hi.x, hi.y);
+  double4 v;  // one 32-byte request, no L1 allocation (L1 is kept for the cell-independent tables)
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p));
+  return v;
 }
 
-// one bicubic evaluation of 3 variables from the staged window: node halves A = (u, u1), B = (u2, u12)
-__device__ __forceinline__ void interp_window(const double *__restrict__ sA, const double *__restrict__ sB, int a11,
-                                              int ni, const double cx[4], const double cy[4], double g[3]) {
-  const int a21 = a11 + 1, a12 = a11 + ni, a22 = a12 + 1;
-  const double2 *A11 = reinterpret_cast<const double2 *>(sA + 6 * a11), *A12 = reinterpret_cast<const double2 *>(sA + 6 * a12);
-  const double2 *A21 = reinterpret_cast<const double2 *>(sA + 6 * a21), *A22 = reinterpret_cast<const double2 *>(sA + 6 * a22);
-  const double2 *B11 = reinterpret_cast<const double2 *>(sB + 6 * a11), *B12 = reinterpret_cast<const double2 *>(sB + 6 * a12);
-  const double2 *B21 = reinterpret_cast<const double2 *>(sB + 6 * a21), *B22 = reinterpret_cast<const double2 *>(sB + 6 * a22);
-  // per node: (u0,u1,u2, d0,d1,d2) with d = d/dtheta (half A) and (e0,e1,e2, f0,f1,f2) = d/dphi, d2/dthdphi (half B)
-  double n11[12], n12[12], n21[12], n22[12];
-#pragma unroll
-  for (int h = 0; h < 3; h++) {
-    double2 v;
-    v = A11[h]; n11[2 * h] = v.x; n11[2 * h + 1] = v.y;
-    v = B11[h]; n11[6 + 2 * h] = v.x; n11[7 + 2 * h] = v.y;
-    v = A12[h]; n12[2 * h] = v.x; n12[2 * h + 1] = v.y;
-    v = B12[h]; n12[6 + 2 * h] = v.x; n12[7 + 2 * h] = v.y;
-    v = A21[h]; n21[2 * h] = v.x; n21[2 * h + 1] = v.y;
-    v = B21[h]; n21[6 + 2 * h] = v.x; n21[7 + 2 * h] = v.y;
-    v = A22[h]; n22[2 * h] = v.x; n22[2 * h + 1] = v.y;
-    v = B22[h]; n22[6 + 2 * h] = v.x; n22[7 + 2 * h] = v.y;
-  }
-#pragma unroll
-  for (int l = 0; l < 3; l++) {
-    // U = n[l], U1 = n[3+l], U2 = n[6+l], U12 = n[9+l]   (same association as spline_interp)
-    const double r0 = n11[l] * cy[0] + n12[l] * cy[1] + n11[6 + l] * cy[2] + n12[6 + l] * cy[3];
-    const double r1 = n21[l] * cy[0] + n22[l] * cy[1] + n21[6 + l] * cy[2] + n22[6 + l] * cy[3];
-    const double r2 = n11[3 + l] * cy[0] + n12[3 + l] * cy[1] + n11[9 + l] * cy[2] + n12[9 + l] * cy[3];
-    const double r3 = n21[3 + l] * cy[0] + n22[3 + l] * cy[1] + n21[9 + l] * cy[2] + n22[9 + l] * cy[3];
-    g[l] = cx[0] * r0 + cx[1] * r1 + cx[2] * r2 + cx[3] * r3;
-  }
-}
-
-// One CTA per (cell, tile row): the band of spline(g detJ) that the row's patches touch (all phi columns, ni theta
-// rows) is staged once and serves the ntn tiles of the row; the per-point tables live in registers for the whole
-// CTA (tile column tn only advances the phi column by tn*SG_TLON); the geometry cache of the NEXT tile is already in
-// flight (one register set, refilled as it is consumed) while the current tile is evaluated.
-template <int KT>  // patch points per thread (0: generic, tables and cache re-read per tile without the register set)
+// One CTA per (cell, tile row).  The band of spline(g detJ) the row's patches touch (all phi columns, ni theta rows)
+// is staged once and serves the ntn tiles of the row.  A thread evaluates one chunk per round: up to SG_PC patch
+// points that lie in the same spline cell, from the 48 Hermite data of the cell's four nodes loaded ONCE into
+// registers (shared-memory traffic per patch point drops from 384 B to ~100 B).  The geometry cache of the next
+// round is in flight while the current one is evaluated.  Contributions go to a target-major shared buffer that one
+// warp per target sums in the reference's patch order.
+template <bool TAB_SMEM>  // the row's chunk / point tables in shared memory (when they fit) or read through L1
 __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -390,73 +374,125 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   const int ilo = a.row_win[tl * 2 + 0], ni = a.row_win[tl * 2 + 1];
   const int m = 2 * a.nlat, n = a.nlon, plane = m * n;
   const int K = a.K, NPT = K * SG_T * 32;
-  double *sA = smem, *sB = smem + (size_t)6 * ni * (n + 1);
-  double *sC = sB + (size_t)6 * ni * (n + 1);  // [3][NPT] contributions, target-major
+  const int wn = ni * (n + 1);                       // nodes of the band
+  double2 *sP = reinterpret_cast<double2 *>(smem);   // [6][n+1][ni]
+  double *sC = smem + (size_t)12 * wn;               // [3][NPT] contributions, target-major
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
-  constexpr int KR = KT > 0 ? KT : 1;
-  int r_pk[KR];
-  double2 r_st[KR];
-  double4 r_c[KR];
-  const size_t ebase = (size_t)tl * NPT + tid;
-  const double4 *cg = a.cache + ((size_t)cell * a.ntl * a.ntn + (size_t)tl * a.ntn) * NPT + tid;
-  if (KT > 0) {
-#pragma unroll
-    for (int k = 0; k < KR; k++) {
-      r_c[k] = ld_stream4(cg + (size_t)k * SG_T * 32);
-      r_pk[k] = a.pk[ebase + (size_t)k * SG_T * 32];
-      r_st[k] = a.st[ebase + (size_t)k * SG_T * 32];
+  const int R = a.row_rounds[tl];
+  const int2 *chunk = a.chunk + (size_t)tl * a.chunk_stride + tid;
+  const int *pt_dest = a.pt_dest + (size_t)tl * NPT;
+  const double2 *pt_st = a.pt_st + (size_t)tl * NPT;
+  if (TAB_SMEM) {  // [NPT] double2, [R*256] int2, [NPT] int behind the contribution buffer
+    double2 *s_st = reinterpret_cast<double2 *>(sC + (size_t)3 * NPT);
+    int2 *s_ch = reinterpret_cast<int2 *>(s_st + NPT);
+    int *s_dest = reinterpret_cast<int *>(s_ch + R * SG_T * 32);
+    for (int u = tid; u < NPT; u += SG_T * 32) {
+      s_st[u] = __ldg(pt_st + u);
+      s_dest[u] = __ldg(pt_dest + u);
     }
+    for (int u = tid; u < R * SG_T * 32; u += SG_T * 32) s_ch[u] = __ldg(chunk - tid + u);
+    pt_st = s_st;
+    pt_dest = s_dest;
+    chunk = s_ch + tid;
+    __syncthreads();
   }
-  // stage the band: rows = (half, phi column 0..n with column n = column 0), each a cyclic run of ni nodes x 48 B
-  for (int row = w; row < 2 * (n + 1); row += SG_T) {
-    const int h = row / (n + 1), wj = row - h * (n + 1);
+  auto ld_tab = [&](auto *ptr) { return TAB_SMEM ? *ptr : __ldg(ptr); };
+  const double4 *cg = a.cache + ((size_t)cell * a.ntl * a.ntn + (size_t)tl * a.ntn) * NPT;
+  // first round of the first tile in flight before the band is staged
+  int2 ch_next = ld_tab(chunk);
+  double4 c_next[SG_PC];
+#pragma unroll
+  for (int p = 0; p < SG_PC; p++)
+    c_next[p] = (p < (ch_next.x >> 18)) ? ld_stream4(cg + ch_next.y + p) : make_double4(0, 0, 0, 0);
+  // stage the band: rows = (plane, phi column 0..n with column n = column 0), each a cyclic run of ni double2
+  for (int row = w; row < 6 * (n + 1); row += SG_T) {
+    const int q = row / (n + 1), wj = row - q * (n + 1);
     const int j = wj == n ? 0 : wj;
-    const double2 *src = reinterpret_cast<const double2 *>(a.spGi + (((size_t)cell * 2 + h) * plane + (size_t)j * m) * 6);
-    double2 *dst = reinterpret_cast<double2 *>((h ? sB : sA) + (size_t)6 * wj * ni);
-    for (int u = lane; u < 3 * ni; u += 32) {
-      const int wi = u / 3, part = u - 3 * wi;
+    const double2 *src = a.spGp + ((size_t)cell * 6 + q) * plane + (size_t)j * m;
+    double2 *dst = sP + (size_t)q * wn + (size_t)wj * ni;
+    for (int wi = lane; wi < ni; wi += 32) {
       int i = ilo + wi;
       if (i >= m) i -= m;
-      dst[u] = __ldg(src + 3 * i + part);
+      dst[wi] = __ldg(src + i);
     }
   }
+  for (int u = tid; u < 3 * NPT; u += SG_T * 32) sC[u] = 0.0;  // slots beyond npatch stay zero
   __syncthreads();
   const int pt0 = a.row_tgt[tl * SG_T + w];
   const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
   for (int tn = 0; tn < a.ntn; tn++) {
     const int jshift = tn * SG_TLON;
-    auto point = [&](int pk, double2 stv, double4 c4) {
-      int j = ((pk >> 8) & 1023) + jshift;
-      if (j >= n) j -= n;
-      const int a11 = j * ni + (pk & 255), dest = pk >> 18;
-      const double s = stv.x, t = stv.y;
-      const double cx[4] = {1.0 + s * s * (-3.0 + 2.0 * s), s * s * (3.0 - 2.0 * s), hx * s * (1.0 + s * (-2.0 + s)),
-                            hx * s * s * (-1.0 + s)};
-      const double cy[4] = {1.0 + t * t * (-3.0 + 2.0 * t), t * t * (3.0 - 2.0 * t), hy * t * (1.0 + t * (-2.0 + t)),
-                            hy * t * t * (-1.0 + t)};
-      double g[3];
-      interp_window(sA, sB, a11, ni, cx, cy, g);
-      const double qd = c4.w * (c4.x * g[0] + c4.y * g[1] + c4.z * g[2]);
-      sC[dest] = qd * c4.x;
-      sC[NPT + dest] = qd * c4.y;
-      sC[2 * NPT + dest] = qd * c4.z;
-    };
-    const double4 *cgn = cg + (size_t)(tn + 1) * NPT;  // next tile of the row
-    const bool more = tn + 1 < a.ntn;
-    if (KT > 0) {
+    const int ti = cell * a.npc + pt0 + tn * SG_TLON * a.nlat;
+    const bool t_on = pt0 >= 0 && lane == 0 && a.active[ti] != 0;  // requested now, needed after the rounds
+    for (int r = 0; r < R; r++) {
+      const int2 ch = ch_next;
+      double4 c4[SG_PC];
 #pragma unroll
-      for (int k = 0; k < KR; k++) {
-        const double4 c4 = r_c[k];
-        if (more) r_c[k] = ld_stream4(cgn + (size_t)k * SG_T * 32);
-        point(r_pk[k], r_st[k], c4);
+      for (int p = 0; p < SG_PC; p++) c4[p] = c_next[p];
+      {  // next round (of this tile or of the next tile of the row)
+        int nr = r + 1, nt = tn;
+        if (nr == R) {
+          nr = 0;
+          nt = tn + 1;
+        }
+        if (nt < a.ntn) {
+          ch_next = ld_tab(chunk + nr * SG_T * 32);
+          const double4 *cgn = cg + (size_t)nt * NPT + ch_next.y;
+          const int cn = ch_next.x >> 18;
+#pragma unroll
+          for (int p = 0; p < SG_PC; p++) c_next[p] = (p < cn) ? ld_stream4(cgn + p) : make_double4(0, 0, 0, 0);
+        }
       }
-    } else {
-      const double4 *cgc = cg + (size_t)tn * NPT;
-      double4 c_next = ld_stream4(cgc);
-      for (int k = 0; k < K; k++) {
-        const double4 c4 = c_next;
-        if (k + 1 < K) c_next = ld_stream4(cgc + (size_t)(k + 1) * SG_T * 32);
-        point(a.pk[ebase + (size_t)k * SG_T * 32], a.st[ebase + (size_t)k * SG_T * 32], c4);
+      const int cnt = ch.x >> 18;
+      if (cnt == 0) continue;
+      int j = ((ch.x >> 8) & 1023) + jshift;
+      if (j >= n) j -= n;
+      const int a11 = j * ni + (ch.x & 255);
+      // tables of the chunk's points, all requested before the first use (clamped index: no branch in the way)
+      double2 stq[SG_PC];
+      int destq[SG_PC];
+#pragma unroll
+      for (int p = 0; p < SG_PC; p++) {
+        const int e = ch.y + min(p, cnt - 1);
+        stq[p] = ld_tab(pt_st + e);
+        destq[p] = ld_tab(pt_dest + e);
+      }
+      // Hermite data of the four nodes: nd[node][plane] = (u_l, u1_l) for plane 2l, (u2_l, u12_l) for plane 2l+1
+      double2 n11[6], n21[6], n12[6], n22[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        const double2 *P = sP + (size_t)q * wn + a11;
+        n11[q] = P[0];
+        n21[q] = P[1];
+        n12[q] = P[ni];
+        n22[q] = P[ni + 1];
+      }
+#pragma unroll
+      for (int p = 0; p < SG_PC; p++) {
+        if (p < cnt) {
+          const double2 stv = stq[p];
+          const int dest = destq[p];
+          const double s = stv.x, t = stv.y;
+          const double cx[4] = {1.0 + s * s * (-3.0 + 2.0 * s), s * s * (3.0 - 2.0 * s), hx * s * (1.0 + s * (-2.0 + s)),
+                                hx * s * s * (-1.0 + s)};
+          const double cy[4] = {1.0 + t * t * (-3.0 + 2.0 * t), t * t * (3.0 - 2.0 * t), hy * t * (1.0 + t * (-2.0 + t)),
+                                hy * t * t * (-1.0 + t)};
+          double g[3];
+#pragma unroll
+          for (int l = 0; l < 3; l++) {
+            // same association as spline_interp (device_math.cuh): U = .x of plane 2l, U1 = .y, U2 = .x of 2l+1, U12 = .y
+            const double r0 = n11[2 * l].x * cy[0] + n12[2 * l].x * cy[1] + n11[2 * l + 1].x * cy[2] + n12[2 * l + 1].x * cy[3];
+            const double r1 = n21[2 * l].x * cy[0] + n22[2 * l].x * cy[1] + n21[2 * l + 1].x * cy[2] + n22[2 * l + 1].x * cy[3];
+            const double r2 = n11[2 * l].y * cy[0] + n12[2 * l].y * cy[1] + n11[2 * l + 1].y * cy[2] + n12[2 * l + 1].y * cy[3];
+            const double r3 = n21[2 * l].y * cy[0] + n22[2 * l].y * cy[1] + n21[2 * l + 1].y * cy[2] + n22[2 * l + 1].y * cy[3];
+            g[l] = cx[0] * r0 + cx[1] * r1 + cx[2] * r2 + cx[3] * r3;
+          }
+          const double4 c = c4[p];
+          const double qd = c.w * (c.x * g[0] + c.y * g[1] + c.z * g[2]);
+          sC[dest] = qd * c.x;
+          sC[NPT + dest] = qd * c.y;
+          sC[2 * NPT + dest] = qd * c.z;
+        }
       }
     }
     __syncthreads();
@@ -472,13 +508,10 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
       dvx = warp_sum(dvx);
       dvy = warp_sum(dvy);
       dvz = warp_sum(dvz);
-      if (lane == 0) {
-        const int ti = cell * a.npc + pt0 + tn * SG_TLON * a.nlat;
-        if (a.active[ti]) {
-          a.acc[ti] += c2m * dvx;
-          a.acc[(size_t)a.Np + ti] += c2m * dvy;
-          a.acc[2 * (size_t)a.Np + ti] += c2m * dvz;
-        }
+      if (t_on) {  // single writer per address: a reduction without return value, no load to wait for
+        atomicAdd(a.acc + ti, c2m * dvx);
+        atomicAdd(a.acc + (size_t)a.Np + ti, c2m * dvy);
+        atomicAdd(a.acc + 2 * (size_t)a.Np + ti, c2m * dvz);
       }
     }
     __syncthreads();
@@ -579,29 +612,33 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   a.ntn = C.sg_ntn;
   a.Np = C.Np;
   a.K = C.sg_K;
+  a.chunk_stride = C.sg_chunk_stride;
   a.row_tgt = C.sg_tile_tgt.p;
   a.row_win = C.sg_tile_win.p;
-  a.pk = C.sg_idx.p;
-  a.st = reinterpret_cast<const double2 *>(C.sg_st.p);
-  a.spGi = C.spGi.p;
+  a.row_rounds = C.sg_rounds.p;
+  a.chunk = C.sg_chunk.p;
+  a.pt_dest = C.sg_idx.p;
+  a.pt_st = reinterpret_cast<const double2 *>(C.sg_st.p);
+  a.spGp = reinterpret_cast<const double2 *>(C.spGi.p);
   a.cache = C.sg_cache.p;
   a.Bcell = C.B.p;
   a.active = t.active.p;
   a.cell_active = C.sg_cell_active.p;
   a.c2 = c2;
   a.acc = t.acc.p;
-  static const bool generic = getenv("RBC3D_SING_GENERIC") != nullptr;
   const int grid = C.ncell * C.sg_ntl;
-  const size_t smem = C.sg_smem;
-  if (C.sg_K == 9 && !generic) {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_band<9><<<grid, SG_T * 32, smem, c->stream>>>(a);
-  } else if (C.sg_K == 4 && !generic) {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_band<4><<<grid, SG_T * 32, smem, c->stream>>>(a);
+  // tables of a tile row in shared memory when they fit behind the band and the contribution buffer
+  const size_t NPT = (size_t)C.sg_K * SG_T * 32;
+  const size_t tab = NPT * (sizeof(double2) + sizeof(int)) + (size_t)C.sg_chunk_stride * sizeof(int2);
+  static const bool no_tab = getenv("RBC3D_SING_TAB_GLOBAL") != nullptr;
+  if (C.sg_smem + tab <= SG_SMEM_MAX && !no_tab) {
+    const size_t smem = C.sg_smem + tab;
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sing_band<true><<<grid, SG_T * 32, smem, c->stream>>>(a);
   } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_band<0><<<grid, SG_T * 32, smem, c->stream>>>(a);
+    const size_t smem = C.sg_smem;
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sing_band<false><<<grid, SG_T * 32, smem, c->stream>>>(a);
   }
   KERNEL_CHECK();
   c->launches++;
