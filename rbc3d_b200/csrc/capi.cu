@@ -141,6 +141,7 @@ static int target_list_finish(rbc3d_ctx *c, TargetList &t) {
   t.valid = true;
   t.version++;
   t.wp.valid = false;
+  t.plist_valid = false;
   return RBC3D_OK;
 }
 
@@ -365,6 +366,8 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
                          &t.ns.overflow})
       b->release();
     t.tiles.release();
+    t.plist_off.release();
+    t.plist_src.release();
     rel_cl(t.cl);
     rel_cl(t.pl);
   }
@@ -490,6 +493,7 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
   RBC_TRY(upload(C.spdetj, spdetj, sp1 * nc, c->stream));
   // source cell lists: real-space cells (HashTable_Build) and PME blocks
   RBC_TRY(celllist_build_realspace(c, C.cl, (int)Np, C.x.p, nullptr));
+  C.geom_version++;
   // PME sources: with several ranks every rank spreads a contiguous block of cells (comm.cu)
   const int *src_own = nullptr;
   if (c->prm.nranks > 1 && Np > 0) {

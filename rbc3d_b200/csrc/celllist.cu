@@ -117,6 +117,17 @@ int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const
   return sort_by_cell(c, cl, n, ncells);
 }
 
+int device_exclusive_scan(rbc3d_ctx *c, int *data, int n) {
+  static dbuf<char> tmp;  // grow-only scratch (one context per process and device in practice)
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, data, data, n, c->stream);
+  RBC_TRY(tmp.resize(bytes + 256));
+  size_t avail = tmp.n;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, avail, data, data, n, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
 // ---- warp tiles of the pair kernel: (cell, first sorted position), <= 32 targets each ----
 __global__ void k_tile_count(int ncells, const int *__restrict__ start, int *__restrict__ ntile) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;

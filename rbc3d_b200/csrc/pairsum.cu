@@ -6,6 +6,8 @@
 // Layout: sources sorted by real-space cell (SoA, FP64); one warp per tile of <= 32 targets of one cell, lane =
 // target, the 27 neighbour cells are walked with warp-uniform source loads, the range test is bit-exact
 // (norm2_exact / min_image / rc2_thr) and the kernel evaluation is predicated per lane.
+#include <algorithm>
+
 #include "device_math.cuh"
 #include "rbc3d_internal.h"
 
@@ -66,6 +68,10 @@ __device__ __forceinline__ void walk_neighbours(const Params &prm, const int *__
         n1 = n1 < 0 ? n1 + Nc1 : (n1 >= Nc1 ? n1 - Nc1 : n1);
         const int nc = n1 + Nc1 * (n2 + Nc2 * n3);
         const int jb = sstart[nc], je = sstart[nc + 1];
+        // sources of a cell are in ascending index order, so its surfaces are the range [first, last]: a cell that
+        // holds only the excluded surface (the usual case in a dilute suspension) is skipped without loading it
+        if (excl_cell >= 0 && je > jb && __ldg(sorder + jb) / npc == excl_cell && __ldg(sorder + je - 1) / npc == excl_cell)
+          continue;
         for (int j0 = jb; j0 < je; j0 += 32) {
           const int jl = j0 + lane;
           const bool have = jl < je;
@@ -110,8 +116,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(PairArgs a) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * PAIR_WARPS + warp;
-  if (tile >= a.ntiles) return;
+  // persistent CTAs: the lookup tables are staged once per CTA, warps stride over the target tiles
+  for (int tile = blockIdx.x * PAIR_WARPS + warp; tile < a.ntiles; tile += gridDim.x * PAIR_WARPS) {
   const int2 tl = a.tiles[tile];
   const int c = tl.x;
   const int kend = min(tl.y + 32, a.tstart[c + 1]);
@@ -197,6 +203,170 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(PairArgs a) {
     acc[(size_t)a.nt + ti] += a.c1 * ay + a.c2 * by;
     acc[2 * (size_t)a.nt + ti] += a.c1 * az + a.c2 * bz;
   }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-geometry pair lists.  Between cells of different surfaces (and for off-surface targets) only a small part of
+// the sources in the 27 neighbour cells is within rc of ANY target of a tile.  The geometry is fixed across the GMRES
+// matvecs of a time step, so the walk is done once per geometry (k_pair_scan: count, then fill, in walk order) and
+// every operator application only visits the listed (tile, source) entries (k_pair_list).  Same arithmetic and
+// summation order as k_pair.
+template <bool FILL, bool EXCL>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_scan(PairArgs a, int *__restrict__ cnt,
+                                                                const int *__restrict__ off, int *__restrict__ src) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * PAIR_WARPS + warp;
+  if (tile >= a.ntiles) return;
+  const int2 tl = a.tiles[tile];
+  const int c = tl.x;
+  const int kend = min(tl.y + 32, a.tstart[c + 1]);
+  const int k = tl.y + lane;
+  const bool valid = k < kend;
+  const int ti = valid ? a.torder[k] : 0;
+  double xi = 0, yi = 0, zi = 0;
+  int my_cell = -2;
+  if (valid) {
+    xi = a.tx[ti];
+    yi = a.tx[(size_t)a.nt + ti];
+    zi = a.tx[2 * (size_t)a.nt + ti];
+    my_cell = a.tsurf[ti];
+  }
+  int excl = -2;
+  if (EXCL) {
+    const int c0 = __shfl_sync(FULL_MASK, my_cell, __ffs(__ballot_sync(FULL_MASK, valid)) - 1);
+    if (__all_sync(FULL_MASK, !valid || my_cell == c0)) excl = c0;
+  }
+  int n = 0;
+  const int o = FILL ? off[tile] : 0;
+  walk_neighbours(a.prm, a.sstart, a.sx, a.sorder, a.Np, a.npc, c, valid, xi, yi, zi, excl,
+                  [&](int j, int pj, double, double, double, double, bool in) {
+                    const int cj = pj / a.npc;
+                    if (__any_sync(FULL_MASK, in && !(EXCL && cj == my_cell))) {
+                      if (FILL && lane == 0) src[o + n] = j;
+                      n++;
+                    }
+                  });
+  if (!FILL && lane == 0) cnt[tile] = n;
+}
+
+template <bool SL, bool DL, bool EXCL>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_list(PairArgs a, const int *__restrict__ off,
+                                                                const int *__restrict__ src) {
+  extern __shared__ double smem[];
+  double *s_dl = smem;
+  double *s_sl = smem + (DL ? (RBC3D_NTAB + 1) : 0);
+  for (int i = threadIdx.x; i <= RBC3D_NTAB; i += blockDim.x) {
+    if (DL) s_dl[i] = a.tab_dl[i];
+    if (SL) {
+      s_sl[2 * i] = a.tab_sl[2 * i];
+      s_sl[2 * i + 1] = a.tab_sl[2 * i + 1];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double r_eps2 = a.prm.r_eps * a.prm.r_eps;
+  const int nlonh = a.nlon / 2 + 1;
+  const size_t Np = a.Np;
+  const double *__restrict__ sy = a.sx + Np;
+  const double *__restrict__ sz = a.sx + 2 * Np;
+  for (int tile = blockIdx.x * PAIR_WARPS + warp; tile < a.ntiles; tile += gridDim.x * PAIR_WARPS) {
+    const int eb = off[tile], ee = off[tile + 1];
+    if (eb == ee) continue;
+    const int2 tl = a.tiles[tile];
+    const int c = tl.x;
+    const int kend = min(tl.y + 32, a.tstart[c + 1]);
+    const int k = tl.y + lane;
+    const bool valid = k < kend;
+    const int ti = valid ? a.torder[k] : 0;
+    double xi = 0, yi = 0, zi = 0;
+    int my_cell = -2, my_lat = 0, my_lon = 0;
+    if (valid) {
+      xi = a.tx[ti];
+      yi = a.tx[(size_t)a.nt + ti];
+      zi = a.tx[2 * (size_t)a.nt + ti];
+      my_cell = a.tsurf[ti];
+      if (my_cell >= 0) {
+        int rem = ti - my_cell * a.npc;
+        my_lon = rem / a.nlat;
+        my_lat = rem - my_lon * a.nlat;
+      }
+    }
+    double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+    for (int e0 = eb; e0 < ee; e0 += 32) {
+      // 32 listed sources at a time: lane = source for the loads, then handed round with shuffles
+      const int el = e0 + lane;
+      const bool have = el < ee;
+      int jl = 0, pjl = -1;
+      double xs = 0, ys = 0, zs = 0;
+      if (have) {
+        jl = __ldg(src + el);
+        xs = __ldg(a.sx + jl);
+        ys = __ldg(sy + jl);
+        zs = __ldg(sz + jl);
+        pjl = __ldg(a.sorder + jl);
+      }
+      const int nb = min(32, ee - e0);
+      for (int b = 0; b < nb; b++) {
+        const int j = __shfl_sync(FULL_MASK, jl, b);
+        const int pj = __shfl_sync(FULL_MASK, pjl, b);
+        const double xx = min_image(__dsub_rn(__shfl_sync(FULL_MASK, xs, b), xi), a.prm.iLb[0], a.prm.Lb[0]);
+        const double yy = min_image(__dsub_rn(__shfl_sync(FULL_MASK, ys, b), yi), a.prm.iLb[1], a.prm.Lb[1]);
+        const double zz = min_image(__dsub_rn(__shfl_sync(FULL_MASK, zs, b), zi), a.prm.iLb[2], a.prm.Lb[2]);
+        const double r2 = norm2_exact(xx, yy, zz);
+        const bool in = valid && !(r2 > a.prm.rc2_thr);
+        const int cj = pj / a.npc;
+        if (in && r2 >= r_eps2 && !(EXCL && cj == my_cell)) {
+          double om = 1.0;  // 1 - mask
+          if (!EXCL && cj == my_cell) {
+            int rem = pj - cj * a.npc;
+            int lon_j = rem / a.nlat, lat_j = rem - lon_j * a.nlat;
+            int dl = abs(my_lon - lon_j);
+            dl = min(dl, a.nlon - dl);
+            int pair = my_lat * a.nlat + lat_j;
+            if (dl <= __ldg(a.dlonmax + pair)) om = __ldg(a.omm + (size_t)pair * nlonh + dl);
+          }
+          const double rinv = rsqrt_pos(r2);
+          const double r = r2 * rinv;
+          const double s = r * a.prm.tab_scale;
+          const int i = (int)s;
+          if (i < RBC3D_NTAB) {
+            const double fr = s - (double)i;
+            if (SL) {
+              const double t10 = s_sl[2 * i], t20 = s_sl[2 * i + 1], t11 = s_sl[2 * i + 2], t21 = s_sl[2 * i + 3];
+              const double e1 = fma(fr, t11 - t10, t10), e2 = fma(fr, t21 - t20, t20);
+              const double ir2 = rinv * rinv;
+              const double EA = e1 * rinv * ir2 + e2 * ir2;  // ModEwaldFunc.F90:126-127
+              const double EB = e1 * rinv - e2;
+              const double fx = __ldg(a.sf + j), fy = __ldg(a.sf + Np + j), fz = __ldg(a.sf + 2 * Np + j);
+              const double xf = EA * (xx * fx + yy * fy + zz * fz);
+              ax += om * (xf * xx + EB * fx);
+              ay += om * (xf * yy + EB * fy);
+              az += om * (xf * zz + EB * fz);
+            }
+            if (DL) {
+              const double t0 = s_dl[i], t1 = s_dl[i + 1];
+              const double e = fma(fr, t1 - t0, t0);
+              const double ir2 = rinv * rinv;
+              const double EA = e * ir2 * ir2 * rinv;  // c1 / r^5, ModEwaldFunc.F90:174
+              const double gx = __ldg(a.sgB + j), gy = __ldg(a.sgB + Np + j), gz = __ldg(a.sgB + 2 * Np + j);
+              const double nx = __ldg(a.sa3 + j), ny = __ldg(a.sa3 + Np + j), nz = __ldg(a.sa3 + 2 * Np + j);
+              const double q = om * EA * (xx * gx + yy * gy + zz * gz) * (xx * nx + yy * ny + zz * nz);
+              bx += q * xx;
+              by += q * yy;
+              bz += q * zz;
+            }
+          }
+        }
+      }
+    }
+    if (valid) {
+      double *acc = a.acc;
+      acc[ti] += a.c1 * ax + a.c2 * bx;
+      acc[(size_t)a.nt + ti] += a.c1 * ay + a.c2 * by;
+      acc[2 * (size_t)a.nt + ti] += a.c1 * az + a.c2 * bz;
+    }
+  }
 }
 
 static void fill_args(rbc3d_ctx *c, TargetList &t, PairArgs &a) {
@@ -237,24 +407,76 @@ int pair_sum(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
   a.c2 = c2;
   const bool sl = (c1 != 0), dl = (c2 != 0);  // ModIntOnRbcs.F90:91,99 test c /= 0 exactly
   if (!sl && !dl) return RBC3D_OK;
-  const int grid = (t.ntiles + PAIR_WARPS - 1) / PAIR_WARPS;
   const size_t sm = sizeof(double) * (RBC3D_NTAB + 1) * ((dl ? 1 : 0) + (sl ? 2 : 0));
+  // persistent grid: as many CTAs as fit (shared memory bound), a few waves of tiles each
+  const int per_sm = std::max(1, std::min(8, (int)((size_t)(227 * 1024) / (sm + 1024))));
+  const int grid = std::min((t.ntiles + PAIR_WARPS - 1) / PAIR_WARPS, c->sm_count * per_sm);
   const bool excl = pairself_available(c, t);  // same-surface pairs: dense per-cell kernel (pairself.cu)
+  static const bool no_list = getenv("RBC3D_PAIR_NO_LIST") != nullptr;
+  const bool use_list = !no_list && (excl || t.kind != RBC3D_TL_CELLS);
+  if (use_list) {
+    // (tile, source) entries with a source within rc of a target of the tile: once per geometry
+    if (!t.plist_valid || t.plist_excl != (int)excl || t.plist_geom != c->cells.geom_version) {
+      const int sgrid = (t.ntiles + PAIR_WARPS - 1) / PAIR_WARPS;
+      RBC_TRY(t.plist_off.resize((size_t)t.ntiles + 2));
+      CUDA_TRY(cudaMemsetAsync(t.plist_off.p, 0, sizeof(int) * ((size_t)t.ntiles + 2), c->stream));
+      if (excl)
+        k_pair_scan<false, true><<<sgrid, PAIR_WARPS * 32, 0, c->stream>>>(a, t.plist_off.p, nullptr, nullptr);
+      else
+        k_pair_scan<false, false><<<sgrid, PAIR_WARPS * 32, 0, c->stream>>>(a, t.plist_off.p, nullptr, nullptr);
+      KERNEL_CHECK();
+      RBC_TRY(device_exclusive_scan(c, t.plist_off.p, t.ntiles + 1));
+      int nent = 0;
+      CUDA_TRY(cudaMemcpyAsync(&nent, t.plist_off.p + t.ntiles, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      RBC_TRY(t.plist_src.resize(nent > 0 ? nent : 1));
+      if (nent > 0) {
+        if (excl)
+          k_pair_scan<true, true><<<sgrid, PAIR_WARPS * 32, 0, c->stream>>>(a, nullptr, t.plist_off.p, t.plist_src.p);
+        else
+          k_pair_scan<true, false><<<sgrid, PAIR_WARPS * 32, 0, c->stream>>>(a, nullptr, t.plist_off.p, t.plist_src.p);
+        KERNEL_CHECK();
+      }
+      c->launches += 3;
+      t.plist_n = nent;
+      t.plist_valid = true;
+      t.plist_excl = (int)excl;
+      t.plist_geom = c->cells.geom_version;
+    }
+    if (t.plist_n > 0) {
+#define LAUNCH_LIST(SL_, DL_, EX_)                                                                                  \
+  do {                                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(k_pair_list<SL_, DL_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_pair_list<SL_, DL_, EX_><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a, t.plist_off.p, t.plist_src.p);         \
+  } while (0)
+      if (sl && dl) {
+        if (excl) LAUNCH_LIST(true, true, true); else LAUNCH_LIST(true, true, false);
+      } else if (sl) {
+        if (excl) LAUNCH_LIST(true, false, true); else LAUNCH_LIST(true, false, false);
+      } else {
+        if (excl) LAUNCH_LIST(false, true, true); else LAUNCH_LIST(false, true, false);
+      }
+#undef LAUNCH_LIST
+      KERNEL_CHECK();
+      c->launches++;
+    }
+  } else {
 #define LAUNCH_PAIR(SL_, DL_, EX_)                                                                              \
   do {                                                                                                          \
     CUDA_TRY(cudaFuncSetAttribute(k_pair<SL_, DL_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
     k_pair<SL_, DL_, EX_><<<grid, PAIR_WARPS * 32, sm, c->stream>>>(a);                                        \
   } while (0)
-  if (sl && dl) {
-    if (excl) LAUNCH_PAIR(true, true, true); else LAUNCH_PAIR(true, true, false);
-  } else if (sl) {
-    if (excl) LAUNCH_PAIR(true, false, true); else LAUNCH_PAIR(true, false, false);
-  } else {
-    if (excl) LAUNCH_PAIR(false, true, true); else LAUNCH_PAIR(false, true, false);
-  }
+    if (sl && dl) {
+      if (excl) LAUNCH_PAIR(true, true, true); else LAUNCH_PAIR(true, true, false);
+    } else if (sl) {
+      if (excl) LAUNCH_PAIR(true, false, true); else LAUNCH_PAIR(true, false, false);
+    } else {
+      if (excl) LAUNCH_PAIR(false, true, true); else LAUNCH_PAIR(false, true, false);
+    }
 #undef LAUNCH_PAIR
-  KERNEL_CHECK();
-  c->launches++;
+    KERNEL_CHECK();
+    c->launches++;
+  }
   if (excl) RBC_TRY(pairself_apply(c, t, c1, c2));
   return RBC3D_OK;
 }

@@ -139,6 +139,11 @@ struct TargetList {
   dbuf<double> host_io; // staging for host v
   WallPairs wp;
   long long version = 0; // bumped whenever the list is rebuilt
+  // per-geometry (tile, source) pair list of the real-space sum over other surfaces (pairsum.cu)
+  bool plist_valid = false;
+  int plist_excl = -1, plist_n = 0;
+  long long plist_geom = -1;
+  dbuf<int> plist_off, plist_src;
 };
 
 // walls (walls.cu): t_Wall arrays of all walls back to back + slist_wall + the self-interaction matrices
@@ -163,6 +168,7 @@ struct Walls {
 struct Cells {
   int ncell = 0, nlat = 0, nlon = 0, npc = 0, Np = 0;
   bool mesh_set = false, geom_set = false, f_set = false, g_set = false;
+  long long geom_version = 0;  // bumped by every SourceList_UpdateCoord
   std::vector<double> h_th, h_phi, h_w, h_A, h_B, h_area, h_mesh;
   dbuf<double> th, phi, w, A, B, area, meshSize;
   dbuf<double> x, a3, f, g;          // SoA(3,Np), original order (f, g already * detJ*w)
@@ -256,6 +262,7 @@ void h_gauleg(double x1, double x2, int n, double *x, double *w);
 int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
 int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3]);
 int tiles_build(rbc3d_ctx *c, TargetList &t);
+int device_exclusive_scan(rbc3d_ctx *c, int *data, int n);  // in place
 
 // ---- real-space operator (pairsum.cu, singular.cu, nearsing.cu) ----
 int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g);
