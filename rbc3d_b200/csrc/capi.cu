@@ -344,6 +344,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.sg_idx.release();
   C.sg_tile_list.release();
   C.sg_rounds.release();
+  C.sg_active_list.release();
   C.sg_chunk.release();
   C.sg_pos.release();
   C.sg_cell_active.release();

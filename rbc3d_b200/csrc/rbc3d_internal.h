@@ -190,7 +190,8 @@ struct Cells {
   int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
   dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active, sg_tile_list, sg_pos;
   int sg_ntl = 0, sg_ntn = 0, sg_ni_max = 0, sg_chunk_stride = 0;
-  dbuf<int> sg_rounds;
+  dbuf<int> sg_rounds, sg_active_list;
+  int sg_nactive = 0;
   dbuf<int2> sg_chunk;
   size_t sg_smem = 0;
   dbuf<double> sg_st;                // (s, t) pairs

@@ -271,17 +271,18 @@ struct CacheArgs {
   const double *spx, *spa3;
   const int *row_tgt;
   const int *pos;  // [tile row][K][T][32] -> position in the tile's sorted order
+  const int *active_list;  // [slot] -> cell
   const double *tab_dl;
-  double4 *cache;  // [cell][tile][sorted position]
+  double4 *cache;  // [slot of an active cell][tile][sorted position]
 };
 
 __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, cell = blockIdx.y;
+  const int tile = blockIdx.x, slot = blockIdx.y, cell = a.active_list[slot];
   const int tl = tile / a.ntn, tn = tile - tl * a.ntn;
   const int pt0 = a.row_tgt[tl * SG_T + w];
   const int NPT = a.K * SG_T * 32;
-  double4 *out = a.cache + ((size_t)cell * gridDim.x + tile) * NPT;
+  double4 *out = a.cache + ((size_t)slot * gridDim.x + tile) * NPT;
   const int *pos = a.pos + (size_t)tl * NPT;
   if (pt0 < 0) return;  // no target in this slot: its cache entries do not exist
   const int pt = pt0 + tn * SG_TLON * a.nlat;
@@ -345,7 +346,7 @@ struct BandArgs {
   const double4 *cache;    // [cell][tile][sorted position]
   const double *Bcell;
   const int *active;
-  const int *cell_active;  // per cell: any active target
+  const int *active_list;  // [slot] -> cell with active targets (the cache is indexed by slot)
   double c2;
   double *acc;
 };
@@ -369,8 +370,8 @@ template <bool TAB_SMEM>  // the row's chunk / point tables in shared memory (wh
 __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int cell = blockIdx.x / a.ntl, tl = blockIdx.x - cell * a.ntl;
-  if (!a.cell_active[cell]) return;  // block-uniform
+  const int slot = blockIdx.x / a.ntl, tl = blockIdx.x - slot * a.ntl;
+  const int cell = a.active_list[slot];
   const int ilo = a.row_win[tl * 2 + 0], ni = a.row_win[tl * 2 + 1];
   const int m = 2 * a.nlat, n = a.nlon, plane = m * n;
   const int K = a.K, NPT = K * SG_T * 32;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
     __syncthreads();
   }
   auto ld_tab = [&](auto *ptr) { return TAB_SMEM ? *ptr : __ldg(ptr); };
-  const double4 *cg = a.cache + ((size_t)cell * a.ntl * a.ntn + (size_t)tl * a.ntn) * NPT;
+  const double4 *cg = a.cache + ((size_t)slot * a.ntl * a.ntn + (size_t)tl * a.ntn) * NPT;
   // first round of the first tile in flight before the band is staged
   int2 ch_next = ld_tab(chunk);
   double4 c_next[SG_PC];
@@ -533,6 +534,17 @@ int cells_active_flags(rbc3d_ctx *c) {
   k_cell_active<<<(C.Np + 255) / 256, 256, 0, c->stream>>>(C.Np, C.npc, t.active.p, C.sg_cell_active.p);
   KERNEL_CHECK();
   c->launches++;
+  // compact list of the cells this rank owns targets of: the singular cache and its kernel only cover those
+  std::vector<int> flags(C.ncell), list;
+  CUDA_TRY(cudaMemcpyAsync(flags.data(), C.sg_cell_active.p, sizeof(int) * C.ncell, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < C.ncell; i++)
+    if (flags[i]) list.push_back(i);
+  C.sg_nactive = (int)list.size();
+  RBC_TRY(C.sg_active_list.resize(list.size() > 0 ? list.size() : 1));
+  if (!list.empty())
+    CUDA_TRY(cudaMemcpyAsync(C.sg_active_list.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
 
@@ -542,14 +554,15 @@ int singular_prepare(rbc3d_ctx *c) {
   C.sg_cache_ok = false;
   if (!C.sg_ok || C.Np == 0 || c->sing_cache_mode == 0) return RBC3D_OK;
   const size_t per_cell = (size_t)C.sg_ntiles * C.sg_K * SG_T * 32;
-  const size_t need = per_cell * C.ncell * sizeof(double4);
-  if (C.sg_cache.n < per_cell * C.ncell) {
+  const size_t ncache = (size_t)std::max(C.sg_nactive, 1);
+  const size_t need = per_cell * ncache * sizeof(double4);
+  if (C.sg_cache.n < per_cell * ncache) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     // leave room for the interleaved density spline and the rest of the working set
     const size_t reserve = (size_t)C.ncell * 12 * 2 * C.nlat * C.nlon * 8 * 2 + ((size_t)2 << 30);
     if (need + reserve > free_b + C.sg_cache.n * sizeof(double4)) return RBC3D_OK;  // direct kernel
-    if (C.sg_cache.resize(per_cell * C.ncell) != RBC3D_OK) return RBC3D_OK;
+    if (C.sg_cache.resize(per_cell * ncache) != RBC3D_OK) return RBC3D_OK;
   }
   CacheArgs a;
   a.prm = c->prm;
@@ -572,12 +585,12 @@ int singular_prepare(rbc3d_ctx *c) {
   a.pos = C.sg_pos.p;
   a.tab_dl = c->tab_dl.p;
   a.cache = C.sg_cache.p;
-  // 65535 limit of gridDim.y: chunk the cells
-  for (int c0 = 0; c0 < C.ncell; c0 += 32768) {
+  a.active_list = C.sg_active_list.p;
+  // 65535 limit of gridDim.y: chunk the active cells
+  for (int c0 = 0; c0 < C.sg_nactive; c0 += 32768) {
     CacheArgs b = a;
-    const int nc = std::min(32768, C.ncell - c0);
-    b.spx = a.spx + (size_t)12 * 2 * C.nlat * C.nlon * c0;
-    b.spa3 = a.spa3 + (size_t)12 * 2 * C.nlat * C.nlon * c0;
+    const int nc = std::min(32768, C.sg_nactive - c0);
+    b.active_list = a.active_list + c0;
     b.cache = a.cache + per_cell * c0;
     k_sing_cache_build<<<dim3(C.sg_ntiles, nc), SG_T * 32, 0, c->stream>>>(b);
     KERNEL_CHECK();
@@ -623,10 +636,11 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   a.cache = C.sg_cache.p;
   a.Bcell = C.B.p;
   a.active = t.active.p;
-  a.cell_active = C.sg_cell_active.p;
+  a.active_list = C.sg_active_list.p;
   a.c2 = c2;
   a.acc = t.acc.p;
-  const int grid = C.ncell * C.sg_ntl;
+  const int grid = C.sg_nactive * C.sg_ntl;
+  if (grid == 0) return RBC3D_OK;
   // tables of a tile row in shared memory when they fit behind the band and the contribution buffer
   const size_t NPT = (size_t)C.sg_K * SG_T * 32;
   const size_t tab = NPT * (sizeof(double2) + sizeof(int)) + (size_t)C.sg_chunk_stride * sizeof(int2);
