@@ -227,7 +227,9 @@ def kernel_table(op, sus, ms, npairs, peaks, world=1):
     add("kspace_scale", ms["kspace"], bytes_=(6 + 3) * 16.0 * M, bound="hbm")
     add("fft_inv(cuFFT Z2D x3)", ms["fft_inv"], bytes_=3 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
     add("interp", ms["interp"], flops=N * P3 * 8.0, bytes_=3 * 8.0 * G + 56.0 * N)
-    add("density_gather", ms["density"], bytes_=(3 * 8 * 2 + 4 + 8) * N, bound="hbm")
+    # SourceList_UpdateDensity gather + (device splines) spline(g detJ): 2 x 4 x 3 x 72 x 72 doubles written per cell
+    add("density(gather + spline build)", ms["density"],
+        bytes_=(3 * 8 * 2 + 4 + 8) * N + 2 * 12 * 8.0 * (2 * sus.nlat) * sus.nlon * (sus.ncell / world), bound="hbm")
     add("combine", ms["combine"], bytes_=(3 * 8 * 2 + 12) * N, bound="hbm")
     return rows
 
@@ -258,13 +260,18 @@ def run_gpu(args):
     t0 = time.perf_counter()
     active = op.ownership_mask(sus, world, rank) if world > 1 else None
     op.set_suspension(sus, active=active, with_f=False)
+    if not args.host_splines:
+        # Rbc_BuildSurfaceSource(gFlag) of every matvec (ModVelSolver.F90:563) on the GPU: only g crosses PCIe
+        op.enable_device_splines(sus.nlat0)
     t_setup = time.perf_counter() - t0
     N = sus.npoint
     g_host = np.ascontiguousarray(sus.weighted(sus.g))
-    spG_host = np.ascontiguousarray(sus.spG)
+    spG_host = np.ascontiguousarray(sus.spG) if args.host_splines else None
     v_host = np.zeros((3, N))
     lib = capi.load()
     for a in (g_host, spG_host, v_host):
+        if a is None:
+            continue
         capi.check(lib.rbc3d_host_register(a.ctypes.data, a.nbytes), "rbc3d_host_register")
 
     def barrier():
@@ -321,7 +328,7 @@ def run_gpu(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t[0])
     clocks = sampler.stop()
-    h2d = g_host.nbytes + spG_host.nbytes + v_host.nbytes
+    h2d = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0) + v_host.nbytes
     d2h = v_host.nbytes
 
     if rank != 0:
@@ -356,6 +363,7 @@ def run_gpu(args):
                       "alpha": op.alpha, "eps": op.eps, "P": op.P, "rc": op.rc, "Nc": op.cell_list_dims(),
                       "visc_ratio": 5.0, "seed": args.seed, "in_range_pairs": npairs,
                       "l2": "inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
+                      "density_splines": "host (uploaded)" if args.host_splines else "device (built from g every step)",
                       "partition": ("targets and PME spreading by owned cell block, sources replicated, meshes and velocities "
                                     "summed with ncclAllReduce") if world > 1 else "single GPU"},
            "clocks": clocks,
@@ -393,6 +401,8 @@ def main():
     ap.add_argument("--ref-spread-stride", type=int, default=8, help="--impl reference: spread every n-th cell")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-splines", action="store_true",
+                    help="upload spline(g detJ) from the host every step instead of building it on the GPU")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: exact --warmup, no CPU leg, 1 e2e step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.profile:

@@ -95,6 +95,12 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *ctx, const double *x, const double *a3, 
                              const int32_t *active);
 int rbc3d_cells_set_density(rbc3d_ctx *ctx, const double *f, const double *g, const double *spF,
                             const double *spG);
+/* Optional: Rbc_BuildSurfaceSource(fFlag/gFlag) on the device (ModRbc.F90:760-802: ShAnalGau + ShFilter(nlat0) +
+ * ShSynthEqu + Spline_Build_on_Sphere, ModSpline.F90:121-142, FFT_Diff, ModFFT.F90:25-93).  After this call a
+ * density passed to rbc3d_cells_set_density with a NULL spline gets its spline built on the GPU (instead of keeping
+ * the previous one), which removes the 2.16 GB spline upload per GMRES matvec at 4096 cells (the matvec only needs
+ * g, ModVelSolver.F90:560-565).  nlat0 = the cells' spherical-harmonic order (ModRbc.F90:55). */
+int rbc3d_cells_enable_device_splines(rbc3d_ctx *ctx, int nlat0);
 
 /* ---- walls ----
  * rbc3d_walls_set: SourceList_UpdateCoord(slist_wall, walls) (element centroids + cell list, ModSourceList.F90:
@@ -170,6 +176,8 @@ int rbc3d_wall_matrix_get(rbc3d_ctx *ctx, int32_t *nblk, int32_t *rowptr, int32_
  * the Duffy rule; self_skip = 1 applies the same-surface exclusion of AddIntOnWalls (:92) */
 int rbc3d_wall_neighbor_signature(rbc3d_ctx *ctx, int tlist, int self_skip, int32_t *count, uint64_t *sig,
                                   int32_t *nduffy);
+/* device copy of a density spline in the ABI layout: which = 0 spline(f detJ), 1 spline(g detJ) */
+int rbc3d_cells_get_density_spline(rbc3d_ctx *ctx, int which, double *sp);
 int rbc3d_pme_get_grid(rbc3d_ctx *ctx, double *vv /* [3][Nz][Ny][Nx] */);
 int rbc3d_get_timings(rbc3d_ctx *ctx, float ms[RBC3D_T_COUNT]);
 int rbc3d_get_launch_count(rbc3d_ctx *ctx, long long *launches);

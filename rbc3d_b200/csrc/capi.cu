@@ -344,6 +344,9 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.sg_idx.release();
   C.sg_tile_list.release();
   C.sg_rounds.release();
+  C.sb_M0.release();
+  C.sb_M1.release();
+  C.sb_cs.release();
   C.sg_active_list.release();
   C.sg_chunk.release();
   C.sg_pos.release();
@@ -469,6 +472,7 @@ int rbc3d_cells_set_mesh(rbc3d_ctx *c, int ncell, int nlat, int nlon, const doub
   RBC_TRY(singular_mesh_prepare(c, thG.data(), phiG.data()));
   RBC_TRY(pairself_mesh_prepare(c, omm));
   C.mesh_set = true;
+  C.sb_ok = false;
   C.geom_set = C.f_set = C.g_set = false;
   c->launches = 0;
   return RBC3D_OK;
@@ -537,6 +541,15 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
   return RBC3D_OK;
 }
 
+// Rbc_BuildSurfaceSource(fFlag / gFlag) on the device (ModRbc.F90:760-802): after this call a density passed to
+// rbc3d_cells_set_density WITHOUT its spline has the spline built on the GPU (SH filter to degree < nlat0 +
+// Spline_Build_on_Sphere), instead of keeping the previous one.
+int rbc3d_cells_enable_device_splines(rbc3d_ctx *c, int nlat0) {
+  if (!c || !c->cells.mesh_set) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return spline_builder_prepare(c, nlat0);
+}
+
 int rbc3d_cells_set_density(rbc3d_ctx *c, const double *f, const double *g, const double *spF, const double *spG) {
   if (!c || !c->cells.geom_set) return RBC3D_ESTATE;
   CUDA_TRY(cudaSetDevice(c->device));
@@ -554,6 +567,12 @@ int rbc3d_cells_set_density(rbc3d_ctx *c, const double *f, const double *g, cons
   if (spG) C.spGi_valid = false;
   RBC_TRY(cells_gather_sorted(c, false, f != nullptr, g != nullptr));
   if (spG) RBC_TRY(singular_density_prepare(c));
+  if (C.sb_ok) {
+    t_begin(c, RBC3D_T_DENSITY);
+    if (f && !spF) RBC_TRY(spline_build_density(c, 0));
+    if (g && !spG) RBC_TRY(spline_build_density(c, 1));
+    t_end(c, RBC3D_T_DENSITY);
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -844,7 +863,12 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   t_begin(c, RBC3D_T_DENSITY);
   if (use_cells) {
     RBC_TRY(cells_gather_sorted(c, false, c1 != 0 && c->cells.f_set, c2 != 0 && c->cells.g_set));
-    if (c2 != 0 && c1 == 0 && t->kind == RBC3D_TL_CELLS) RBC_TRY(singular_density_prepare(c));
+    if (c->cells.sb_ok) {  // the per-matvec Rbc_BuildSurfaceSource of ModVelSolver.F90:563, on the device
+      if (c1 != 0 && c->cells.f_set) RBC_TRY(spline_build_density(c, 0));
+      if (c2 != 0 && c->cells.g_set) RBC_TRY(spline_build_density(c, 1));
+    } else if (c2 != 0 && c1 == 0 && t->kind == RBC3D_TL_CELLS) {
+      RBC_TRY(singular_density_prepare(c));
+    }
   }
   t_end(c, RBC3D_T_DENSITY);
   RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
@@ -904,6 +928,17 @@ int rbc3d_nearsing_get(rbc3d_ctx *c, int tlist, int *n, int32_t *target, int32_t
   if (th0) CUDA_TRY(cudaMemcpy(th0, ns.th0.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
   if (phi0) CUDA_TRY(cudaMemcpy(phi0, ns.phi0.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
   if (dist) CUDA_TRY(cudaMemcpy(dist, ns.dist.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+  return RBC3D_OK;
+}
+
+int rbc3d_cells_get_density_spline(rbc3d_ctx *c, int which, double *sp) {
+  if (!c || !sp || !c->cells.geom_set) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Cells &C = c->cells;
+  dbuf<double> &b = which ? C.spG : C.spF;
+  const size_t n = (size_t)C.ncell * 12 * 2 * C.nlat * C.nlon;
+  if (b.n < n) return RBC3D_ESTATE;
+  CUDA_TRY(cudaMemcpy(sp, b.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return RBC3D_OK;
 }
 

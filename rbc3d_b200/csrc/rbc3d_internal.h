@@ -205,6 +205,10 @@ struct Cells {
   dbuf<unsigned char> ps_compact;
   dbuf<unsigned char> ps_needmask;   // [patch][patch]: mask table needed for this patch pair
   dbuf<int> src_own;                 // multi-GPU: 1 for the points of the cells this rank spreads
+  // density splines built on the device (splinebuild.cu)
+  bool sb_ok = false;
+  int sb_nlat0 = 0;
+  dbuf<double> sb_M0, sb_M1, sb_cs;
 };
 
 struct Pme {
@@ -283,6 +287,10 @@ int singular_density_prepare(rbc3d_ctx *c);
 int singular_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
 int linear_term(rbc3d_ctx *c, TargetList &t, double c2);
 int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate);
+
+// ---- density splines on the device (splinebuild.cu) ----
+int spline_builder_prepare(rbc3d_ctx *c, int nlat0);
+int spline_build_density(rbc3d_ctx *c, int which);
 
 // ---- PME (pme.cu) ----
 int pme_block_edge();

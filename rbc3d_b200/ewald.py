@@ -134,6 +134,16 @@ class EwaldOperator:
         f, g, spF, spG = f64(f), f64(g), f64(spF), f64(spG)
         check(self.lib.rbc3d_cells_set_density(self._h, dp(f), dp(g), dp(spF), dp(spG)), "rbc3d_cells_set_density")
 
+    def enable_device_splines(self, nlat0):
+        """Rbc_BuildSurfaceSource(fFlag/gFlag) on the GPU: densities passed without splines get them built there."""
+        check(self.lib.rbc3d_cells_enable_device_splines(self._h, int(nlat0)), "rbc3d_cells_enable_device_splines")
+
+    def get_density_spline(self, which="g"):
+        """device copy of spline(f detJ) / spline(g detJ) in the ABI layout (tests)."""
+        out = np.zeros((self.ncell, 4, 3, self.nlon, 2 * self.nlat))
+        check(self.lib.rbc3d_cells_get_density_spline(self._h, 1 if which == "g" else 0, dp(out)), "get_density_spline")
+        return out
+
     def set_suspension(self, sus, active=None, with_f=True, with_g=True):
         """Convenience: load a rbc3d_b200.synth.Suspension."""
         self.set_mesh(sus.ncell, sus.nlat, sus.nlon, sus.th, sus.phi, sus.w)

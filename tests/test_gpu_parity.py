@@ -277,3 +277,50 @@ def test_multi_gpu_parity_when_several_gpus_are_visible():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(root, "tests", "run_multi_gpu.py")], capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- density splines built on the device (Rbc_BuildSurfaceSource on the GPU) ---------------
+@pytest.fixture(scope="module")
+def dev_spline_op(sus8):
+    from rbc3d_b200.ewald import EwaldOperator
+    op = EwaldOperator(sus8.Lb)
+    op.set_mesh(sus8.ncell, sus8.nlat, sus8.nlon, sus8.th, sus8.phi, sus8.w)
+    op.enable_device_splines(sus8.nlat0)
+    op.SourceList_UpdateCoord(sus8.x, sus8.a3, sus8.Acoef, sus8.Bcoef, sus8.area, sus8.meshSize, sus8.spx, sus8.spa3,
+                              sus8.spdetj)
+    op.SourceList_UpdateDensity(f=sus8.weighted(sus8.f), g=sus8.weighted(sus8.g))   # no splines passed
+    yield op
+    op.close()
+
+
+def test_device_splines_match_host_splines(dev_spline_op, sus8):
+    """ShAnalGau + ShFilter + ShSynthEqu + Spline_Build_on_Sphere as dense operators on the GPU vs the NumPy/FFT chain"""
+    for which, ref in (("g", sus8.spG), ("f", sus8.spF)):
+        sp = dev_spline_op.get_density_spline(which)
+        for arr in range(4):     # u, u1, u2, u12 separately (different magnitudes)
+            assert rel_l2(sp[:, arr], ref[:, arr]) < 1e-12, (which, arr)
+
+
+@pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0)])
+def test_operator_with_device_splines(dev_spline_op, pair8, c1, c2):
+    _, orc = pair8
+    ref = orc.apply_cells(c1, c2, orc.cell_targets())
+    assert rel_l2(dev_spline_op.apply(c1, c2), ref) < TOL
+    dev_spline_op.apply_resident(c1, c2)
+    assert rel_l2(dev_spline_op.get_velocity(), ref) < TOL
+
+
+def test_device_splines_follow_a_new_density(dev_spline_op, sus8, oracle_lib):
+    """GMRES protocol: only g changes between matvecs (ModVelSolver.F90:560-565)"""
+    import copy
+    rng = np.random.default_rng(12)
+    sus2 = copy.copy(sus8)
+    sus2.g = sus8.g * rng.uniform(0.5, 1.5, size=(3, 1)) + 0.1 * np.roll(sus8.g, 1, axis=0)
+    from rbc3d_b200 import synth
+    synth.build_splines(sus2, sus8._builder, which=("G",))
+    dev_spline_op.SourceList_UpdateDensity(g=sus2.weighted(sus2.g))
+    assert rel_l2(dev_spline_op.get_density_spline("g"), sus2.spG) < 1e-12
+    orc = oracle_lib.Oracle(sus2.Lb).set_cells(sus2)
+    ref = orc.apply_cells(0.0, C2_MATVEC, orc.cell_targets())
+    assert rel_l2(dev_spline_op.apply(0.0, C2_MATVEC), ref) < TOL
+    dev_spline_op.SourceList_UpdateDensity(g=sus8.weighted(sus8.g))
