@@ -147,6 +147,78 @@ module ModB200
       real(c_double) :: A
       integer(c_int) :: ierr
     end function
+    function rbc3d_walls_set(ctx, nwall, nvert, nele, x, e2v, area, epsDist, active) &
+        bind(C, name="rbc3d_walls_set") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nwall
+      integer(c_int) :: nvert(*), nele(*), e2v(*), active(*)
+      real(c_double) :: x(*), area(*), epsDist(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_walls_set_traction(ctx, f) bind(C, name="rbc3d_walls_set_traction") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: f(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_wall_prepare_sing(ctx) bind(C, name="rbc3d_wall_prepare_sing") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_sing_int_on_wall(ctx, c1, iwall, v) bind(C, name="rbc3d_sing_int_on_wall") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double), value :: c1
+      integer(c_int), value :: iwall
+      real(c_double) :: v(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_add_int_on_walls(ctx, c1, tlist, v) bind(C, name="rbc3d_add_int_on_walls") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double), value :: c1
+      integer(c_int), value :: tlist
+      real(c_double) :: v(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_min_dist_to_tri(ctx, n, xtar, xtri, dist, s0, t0) bind(C, name="rbc3d_min_dist_to_tri") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: n
+      real(c_double) :: xtar(*), xtri(*), dist(*), s0(*), t0(*)
+      integer(c_int) :: ierr
+    end function
+    ! two Fortran views of the same C symbol: s0/t0/lhs may be NULL (c_ptr, by value) or arrays
+    function rbc3d_tri_int(ctx, n, xtri, ftri, xtar, s0, t0, rhs, lhs) bind(C, name="rbc3d_tri_int") result(ierr)
+      import
+      type(c_ptr), value :: ctx, s0, t0
+      integer(c_int), value :: n
+      real(c_double) :: xtri(*), ftri(*), xtar(*), rhs(*), lhs(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_tri_int_rhs(ctx, n, xtri, ftri, xtar, s0, t0, rhs, lhs) bind(C, name="rbc3d_tri_int") result(ierr)
+      import
+      type(c_ptr), value :: ctx, s0, t0, lhs
+      integer(c_int), value :: n
+      real(c_double) :: xtri(*), ftri(*), xtar(*), rhs(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_cells_enable_device_splines(ctx, nlat0) bind(C, name="rbc3d_cells_enable_device_splines") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nlat0
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_apply_assign(ctx, c1, c2, use_cells, use_walls, tlist, v) bind(C, name="rbc3d_apply_assign") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double), value :: c1, c2
+      integer(c_int), value :: use_cells, use_walls, tlist
+      real(c_double) :: v(*)
+      integer(c_int) :: ierr
+    end function
     function rbc3d_last_error() bind(C, name="rbc3d_last_error") result(msg)
       import
       type(c_ptr) :: msg
@@ -249,6 +321,47 @@ contains
     ierr = rbc3d_cells_set_density(b200_ctx, pf, pg, psf, psg)
     call B200_Check(ierr, 'rbc3d_cells_set_density')
   end subroutine B200_SyncDensity
+
+  ! SourceList_UpdateCoord(slist_wall, walls) + TargetList_Update(tlist_wall, walls): wall meshes are static, so this
+  ! runs once (from PrepareSingIntOnWall).  tlist_wall%x is the concatenation of wall%x the ABI expects; e2v, area
+  ! and epsDist are packed wall after wall.
+  subroutine B200_SyncWalls
+    integer(c_int), allocatable :: nv(:), ne(:), e2v(:), act(:)
+    real(WP), allocatable :: area(:), eps(:)
+    integer :: iwall, NE, p, l, ierr
+    allocate (nv(nwall), ne(nwall))
+    do iwall = 1, nwall
+      nv(iwall) = walls(iwall)%nvert; ne(iwall) = walls(iwall)%nele
+    end do
+    NE = sum(ne)
+    allocate (e2v(3*NE), area(NE), eps(NE), act(tlist_wall%nPoint))
+    p = 0
+    do iwall = 1, nwall
+      do l = 1, 3
+        e2v((l - 1)*NE + p + 1:(l - 1)*NE + p + ne(iwall)) = walls(iwall)%e2v(:, l)
+      end do
+      area(p + 1:p + ne(iwall)) = walls(iwall)%area
+      eps(p + 1:p + ne(iwall)) = walls(iwall)%epsDist
+      p = p + ne(iwall)
+    end do
+    act = merge(1, 0, tlist_wall%active)
+    ierr = rbc3d_walls_set(b200_ctx, nwall, nv, ne, tlist_wall%x, e2v, area, eps, act)
+    call B200_Check(ierr, 'rbc3d_walls_set')
+  end subroutine B200_SyncWalls
+
+  ! wall%f of every wall, concatenated like tlist_wall%x
+  subroutine B200_SyncWallTraction
+    real(WP), allocatable :: f(:, :)
+    integer :: iwall, p, ierr
+    allocate (f(tlist_wall%nPoint, 3))
+    p = 0
+    do iwall = 1, nwall
+      f(p + 1:p + walls(iwall)%nvert, :) = walls(iwall)%f
+      p = p + walls(iwall)%nvert
+    end do
+    ierr = rbc3d_walls_set_traction(b200_ctx, f)
+    call B200_Check(ierr, 'rbc3d_walls_set_traction')
+  end subroutine B200_SyncWallTraction
 
   ! t_spline (ModDataStruct.F90:37-43) u, u1, u2, u12 (0:m-1, 0:n-1, nvar) -> [4][nvar][n][m], m fastest
   subroutine PackSpline(spln, nvar, buf)

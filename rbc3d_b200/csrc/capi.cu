@@ -854,6 +854,20 @@ int rbc3d_apply(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls
   return v_roundtrip_end(c, *t, v);
 }
 
+// v = operator (not accumulated): the caller's "v = 0" before AddIntOnRbcs (ModVelSolver.F90:473,571) is part of the
+// call, so v is never uploaded
+int rbc3d_apply_assign(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls, int tlist, double *v) {
+  TargetList *t;
+  RBC_TRY(get_tl(c, tlist, &t));
+  RBC_TRY(begin_apply(c, *t));
+  RBC_TRY(t->host_io.resize(3 * (size_t)(t->n > 0 ? t->n : 1)));
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  t_begin(c, RBC3D_T_COMBINE);
+  RBC_TRY(combine(c, *t, t->host_io.p, false));
+  t_end(c, RBC3D_T_COMBINE);
+  return v_roundtrip_end(c, *t, v);
+}
+
 int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls, int tlist) {
   TargetList *t;
   RBC_TRY(get_tl(c, tlist, &t));

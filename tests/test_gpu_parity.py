@@ -324,3 +324,10 @@ def test_device_splines_follow_a_new_density(dev_spline_op, sus8, oracle_lib):
     ref = orc.apply_cells(0.0, C2_MATVEC, orc.cell_targets())
     assert rel_l2(dev_spline_op.apply(0.0, C2_MATVEC), ref) < TOL
     dev_spline_op.SourceList_UpdateDensity(g=sus8.weighted(sus8.g))
+
+
+def test_apply_assign_equals_zero_then_accumulate(pair8):
+    op, _ = pair8
+    v_acc = op.apply(0.0, C2_MATVEC)                       # caller zeroes v, operator accumulates
+    v_set = op.apply_assign(0.0, C2_MATVEC, v=np.full_like(v_acc, 7.0))   # previous contents are ignored
+    assert np.array_equal(v_acc, v_set)
