@@ -35,7 +35,23 @@ namespace rbc3d {
 constexpr int SING_WARPS = 8;
 constexpr int SG_TLAT = 4, SG_TLON = 2, SG_T = SG_TLAT * SG_TLON;  // targets per tile = warps per CTA
 constexpr size_t SG_SMEM_MAX = 227 * 1024;                          // one CTA per SM
-constexpr int SG_PC = 4;  // patch points of one spline cell evaluated per thread from one load of its 4 nodes
+constexpr int SG_PC_DEFAULT = 4;  // patch points of one spline cell evaluated per thread from one load of its 4 nodes
+static int sg_nt() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_SING_NT");
+    const int q = e ? atoi(e) : 256;
+    return (q == 256 || q == 384 || q == 512) ? q : 256;
+  }();
+  return v;
+}
+static int sg_pc() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_SING_PC");
+    const int q = e ? atoi(e) : SG_PC_DEFAULT;
+    return (q == 2 || q == 3 || q == 4 || q == 6) ? q : SG_PC_DEFAULT;
+  }();
+  return v;
+}
 
 struct SingArgs {
   Params prm;
@@ -162,6 +178,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   // Tables of tile column 0 of every tile row.  The patch of (ilat, ilon) is the patch of (ilat, 0) rotated by
   // phi(ilon) about the polar axis (PolarPatch_Build, ModPolarPatch.F90:99-148: thG does not depend on phi0, phiG
   // = atan2(..) + phi0), so tile column tn uses the same tables with the phi node index advanced by tn*SG_TLON.
+  const int pc_max = sg_pc();
   std::vector<int> row_tgt((size_t)ntl * SG_T, -1), row_win((size_t)ntl * 2, 0), row_rounds(ntl, 0);
   std::vector<int> pt_dest((size_t)ntl * NPT, 0), pos((size_t)ntl * NPT, -1);
   std::vector<double> st((size_t)ntl * NPT * 2, 0.0);
@@ -212,7 +229,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
     while (sp < keys.size()) {
       const long long cellkey = keys[sp].first / NPT;
       int cnt = 0;
-      while (sp + cnt < keys.size() && cnt < SG_PC && keys[sp + cnt].first / NPT == cellkey) cnt++;
+      while (sp + cnt < keys.size() && cnt < pc_max && keys[sp + cnt].first / NPT == cellkey) cnt++;
       const int wi = (int)(cellkey % ni), j0 = (int)(cellkey / ni);
       chunks[tl].push_back(make_int2(wi | (j0 << 8) | (cnt << 18), (int)sp));
       for (int u = 0; u < cnt; u++) {
@@ -225,10 +242,10 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
       }
       sp += cnt;
     }
-    row_rounds[tl] = (int)((chunks[tl].size() + SG_T * 32 - 1) / (SG_T * 32));
+    row_rounds[tl] = (int)((chunks[tl].size() + sg_nt() - 1) / sg_nt());
     rounds_max = std::max(rounds_max, row_rounds[tl]);
   }
-  const int CH = rounds_max * SG_T * 32;  // chunk slots per tile row (empty chunks: cnt = 0)
+  const int CH = rounds_max * sg_nt();  // chunk slots per tile row (empty chunks: cnt = 0)
   std::vector<int2> chunk_tab((size_t)ntl * CH, make_int2(0, 0));
   for (int tl = 0; tl < ntl; tl++)
     for (size_t u = 0; u < chunks[tl].size(); u++) chunk_tab[(size_t)tl * CH + u] = chunks[tl][u];
@@ -366,8 +383,8 @@ __device__ __forceinline__ double4 ld_stream4(const double4 *p) {
 // registers (shared-memory traffic per patch point drops from 384 B to ~100 B).  The geometry cache of the next
 // round is in flight while the current one is evaluated.  Contributions go to a target-major shared buffer that one
 // warp per target sums in the reference's patch order.
-template <bool TAB_SMEM>  // the row's chunk / point tables in shared memory (when they fit) or read through L1
-__global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
+template <bool TAB_SMEM, int SG_PC, int NT>  // tables in shared memory (when they fit) or read through L1; NT threads
+__global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int slot = blockIdx.x / a.ntl, tl = blockIdx.x - slot * a.ntl;
@@ -386,12 +403,12 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   if (TAB_SMEM) {  // [NPT] double2, [R*256] int2, [NPT] int behind the contribution buffer
     double2 *s_st = reinterpret_cast<double2 *>(sC + (size_t)3 * NPT);
     int2 *s_ch = reinterpret_cast<int2 *>(s_st + NPT);
-    int *s_dest = reinterpret_cast<int *>(s_ch + R * SG_T * 32);
-    for (int u = tid; u < NPT; u += SG_T * 32) {
+    int *s_dest = reinterpret_cast<int *>(s_ch + R * NT);
+    for (int u = tid; u < NPT; u += NT) {
       s_st[u] = __ldg(pt_st + u);
       s_dest[u] = __ldg(pt_dest + u);
     }
-    for (int u = tid; u < R * SG_T * 32; u += SG_T * 32) s_ch[u] = __ldg(chunk - tid + u);
+    for (int u = tid; u < R * NT; u += NT) s_ch[u] = __ldg(chunk - tid + u);
     pt_st = s_st;
     pt_dest = s_dest;
     chunk = s_ch + tid;
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
   for (int p = 0; p < SG_PC; p++)
     c_next[p] = (p < (ch_next.x >> 18)) ? ld_stream4(cg + ch_next.y + p) : make_double4(0, 0, 0, 0);
   // stage the band: rows = (plane, phi column 0..n with column n = column 0), each a cyclic run of ni double2
-  for (int row = w; row < 6 * (n + 1); row += SG_T) {
+  for (int row = w; row < 6 * (n + 1); row += NT / 32) {
     const int q = row / (n + 1), wj = row - q * (n + 1);
     const int j = wj == n ? 0 : wj;
     const double2 *src = a.spGp + ((size_t)cell * 6 + q) * plane + (size_t)j * m;
@@ -417,9 +434,9 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
       dst[wi] = __ldg(src + i);
     }
   }
-  for (int u = tid; u < 3 * NPT; u += SG_T * 32) sC[u] = 0.0;  // slots beyond npatch stay zero
+  for (int u = tid; u < 3 * NPT; u += NT) sC[u] = 0.0;  // slots beyond npatch stay zero
   __syncthreads();
-  const int pt0 = a.row_tgt[tl * SG_T + w];
+  const int pt0 = w < SG_T ? a.row_tgt[tl * SG_T + w] : -1;  // warps beyond the tile's targets only evaluate chunks
   const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
   for (int tn = 0; tn < a.ntn; tn++) {
     const int jshift = tn * SG_TLON;
@@ -437,7 +454,7 @@ __global__ void __launch_bounds__(SG_T * 32, 1) k_sing_band(BandArgs a) {
           nt = tn + 1;
         }
         if (nt < a.ntn) {
-          ch_next = ld_tab(chunk + nr * SG_T * 32);
+          ch_next = ld_tab(chunk + nr * NT);
           const double4 *cgn = cg + (size_t)nt * NPT + ch_next.y;
           const int cn = ch_next.x >> 18;
 #pragma unroll
@@ -645,15 +662,31 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   const size_t NPT = (size_t)C.sg_K * SG_T * 32;
   const size_t tab = NPT * (sizeof(double2) + sizeof(int)) + (size_t)C.sg_chunk_stride * sizeof(int2);
   static const bool no_tab = getenv("RBC3D_SING_TAB_GLOBAL") != nullptr;
-  if (C.sg_smem + tab <= SG_SMEM_MAX && !no_tab) {
-    const size_t smem = C.sg_smem + tab;
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_band<true><<<grid, SG_T * 32, smem, c->stream>>>(a);
-  } else {
-    const size_t smem = C.sg_smem;
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sing_band<false><<<grid, SG_T * 32, smem, c->stream>>>(a);
+  const bool tab_smem = C.sg_smem + tab <= SG_SMEM_MAX && !no_tab;
+  const size_t smem = C.sg_smem + (tab_smem ? tab : 0);
+#define LAUNCH_BAND(TS_, PC_, NT_)                                                                                       \
+  do {                                                                                                                   \
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, PC_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_sing_band<TS_, PC_, NT_><<<grid, NT_, smem, c->stream>>>(a);                                                      \
+  } while (0)
+#define LAUNCH_BAND_NT(TS_, PC_)                      \
+  do {                                                \
+    if (sg_nt() == 512) LAUNCH_BAND(TS_, PC_, 512);   \
+    else if (sg_nt() == 384) LAUNCH_BAND(TS_, PC_, 384); \
+    else LAUNCH_BAND(TS_, PC_, 256);                  \
+  } while (0)
+  switch (sg_pc() * 2 + (tab_smem ? 1 : 0)) {
+    case 4: LAUNCH_BAND_NT(false, 2); break;
+    case 5: LAUNCH_BAND_NT(true, 2); break;
+    case 6: LAUNCH_BAND_NT(false, 3); break;
+    case 7: LAUNCH_BAND_NT(true, 3); break;
+    case 8: LAUNCH_BAND_NT(false, 4); break;
+    case 9: LAUNCH_BAND_NT(true, 4); break;
+    case 12: LAUNCH_BAND_NT(false, 6); break;
+    default: LAUNCH_BAND_NT(true, 6); break;
   }
+#undef LAUNCH_BAND_NT
+#undef LAUNCH_BAND
   KERNEL_CHECK();
   c->launches++;
   return RBC3D_OK;
