@@ -35,12 +35,22 @@ namespace rbc3d {
 constexpr int SING_WARPS = 8;
 constexpr int SG_TLAT = 4, SG_TLON = 2, SG_T = SG_TLAT * SG_TLON;  // targets per tile = warps per CTA
 constexpr size_t SG_SMEM_MAX = 227 * 1024;                          // one CTA per SM
-constexpr int SG_PC_DEFAULT = 4;  // patch points of one spline cell evaluated per thread from one load of its 4 nodes
+constexpr int SG_PC_DEFAULT = 2;  // patch points of one spline cell evaluated per thread from one load of its 4 nodes
+// 0 (default): the tile's points sorted by spline cell across its targets + shared contribution buffer; 1: every warp
+// owns one target of the tile (register accumulation, no contribution buffer, no barriers in the tile loop).  Measured
+// at 512 cells: 7.8 ms vs 8.1 ms (profiles/r01_summary)
+static int sg_per_warp() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_SING_PER_WARP");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
 static int sg_nt() {
   static const int v = [] {
     const char *e = getenv("RBC3D_SING_NT");
-    const int q = e ? atoi(e) : 256;
-    return (q == 256 || q == 384 || q == 512) ? q : 256;
+    const int q = e ? atoi(e) : SG_T * 32;
+    return (!sg_per_warp() && (q == 256 || q == 384 || q == 512)) ? q : SG_T * 32;
   }();
   return v;
 }
@@ -179,6 +189,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   // phi(ilon) about the polar axis (PolarPatch_Build, ModPolarPatch.F90:99-148: thG does not depend on phi0, phiG
   // = atan2(..) + phi0), so tile column tn uses the same tables with the phi node index advanced by tn*SG_TLON.
   const int pc_max = sg_pc();
+  const bool per_warp = sg_per_warp() != 0;
   std::vector<int> row_tgt((size_t)ntl * SG_T, -1), row_win((size_t)ntl * 2, 0), row_rounds(ntl, 0);
   std::vector<int> pt_dest((size_t)ntl * NPT, 0), pos((size_t)ntl * NPT, -1);
   std::vector<double> st((size_t)ntl * NPT * 2, 0.0);
@@ -219,19 +230,27 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
       for (int q = 0; q < npatch; q++) {
         const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
         const long long cellkey = (long long)nj1[(size_t)w * npatch + q] * ni + wi;
-        keys.push_back({cellkey * (long long)NPT + (w * K * 32 + q), w * npatch + q});
+        // per-warp mode: target first, then spline cell; tile mode: spline cell first
+        const long long major = per_warp ? (long long)w * (1LL << 24) + cellkey : cellkey;
+        keys.push_back({major * (long long)NPT + (w * K * 32 + q), w * npatch + q});
       }
     }
     std::sort(keys.begin(), keys.end());
+    std::vector<std::vector<int2>> wchunks(SG_T);
     // chunks: runs of <= SG_PC consecutive points of one spline cell; a thread evaluates one chunk per round from
     // node data it loads once
     size_t sp = 0;
     while (sp < keys.size()) {
-      const long long cellkey = keys[sp].first / NPT;
+      const long long major = keys[sp].first / NPT;
+      const long long cellkey = per_warp ? major % (1LL << 24) : major;
       int cnt = 0;
-      while (sp + cnt < keys.size() && cnt < pc_max && keys[sp + cnt].first / NPT == cellkey) cnt++;
+      while (sp + cnt < keys.size() && cnt < pc_max && keys[sp + cnt].first / NPT == major) cnt++;
       const int wi = (int)(cellkey % ni), j0 = (int)(cellkey / ni);
-      chunks[tl].push_back(make_int2(wi | (j0 << 8) | (cnt << 18), (int)sp));
+      const int2 chv = make_int2(wi | (j0 << 8) | (cnt << 18), (int)sp);
+      if (per_warp)
+        wchunks[keys[sp].second / npatch].push_back(chv);
+      else
+        chunks[tl].push_back(chv);
       for (int u = 0; u < cnt; u++) {
         const int wq = keys[sp + u].second, w = wq / npatch, q = wq - w * npatch;
         pt_dest[(size_t)tl * NPT + sp + u] = w * K * 32 + q;
@@ -241,6 +260,16 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
         pos[(size_t)tl * NPT + (k * SG_T + w) * 32 + lane] = (int)(sp + u);
       }
       sp += cnt;
+    }
+    if (per_warp) {
+      // warp w of the CTA owns target w: its chunks go to slots (round*SG_T + w)*32 + lane
+      size_t mx = 0;
+      for (int w = 0; w < SG_T; w++) mx = std::max(mx, wchunks[w].size());
+      const int R = (int)((mx + 31) / 32);
+      chunks[tl].assign((size_t)R * SG_T * 32, make_int2(0, 0));
+      for (int w = 0; w < SG_T; w++)
+        for (size_t u = 0; u < wchunks[w].size(); u++)
+          chunks[tl][((u / 32) * SG_T + w) * 32 + (u % 32)] = wchunks[w][u];
     }
     row_rounds[tl] = (int)((chunks[tl].size() + sg_nt() - 1) / sg_nt());
     rounds_max = std::max(rounds_max, row_rounds[tl]);
@@ -252,7 +281,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   C.sg_ni_max = ni_max;
   C.sg_chunk_stride = CH;
   // shared memory: band of the spline (6 double2 planes x (n+1) phi columns x ni theta rows) + contribution buffer
-  const size_t smem = (size_t)12 * ni_max * (n + 1) * sizeof(double) + (size_t)3 * NPT * sizeof(double);
+  const size_t smem = (size_t)12 * ni_max * (n + 1) * sizeof(double) + (per_warp ? 0 : (size_t)3 * NPT * sizeof(double));
   if (smem > SG_SMEM_MAX || ni_max > 255) return RBC3D_OK;  // direct kernel only
   C.sg_smem = smem;
   RBC_TRY(C.sg_tile_tgt.resize(row_tgt.size()));
@@ -383,7 +412,8 @@ __device__ __forceinline__ double4 ld_stream4(const double4 *p) {
 // registers (shared-memory traffic per patch point drops from 384 B to ~100 B).  The geometry cache of the next
 // round is in flight while the current one is evaluated.  Contributions go to a target-major shared buffer that one
 // warp per target sums in the reference's patch order.
-template <bool TAB_SMEM, int SG_PC, int NT>  // tables in shared memory (when they fit) or read through L1; NT threads
+template <bool TAB_SMEM, int SG_PC, int NT, bool PW>  // tables in shared memory (when they fit) or through L1; NT threads;
+                                                       // PW: warp = target, register accumulation
 __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -394,19 +424,19 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   const int K = a.K, NPT = K * SG_T * 32;
   const int wn = ni * (n + 1);                       // nodes of the band
   double2 *sP = reinterpret_cast<double2 *>(smem);   // [6][n+1][ni]
-  double *sC = smem + (size_t)12 * wn;               // [3][NPT] contributions, target-major
+  double *sC = smem + (size_t)12 * wn;               // [3][NPT] contributions, target-major (tile mode only)
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   const int R = a.row_rounds[tl];
   const int2 *chunk = a.chunk + (size_t)tl * a.chunk_stride + tid;
   const int *pt_dest = a.pt_dest + (size_t)tl * NPT;
   const double2 *pt_st = a.pt_st + (size_t)tl * NPT;
   if (TAB_SMEM) {  // [NPT] double2, [R*256] int2, [NPT] int behind the contribution buffer
-    double2 *s_st = reinterpret_cast<double2 *>(sC + (size_t)3 * NPT);
+    double2 *s_st = reinterpret_cast<double2 *>(sC + (PW ? 0 : (size_t)3 * NPT));
     int2 *s_ch = reinterpret_cast<int2 *>(s_st + NPT);
     int *s_dest = reinterpret_cast<int *>(s_ch + R * NT);
     for (int u = tid; u < NPT; u += NT) {
       s_st[u] = __ldg(pt_st + u);
-      s_dest[u] = __ldg(pt_dest + u);
+      if (!PW) s_dest[u] = __ldg(pt_dest + u);
     }
     for (int u = tid; u < R * NT; u += NT) s_ch[u] = __ldg(chunk - tid + u);
     pt_st = s_st;
@@ -434,7 +464,8 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
       dst[wi] = __ldg(src + i);
     }
   }
-  for (int u = tid; u < 3 * NPT; u += NT) sC[u] = 0.0;  // slots beyond npatch stay zero
+  if (!PW)
+    for (int u = tid; u < 3 * NPT; u += NT) sC[u] = 0.0;  // slots beyond npatch stay zero
   __syncthreads();
   const int pt0 = w < SG_T ? a.row_tgt[tl * SG_T + w] : -1;  // warps beyond the tile's targets only evaluate chunks
   const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
@@ -442,6 +473,7 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
     const int jshift = tn * SG_TLON;
     const int ti = cell * a.npc + pt0 + tn * SG_TLON * a.nlat;
     const bool t_on = pt0 >= 0 && lane == 0 && a.active[ti] != 0;  // requested now, needed after the rounds
+    double pvx = 0, pvy = 0, pvz = 0;  // PW: this lane's share of the target's sum
     for (int r = 0; r < R; r++) {
       const int2 ch = ch_next;
       double4 c4[SG_PC];
@@ -473,7 +505,7 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
       for (int p = 0; p < SG_PC; p++) {
         const int e = ch.y + min(p, cnt - 1);
         stq[p] = ld_tab(pt_st + e);
-        destq[p] = ld_tab(pt_dest + e);
+        destq[p] = PW ? 0 : ld_tab(pt_dest + e);
       }
       // Hermite data of the four nodes: nd[node][plane] = (u_l, u1_l) for plane 2l, (u2_l, u12_l) for plane 2l+1
       double2 n11[6], n21[6], n12[6], n22[6];
@@ -507,11 +539,28 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
           }
           const double4 c = c4[p];
           const double qd = c.w * (c.x * g[0] + c.y * g[1] + c.z * g[2]);
-          sC[dest] = qd * c.x;
-          sC[NPT + dest] = qd * c.y;
-          sC[2 * NPT + dest] = qd * c.z;
+          if (PW) {
+            pvx += qd * c.x;
+            pvy += qd * c.y;
+            pvz += qd * c.z;
+          } else {
+            sC[dest] = qd * c.x;
+            sC[NPT + dest] = qd * c.y;
+            sC[2 * NPT + dest] = qd * c.z;
+          }
         }
       }
+    }
+    if (PW) {  // fixed order: chunk order per lane, then the shuffle tree -- no barrier, warps run independently
+      pvx = warp_sum(pvx);
+      pvy = warp_sum(pvy);
+      pvz = warp_sum(pvz);
+      if (t_on) {
+        atomicAdd(a.acc + ti, c2m * pvx);
+        atomicAdd(a.acc + (size_t)a.Np + ti, c2m * pvy);
+        atomicAdd(a.acc + 2 * (size_t)a.Np + ti, c2m * pvz);
+      }
+      continue;
     }
     __syncthreads();
     // one warp per target: sum its patch in the reference's order (lane = point mod 32, then the shuffle tree)
@@ -664,16 +713,17 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   static const bool no_tab = getenv("RBC3D_SING_TAB_GLOBAL") != nullptr;
   const bool tab_smem = C.sg_smem + tab <= SG_SMEM_MAX && !no_tab;
   const size_t smem = C.sg_smem + (tab_smem ? tab : 0);
-#define LAUNCH_BAND(TS_, PC_, NT_)                                                                                       \
-  do {                                                                                                                   \
-    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, PC_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_sing_band<TS_, PC_, NT_><<<grid, NT_, smem, c->stream>>>(a);                                                      \
+#define LAUNCH_BAND(TS_, PC_, NT_, PW_)                                                                                       \
+  do {                                                                                                                        \
+    CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, PC_, NT_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_sing_band<TS_, PC_, NT_, PW_><<<grid, NT_, smem, c->stream>>>(a);                                                      \
   } while (0)
-#define LAUNCH_BAND_NT(TS_, PC_)                      \
-  do {                                                \
-    if (sg_nt() == 512) LAUNCH_BAND(TS_, PC_, 512);   \
-    else if (sg_nt() == 384) LAUNCH_BAND(TS_, PC_, 384); \
-    else LAUNCH_BAND(TS_, PC_, 256);                  \
+#define LAUNCH_BAND_NT(TS_, PC_)                                \
+  do {                                                          \
+    if (sg_per_warp()) LAUNCH_BAND(TS_, PC_, SG_T * 32, true);  \
+    else if (sg_nt() == 512) LAUNCH_BAND(TS_, PC_, 512, false); \
+    else if (sg_nt() == 384) LAUNCH_BAND(TS_, PC_, 384, false); \
+    else LAUNCH_BAND(TS_, PC_, 256, false);                     \
   } while (0)
   switch (sg_pc() * 2 + (tab_smem ? 1 : 0)) {
     case 4: LAUNCH_BAND_NT(false, 2); break;
