@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(SPR_THREADS) k_spread8(SpreadArgs a) {
   __shared__ __align__(16) double s_wz[SPREAD_CHUNK][SPR_PADW];
   __shared__ __align__(16) double s_str[SPREAD_CHUNK][NCOMP + (NCOMP & 1)];
   __shared__ int s_rel[SPREAD_CHUNK][4];
-  __shared__ double s_out[SPR_TZ * SPR_TY * SPR_TX];
+  extern __shared__ __align__(128) double s_flush[];  // [NCOMP][SPR_COLS][16] rows of the flush
   const int blk = blockIdx.x;
   const int sb = a.start[blk], se = a.start[blk + 1];
   if (sb == se) return;
@@ -338,25 +338,48 @@ __global__ void __launch_bounds__(SPR_THREADS) k_spread8(SpreadArgs a) {
       }
     }
   }
-  // flush: component by component through shared memory, then coalesced reductions into the mesh
-  const int ox = bx * SPR_BX - 7, oy = by * SPR_BY - 7, oz = bz * SPR_BZ - 7;
-  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  // flush: every thread owns the x-row of its (y,z) column in registers.  The row goes to shared memory as 16
+  // doubles [x0-8 .. x0+7] (first one a zero pad: 128-byte rows, 64-byte aligned in the mesh) and is added to the mesh
+  // by ONE bulk reduction per row and component (cp.reduce.async.bulk ... add.f64: the additions happen in L2 and
+  // cost the SM one instruction per row instead of 15 lane-wise reductions with their index arithmetic).
+  if (col) {
+    const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+    const int gy = imodulo(by * SPR_BY - 7 + ty, Ny), gz = imodulo(bz * SPR_BZ - 7 + tz, Nz);
+    const int gx0 = bx * SPR_BX - 8;  // multiple of 8; only the first block of a row wraps (gx0 = -8)
+    double *srow = s_flush + (size_t)tid * 16;
+    bool issued = false;
 #pragma unroll
-  for (int cc = 0; cc < NCOMP; cc++) {
-    __syncthreads();
-    if (col) {
+    for (int cc = 0; cc < NCOMP; cc++) {
+      bool any = false;
 #pragma unroll
-      for (int i = 0; i < SPR_TX; i++) s_out[(tz * SPR_TY + ty) * SPR_TX + i] = acc[i][cc];
-    }
-    __syncthreads();
-    double *mesh = a.mesh + (size_t)(a.comp0 + cc) * a.G;
-    for (int i = tid; i < SPR_TZ * SPR_TY * SPR_TX; i += SPR_THREADS) {
-      const double v = s_out[i];
-      if (v != 0.0) {
-        const int lx = i % SPR_TX, ly = (i / SPR_TX) % SPR_TY, lz = i / (SPR_TX * SPR_TY);
-        const int gx = imodulo(ox + lx, Nx), gy = imodulo(oy + ly, Ny), gz = imodulo(oz + lz, Nz);
-        atomicAdd(mesh + ((size_t)gz * Ny + gy) * Nx + gx, v);
+      for (int i = 0; i < SPR_TX; i++) any = any || (acc[i][cc] != 0.0);
+      if (!any) continue;
+      double *r = srow + (size_t)cc * SPR_COLS * 16;
+      r[0] = 0.0;
+#pragma unroll
+      for (int i = 0; i < SPR_TX; i++) r[1 + i] = acc[i][cc];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      double *mrow = a.mesh + (size_t)(a.comp0 + cc) * a.G + ((size_t)gz * Ny + gy) * Nx;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(r);
+      if (gx0 >= 0 && gx0 + 16 <= Nx) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;" ::"l"(mrow + gx0), "r"(sa)
+                     : "memory");
+      } else if (gx0 >= 0 || Nx < 16) {  // mesh width not a multiple of 8: the last block wraps on the right
+#pragma unroll
+        for (int i = 0; i < SPR_TX; i++)
+          if (acc[i][cc] != 0.0) atomicAdd(mrow + imodulo(gx0 + 1 + i, Nx), acc[i][cc]);
+        continue;
+      } else {  // periodic wrap of the left halo: [Nx-8, Nx) and [0, 8)
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 64;" ::"l"(mrow + Nx - 8), "r"(sa)
+                     : "memory");
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 64;" ::"l"(mrow), "r"(sa + 64)
+                     : "memory");
       }
+      issued = true;
+    }
+    if (issued) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared rows must outlive the reads
     }
   }
 }
@@ -375,13 +398,15 @@ static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
       if (pmf.flag_sl) {
         a.comp0 = 0;
         a.ncomp = 3;
-        k_spread8<3><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        CUDA_TRY(cudaFuncSetAttribute(k_spread8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SPR_COLS * 128));
+        k_spread8<3><<<nblocks, SPR_THREADS, 3 * SPR_COLS * 128, c->stream>>>(a);
         c->launches++;
       }
       if (pmf.flag_dl) {
         a.comp0 = 3;
         a.ncomp = 6;
-        k_spread8<6><<<nblocks, SPR_THREADS, 0, c->stream>>>(a);
+        CUDA_TRY(cudaFuncSetAttribute(k_spread8<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * SPR_COLS * 128));
+        k_spread8<6><<<nblocks, SPR_THREADS, 6 * SPR_COLS * 128, c->stream>>>(a);
         c->launches++;
       }
       KERNEL_CHECK();
