@@ -87,7 +87,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + link + ["-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + link + ["-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     if verbose:
         print("\n".join(log))
