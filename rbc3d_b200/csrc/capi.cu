@@ -133,7 +133,8 @@ __global__ void k_raw_target_meta(int n, int *__restrict__ surf, double *__restr
 static int target_list_finish(rbc3d_ctx *c, TargetList &t) {
   // cell lists (real-space cells, PME blocks) of the ACTIVE targets, warp tiles, near-singular geometry
   RBC_TRY(celllist_build_realspace(c, t.cl, t.n, t.x.p, t.active.p));
-  RBC_TRY(celllist_build_pme(c, t.pl, t.n, t.x.p, t.active.p, c->pme.iblk));
+  RBC_TRY(celllist_build_pme(c, t.pl, t.n, t.x.p, t.active.p, c->pme.iblk, c->pme.walk));
+  if (c->pme.walk) RBC_TRY(celllist_pme_weights(c, t.pl, t.x.p));
   RBC_TRY(tiles_build(c, t));
   RBC_TRY(t.acc.resize(3 * (size_t)(t.n > 0 ? t.n : 1)));
   RBC_TRY(t.v.resize(3 * (size_t)(t.n > 0 ? t.n : 1)));
@@ -332,6 +333,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
     l.keys_tmp.release();
     l.vals_tmp.release();
     l.cub_tmp.release();
+    l.w.release();
   };
   Cells &C = c->cells;
   for (dbuf<double> *b : {&C.th, &C.phi, &C.w, &C.A, &C.B, &C.area, &C.meshSize, &C.x, &C.a3, &C.f, &C.g, &C.spx,
@@ -509,7 +511,8 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
     KERNEL_CHECK();
     src_own = C.src_own.p;
   }
-  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own, c->pme.sblk));
+  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own, c->pme.sblk, c->pme.swalk));
+  if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, C.pl, C.x.p));
   C.geom_set = true;
   RBC_TRY(cells_gather_sorted(c, true, false, false));
   // tlist_rbc: TargetList_Update, ModTargetList.F90:95-135

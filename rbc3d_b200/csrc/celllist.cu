@@ -27,8 +27,9 @@ __global__ void k_cid_realspace(int n, const double *__restrict__ x, const int *
 
 // PME block of a point: mesh cell floor(x*Nb/Lb) (the product rounded like ModPME.F90:420-427), wrapped into
 // [0,Nb), divided by the block edge.
+// zfast: key = bz + nbz * (bx + nbx * by) -- the column walks of the P = 8 kernels (pme.cu) run along z.
 __global__ void k_cid_pme(int n, const double *__restrict__ x, const int *__restrict__ active, Params prm,
-                          int bx, int by, int bz, int nbx, int nby, int nbz, int *__restrict__ cid,
+                          int bx, int by, int bz, int nbx, int nby, int nbz, int zfast, int *__restrict__ cid,
                           int *__restrict__ count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -37,7 +38,7 @@ __global__ void k_cid_pme(int n, const double *__restrict__ x, const int *__rest
     int m0 = imodulo((int)floor(__dmul_rn(x[i], prm.ih[0])), prm.Nb[0]);
     int m1 = imodulo((int)floor(__dmul_rn(x[(size_t)n + i], prm.ih[1])), prm.Nb[1]);
     int m2 = imodulo((int)floor(__dmul_rn(x[2 * (size_t)n + i], prm.ih[2])), prm.Nb[2]);
-    c = (m0 / bx) + nbx * ((m1 / by) + nby * (m2 / bz));
+    c = zfast ? (m2 / bz) + nbz * ((m0 / bx) + nbx * (m1 / by)) : (m0 / bx) + nbx * ((m1 / by) + nby * (m2 / bz));
   }
   cid[i] = c;
   atomicAdd(&count[c], 1);
@@ -99,7 +100,8 @@ int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x,
   return sort_by_cell(c, cl, n, ncells);
 }
 
-int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3]) {
+int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3],
+                       bool zfast) {
   const Params &p = c->prm;
   int nb[3];
   for (int d = 0; d < 3; d++) nb[d] = (p.Nb[d] + blk[d] - 1) / blk[d];
@@ -111,10 +113,40 @@ int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const
     return RBC3D_OK;
   }
   k_cid_pme<<<(n + 255) / 256, 256, 0, c->stream>>>(n, x, active, p, blk[0], blk[1], blk[2], nb[0], nb[1], nb[2],
-                                                    cl.cid.p, cl.start.p);
+                                                    zfast ? 1 : 0, cl.cid.p, cl.start.p);
   KERNEL_CHECK();
   c->launches++;
   return sort_by_cell(c, cl, n, ncells);
+}
+
+// B-spline weights of the sorted points of a PME list (BSplineFunc at x*Nb/Lb, ModPME.F90:418-424), P = 8
+__global__ void k_pme_weights(int ns, int n, const int *__restrict__ order, const double *__restrict__ x, Params prm,
+                              double *__restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = i / 3, ax = i - 3 * s;
+  if (s >= ns) return;
+  const int p = order[s];
+  const double u = __dmul_rn(x[(size_t)ax * n + p], prm.ih[ax]);
+  int imin;
+  double ww[8];
+  bspline_func<8>(u, 8, imin, ww);
+  double *dst = w + (size_t)s * PME_WREC + ax * 8;
+#pragma unroll
+  for (int q = 0; q < 8; q++) dst[q] = ww[q];
+  if (ax == 0) {
+    w[(size_t)s * PME_WREC + 24] = __hiloint2double(0, imodulo(imin + 7, prm.Nb[0]));
+    w[(size_t)s * PME_WREC + 25] = 0.0;
+  }
+}
+
+int celllist_pme_weights(rbc3d_ctx *c, CellList &cl, const double *x) {
+  const int ns = cl.n_sorted;
+  RBC_TRY(cl.w.resize((size_t)(ns > 0 ? ns : 1) * PME_WREC));
+  if (ns == 0) return RBC3D_OK;
+  k_pme_weights<<<(3 * ns + 255) / 256, 256, 0, c->stream>>>(ns, cl.n, cl.order.p, x, c->prm, cl.w.p);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
 }
 
 int device_exclusive_scan(rbc3d_ctx *c, int *data, int n) {

@@ -13,6 +13,7 @@
 // y/z transforms; the scaling kernel reproduces that by Hermitian-symmetrising those two planes.
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 
 #include "device_math.cuh"
 #include "rbc3d_internal.h"
@@ -23,6 +24,7 @@ constexpr int PME_BLK = 4;   // edge of a PME block in mesh cells (y, z; and x f
 constexpr int SPR_BX = 8, SPR_BY = 4, SPR_BZ = 4;  // source blocks of the P = 8 spreading kernel
 constexpr int PME_PMAX = 8;  // largest supported B-spline support (PBspln_Ewd = 8 in every example)
 constexpr int SPREAD_CHUNK = 32;
+constexpr int SW_XR = 8;     // mesh cells per x run of the walking spread kernel (k_spread_walk)
 
 int pme_block_edge() { return PME_BLK; }
 
@@ -46,12 +48,17 @@ int pme_init(rbc3d_ctx *c) {
   pm.G = (size_t)pm.Nx * pm.Ny * pm.Nz;
   pm.M = (size_t)pm.Nxh * pm.Ny * pm.Nz;
   const int sb[3] = {SPR_BX, SPR_BY, SPR_BZ};
+  {
+    const char *e = getenv("RBC3D_SPREAD_BLOCKS");  // 1: the 8 x 4 x 4 source-block kernel (k_spread8) instead of the walk
+    pm.swalk = (p.P == 8) && !(e && atoi(e) == 1);
+  }
   for (int d = 0; d < 3; d++) {
-    pm.iblk[d] = PME_BLK;
-    pm.nblk[d] = (p.Nb[d] + PME_BLK - 1) / PME_BLK;
-    pm.sblk[d] = (p.P == 8) ? sb[d] : PME_BLK;
+    pm.iblk[d] = (p.P == 8) ? 1 : PME_BLK;  // P = 8: targets keyed by mesh cell for the column walk (k_interp_walk)
+    pm.nblk[d] = (p.Nb[d] + pm.iblk[d] - 1) / pm.iblk[d];
+    pm.sblk[d] = (p.P == 8) ? (pm.swalk ? (d == 0 ? SW_XR : 1) : sb[d]) : PME_BLK;
     pm.nsblk[d] = (p.Nb[d] + pm.sblk[d] - 1) / pm.sblk[d];
   }
+  pm.walk = (p.P == 8);
   RBC_TRY(pm.src.resize(9 * pm.G));
   RBC_TRY(pm.srcC.resize(9 * pm.M));
   RBC_TRY(pm.vvC.resize(3 * pm.M));
@@ -141,6 +148,7 @@ struct SpreadArgs {
   int nbx, nby, nbz;
   double *mesh;          // [9][G]
   size_t G;
+  const CellList *list;  // host pointer: the PME list the arguments were taken from
 };
 
 template <int NCOMP>
@@ -384,6 +392,277 @@ __global__ void __launch_bounds__(SPR_THREADS) k_spread8(SpreadArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Record staging of the P = 8 walk kernels.  A warp consumes the sorted points of its column in rounds of 8; the
+// records of round r + 1 (weights, mesh cell x, point index or strengths: geometry-time / pre-pass products read
+// exactly once) are copied global -> shared with cp.async while round r is evaluated, so no global-memory latency
+// sits on the per-point critical path.
+constexpr int WK_ROUND = 8, WK_REC = 32;  // shared record: 26 doubles of the list record, [26..29] aux, pad
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage the records of sorted points [s0, s0 + 8) (clamped to last): 13 16-byte chunks of the list record each, plus
+// either a 32-byte strength record (aux32, spreading) or the point index (order, interpolation)
+__device__ __forceinline__ void wk_stage(double *buf, int lane, int s0, int last, const double *__restrict__ wrec,
+                                         const double *__restrict__ aux32, const int *__restrict__ order) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int ch = lane + 32 * k;
+    if (ch < WK_ROUND * 13) {
+      const int slot = ch / 13, part = ch - 13 * slot;
+      const int s = min(s0 + slot, last);
+      cp_async16(buf + slot * WK_REC + 2 * part, wrec + (size_t)s * PME_WREC + 2 * part);
+    }
+  }
+  if (aux32) {
+    if (lane < 2 * WK_ROUND) {
+      const int slot = lane >> 1, part = lane & 1;
+      const int s = min(s0 + slot, last);
+      cp_async16(buf + slot * WK_REC + 26 + 2 * part, aux32 + (size_t)s * 4 + 2 * part);
+    }
+  } else if (lane < WK_ROUND) {
+    const int s = min(s0 + lane, last);
+    cp_async4(buf + lane * WK_REC + 26, order + s);
+  }
+  cp_async_commit();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// P = 8 spreading, v3: register-ring pencil walk.  One warp per (x run of 8 mesh cells, y cell, component triple);
+// its sources are sorted by z cell.  Every source of the pencil touches the same 15 x 8 (x, y) footprint, so no lane
+// ever multiplies by a padded zero weight (the block kernel k_spread8 wastes 47 % of its columns).  Lane = (y offset,
+// z-slot pair): a ring of the last 8 z planes, two slots per lane, 15 x-points x 3 components each = 90 accumulators in
+// registers.  Per source and lane: 8 multiplies for w_y w_z (strength) and 48 FMAs with w_x; the x offset of the
+// source's cell inside the run is warp-uniform and selects one of 8 unrolled bodies.  Moving up in z retires ring
+// slots: the 8 lanes that own the retiring plane write their 15-point rows to a double-buffered shared staging
+// area and add them to the mesh with one 128-byte bulk reduction per row and component (cp.reduce.async.bulk
+// add.f64, performed in L2); every row is written by the lane that issues its reduction, so no barrier is needed.
+// Weights are geometry-time records, strengths come from a pre-pass in sorted order (k_spread_strength); both are
+// staged one round ahead by wk_stage.
+constexpr int SW_WARPS = 2, SW_TX = SW_XR + 7;
+
+struct SpreadWArgs {
+  Params prm;
+  int n;
+  const int *start;          // pencil list, key = cz + Nz * (xrun + nxr * cy)
+  const double *wrec;        // [sorted source][PME_WREC]
+  const double *str;         // [sorted source][npass][4]
+  int comp0, npass, nxr;     // components [comp0, comp0 + 3 npass)
+  double *mesh;              // [9][G]
+  size_t G;
+};
+
+// strengths of the sorted sources: c1 f (pass 0 of the single layer) or c2 sym(g (x) a3 B) (diagonal, off-diagonal)
+struct StrengthArgs {
+  int ns, n, npc, dl;
+  const int *order;
+  const double *f, *g, *a3, *Bcell;
+  double c1, c2;
+  double *str;
+};
+__global__ void k_spread_strength(StrengthArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.ns) return;
+  const int p = a.order[s];
+  const size_t n = a.n;
+  if (!a.dl) {
+    double4 v = make_double4(a.c1 * a.f[p], a.c1 * a.f[n + p], a.c1 * a.f[2 * n + p], 0.0);
+    reinterpret_cast<double4 *>(a.str)[s] = v;
+  } else {
+    const double B = a.Bcell[p / a.npc];
+    const double g0 = a.g[p], g1 = a.g[n + p], g2 = a.g[2 * n + p];
+    const double n0 = a.a3[p] * B, n1 = a.a3[n + p] * B, n2 = a.a3[2 * n + p] * B;
+    double4 d = make_double4(a.c2 * (g0 * n0), a.c2 * (g1 * n1), a.c2 * (g2 * n2), 0.0);
+    double4 o = make_double4(a.c2 * (0.5 * (g0 * n1 + g1 * n0)), a.c2 * (0.5 * (g0 * n2 + g2 * n0)),
+                             a.c2 * (0.5 * (g1 * n2 + g2 * n1)), 0.0);
+    reinterpret_cast<double4 *>(a.str)[2 * (size_t)s] = d;
+    reinterpret_cast<double4 *>(a.str)[2 * (size_t)s + 1] = o;
+  }
+}
+
+template <int RX>
+__device__ __forceinline__ void sw_update(double (&A)[2][SW_TX][3], const double *__restrict__ w,
+                                          const double (&s0)[3], const double (&s1)[3]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double2 wx = reinterpret_cast<const double2 *>(w)[k];
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      A[0][RX + 2 * k][cc] = fma(wx.x, s0[cc], A[0][RX + 2 * k][cc]);
+      A[1][RX + 2 * k][cc] = fma(wx.x, s1[cc], A[1][RX + 2 * k][cc]);
+      A[0][RX + 2 * k + 1][cc] = fma(wx.y, s0[cc], A[0][RX + 2 * k + 1][cc]);
+      A[1][RX + 2 * k + 1][cc] = fma(wx.y, s1[cc], A[1][RX + 2 * k + 1][cc]);
+    }
+  }
+}
+
+// add the 15-point rows of ring column COL (3 components) of this lane to mesh rows (gy, gz) and clear them.  The rows
+// go through this lane's private staging area [3][16] (first entry a zero pad: 128-byte rows, 64-byte aligned in the
+// mesh) and leave as one bulk reduction per row; meshes narrower than 16 or a last run that wraps on the right take a
+// rolled loop of scalar reductions from the same staging rows.
+template <int COL>
+__device__ __forceinline__ void sw_flush(double (&A)[2][SW_TX][3], double *stage, const SpreadWArgs &a, int comp_first,
+                                         int gx0, int gy, int gz) {
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1];
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous flush of this lane has left the stage
+#pragma unroll
+  for (int cc = 0; cc < 3; cc++) {
+    double *r = stage + cc * 16;
+    r[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < SW_TX; i++) {
+      r[1 + i] = A[COL][i][cc];
+      A[COL][i][cc] = 0.0;
+    }
+  }
+  double *mrow = a.mesh + (size_t)comp_first * a.G + ((size_t)gz * Ny + gy) * Nx;
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
+  if ((gx0 >= 0 && gx0 + 16 <= Nx) || (gx0 < 0 && Nx >= 16)) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll 1
+    for (int cc = 0; cc < 3; cc++) {
+      double *m = mrow + (size_t)cc * a.G;
+      const unsigned sr = sa + cc * 128;
+      if (gx0 >= 0) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;" ::"l"(m + gx0), "r"(sr)
+                     : "memory");
+      } else {  // periodic wrap of the left halo: [Nx-8, Nx) and [0, 8)
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 64;" ::"l"(m + Nx - 8), "r"(sr)
+                     : "memory");
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 64;" ::"l"(m), "r"(sr + 64)
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < 3 * 16; k++) {
+      const int cc = k >> 4, i = (k & 15) - 1;
+      const double v = stage[k];
+      if (i >= 0 && v != 0.0) atomicAdd(mrow + (size_t)cc * a.G + imodulo(gx0 + 1 + i, Nx), v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a) {
+  __shared__ __align__(16) double s_rec[SW_WARPS][2][WK_ROUND * WK_REC];
+  __shared__ __align__(128) double s_fl[SW_WARPS][32][3 * 16];  // flush staging, private to a lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  const int task = blockIdx.x * SW_WARPS + warp;
+  const int pencil = task / a.npass, pass = task - pencil * a.npass;
+  if (pencil >= a.nxr * Ny) return;
+  const int *st = a.start + (size_t)pencil * Nz;
+  const int pos0 = st[0], end = st[Nz];
+  if (pos0 == end) return;
+  const double *aux = a.str + 4 * pass;  // record of point s at aux + s * 4 * npass
+  // (wk_stage addresses aux32 + s * 4: fold npass into the pointer arithmetic below)
+  const int xr = pencil % a.nxr, cy = pencil / a.nxr;
+  const int jy = lane & 7, zq = lane >> 3;
+  const int gy = imodulo(cy - 7 + jy, Ny);
+  const int gx0 = xr * SW_XR - 8;
+  const int comp_first = a.comp0 + 3 * pass;
+  auto stage = [&](double *buf, int s0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ch = lane + 32 * k;
+      if (ch < WK_ROUND * 13) {
+        const int slot = ch / 13, part = ch - 13 * slot;
+        const int s = min(s0 + slot, end - 1);
+        cp_async16(buf + slot * WK_REC + 2 * part, a.wrec + (size_t)s * PME_WREC + 2 * part);
+      }
+    }
+    if (lane < 2 * WK_ROUND) {
+      const int slot = lane >> 1, part = lane & 1;
+      const int s = min(s0 + slot, end - 1);
+      cp_async16(buf + slot * WK_REC + 26 + 2 * part, aux + (size_t)s * 4 * a.npass + 2 * part);
+    }
+    cp_async_commit();
+  };
+  stage(s_rec[warp][0], pos0);
+  double A[2][SW_TX][3];
+#pragma unroll
+  for (int col = 0; col < 2; col++)
+#pragma unroll
+    for (int i = 0; i < SW_TX; i++)
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) A[col][i][cc] = 0.0;
+  int pos = pos0, cz = 0, sprev = -64, cur_round = -1;
+  double *stg = &s_fl[warp][lane][0];
+  int zwin = 0;
+  int e = (lane < Nz) ? st[lane + 1] : end + 1;
+  for (;;) {
+    int cnt = 0;
+    if (pos < end) {
+      for (;;) {  // next occupied z cell of the pencil
+        const unsigned m = __ballot_sync(FULL_MASK, e > pos);
+        if (m) {
+          const int f = __ffs(m) - 1;
+          cnt = __shfl_sync(FULL_MASK, e, f) - pos;
+          cz = zwin + f;
+          break;
+        }
+        zwin += 32;
+        e = (zwin + lane < Nz) ? st[zwin + lane + 1] : end + 1;
+      }
+    } else {
+      cz = sprev + 8;  // past the last source: everything retires
+    }
+    if (sprev >= 0) {  // retire this lane's ring slots (zq, zq + 4) whose planes lie in [sprev - 7, cz - 8]
+      const int u0 = sprev - ((sprev - zq) & 7), u1 = sprev - ((sprev - zq - 4) & 7);
+      if (u0 <= cz - 8) sw_flush<0>(A, stg, a, comp_first, gx0, gy, imodulo(u0, Nz));
+      if (u1 <= cz - 8) sw_flush<1>(A, stg, a, comp_first, gx0, gy, imodulo(u1, Nz));
+    }
+    if (pos >= end) break;
+    const int b = cz & 7;
+    const int i0 = (zq - b + 7) & 7;  // weight index of ring slot zq at this step; slot zq + 4 has i0 ^ 4
+    for (int t = 0; t < cnt; t++) {
+      const int rel = pos + t - pos0, r = rel >> 3;
+      if (r != cur_round) {  // warp-uniform: enter round r (staged one round ahead), prefetch round r + 1
+        cp_async_wait_all();
+        __syncwarp();
+        cur_round = r;
+        const int s1 = pos0 + 8 * (r + 1);
+        if (s1 < end) stage(s_rec[warp][(r + 1) & 1], s1);
+      }
+      const double *w = s_rec[warp][r & 1] + (rel & 7) * WK_REC;
+      const int rx = __double2loint(w[24]) - xr * SW_XR;
+      const double wy = w[8 + jy];
+      const double wyz0 = wy * w[16 + i0], wyz1 = wy * w[16 + (i0 ^ 4)];
+      double s0[3], s1v[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        const double sv = w[26 + cc];
+        s0[cc] = wyz0 * sv;
+        s1v[cc] = wyz1 * sv;
+      }
+      switch (rx) {
+        case 0: sw_update<0>(A, w, s0, s1v); break;
+        case 1: sw_update<1>(A, w, s0, s1v); break;
+        case 2: sw_update<2>(A, w, s0, s1v); break;
+        case 3: sw_update<3>(A, w, s0, s1v); break;
+        case 4: sw_update<4>(A, w, s0, s1v); break;
+        case 5: sw_update<5>(A, w, s0, s1v); break;
+        case 6: sw_update<6>(A, w, s0, s1v); break;
+        default: sw_update<7>(A, w, s0, s1v); break;
+      }
+    }
+    sprev = cz;
+    pos += cnt;
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared rows must outlive the reads
+}
+
 // launch the spreading kernel(s) for one source list (cells or wall centroids); the meshes are accumulated into
 static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
   Pme &pm = c->pme;
@@ -394,7 +673,30 @@ static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
     a.mesh = pm.src.p;
     a.G = pm.G;
     const int nblocks = a.nbx * a.nby * a.nbz;
-    if (c->prm.P == 8) {
+    if (pm.swalk) {
+      const CellList &L = *a.list;
+      const int ns = L.n_sorted;
+      if (ns > 0) {
+        SpreadWArgs w;
+        w.prm = a.prm, w.n = a.n, w.start = a.start, w.wrec = L.w.p;
+        w.nxr = pm.nsblk[0], w.mesh = pm.src.p, w.G = pm.G;
+        for (int which = 0; which < 2; which++) {
+          if (which == 0 ? !pmf.flag_sl : !pmf.flag_dl) continue;
+          w.comp0 = which == 0 ? 0 : 3;
+          w.npass = which == 0 ? 1 : 2;
+          RBC_TRY(pm.str.resize((size_t)ns * 4 * w.npass));
+          StrengthArgs sa;
+          sa.ns = ns, sa.n = a.n, sa.npc = a.npc, sa.dl = which, sa.order = a.order;
+          sa.f = a.f, sa.g = a.g, sa.a3 = a.a3, sa.Bcell = a.Bcell, sa.c1 = a.c1, sa.c2 = a.c2, sa.str = pm.str.p;
+          k_spread_strength<<<(ns + 255) / 256, 256, 0, c->stream>>>(sa);
+          w.str = pm.str.p;
+          const int ntask = pm.nsblk[0] * pm.Ny * w.npass;
+          k_spread_walk<<<(ntask + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, 0, c->stream>>>(w);
+          c->launches += 2;
+        }
+        KERNEL_CHECK();
+      }
+    } else if (c->prm.P == 8) {
       if (pmf.flag_sl) {
         a.comp0 = 0;
         a.ncomp = 3;
@@ -458,6 +760,7 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     SpreadArgs a;
     a.prm = c->prm;
     a.n = C.Np;
+    a.list = &C.pl;
     a.start = C.pl.start.p;
     a.order = C.pl.order.p;
     a.x = C.x.p;
@@ -480,6 +783,7 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     SpreadArgs a;
     a.prm = c->prm;
     a.n = W.NE;
+    a.list = &W.pl;
     a.start = W.pl.start.p;
     a.order = W.pl.order.p;
     a.x = W.xc.p;
@@ -743,6 +1047,144 @@ __global__ void __launch_bounds__(INTERP_WARPS * 32) k_interp(InterpArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// P = 8 interpolation, v2: register-ring column walk.  One warp per (x, y) column of mesh cells; its targets are
+// sorted by z cell.  The 8 x 8 x 8 support of a mesh cell lives in REGISTERS: lane = (x offset, y offset pair) holds a
+// ring of the last 8 z planes of its two (x, y) columns for the 3 velocity components (48 doubles).  Moving up one
+// cell in z replaces one ring slot (64-byte row segments from L1/L2); the ring position is warp-uniform, so a switch
+// selects one of 8 bodies with static register indices.  Per target and lane: 48 FMAs against the z weights, 9
+// multiply-adds with w_x w_y, then a transposed shuffle reduction over 4 targets at a time -- no shared-memory
+// traffic per mesh value at all (v1 needed one LDS per FMA).  The B-spline weights are geometry-time records
+// (celllist_pme_weights) staged by wk_stage; results leave as one FP64 reduction per target and component.
+constexpr int IW_WARPS = 4;
+
+struct InterpWArgs {
+  Params prm;
+  int n;
+  const int *start, *order;  // mesh-cell list, key = cz + Nz * (cx + Nx * cy)
+  const double *wrec;        // [sorted target][PME_WREC]
+  const double *vv;          // [3][G]
+  size_t G;
+  double *acc;               // SoA(3,n)
+};
+
+// up to 4 targets against the ring: slot d holds plane cz - 7 + ((d - b + 7) & 7), so the z weights are read rotated
+// (warp-uniform address) and the register indices stay static -- one body for all ring positions
+__device__ __forceinline__ void iw_batch(const double (&R)[8][2][3], const double *__restrict__ w, int nb, int b7,
+                                         int ix, int jq, double (&v)[12]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (q < nb) {
+      const double *wq = w + q * WK_REC;
+      double wz[8];
+#pragma unroll
+      for (int d = 0; d < 8; d++) wz[d] = wq[16 + ((d + b7) & 7)];
+      const double wxl = wq[ix], wy0 = wq[8 + jq], wy1 = wq[12 + jq];
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+          t0 = fma(wz[d], R[d][0][cc], t0);
+          t1 = fma(wz[d], R[d][1][cc], t1);
+        }
+        v[3 * q + cc] = wxl * fma(wy1, t1, wy0 * t0);
+      }
+    } else {
+      v[3 * q] = v[3 * q + 1] = v[3 * q + 2] = 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(IW_WARPS * 32, 3) k_interp_walk(InterpWArgs a) {
+  __shared__ __align__(16) double s_rec[IW_WARPS][2][WK_ROUND * WK_REC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  const int col = blockIdx.x * IW_WARPS + warp;
+  if (col >= Nx * Ny) return;
+  const int *st = a.start + (size_t)col * Nz;
+  const int pos0 = st[0], end = st[Nz];
+  if (pos0 == end) return;
+  wk_stage(s_rec[warp][0], lane, pos0, end - 1, a.wrec, nullptr, a.order);
+  const int cx = col % Nx, cy = col / Nx;
+  const int ix = lane & 7, jq = lane >> 3;
+  const int gx = imodulo(cx - 7 + ix, Nx);
+  const size_t off0 = (size_t)imodulo(cy - 7 + jq, Ny) * Nx + gx, off1 = (size_t)imodulo(cy - 3 + jq, Ny) * Nx + gx;
+  const size_t plane = (size_t)Nx * Ny;
+  double R[8][2][3];
+  int pos = pos0, cz = 0, sprev = -64, cur_round = -1;
+  int zwin = 0;                                          // scan window: e = st[zwin + lane + 1]
+  int e = (lane < Nz) ? st[lane + 1] : end + 1;
+  while (pos < end) {
+    int cnt;
+    for (;;) {  // next occupied z cell of the column
+      const unsigned m = __ballot_sync(FULL_MASK, e > pos);
+      if (m) {
+        const int f = __ffs(m) - 1;
+        cnt = __shfl_sync(FULL_MASK, e, f) - pos;
+        cz = zwin + f;
+        break;
+      }
+      zwin += 32;
+      e = (zwin + lane < Nz) ? st[zwin + lane + 1] : end + 1;
+    }
+    const int b = cz & 7;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {  // ring slots that are not yet loaded: planes (sprev, cz]
+      const int ud = cz - ((b - d) & 7);
+      if (ud > sprev) {
+        const double *pl = a.vv + (size_t)imodulo(ud, Nz) * plane;
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          R[d][0][cc] = __ldg(pl + cc * a.G + off0);
+          R[d][1][cc] = __ldg(pl + cc * a.G + off1);
+        }
+      }
+    }
+    sprev = cz;
+    for (int tb = 0; tb < cnt;) {
+      const int rel = pos + tb - pos0, r = rel >> 3, slot = rel & 7;
+      if (r != cur_round) {  // warp-uniform: enter round r (staged one round ahead), prefetch round r + 1
+        cp_async_wait_all();
+        __syncwarp();
+        cur_round = r;
+        const int s1 = pos0 + 8 * (r + 1);
+        if (s1 < end) wk_stage(s_rec[warp][(r + 1) & 1], lane, s1, end - 1, a.wrec, nullptr, a.order);
+      }
+      const int nb = min(min(4, cnt - tb), WK_ROUND - slot);
+      const double *w = s_rec[warp][r & 1] + slot * WK_REC;
+      double v[12];
+      iw_batch(R, w, nb, 7 - b, ix, jq, v);
+      // transposed reduction: 12 -> 6 -> 3 values per lane, then three butterflies; lanes 8q..8q+7 end with target q
+      const bool hiA = (lane & 16) != 0, hiB = (lane & 8) != 0;
+      double r6[6], r3[3];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double send = hiA ? v[k] : v[k + 6], keep = hiA ? v[k + 6] : v[k];
+        r6[k] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double send = hiB ? r6[k] : r6[k + 3], keep = hiB ? r6[k + 3] : r6[k];
+        r3[k] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; k++) r3[k] += __shfl_xor_sync(FULL_MASK, r3[k], o);
+      if (ix == 0 && jq < nb) {  // single writer per address and kernel: a reduction without return value
+        const int p = reinterpret_cast<const int *>(w + jq * WK_REC + 26)[0];
+        atomicAdd(a.acc + p, r3[0]);
+        atomicAdd(a.acc + (size_t)a.n + p, r3[1]);
+        atomicAdd(a.acc + 2 * (size_t)a.n + p, r3[2]);
+      }
+      tb += nb;
+    }
+    pos += cnt;
+  }
+}
+
 int pme_interp(rbc3d_ctx *c, TargetList &t) {
   Pme &pm = c->pme;
   if (!pm.transformed) {
@@ -751,6 +1193,22 @@ int pme_interp(rbc3d_ctx *c, TargetList &t) {
   }
   if (t.n == 0) return RBC3D_OK;
   CellList &pl = t.pl;
+  if (pm.walk) {
+    InterpWArgs w;
+    w.prm = c->prm;
+    w.n = t.n;
+    w.start = pl.start.p;
+    w.order = pl.order.p;
+    w.wrec = pl.w.p;
+    w.vv = pm.vv.p;
+    w.G = pm.G;
+    w.acc = t.acc.p;
+    const int ncol = pm.Nx * pm.Ny;
+    k_interp_walk<<<(ncol + IW_WARPS - 1) / IW_WARPS, IW_WARPS * 32, 0, c->stream>>>(w);
+    KERNEL_CHECK();
+    c->launches++;
+    return RBC3D_OK;
+  }
   InterpArgs a;
   a.prm = c->prm;
   a.n = t.n;

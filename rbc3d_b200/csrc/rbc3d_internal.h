@@ -93,7 +93,11 @@ struct CellList {
   dbuf<int> start;      // [ncells + 2]
   dbuf<int> keys_tmp, vals_tmp;
   dbuf<char> cub_tmp;
+  // PME lists of the P = 8 walk kernels: per SORTED point a 26-double record (B-spline weights wx[8] wy[8] wz[8],
+  // mesh cell x in the low half of slot 24, pad) -- geometry-only data, computed once per list
+  dbuf<double> w;
 };
+constexpr int PME_WREC = 26;
 
 struct NearSing {      // geometry-time products of the neighbour scan + Spline_FindProjection
   int n = 0;           // entries (target, other cell within rc)
@@ -219,6 +223,7 @@ struct Pme {
   dbuf<cufftDoubleComplex> vvC;     // [3][Nz][Ny][Nxh]
   dbuf<double> vv;                  // [3][Nz][Ny][Nx]
   dbuf<double> bx, by, bz;          // B-spline modulus factors per axis (ModPME.F90:318-325)
+  dbuf<double> str;                 // walk spreading: strengths in sorted order, [point][pass][4]
   cufftHandle planF[3] = {0, 0, 0}; // batch 3, 6, 9
   bool planF_ok[3] = {false, false, false};
   cufftHandle planB = 0;
@@ -230,6 +235,8 @@ struct Pme {
   int iblk[3] = {4, 4, 4};          // their edges
   int sblk[3] = {4, 4, 4};          // edges of the source blocks of the spreading kernel
   int nsblk[3] = {0, 0, 0};
+  bool swalk = false;               // P = 8: spreading by pencil walks (k_spread_walk), else source blocks
+  bool walk = false;                // P = 8: register-ring column walks along z (lists keyed z-fastest)
 };
 
 }  // namespace rbc3d
@@ -265,9 +272,11 @@ void h_gauleg(double x1, double x2, int n, double *x, double *w);
 
 // ---- cell list (celllist.cu) ----
 int celllist_build_realspace(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active);
-int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3]);
+int celllist_build_pme(rbc3d_ctx *c, CellList &cl, int n, const double *x, const int *active, const int blk[3],
+                       bool zfast = false);
 int tiles_build(rbc3d_ctx *c, TargetList &t);
 int device_exclusive_scan(rbc3d_ctx *c, int *data, int n);  // in place
+int celllist_pme_weights(rbc3d_ctx *c, CellList &cl, const double *x);
 
 // ---- real-space operator (pairsum.cu, singular.cu, nearsing.cu) ----
 int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g);

@@ -574,7 +574,8 @@ int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nel
     CUDA_TRY(cudaMemcpy(W.src_own.p, o.data(), sizeof(int) * NE, cudaMemcpyHostToDevice));
     own = W.src_own.p;
   }
-  RBC_TRY(celllist_build_pme(c, W.pl, NE, W.xc.p, own, c->pme.sblk));
+  RBC_TRY(celllist_build_pme(c, W.pl, NE, W.xc.p, own, c->pme.sblk, c->pme.swalk));
+  if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, W.pl, W.xc.p));
   W.geom_set = true;
   return RBC3D_OK;
 }
@@ -1014,6 +1015,7 @@ void walls_release(rbc3d_ctx *c) {
   for (CellList *l : {&W.cl, &W.pl}) {
     l->cid.release(), l->order.release(), l->start.release(), l->keys_tmp.release(), l->vals_tmp.release();
     l->cub_tmp.release();
+    l->w.release();
   }
   for (int k = 0; k < 3; k++) c->tl[k].wp.release();
 }
