@@ -158,9 +158,12 @@ int rbc3d_set_skip_flags(rbc3d_ctx *ctx, int flags);
  * device memory allows, so that GMRES matvecs only interpolate the density; mode 0 always evaluates directly.
  * Takes effect at the next rbc3d_cells_set_geometry. */
 int rbc3d_set_sing_cache(rbc3d_ctx *ctx, int mode);
-/* Same-surface pairs of the real-space sum (ModIntOnRbcs.F90:81-84): mode 1 (default) symmetric patch-pair kernel
- * (each unordered pair evaluated once), mode 2 dense per-cell kernel, mode 0 through the hashed cell list like every
- * other pair (testing). */
+/* Same-surface pairs of the real-space sum (ModIntOnRbcs.F90:81-84): mode 3 (default) symmetric patch-pair kernel
+ * (each unordered pair evaluated once) that, for the double-layer operator alone (the GMRES matvec), streams a
+ * per-geometry cache of (1 - mask) * EwaldCoeff_DL per unordered pair (8 B per pair slot, ~16 MB per 36x72 cell; built
+ * at rbc3d_cells_set_geometry for as many cells as device memory allows, the rest is evaluated directly);
+ * mode 1 the same kernel without the cache, mode 2 dense per-cell kernel, mode 0 through the hashed cell list like
+ * every other pair (testing). */
 int rbc3d_set_pair_self(rbc3d_ctx *ctx, int mode);
 
 /* ---- introspection (tests, profiling) ---- */

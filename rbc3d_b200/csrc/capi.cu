@@ -360,6 +360,9 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.ps_maskbits.release();
   C.ps_compact.release();
   C.ps_needmask.release();
+  C.pc_mask.release();
+  C.pc_cnt.release();
+  C.pc_coef.release();
   C.src_own.release();
   rel_cl(C.cl);
   rel_cl(C.pl);
@@ -537,6 +540,7 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *c, const double *x, const double *a3, co
   RBC_TRY(cells_active_flags(c));
   RBC_TRY(pairself_geometry_prepare(c));
   RBC_TRY(singular_prepare(c));
+  RBC_TRY(pairself_cache_prepare(c));
   // other target lists depend on the cell geometry through their near-singular entries
   for (int k = 1; k < 3; k++)
     if (c->tl[k].valid) RBC_TRY(nearsing_prepare(c, c->tl[k]));

@@ -131,8 +131,16 @@ __global__ void k_pme_weights(int ns, int n, const int *__restrict__ order, cons
   double ww[8];
   bspline_func<8>(u, 8, imin, ww);
   double *dst = w + (size_t)s * PME_WREC + ax * 8;
+  if (ax < 2) {
 #pragma unroll
-  for (int q = 0; q < 8; q++) dst[q] = ww[q];
+    for (int q = 0; q < 8; q++) dst[q] = ww[q];
+  } else {
+    // the z weights are stored in ring order: the walk kernels keep plane u in ring slot u & 7, so with the point in
+    // z cell cz the slot d holds plane cz - 7 + ((d - cz + 7) & 7)
+    const int cz = imodulo(imin + 7, prm.Nb[2]);
+#pragma unroll
+    for (int q = 0; q < 8; q++) dst[(q + cz + 1) & 7] = ww[q];
+  }
   if (ax == 0) {
     w[(size_t)s * PME_WREC + 24] = __hiloint2double(0, imodulo(imin + 7, prm.Nb[0]));
     w[(size_t)s * PME_WREC + 25] = 0.0;

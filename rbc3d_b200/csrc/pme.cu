@@ -450,6 +450,7 @@ __device__ __forceinline__ void wk_stage(double *buf, int lane, int s0, int last
 // Weights are geometry-time records, strengths come from a pre-pass in sorted order (k_spread_strength); both are
 // staged one round ahead by wk_stage.
 constexpr int SW_WARPS = 2, SW_TX = SW_XR + 7;
+constexpr int SW_STG = 3 * 16 + 2;  // per-lane staging stride: 400 B, lanes 16 B apart in the banks
 
 struct SpreadWArgs {
   Params prm;
@@ -556,7 +557,7 @@ __device__ __forceinline__ void sw_flush(double (&A)[2][SW_TX][3], double *stage
 
 __global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a) {
   __shared__ __align__(16) double s_rec[SW_WARPS][2][WK_ROUND * WK_REC];
-  __shared__ __align__(128) double s_fl[SW_WARPS][32][3 * 16];  // flush staging, private to a lane
+  __shared__ __align__(128) double s_fl[SW_WARPS][32][SW_STG];  // flush staging, private to a lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
   const int task = blockIdx.x * SW_WARPS + warp;
@@ -624,8 +625,6 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a)
       if (u1 <= cz - 8) sw_flush<1>(A, stg, a, comp_first, gx0, gy, imodulo(u1, Nz));
     }
     if (pos >= end) break;
-    const int b = cz & 7;
-    const int i0 = (zq - b + 7) & 7;  // weight index of ring slot zq at this step; slot zq + 4 has i0 ^ 4
     for (int t = 0; t < cnt; t++) {
       const int rel = pos + t - pos0, r = rel >> 3;
       if (r != cur_round) {  // warp-uniform: enter round r (staged one round ahead), prefetch round r + 1
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a)
       const double *w = s_rec[warp][r & 1] + (rel & 7) * WK_REC;
       const int rx = __double2loint(w[24]) - xr * SW_XR;
       const double wy = w[8 + jy];
-      const double wyz0 = wy * w[16 + i0], wyz1 = wy * w[16 + (i0 ^ 4)];
+      const double wyz0 = wy * w[16 + zq], wyz1 = wy * w[20 + zq];  // z weights are stored in ring order
       double s0[3], s1v[3];
 #pragma unroll
       for (int cc = 0; cc < 3; cc++) {
@@ -1069,9 +1068,9 @@ struct InterpWArgs {
   double *acc;               // SoA(3,n)
 };
 
-// up to 4 targets against the ring: slot d holds plane cz - 7 + ((d - b + 7) & 7), so the z weights are read rotated
-// (warp-uniform address) and the register indices stay static -- one body for all ring positions
-__device__ __forceinline__ void iw_batch(const double (&R)[8][2][3], const double *__restrict__ w, int nb, int b7,
+// up to 4 targets against the ring: slot d holds plane cz - 7 + ((d - cz + 7) & 7); the records carry the z weights
+// already in ring order, so the register indices are static -- one body for all ring positions
+__device__ __forceinline__ void iw_batch(const double (&R)[8][2][3], const double *__restrict__ w, int nb,
                                          int ix, int jq, double (&v)[12]) {
 #pragma unroll
   for (int q = 0; q < 4; q++) {
@@ -1079,7 +1078,11 @@ __device__ __forceinline__ void iw_batch(const double (&R)[8][2][3], const doubl
       const double *wq = w + q * WK_REC;
       double wz[8];
 #pragma unroll
-      for (int d = 0; d < 8; d++) wz[d] = wq[16 + ((d + b7) & 7)];
+      for (int k = 0; k < 4; k++) {
+        const double2 t = reinterpret_cast<const double2 *>(wq + 16)[k];
+        wz[2 * k] = t.x;
+        wz[2 * k + 1] = t.y;
+      }
       const double wxl = wq[ix], wy0 = wq[8 + jq], wy1 = wq[12 + jq];
 #pragma unroll
       for (int cc = 0; cc < 3; cc++) {
@@ -1155,7 +1158,7 @@ __global__ void __launch_bounds__(IW_WARPS * 32, 3) k_interp_walk(InterpWArgs a)
       const int nb = min(min(4, cnt - tb), WK_ROUND - slot);
       const double *w = s_rec[warp][r & 1] + slot * WK_REC;
       double v[12];
-      iw_batch(R, w, nb, 7 - b, ix, jq, v);
+      iw_batch(R, w, nb, ix, jq, v);
       // transposed reduction: 12 -> 6 -> 3 values per lane, then three butterflies; lanes 8q..8q+7 end with target q
       const bool hiA = (lane & 16) != 0, hiB = (lane & 8) != 0;
       double r6[6], r3[3];

@@ -208,6 +208,14 @@ struct Cells {
   dbuf<unsigned long long> ps_maskbits;
   dbuf<unsigned char> ps_compact;
   dbuf<unsigned char> ps_needmask;   // [patch][patch]: mask table needed for this patch pair
+  // geometry cache of the symmetric same-surface double-layer pair sum (pairself.cu): per active cell slot and
+  // patch pair the 32-bit set of rotation steps with an in-range pair, per such step 32 coefficients (1 - mask) EA
+  bool pc_ok = false;
+  int pc_ncached = 0;                // the first pc_ncached cells of sg_active_list are cached
+  long long pc_geom = -1;
+  dbuf<unsigned> pc_mask;            // [slot][G][G]
+  dbuf<int> pc_cnt;                  // [slot * G + I] -> first step of (slot, I) after the scan
+  dbuf<double> pc_coef;              // [step][32]
   dbuf<int> src_own;                 // multi-GPU: 1 for the points of the cells this rank spreads
   // density splines built on the device (splinebuild.cu)
   bool sb_ok = false;
@@ -253,7 +261,8 @@ struct rbc3d_ctx {
   rbc3d::Walls walls;
   rbc3d::Pme pme;
   int skip_flags = 0;
-  int pair_self_mode = 1;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel
+  int pair_self_mode = 3;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel,
+                            // 3 symmetric kernel streaming a per-geometry coefficient cache (double layer only)
   int sing_cache_mode = 1;  // 0: never cache the singular double-layer integrand, 1: when memory allows
   cudaEvent_t ev[2 * RBC3D_T_COUNT];
   bool ev_used[RBC3D_T_COUNT];
@@ -283,6 +292,7 @@ int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g);
 int pair_sum(rbc3d_ctx *c, TargetList &t, double c1, double c2);
 int pairself_mesh_prepare(rbc3d_ctx *c, const std::vector<double> &omm);
 int pairself_geometry_prepare(rbc3d_ctx *c);
+int pairself_cache_prepare(rbc3d_ctx *c);
 bool pairself_available(rbc3d_ctx *c, const TargetList &t);
 int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
 int cells_active_flags(rbc3d_ctx *c);

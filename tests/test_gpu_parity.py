@@ -229,14 +229,31 @@ def test_pair_sum_dense_self_kernel_vs_cell_list(sus8, oracle_lib, c1, c2):
     orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
     ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
     out = []
-    for mode in (1, 2, 0):   # symmetric patch pairs, dense per cell, hashed cell list
+    for mode in (3, 1, 2, 0):   # symmetric + geometry cache (default), symmetric, dense per cell, hashed cell list
         op = EwaldOperator(sus8.Lb)
         op.set_pair_self(mode)
         op.set_suspension(sus8)
         op.set_skip_flags(1 | 2 | 4)
         out.append(op.AddIntOnRbcs(c1, c2))
         op.close()
-    assert rel_l2(out[0], ref) < TOL and rel_l2(out[1], ref) < TOL and rel_l2(out[2], ref) < TOL
+    assert all(rel_l2(o, ref) < TOL for o in out)
+
+
+def test_pair_cache_partial_and_density_update(sus8, oracle_lib, monkeypatch):
+    """the per-geometry coefficient cache of the same-surface double-layer pairs: only 3 of the 8 cells cached (the
+    rest takes the direct kernel), and a second density on the same geometry reuses the cache."""
+    from rbc3d_b200.ewald import EwaldOperator
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
+    ref = orc.add_int_on_rbcs(0.0, C2_MATVEC, orc.cell_targets(), flags=orc.FLAG_NO_SING | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR)
+    for max_cells in ("3", "8"):
+        monkeypatch.setenv("RBC3D_PAIR_CACHE_MAX_CELLS", max_cells)
+        op = EwaldOperator(sus8.Lb)
+        op.set_suspension(sus8)
+        op.set_skip_flags(1 | 2 | 4)
+        assert rel_l2(op.AddIntOnRbcs(0.0, C2_MATVEC), ref) < TOL
+        op.SourceList_UpdateDensity(g=sus8.weighted(sus8.g) * 0.25, spG=sus8.spG * 0.25)
+        assert rel_l2(op.AddIntOnRbcs(0.0, C2_MATVEC), 0.25 * ref) < TOL
+        op.close()
 
 
 def test_cell_straddling_the_periodic_boundary(oracle_lib):
