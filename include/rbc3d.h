@@ -165,6 +165,9 @@ int rbc3d_set_sing_cache(rbc3d_ctx *ctx, int mode);
  * mode 1 the same kernel without the cache, mode 2 dense per-cell kernel, mode 0 through the hashed cell list like
  * every other pair (testing). */
 int rbc3d_set_pair_self(rbc3d_ctx *ctx, int mode);
+/* state of that cache after rbc3d_cells_set_geometry: cells cached (of the cells this rank owns targets of) and
+ * 256-byte coefficient rows held (= bytes streamed per matvec / 256); either pointer may be NULL */
+int rbc3d_pair_cache_info(rbc3d_ctx *ctx, int32_t *cells_cached, int64_t *rows);
 
 /* ---- introspection (tests, profiling) ---- */
 /* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,

@@ -360,6 +360,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.ps_maskbits.release();
   C.ps_compact.release();
   C.ps_needmask.release();
+  C.sb_need.release();
   C.pc_mask.release();
   C.pc_cnt.release();
   C.pc_coef.release();
@@ -406,6 +407,13 @@ int rbc3d_set_sing_cache(rbc3d_ctx *c, int mode) {
 int rbc3d_set_pair_self(rbc3d_ctx *c, int mode) {
   if (!c) return RBC3D_EINVAL;
   c->pair_self_mode = mode;
+  return RBC3D_OK;
+}
+
+int rbc3d_pair_cache_info(rbc3d_ctx *c, int32_t *cells_cached, int64_t *rows) {
+  if (!c) return RBC3D_EINVAL;
+  if (cells_cached) *cells_cached = c->cells.pc_ok ? c->cells.pc_ncached : 0;
+  if (rows) *rows = c->cells.pc_ok ? c->cells.pc_rows : 0;
   return RBC3D_OK;
 }
 

@@ -904,6 +904,7 @@ int pairself_cache_prepare(rbc3d_ctx *c) {
   c->launches++;
   CUDA_TRY(cudaStreamSynchronize(c->stream));  // cnt (host vector) must outlive the upload
   C.pc_ncached = ncached;
+  C.pc_rows = steps;
   C.pc_ok = true;
   return RBC3D_OK;
 }

@@ -212,7 +212,7 @@ struct Cells {
   // patch pair the 32-bit set of rotation steps with an in-range pair, per such step 32 coefficients (1 - mask) EA
   bool pc_ok = false;
   int pc_ncached = 0;                // the first pc_ncached cells of sg_active_list are cached
-  long long pc_geom = -1;
+  long long pc_rows = 0;
   dbuf<unsigned> pc_mask;            // [slot][G][G]
   dbuf<int> pc_cnt;                  // [slot * G + I] -> first step of (slot, I) after the scan
   dbuf<double> pc_coef;              // [step][32]
@@ -221,6 +221,7 @@ struct Cells {
   bool sb_ok = false;
   int sb_nlat0 = 0;
   dbuf<double> sb_M0, sb_M1, sb_cs;
+  dbuf<int> sb_need;                 // several ranks: cells whose density spline this rank reads
 };
 
 struct Pme {

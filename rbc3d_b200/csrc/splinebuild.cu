@@ -116,6 +116,7 @@ struct BuildArgs {
   const double *M0, *M1, *cs;
   double *sp_abi;       // [cell][4][3][nlon][2 nlat] or null
   double2 *sp_planes;   // [cell][6][nlon][2 nlat] or null
+  const int *need;      // [cell] or null: build only flagged cells
 };
 
 // one CTA per (cell, variable)
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
   extern __shared__ double sm[];
   const int nlat = a.nlat, nlon = a.nlon, M = 2 * nlat, m0 = a.nlat0;
   const int cell = blockIdx.x / 3, var = blockIdx.x - 3 * cell;
+  if (a.need && !a.need[cell]) return;         // several ranks: only the cells this rank evaluates splines of
   double *s_gd = sm;                           // [nlon][nlat]
   double *s_cs = s_gd + (size_t)nlon * nlat;   // [m0][nlon][2]
   double *s_F = s_cs + (size_t)2 * m0 * nlon;  // [2][m0][nlat]   (Fc, Fs)
@@ -197,9 +199,28 @@ __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
 }
 
 // which: 0 = f -> spF, 1 = g -> spG (+ the plane layout of the cached singular kernel)
+__global__ void k_mark_cells(int n, const int *__restrict__ cell, int *__restrict__ need) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) need[cell[i]] = 1;
+}
+
 int spline_build_density(rbc3d_ctx *c, int which) {
   Cells &C = c->cells;
   if (!C.sb_ok || C.Np == 0) return RBC3D_OK;
+  const int *need = nullptr;
+  if (c->prm.nranks > 1 && C.sg_cell_active.p) {
+    // with several ranks the density splines are read by the singular integrals of the owned cells and by the
+    // near-singular entries of this rank's targets (which may point at cells of other ranks): skip the rest
+    RBC_TRY(C.sb_need.resize(C.ncell));
+    CUDA_TRY(cudaMemcpyAsync(C.sb_need.p, C.sg_cell_active.p, sizeof(int) * C.ncell, cudaMemcpyDeviceToDevice, c->stream));
+    for (int k = 0; k < 3; k++) {
+      const TargetList &t = c->tl[k];
+      if (t.valid && t.ns.n > 0)
+        k_mark_cells<<<(t.ns.n + 255) / 256, 256, 0, c->stream>>>(t.ns.n, t.ns.cell.p, C.sb_need.p);
+    }
+    KERNEL_CHECK();
+    need = C.sb_need.p;
+  }
   const size_t plane = (size_t)2 * C.nlat * C.nlon;
   BuildArgs a;
   a.ncell = C.ncell;
@@ -213,6 +234,7 @@ int spline_build_density(rbc3d_ctx *c, int which) {
   a.M1 = C.sb_M1.p;
   a.cs = C.sb_cs.p;
   a.sp_planes = nullptr;
+  a.need = need;
   if (which == 0) {
     RBC_TRY(C.spF.resize((size_t)C.ncell * 12 * plane));
     a.dens = C.f.p;

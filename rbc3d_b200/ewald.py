@@ -276,6 +276,12 @@ class EwaldOperator:
     def set_pair_self(self, mode):
         check(self.lib.rbc3d_set_pair_self(self._h, int(mode)))
 
+    def pair_cache_info(self):
+        """(cells cached, 256-byte coefficient rows) of the same-surface double-layer pair cache."""
+        nc, rows = C.c_int32(), C.c_int64()
+        check(self.lib.rbc3d_pair_cache_info(self._h, C.byref(nc), C.byref(rows)))
+        return nc.value, rows.value
+
     def set_sing_cache(self, mode):
         check(self.lib.rbc3d_set_sing_cache(self._h, int(mode)))
 
