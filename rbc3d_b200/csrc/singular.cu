@@ -39,10 +39,18 @@ constexpr int SG_PC_DEFAULT = 2;  // patch points of one spline cell evaluated p
 // 0 (default): the tile's points sorted by spline cell across its targets + shared contribution buffer; 1: every warp
 // owns one target of the tile (register accumulation, no contribution buffer, no barriers in the tile loop).  Measured
 // at 512 cells: 7.8 ms vs 8.1 ms (profiles/r01_summary)
+static int sg_lr();
 static int sg_per_warp() {
   static const int v = [] {
     const char *e = getenv("RBC3D_SING_PER_WARP");
-    return e ? atoi(e) : 0;
+    return (e ? atoi(e) : 0) || sg_lr() == 2;
+  }();
+  return v;
+}
+static int sg_lr() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_SING_LR");  // 0: 256 threads, full-register body; 1: 512 threads, tile mode
+    return e ? atoi(e) : 2;                   // 2 (default): 512 threads, warp = target, low-register body
   }();
   return v;
 }
@@ -50,6 +58,7 @@ static int sg_nt() {
   static const int v = [] {
     const char *e = getenv("RBC3D_SING_NT");
     const int q = e ? atoi(e) : SG_T * 32;
+    if (sg_lr() == 1 && !sg_per_warp()) return 512;
     return (!sg_per_warp() && (q == 256 || q == 384 || q == 512)) ? q : SG_T * 32;
   }();
   return v;
@@ -281,7 +290,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   C.sg_ni_max = ni_max;
   C.sg_chunk_stride = CH;
   // shared memory: band of the spline (6 double2 planes x (n+1) phi columns x ni theta rows) + contribution buffer
-  const size_t smem = (size_t)12 * ni_max * (n + 1) * sizeof(double) + (per_warp ? 0 : (size_t)3 * NPT * sizeof(double));
+  const size_t smem = (size_t)12 * (ni_max | 1) * (n + 1) * sizeof(double) + (per_warp ? 0 : (size_t)3 * NPT * sizeof(double));
   if (smem > SG_SMEM_MAX || ni_max > 255) return RBC3D_OK;  // direct kernel only
   C.sg_smem = smem;
   RBC_TRY(C.sg_tile_tgt.resize(row_tgt.size()));
@@ -412,18 +421,24 @@ __device__ __forceinline__ double4 ld_stream4(const double4 *p) {
 // registers (shared-memory traffic per patch point drops from 384 B to ~100 B).  The geometry cache of the next
 // round is in flight while the current one is evaluated.  Contributions go to a target-major shared buffer that one
 // warp per target sums in the reference's patch order.
-template <bool TAB_SMEM, int SG_PC, int NT, bool PW>  // tables in shared memory (when they fit) or through L1; NT threads;
-                                                       // PW: warp = target, register accumulation
+template <bool TAB_SMEM, int SG_PC, int NT, bool PW, bool LR = false>  // tables in shared memory (when they fit) or
+                                                       // through L1; NT threads; PW: warp = target, register accumulation;
+                                                       // LR: low-register body (one density component at a time)
 __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   extern __shared__ double smem[];
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  // PW with more than SG_T warps: warp groups of SG_T warps take the tiles of the row in turn (no barriers in PW mode)
+  constexpr int NTT = PW ? SG_T * 32 : NT, NG = NT / NTT;
+  const int tid_cta = threadIdx.x, w_cta = tid_cta >> 5, lane = tid_cta & 31;
+  const int tid = PW ? tid_cta % NTT : tid_cta, w = PW ? w_cta % SG_T : w_cta, grp = PW ? w_cta / SG_T : 0;
   const int slot = blockIdx.x / a.ntl, tl = blockIdx.x - slot * a.ntl;
   const int cell = a.active_list[slot];
   const int ilo = a.row_win[tl * 2 + 0], ni = a.row_win[tl * 2 + 1];
   const int m = 2 * a.nlat, n = a.nlon, plane = m * n;
   const int K = a.K, NPT = K * SG_T * 32;
-  const int wn = ni * (n + 1);                       // nodes of the band
-  double2 *sP = reinterpret_cast<double2 *>(smem);   // [6][n+1][ni]
+  const int nip = ni | 1;                            // odd pitch of a phi column: neighbouring columns fall into
+                                                     // different 16-byte bank groups
+  const int wn = nip * (n + 1);                      // node slots of the band
+  double2 *sP = reinterpret_cast<double2 *>(smem);   // [6][n+1][nip]
   double *sC = smem + (size_t)12 * wn;               // [3][NPT] contributions, target-major (tile mode only)
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   const int R = a.row_rounds[tl];
@@ -433,12 +448,12 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   if (TAB_SMEM) {  // [NPT] double2, [R*256] int2, [NPT] int behind the contribution buffer
     double2 *s_st = reinterpret_cast<double2 *>(sC + (PW ? 0 : (size_t)3 * NPT));
     int2 *s_ch = reinterpret_cast<int2 *>(s_st + NPT);
-    int *s_dest = reinterpret_cast<int *>(s_ch + R * NT);
-    for (int u = tid; u < NPT; u += NT) {
+    int *s_dest = reinterpret_cast<int *>(s_ch + R * NTT);
+    for (int u = tid_cta; u < NPT; u += NT) {
       s_st[u] = __ldg(pt_st + u);
       if (!PW) s_dest[u] = __ldg(pt_dest + u);
     }
-    for (int u = tid; u < R * NT; u += NT) s_ch[u] = __ldg(chunk - tid + u);
+    for (int u = tid_cta; u < R * NTT; u += NT) s_ch[u] = __ldg(chunk - tid + u);
     pt_st = s_st;
     pt_dest = s_dest;
     chunk = s_ch + tid;
@@ -451,13 +466,14 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   double4 c_next[SG_PC];
 #pragma unroll
   for (int p = 0; p < SG_PC; p++)
-    c_next[p] = (p < (ch_next.x >> 18)) ? ld_stream4(cg + ch_next.y + p) : make_double4(0, 0, 0, 0);
+    c_next[p] = (p < (ch_next.x >> 18) && grp < a.ntn) ? ld_stream4(cg + (size_t)grp * NPT + ch_next.y + p)
+                                                       : make_double4(0, 0, 0, 0);
   // stage the band: rows = (plane, phi column 0..n with column n = column 0), each a cyclic run of ni double2
-  for (int row = w; row < 6 * (n + 1); row += NT / 32) {
+  for (int row = w_cta; row < 6 * (n + 1); row += NT / 32) {
     const int q = row / (n + 1), wj = row - q * (n + 1);
     const int j = wj == n ? 0 : wj;
     const double2 *src = a.spGp + ((size_t)cell * 6 + q) * plane + (size_t)j * m;
-    double2 *dst = sP + (size_t)q * wn + (size_t)wj * ni;
+    double2 *dst = sP + (size_t)q * wn + (size_t)wj * nip;
     for (int wi = lane; wi < ni; wi += 32) {
       int i = ilo + wi;
       if (i >= m) i -= m;
@@ -465,11 +481,11 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
     }
   }
   if (!PW)
-    for (int u = tid; u < 3 * NPT; u += NT) sC[u] = 0.0;  // slots beyond npatch stay zero
+    for (int u = tid_cta; u < 3 * NPT; u += NT) sC[u] = 0.0;  // slots beyond npatch stay zero
   __syncthreads();
   const int pt0 = w < SG_T ? a.row_tgt[tl * SG_T + w] : -1;  // warps beyond the tile's targets only evaluate chunks
   const double c2m = a.c2 * a.Bcell[cell];  // c2Mod, ModIntOnRbcs.F90:116
-  for (int tn = 0; tn < a.ntn; tn++) {
+  for (int tn = grp; tn < a.ntn; tn += NG) {
     const int jshift = tn * SG_TLON;
     const int ti = cell * a.npc + pt0 + tn * SG_TLON * a.nlat;
     const bool t_on = pt0 >= 0 && lane == 0 && a.active[ti] != 0;  // requested now, needed after the rounds
@@ -483,10 +499,10 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
         int nr = r + 1, nt = tn;
         if (nr == R) {
           nr = 0;
-          nt = tn + 1;
+          nt = tn + NG;
         }
         if (nt < a.ntn) {
-          ch_next = ld_tab(chunk + nr * NT);
+          ch_next = ld_tab(chunk + nr * NTT);
           const double4 *cgn = cg + (size_t)nt * NPT + ch_next.y;
           const int cn = ch_next.x >> 18;
 #pragma unroll
@@ -497,7 +513,7 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
       if (cnt == 0) continue;
       int j = ((ch.x >> 8) & 1023) + jshift;
       if (j >= n) j -= n;
-      const int a11 = j * ni + (ch.x & 255);
+      const int a11 = j * nip + (ch.x & 255);
       // tables of the chunk's points, all requested before the first use (clamped index: no branch in the way)
       double2 stq[SG_PC];
       int destq[SG_PC];
@@ -507,6 +523,56 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
         stq[p] = ld_tab(pt_st + e);
         destq[p] = PW ? 0 : ld_tab(pt_dest + e);
       }
+      if (LR) {
+        // low-register body: the Hermite data of ONE density component at a time (8 double2 instead of 24 live at
+        // once), so that 512 threads fit the register file without spills and 16 warps hide the LDS / HBM latency
+        double cxq[SG_PC][4], cyq[SG_PC][4], qd[SG_PC];
+#pragma unroll
+        for (int p = 0; p < SG_PC; p++) {
+          const double s = stq[p].x, t = stq[p].y;
+          cxq[p][0] = 1.0 + s * s * (-3.0 + 2.0 * s), cxq[p][1] = s * s * (3.0 - 2.0 * s);
+          cxq[p][2] = hx * s * (1.0 + s * (-2.0 + s)), cxq[p][3] = hx * s * s * (-1.0 + s);
+          cyq[p][0] = 1.0 + t * t * (-3.0 + 2.0 * t), cyq[p][1] = t * t * (3.0 - 2.0 * t);
+          cyq[p][2] = hy * t * (1.0 + t * (-2.0 + t)), cyq[p][3] = hy * t * t * (-1.0 + t);
+          qd[p] = 0.0;
+        }
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const double2 *P0 = sP + (size_t)(2 * l) * wn + a11, *P1 = P0 + wn;
+          const double2 u11 = P0[0], u21 = P0[1], u12 = P0[nip], u22 = P0[nip + 1];
+          const double2 w11 = P1[0], w21 = P1[1], w12 = P1[nip], w22 = P1[nip + 1];
+#pragma unroll
+          for (int p = 0; p < SG_PC; p++) {
+            const double *cx = cxq[p], *cy = cyq[p];
+            const double r0 = u11.x * cy[0] + u12.x * cy[1] + w11.x * cy[2] + w12.x * cy[3];
+            const double r1 = u21.x * cy[0] + u22.x * cy[1] + w21.x * cy[2] + w22.x * cy[3];
+            const double r2 = u11.y * cy[0] + u12.y * cy[1] + w11.y * cy[2] + w12.y * cy[3];
+            const double r3 = u21.y * cy[0] + u22.y * cy[1] + w21.y * cy[2] + w22.y * cy[3];
+            const double gl = cx[0] * r0 + cx[1] * r1 + cx[2] * r2 + cx[3] * r3;
+            const double cl = l == 0 ? c4[p].x : l == 1 ? c4[p].y : c4[p].z;
+            qd[p] = fma(cl, gl, qd[p]);
+          }
+          asm volatile("" ::: "memory");  // keep the next component's loads behind this component's arithmetic
+        }
+#pragma unroll
+        for (int p = 0; p < SG_PC; p++) {
+          if (p < cnt) {
+            const double4 c = c4[p];
+            const double q = c.w * qd[p];
+            const int dest = destq[p];
+            if (PW) {
+              pvx += q * c.x;
+              pvy += q * c.y;
+              pvz += q * c.z;
+            } else {
+              sC[dest] = q * c.x;
+              sC[NPT + dest] = q * c.y;
+              sC[2 * NPT + dest] = q * c.z;
+            }
+          }
+        }
+        continue;
+      }
       // Hermite data of the four nodes: nd[node][plane] = (u_l, u1_l) for plane 2l, (u2_l, u12_l) for plane 2l+1
       double2 n11[6], n21[6], n12[6], n22[6];
 #pragma unroll
@@ -514,8 +580,8 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
         const double2 *P = sP + (size_t)q * wn + a11;
         n11[q] = P[0];
         n21[q] = P[1];
-        n12[q] = P[ni];
-        n22[q] = P[ni + 1];
+        n12[q] = P[nip];
+        n22[q] = P[nip + 1];
       }
 #pragma unroll
       for (int p = 0; p < SG_PC; p++) {
@@ -720,6 +786,13 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   } while (0)
 #define LAUNCH_BAND_NT(TS_, PC_)                                \
   do {                                                          \
+    if (sg_lr() == 1 && PC_ == 2) {                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, 2, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_sing_band<TS_, 2, 512, false, true><<<grid, 512, smem, c->stream>>>(a);                                               \
+    } else if (sg_lr() == 2 && PC_ == 2) {                                                                                     \
+      CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, 2, 512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_sing_band<TS_, 2, 512, true, true><<<grid, 512, smem, c->stream>>>(a);                                                \
+    } else                                                      \
     if (sg_per_warp()) LAUNCH_BAND(TS_, PC_, SG_T * 32, true);  \
     else if (sg_nt() == 512) LAUNCH_BAND(TS_, PC_, 512, false); \
     else if (sg_nt() == 384) LAUNCH_BAND(TS_, PC_, 384, false); \
