@@ -217,9 +217,12 @@ def kernel_table(op, sus, ms, npairs, peaks, world=1):
             r["frac_hbm"] = r["gbs"] / hbm_peak
         rows.append(r)
 
-    add("pair_sum(DL)", ms["pair"], flops=npairs * FLOPS_DL_PAIR)
+    # same-surface pairs stream (1 - mask) EA per unordered pair slot from the per-geometry cache (256-byte rows)
+    pc_cells, pc_rows = op.pair_cache_info()
+    add("pair_sum(DL, %d of %d cells from the coefficient cache)" % (pc_cells, max(1, sus.ncell // world)), ms["pair"],
+        flops=npairs * FLOPS_DL_PAIR, bytes_=(pc_rows * 256.0) if pc_rows else None)
     add("singular(DL, cached geometry)", ms["sing"], flops=N * npatch * FLOPS_PATCH_CACHED,
-        bytes_=N * npatch * 32.0)
+        bytes_=N * npatch * 32.0, bound="hbm")
     add("near_singular", ms["nearsing"])
     add("spread(DL,6 sym comps)", ms["spread"], flops=N * P3 * (2 + 2 * 6), bytes_=80.0 * N + 2 * 6 * 8.0 * G)
     add("mesh_allreduce+velocity_allreduce(NCCL)", ms["comm"], bound="nvlink")
@@ -339,13 +342,22 @@ def run_gpu(args):
     npairs = float(cnt.astype(np.float64).sum())
     rows = kernel_table(op, sus, stage_ms, npairs, (hbm_peak, fp64_peak), world)
     dom = max(rows, key=lambda r: r["ms"])
+    traffic = None
+    try:   # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+            tr = json.load(fh)
+        traffic = tr.get("%s@%d" % (dom["kernel"].split("(")[0], sus.ncell // world))
+    except Exception:
+        traffic = None
     if dom.get("tflops") is not None and dom["bound"] == "fp64":
         roof = {"kernel": dom["kernel"], "bound": "fp64", "achieved": dom["tflops"], "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": dom["tflops"] / fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": dom["tflops"] / fp64_peak, "traffic": traffic,
                 "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)"}
     else:
         roof = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom.get("gbs"), "peak": hbm_peak, "unit": "GB/s",
-                "frac": (dom.get("gbs") or 0.0) / hbm_peak, "traffic": None, "peak_source": peak_src}
+                "frac": (dom.get("gbs") or 0.0) / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": (dom.get("gbs") or 0.0) * 1e9 * dom["ms"] * 1e-3,
+                "frac_fp64": dom.get("frac_fp64")}
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
@@ -396,7 +408,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-cells", type=int, default=32)
     ap.add_argument("--ref-sample-cells", type=int, default=8, help="--impl reference: target cells per step")
-    ap.add_argument("--ref-spread-stride", type=int, default=8, help="--impl reference: spread every n-th cell")
+    ap.add_argument("--ref-spread-stride", type=int, default=1,
+                    help="--impl reference: spread every n-th cell (1 = all: the oracle's spread has a fixed per-thread "
+                         "mesh cost, so a strided sample overstates the CPU time when extrapolated)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-splines", action="store_true",
