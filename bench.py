@@ -312,16 +312,12 @@ def run_gpu(args):
     e2e_steps = 1 if args.profile else max(1, min(args.steps, args.e2e_steps))
     for _ in range(0 if args.profile else min(2, args.warmup)):
         op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
-        op.apply_assign(0.0, C2_MATVEC, v=v_host)
-        if world > 1:
-            op.TargetList_CollectArray(v_host)
+        op.apply_collect(0.0, C2_MATVEC, v=v_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
-        op.apply_assign(0.0, C2_MATVEC, v=v_host)         # "v = 0" + operator (ModVelSolver.F90:571-582)
-        if world > 1:
-            op.TargetList_CollectArray(v_host)            # ModVelSolver.F90:584
+        op.apply_collect(0.0, C2_MATVEC, v=v_host)        # "v = 0" + operator + CollectArray (ModVelSolver.F90:571-584)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

@@ -219,6 +219,14 @@ module ModB200
       real(c_double) :: v(*)
       integer(c_int) :: ierr
     end function
+    function rbc3d_apply_collect(ctx, c1, c2, use_cells, use_walls, tlist, v) bind(C, name="rbc3d_apply_collect") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double), value :: c1, c2
+      integer(c_int), value :: use_cells, use_walls, tlist
+      real(c_double) :: v(*)
+      integer(c_int) :: ierr
+    end function
     function rbc3d_last_error() bind(C, name="rbc3d_last_error") result(msg)
       import
       type(c_ptr) :: msg

@@ -147,6 +147,10 @@ int rbc3d_apply(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_wal
 /* Same, but v is ASSIGNED (rows of inactive targets = 0): the caller's "v = 0" is folded into the call and v is not
  * uploaded (saves 24 B per target of host->device traffic per application). */
 int rbc3d_apply_assign(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist, double *v);
+/* Same as rbc3d_apply_assign followed by TargetList_CollectArray (ModTargetList.F90:172-202, the call right after the
+ * operator in MyMatMult / Compute_Rhs, ModVelSolver.F90:493, 584): with several ranks the rows are summed on the
+ * devices (ncclAllReduce) before the single device->host copy, so every rank receives the complete v. */
+int rbc3d_apply_collect(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist, double *v);
 /* Same with everything resident: result written (not accumulated) to the context's device velocity buffer;
  * rbc3d_get_velocity copies it out.  Used by the benchmark's device-resident timing. */
 int rbc3d_apply_resident(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rbc3d_pme_add_interp_vel": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_apply": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp]),
     "rbc3d_apply_assign": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp]),
+    "rbc3d_apply_collect": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp]),
     "rbc3d_apply_resident": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     "rbc3d_get_velocity": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_set_skip_flags": (C.c_int, [C.c_void_p, C.c_int]),

@@ -883,6 +883,31 @@ int rbc3d_apply_assign(rbc3d_ctx *c, double c1, double c2, int use_cells, int us
   return v_roundtrip_end(c, *t, v);
 }
 
+// v = operator summed over the ranks: "v = 0", AddIntOnRbcs/AddIntOnWalls, the PME triple and
+// TargetList_CollectArray of ModVelSolver.F90:571-584 as one call.  The sum over ranks happens on the devices
+// (ncclAllReduce) before the one device-to-host copy, instead of download + upload + reduce + download.
+int rbc3d_apply_collect(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls, int tlist, double *v) {
+  TargetList *t;
+  RBC_TRY(get_tl(c, tlist, &t));
+  if (!v) return RBC3D_EINVAL;
+  RBC_TRY(begin_apply(c, *t));
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  t_begin(c, RBC3D_T_COMBINE);
+  RBC_TRY(combine(c, *t, t->v.p, false));
+  t_end(c, RBC3D_T_COMBINE);
+  if (c->prm.nranks > 1) {
+    t_begin(c, RBC3D_T_COMM);
+    RBC_TRY(comm_allreduce_sum(c, t->v.p, 3 * (size_t)t->n));
+    t_end(c, RBC3D_T_COMM);
+  }
+  t_begin(c, RBC3D_T_D2H);
+  if (t->n) CUDA_TRY(cudaMemcpyAsync(v, t->v.p, sizeof(double) * 3 * t->n, cudaMemcpyDeviceToHost, c->stream));
+  t_end(c, RBC3D_T_D2H);
+  t_end(c, RBC3D_T_TOTAL);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
 int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls, int tlist) {
   TargetList *t;
   RBC_TRY(get_tl(c, tlist, &t));

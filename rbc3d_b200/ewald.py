@@ -262,6 +262,12 @@ class EwaldOperator:
         check(self.lib.rbc3d_apply_assign(self._h, c1, c2, int(cells), int(walls), tlist, dp(v)), "rbc3d_apply_assign")
         return v
 
+    def apply_collect(self, c1, c2, tlist=TL_CELLS, v=None, cells=True, walls=False):
+        """v = operator summed over the ranks (apply_assign + TargetList_CollectArray, reduced on the devices)."""
+        v = self._v(tlist, v)
+        check(self.lib.rbc3d_apply_collect(self._h, c1, c2, int(cells), int(walls), tlist, dp(v)), "rbc3d_apply_collect")
+        return v
+
     def apply_resident(self, c1, c2, tlist=TL_CELLS, cells=True, walls=False):
         check(self.lib.rbc3d_apply_resident(self._h, c1, c2, int(cells), int(walls), tlist), "rbc3d_apply_resident")
 

@@ -33,15 +33,17 @@ def main():
         v = op.apply(c1, c2)
         op.TargetList_CollectArray(v)
         op.apply_resident(c1, c2)
-        res[name] = (v, op.get_velocity())
+        vc = op.apply_collect(c1, c2)            # operator + CollectArray, reduced on the devices
+        res[name] = (v, op.get_velocity(), vc)
     if rank == 0:
         from oracle import oracle
         orc = oracle.Oracle(sus.Lb).set_cells(sus)
         for name, c1, c2 in [("matvec", 0.0, util.C2_MATVEC), ("rhs", util.C1_RHS, 0.0)]:
             ref = orc.apply_cells(c1, c2, orc.cell_targets())
-            e1, e2 = util.rel_l2(res[name][0], ref), util.rel_l2(res[name][1], ref)
-            print(f"multi-gpu {world} ranks {name}: host path err {e1:.2e}, resident path err {e2:.2e}")
-            ok = ok and e1 < 1e-10 and e2 < 1e-10
+            e1, e2, e3 = (util.rel_l2(res[name][k], ref) for k in range(3))
+            print(f"multi-gpu {world} ranks {name}: host path err {e1:.2e}, resident path err {e2:.2e}, "
+                  f"apply_collect err {e3:.2e}")
+            ok = ok and e1 < 1e-10 and e2 < 1e-10 and e3 < 1e-10
     op.close()
     dist.barrier()
     dist.destroy_process_group()

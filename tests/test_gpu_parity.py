@@ -348,3 +348,5 @@ def test_apply_assign_equals_zero_then_accumulate(pair8):
     v_acc = op.apply(0.0, C2_MATVEC)                       # caller zeroes v, operator accumulates
     v_set = op.apply_assign(0.0, C2_MATVEC, v=np.full_like(v_acc, 7.0))   # previous contents are ignored
     assert rel_l2(v_set, v_acc) < 1e-13    # FP64 mesh reductions are unordered: equal up to rounding
+    v_col = op.apply_collect(0.0, C2_MATVEC, v=np.full_like(v_acc, -3.0))  # one rank: CollectArray is the identity
+    assert rel_l2(v_col, v_acc) < 1e-13
