@@ -260,6 +260,7 @@ def run_gpu(args):
     op = EwaldOperator(sus.Lb, device=local, nranks=1)
     if world > 1:
         op.attach_comm(world, rank, dist)
+        op.set_replicated_density(True)   # g is replicated on the ranks, as in the reference: PCIe carries 1/world of it
     t0 = time.perf_counter()
     active = op.ownership_mask(sus, world, rank) if world > 1 else None
     op.set_suspension(sus, active=active, with_f=False)
@@ -326,7 +327,8 @@ def run_gpu(args):
     e2e_s = float(e2e_t[0])
     clocks = sampler.stop()
     h2d = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0)
-    d2h = v_host.nbytes
+    d2h = v_host.nbytes * world    # whole job: every rank receives the complete v (CollectArray semantics);
+                                   # h2d stays g_host.nbytes: every rank uploads 1/world of g (replicated density)
 
     if rank != 0:
         op.close()
@@ -370,8 +372,10 @@ def run_gpu(args):
                       "visc_ratio": 5.0, "seed": args.seed, "in_range_pairs": npairs,
                       "l2": "inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
                       "density_splines": "host (uploaded)" if args.host_splines else "device (built from g every step)",
-                      "partition": ("targets and PME spreading by owned cell block, sources replicated, meshes and velocities "
-                                    "summed with ncclAllReduce") if world > 1 else "single GPU"},
+                      "partition": ("targets, singular/pair work, geometry caches and PME spreading by owned cell block; "
+                                    "densities uploaded 1/world per rank + ncclAllGather; meshes and velocities summed "
+                                    "with ncclAllReduce; the PME chain overlaps the real-space kernels on a second "
+                                    "stream (stage_ms overlap)") if world > 1 else "single GPU"},
            "clocks": clocks,
            "e2e": {"value": 1.0 / e2e_s, "unit": "matvecs/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -169,6 +169,11 @@ int rbc3d_set_sing_cache(rbc3d_ctx *ctx, int mode);
  * mode 1 the same kernel without the cache, mode 2 dense per-cell kernel, mode 0 through the hashed cell list like
  * every other pair (testing). */
 int rbc3d_set_pair_self(rbc3d_ctx *ctx, int mode);
+/* Several ranks: declare that the host densities passed to rbc3d_cells_set_density are identical on all ranks (the
+ * reference replicates rbc%f / rbc%g, ModVelSolver.F90:552-565).  Each rank then uploads only the rows of its own
+ * cell block and the blocks are all-gathered over NVLink; rbc3d_cells_set_density becomes a collective call.
+ * Needs ncell divisible by the number of ranks (otherwise the full arrays are uploaded as before). */
+int rbc3d_set_replicated_density(rbc3d_ctx *ctx, int on);
 /* state of that cache after rbc3d_cells_set_geometry: cells cached (of the cells this rank owns targets of) and
  * 256-byte coefficient rows held (= bytes streamed per matvec / 256); either pointer may be NULL */
 int rbc3d_pair_cache_info(rbc3d_ctx *ctx, int32_t *cells_cached, int64_t *rows);

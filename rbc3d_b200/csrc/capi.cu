@@ -253,6 +253,10 @@ int rbc3d_ctx_create(rbc3d_ctx **out, const double Lb[3], double alpha, double e
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  if (const char *e = getenv("RBC3D_OVERLAP")) c->overlap = atoi(e);
   for (int i = 0; i < 2 * RBC3D_T_COUNT; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < RBC3D_T_COUNT; i++) {
     c->ev_used[i] = false;
@@ -325,6 +329,9 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   walls_release(c);
   for (int i = 0; i < 2 * RBC3D_T_COUNT; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   // device buffers are released with the context's allocations
   auto rel_cl = [](CellList &l) {
     l.cid.release();
@@ -369,7 +376,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   rel_cl(C.pl);
   for (int k = 0; k < 3; k++) {
     TargetList &t = c->tl[k];
-    for (dbuf<double> *b : {&t.x, &t.Acoef, &t.acc, &t.v, &t.host_io, &t.ns.th0, &t.ns.phi0, &t.ns.dist, &t.ns.x0,
+    for (dbuf<double> *b : {&t.x, &t.Acoef, &t.acc, &t.acc2, &t.v, &t.host_io, &t.ns.th0, &t.ns.phi0, &t.ns.dist, &t.ns.x0,
                             &t.ns.a30, &t.ns.xi, &t.ns.dv})
       b->release();
     for (dbuf<int> *b : {&t.active, &t.surf, &t.ns.cnt, &t.ns.off, &t.ns.target, &t.ns.cell, &t.ns.pt, &t.ns.flag,
@@ -407,6 +414,12 @@ int rbc3d_set_sing_cache(rbc3d_ctx *c, int mode) {
 int rbc3d_set_pair_self(rbc3d_ctx *c, int mode) {
   if (!c) return RBC3D_EINVAL;
   c->pair_self_mode = mode;
+  return RBC3D_OK;
+}
+
+int rbc3d_set_replicated_density(rbc3d_ctx *c, int on) {
+  if (!c) return RBC3D_EINVAL;
+  c->replicated_density = on ? 1 : 0;
   return RBC3D_OK;
 }
 
@@ -572,8 +585,26 @@ int rbc3d_cells_set_density(rbc3d_ctx *c, const double *f, const double *g, cons
   const size_t Np = C.Np, nc = C.ncell;
   const size_t sp3 = (size_t)12 * 2 * C.nlat * C.nlon;
   t_begin(c, RBC3D_T_H2D);
-  if (f) RBC_TRY(upload(C.f, f, 3 * Np, c->stream));
-  if (g) RBC_TRY(upload(C.g, g, 3 * Np, c->stream));
+  const int nr = c->prm.nranks;
+  if (nr > 1 && c->replicated_density && nc % nr == 0) {
+    // every rank holds the same host arrays (the reference replicates surface state): each rank uploads the rows of
+    // its own cell block over PCIe and the blocks are all-gathered over NVLink, component plane by component plane
+    const size_t blk = (nc / nr) * (size_t)C.npc;
+    for (int which = 0; which < 2; which++) {
+      const double *src = which ? g : f;
+      dbuf<double> &dst = which ? C.g : C.f;
+      if (!src) continue;
+      RBC_TRY(dst.resize(3 * Np));
+      for (int d = 0; d < 3; d++) {
+        const size_t off = (size_t)d * Np + (size_t)c->prm.rank * blk;
+        CUDA_TRY(cudaMemcpyAsync(dst.p + off, src + off, sizeof(double) * blk, cudaMemcpyHostToDevice, c->stream));
+      }
+      for (int d = 0; d < 3; d++) RBC_TRY(comm_allgather_inplace(c, dst.p + (size_t)d * Np, blk));
+    }
+  } else {
+    if (f) RBC_TRY(upload(C.f, f, 3 * Np, c->stream));
+    if (g) RBC_TRY(upload(C.g, g, 3 * Np, c->stream));
+  }
   if (spF) RBC_TRY(upload(C.spF, spF, sp3 * nc, c->stream));
   if (spG) RBC_TRY(upload(C.spG, spG, sp3 * nc, c->stream));
   t_end(c, RBC3D_T_H2D);
@@ -837,7 +868,37 @@ int rbc3d_pme_add_interp_vel(rbc3d_ctx *c, int tlist, double *v) {
   return v_roundtrip_end(c, *t, v);
 }
 
-static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int use_cells, int use_walls) {
+static int pme_chain(rbc3d_ctx *c, TargetList &t, double c1, double c2, int use_cells, int use_walls, double *acc) {
+  t_begin(c, RBC3D_T_SPREAD);
+  RBC_TRY(pme_spread(c, c1, c2, use_cells != 0, use_walls != 0));
+  t_end(c, RBC3D_T_SPREAD);
+  RBC_TRY(pme_transform(c));
+  t_begin(c, RBC3D_T_INTERP);
+  RBC_TRY(pme_interp(c, t, acc));
+  t_end(c, RBC3D_T_INTERP);
+  return RBC3D_OK;
+}
+
+// Returns in *acc2 the second accumulator the caller has to hand to combine() (null when the chain ran in line).
+static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int use_cells, int use_walls,
+                        const double **acc2 = nullptr) {
+  const bool overlap = acc2 && (c->overlap == 1 || (c->overlap < 0 && c->prm.nranks > 1));
+  if (acc2) *acc2 = nullptr;
+  if (overlap) {
+    // fork: the PME chain on stream2 (issued first so that its all-reduce and FFTs start early), real space on stream
+    RBC_TRY(t.acc2.resize(3 * (size_t)(t.n > 0 ? t.n : 1)));
+    CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    std::swap(c->stream, c->stream2);
+    int rc = cudaMemsetAsync(t.acc2.p, 0, sizeof(double) * 3 * (size_t)(t.n > 0 ? t.n : 1), c->stream) == cudaSuccess
+                 ? RBC3D_OK
+                 : RBC3D_ECUDA;
+    if (rc == RBC3D_OK) rc = pme_chain(c, t, c1, c2, use_cells, use_walls, t.acc2.p);
+    if (rc == RBC3D_OK && cudaEventRecord(c->ev_join, c->stream) != cudaSuccess) rc = RBC3D_ECUDA;
+    std::swap(c->stream, c->stream2);
+    RBC_TRY(rc);
+    *acc2 = t.acc2.p;
+  }
   if (use_cells) RBC_TRY(realspace_cells(c, t, c1, c2));
   if (use_walls && c1 != 0) {
     t_begin(c, RBC3D_T_WALL);
@@ -847,13 +908,10 @@ static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int u
   t_begin(c, RBC3D_T_LINEAR);
   RBC_TRY(linear_term(c, t, (use_cells && !(c->skip_flags & 4)) ? c2 : 0.0));
   t_end(c, RBC3D_T_LINEAR);
-  t_begin(c, RBC3D_T_SPREAD);
-  RBC_TRY(pme_spread(c, c1, c2, use_cells != 0, use_walls != 0));
-  t_end(c, RBC3D_T_SPREAD);
-  RBC_TRY(pme_transform(c));
-  t_begin(c, RBC3D_T_INTERP);
-  RBC_TRY(pme_interp(c, t));
-  t_end(c, RBC3D_T_INTERP);
+  if (overlap)
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join before combine
+  else
+    RBC_TRY(pme_chain(c, t, c1, c2, use_cells, use_walls, nullptr));
   return RBC3D_OK;
 }
 
@@ -862,9 +920,10 @@ int rbc3d_apply(rbc3d_ctx *c, double c1, double c2, int use_cells, int use_walls
   RBC_TRY(get_tl(c, tlist, &t));
   RBC_TRY(begin_apply(c, *t));
   RBC_TRY(v_roundtrip_begin(c, *t, v));
-  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  const double *acc2 = nullptr;
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls, &acc2));
   t_begin(c, RBC3D_T_COMBINE);
-  RBC_TRY(combine(c, *t, t->host_io.p, true));
+  RBC_TRY(combine(c, *t, t->host_io.p, true, acc2));
   t_end(c, RBC3D_T_COMBINE);
   return v_roundtrip_end(c, *t, v);
 }
@@ -876,9 +935,10 @@ int rbc3d_apply_assign(rbc3d_ctx *c, double c1, double c2, int use_cells, int us
   RBC_TRY(get_tl(c, tlist, &t));
   RBC_TRY(begin_apply(c, *t));
   RBC_TRY(t->host_io.resize(3 * (size_t)(t->n > 0 ? t->n : 1)));
-  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  const double *acc2 = nullptr;
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls, &acc2));
   t_begin(c, RBC3D_T_COMBINE);
-  RBC_TRY(combine(c, *t, t->host_io.p, false));
+  RBC_TRY(combine(c, *t, t->host_io.p, false, acc2));
   t_end(c, RBC3D_T_COMBINE);
   return v_roundtrip_end(c, *t, v);
 }
@@ -891,9 +951,10 @@ int rbc3d_apply_collect(rbc3d_ctx *c, double c1, double c2, int use_cells, int u
   RBC_TRY(get_tl(c, tlist, &t));
   if (!v) return RBC3D_EINVAL;
   RBC_TRY(begin_apply(c, *t));
-  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  const double *acc2 = nullptr;
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls, &acc2));
   t_begin(c, RBC3D_T_COMBINE);
-  RBC_TRY(combine(c, *t, t->v.p, false));
+  RBC_TRY(combine(c, *t, t->v.p, false, acc2));
   t_end(c, RBC3D_T_COMBINE);
   if (c->prm.nranks > 1) {
     t_begin(c, RBC3D_T_COMM);
@@ -925,9 +986,10 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
     }
   }
   t_end(c, RBC3D_T_DENSITY);
-  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls));
+  const double *acc2 = nullptr;
+  RBC_TRY(apply_common(c, *t, c1, c2, use_cells, use_walls, &acc2));
   t_begin(c, RBC3D_T_COMBINE);
-  RBC_TRY(combine(c, *t, t->v.p, false));
+  RBC_TRY(combine(c, *t, t->v.p, false, acc2));
   t_end(c, RBC3D_T_COMBINE);
   if (c->prm.nranks > 1) {  // TargetList_CollectArray
     t_begin(c, RBC3D_T_COMM);

@@ -39,6 +39,18 @@ int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n) {
 #endif
 }
 
+// in-place all-gather: rank r's block sits at buf + r * count
+int comm_allgather_inplace(rbc3d_ctx *c, double *buf, size_t count) {
+  if (c->prm.nranks <= 1 || count == 0) return RBC3D_OK;
+#ifdef RBC3D_WITH_NCCL
+  NCCL_TRY(ncclAllGather(buf + (size_t)c->prm.rank * count, buf, count, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
 void comm_destroy(rbc3d_ctx *c) {
 #ifdef RBC3D_WITH_NCCL
   if (c->nccl_comm) ncclCommDestroy((ncclComm_t)c->nccl_comm);

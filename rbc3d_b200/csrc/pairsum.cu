@@ -726,16 +726,18 @@ int linear_term(rbc3d_ctx *c, TargetList &t, double c2) {
 }
 
 // ---- v (+)= (acc + c2*xvint) / Acoef for active targets (the "/tlist%Acoef(i)" of every term) ----
-__global__ void k_combine(int n, const double *__restrict__ acc, const double *__restrict__ xv,
-                          const double *__restrict__ A, const int *__restrict__ active, double *__restrict__ v,
-                          int accumulate) {
+__global__ void k_combine(int n, const double *__restrict__ acc, const double *__restrict__ acc2,
+                          const double *__restrict__ xv, const double *__restrict__ A, const int *__restrict__ active,
+                          double *__restrict__ v, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool on = active[i] != 0;
   const double ia = 1.0 / A[i];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    double r = on ? (acc[(size_t)d * n + i] + xv[d]) * ia : 0.0;
+    double s = acc[(size_t)d * n + i];
+    if (acc2) s += acc2[(size_t)d * n + i];
+    double r = on ? (s + xv[d]) * ia : 0.0;
     if (accumulate)
       v[(size_t)d * n + i] += r;
     else
@@ -743,10 +745,10 @@ __global__ void k_combine(int n, const double *__restrict__ acc, const double *_
   }
 }
 
-int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate) {
+int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate, const double *acc2) {
   if (t.n == 0) return RBC3D_OK;
   Cells &C = c->cells;
-  k_combine<<<(t.n + 255) / 256, 256, 0, c->stream>>>(t.n, t.acc.p, C.xvint_part.p + 3 * LIN_BLOCKS, t.Acoef.p,
+  k_combine<<<(t.n + 255) / 256, 256, 0, c->stream>>>(t.n, t.acc.p, acc2, C.xvint_part.p + 3 * LIN_BLOCKS, t.Acoef.p,
                                                       t.active.p, v_dev, accumulate ? 1 : 0);
   KERNEL_CHECK();
   c->launches++;

@@ -108,10 +108,10 @@ static int get_plan_fwd(rbc3d_ctx *c, int batch, cufftHandle *out) {
   if (!pm.planF_ok[slot]) {
     int n[3] = {pm.Nz, pm.Ny, pm.Nx};
     CUFFT_TRY(cufftPlanMany(&pm.planF[slot], 3, n, nullptr, 1, (int)pm.G, nullptr, 1, (int)pm.M, CUFFT_D2Z, batch));
-    CUFFT_TRY(cufftSetStream(pm.planF[slot], c->stream));
     pm.planF_ok[slot] = true;
   }
   *out = pm.planF[slot];
+  CUFFT_TRY(cufftSetStream(pm.planF[slot], c->stream));  // the chain may run on either stream of the context
   return RBC3D_OK;
 }
 
@@ -120,10 +120,10 @@ static int get_plan_bwd(rbc3d_ctx *c, cufftHandle *out) {
   if (!pm.planB_ok) {
     int n[3] = {pm.Nz, pm.Ny, pm.Nx};
     CUFFT_TRY(cufftPlanMany(&pm.planB, 3, n, nullptr, 1, (int)pm.M, nullptr, 1, (int)pm.G, CUFFT_Z2D, 3));
-    CUFFT_TRY(cufftSetStream(pm.planB, c->stream));
     pm.planB_ok = true;
   }
   *out = pm.planB;
+  CUFFT_TRY(cufftSetStream(pm.planB, c->stream));
   return RBC3D_OK;
 }
 
@@ -1188,7 +1188,7 @@ __global__ void __launch_bounds__(IW_WARPS * 32, 3) k_interp_walk(InterpWArgs a)
   }
 }
 
-int pme_interp(rbc3d_ctx *c, TargetList &t) {
+int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc) {
   Pme &pm = c->pme;
   if (!pm.transformed) {
     set_error("PME_Add_Interp_Vel called before PME_Transform");
@@ -1205,7 +1205,7 @@ int pme_interp(rbc3d_ctx *c, TargetList &t) {
     w.wrec = pl.w.p;
     w.vv = pm.vv.p;
     w.G = pm.G;
-    w.acc = t.acc.p;
+    w.acc = acc ? acc : t.acc.p;
     const int ncol = pm.Nx * pm.Ny;
     k_interp_walk<<<(ncol + IW_WARPS - 1) / IW_WARPS, IW_WARPS * 32, 0, c->stream>>>(w);
     KERNEL_CHECK();
@@ -1223,7 +1223,7 @@ int pme_interp(rbc3d_ctx *c, TargetList &t) {
   a.nbx = pm.nblk[0];
   a.nby = pm.nblk[1];
   a.nbz = pm.nblk[2];
-  a.acc = t.acc.p;
+  a.acc = acc ? acc : t.acc.p;
   const int T = PME_BLK + c->prm.P - 1;
   const size_t smem = sizeof(double) * (3 * (size_t)T * T * T + INTERP_WARPS * 3 * PME_PMAX);
   CUDA_TRY(cudaFuncSetAttribute(k_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

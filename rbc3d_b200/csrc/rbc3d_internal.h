@@ -139,6 +139,7 @@ struct TargetList {
   int ntiles = 0;
   NearSing ns;
   dbuf<double> acc;     // SoA(3,n) un-normalised sums of the current application
+  dbuf<double> acc2;    // same for the PME chain when it runs on the second stream (kept apart: deterministic sums)
   dbuf<double> v;       // SoA(3,n) result of rbc3d_apply_resident
   dbuf<double> host_io; // staging for host v
   WallPairs wp;
@@ -254,6 +255,12 @@ struct rbc3d_ctx {
   int device = 0;
   rbc3d::Params prm;
   cudaStream_t stream = nullptr;
+  // the PME chain (spread, mesh all-reduce, FFTs, scaling, interpolation) does not depend on the real-space sums:
+  // with overlap on it is issued on stream2 while singular / pair kernels run on stream (joined before combine)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int replicated_density = 0;  // 1: host densities are identical on all ranks -> upload 1/nranks each + all-gather
+  int overlap = -1;         // -1: on with several ranks (hides the mesh all-reduce), 0 off, 1 on
   // lookup tables (device): interleaved SL (c1,c2) pairs, DL, mask
   rbc3d::dbuf<double> tab_sl, tab_dl, tab_mask;
   std::vector<double> h_tab_sl1, h_tab_sl2, h_tab_dl, h_tab_mask;
@@ -306,7 +313,7 @@ int singular_prepare(rbc3d_ctx *c);
 int singular_density_prepare(rbc3d_ctx *c);
 int singular_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
 int linear_term(rbc3d_ctx *c, TargetList &t, double c2);
-int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate);
+int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate, const double *acc2 = nullptr);
 
 // ---- density splines on the device (splinebuild.cu) ----
 int spline_builder_prepare(rbc3d_ctx *c, int nlat0);
@@ -318,7 +325,7 @@ int pme_init(rbc3d_ctx *c);
 void pme_destroy(rbc3d_ctx *c);
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls);
 int pme_transform(rbc3d_ctx *c);
-int pme_interp(rbc3d_ctx *c, TargetList &t);
+int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc = nullptr);  // acc: SoA(3,n) to add into (default t.acc)
 
 // ---- walls (walls.cu) ----
 int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nele, const double *x, const int *e2v,
@@ -337,6 +344,7 @@ void walls_release(rbc3d_ctx *c);
 
 // ---- multi-GPU (comm.cu) ----
 int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);
+int comm_allgather_inplace(rbc3d_ctx *c, double *buf, size_t count);
 void comm_destroy(rbc3d_ctx *c);
 
 // timing helpers

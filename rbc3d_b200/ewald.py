@@ -282,6 +282,10 @@ class EwaldOperator:
     def set_pair_self(self, mode):
         check(self.lib.rbc3d_set_pair_self(self._h, int(mode)))
 
+    def set_replicated_density(self, on=True):
+        """host densities identical on all ranks: upload 1/nranks each, all-gather over NVLink (collective)."""
+        check(self.lib.rbc3d_set_replicated_density(self._h, int(bool(on))))
+
     def pair_cache_info(self):
         """(cells cached, 256-byte coefficient rows) of the same-surface double-layer pair cache."""
         nc, rows = C.c_int32(), C.c_int64()

@@ -30,6 +30,9 @@ def main():
     ok = True
     res = {}
     for name, c1, c2 in [("matvec", 0.0, util.C2_MATVEC), ("rhs", util.C1_RHS, 0.0)]:
+        if name == "rhs":   # second half with the sharded density upload (upload own block + all-gather)
+            op.set_replicated_density(True)
+            op.SourceList_UpdateDensity(f=sus.weighted(sus.f), g=sus.weighted(sus.g), spF=sus.spF, spG=sus.spG)
         v = op.apply(c1, c2)
         op.TargetList_CollectArray(v)
         op.apply_resident(c1, c2)
