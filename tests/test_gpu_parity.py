@@ -191,6 +191,35 @@ def test_noncubic_box_small_cells(oracle_lib):
     op.close()
 
 
+@pytest.mark.parametrize("Nb,P", [([44, 40, 36], 8), ([12, 20, 28], 8), ([8, 8, 8], 8), ([40, 44, 36], 6), ([20, 24, 28], 4)])
+def test_pme_odd_mesh_sizes_and_spline_orders(oracle_lib, Nb, P):
+    """PME with meshes that are not multiples of the 8-cell x runs of the spreading walk (last run wraps on the right:
+    scalar-reduction flush), narrower than 16 points, as small as the B-spline support (every ring slot aliases), and
+    with P != 8 (the generic block kernels).  Accuracy of the Ewald split is irrelevant here: GPU and oracle use the
+    same mesh."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    Lb = np.array([10.5, 9.0, 8.0])
+    centers = np.array([[3.0, 3.0, 2.0], [7.0, 6.5, 5.5], [9.9, 1.0, 7.6]])   # the last cell straddles three faces
+    sus = synth.make_suspension(1, nlat0=6, centers=centers, L=1.0, seed=12)
+    sus.Lb = Lb
+    op = EwaldOperator(Lb, P=P, Nb=Nb)
+    op.set_suspension(sus)
+    orc = oracle_lib.Oracle(Lb, P=P, Nb=Nb).set_cells(sus)
+    assert op.Nb == orc.Nb == Nb
+    npc = sus.nlat * sus.nlon
+    for c1, c2 in [(C1_RHS, 0.0), (0.0, C2_MATVEC), (C1_RHS, C2_MATVEC)]:
+        op.PME_Distrib_Source(c1, c2, cells=True)
+        op.PME_Transform()
+        v = op.PME_Add_Interp_Vel()
+        orc.pme_distrib(c1, c2, sus.x, sus.weighted(sus.f), sus.weighted(sus.g), sus.a3, np.repeat(sus.Bcoef, npc))
+        orc.pme_transform()
+        ref = orc.pme_interp(orc.cell_targets())
+        assert rel_l2(op.pme_grid(), orc.pme_vv()) < TOL
+        assert rel_l2(v, ref) < TOL
+    op.close()
+
+
 def test_timings_and_launch_count(pair8):
     op, _ = pair8
     n0 = op.launch_count()
