@@ -221,8 +221,10 @@ def kernel_table(op, sus, ms, npairs, peaks, world=1):
     pc_cells, pc_rows = op.pair_cache_info()
     add("pair_sum(DL, %d of %d cells from the coefficient cache)" % (pc_cells, max(1, sus.ncell // world)), ms["pair"],
         flops=npairs * FLOPS_DL_PAIR, bytes_=(pc_rows * 256.0) if pc_rows else None)
-    add("singular(DL, cached geometry)", ms["sing"], flops=N * npatch * FLOPS_PATCH_CACHED,
-        bytes_=N * npatch * 32.0, bound="hbm")
+    # the cache holds (and the kernel streams) only patch points with a non-zero quadrature weight
+    sg_on, sg_pts = op.sing_cache_info()
+    add("singular(DL, cached geometry, %d of %d patch points)" % (sg_pts, npatch), ms["sing"],
+        flops=N * npatch * FLOPS_PATCH_CACHED, bytes_=N * (sg_pts if sg_on else npatch) * 32.0, bound="hbm")
     add("near_singular", ms["nearsing"])
     add("spread(DL,6 sym comps)", ms["spread"], flops=N * P3 * (2 + 2 * 6), bytes_=80.0 * N + 2 * 6 * 8.0 * G)
     add("mesh_allreduce+velocity_allreduce(NCCL)", ms["comm"], bound="nvlink")

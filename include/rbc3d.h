@@ -162,6 +162,10 @@ int rbc3d_set_skip_flags(rbc3d_ctx *ctx, int flags);
  * device memory allows, so that GMRES matvecs only interpolate the density; mode 0 always evaluates directly.
  * Takes effect at the next rbc3d_cells_set_geometry. */
 int rbc3d_set_sing_cache(rbc3d_ctx *ctx, int mode);
+/* state of that cache: 1 if the cached path is active, and the patch points per target it streams (those with a
+ * non-zero quadrature weight: the mask table vanishes on its last interval, so the outermost radial node of every ray
+ * contributes exactly zero and is left out; 32 B each per matvec) */
+int rbc3d_sing_cache_info(rbc3d_ctx *ctx, int32_t *cached, int32_t *points_per_target);
 /* Same-surface pairs of the real-space sum (ModIntOnRbcs.F90:81-84): mode 3 (default) symmetric patch-pair kernel
  * (each unordered pair evaluated once) that, for the double-layer operator alone (the GMRES matvec), streams a
  * per-geometry cache of (1 - mask) * EwaldCoeff_DL per unordered pair (8 B per pair slot, ~16 MB per 36x72 cell; built

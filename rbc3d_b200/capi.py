@@ -62,6 +62,7 @@ SIGNATURES = {
     "rbc3d_set_skip_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_set_sing_cache": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_set_pair_self": (C.c_int, [C.c_void_p, C.c_int]),
+    "rbc3d_sing_cache_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rbc3d_set_replicated_density": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_pair_cache_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rbc3d_cell_list_get": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),

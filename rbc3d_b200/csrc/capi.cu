@@ -417,6 +417,13 @@ int rbc3d_set_pair_self(rbc3d_ctx *c, int mode) {
   return RBC3D_OK;
 }
 
+int rbc3d_sing_cache_info(rbc3d_ctx *c, int32_t *cached, int32_t *points_per_target) {
+  if (!c) return RBC3D_EINVAL;
+  if (cached) *cached = c->cells.sg_cache_ok ? 1 : 0;
+  if (points_per_target) *points_per_target = c->cells.sg_npatch_active;
+  return RBC3D_OK;
+}
+
 int rbc3d_set_replicated_density(rbc3d_ctx *c, int on) {
   if (!c) return RBC3D_EINVAL;
   c->replicated_density = on ? 1 : 0;
@@ -495,7 +502,7 @@ int rbc3d_cells_set_mesh(rbc3d_ctx *c, int ncell, int nlat, int nlon, const doub
   RBC_TRY(upload(C.omm, omm.data(), omm.size(), c->stream));
   RBC_TRY(upload(C.dlonmax, dmax.data(), dmax.size(), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  RBC_TRY(singular_mesh_prepare(c, thG.data(), phiG.data()));
+  RBC_TRY(singular_mesh_prepare(c, thG.data(), phiG.data(), pw.data()));
   RBC_TRY(pairself_mesh_prepare(c, omm));
   C.mesh_set = true;
   C.sb_ok = false;

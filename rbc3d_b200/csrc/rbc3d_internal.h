@@ -193,6 +193,7 @@ struct Cells {
   // cached double-layer singular path (singular.cu): cell-independent tile tables, per-geometry cache
   bool sg_ok = false, sg_cache_ok = false, spGi_valid = false;
   int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
+  int sg_npatch_active = 0;          // patch points per target with a non-zero quadrature weight (cached path)
   dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active, sg_tile_list, sg_pos;
   int sg_ntl = 0, sg_ntn = 0, sg_ni_max = 0, sg_chunk_stride = 0;
   dbuf<int> sg_rounds, sg_active_list;
@@ -308,7 +309,7 @@ int neighbor_signature(rbc3d_ctx *c, TargetList &t, int *count, unsigned long lo
 int nearsing_scan(rbc3d_ctx *c, TargetList &t, bool fill);
 int nearsing_prepare(rbc3d_ctx *c, TargetList &t);
 int nearsing_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);
-int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG);
+int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, const double *pw);
 int singular_prepare(rbc3d_ctx *c);
 int singular_density_prepare(rbc3d_ctx *c);
 int singular_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2);

@@ -180,7 +180,7 @@ static void cyclic_cover(const std::vector<char> &used, int mod, int &lo, int &l
   len = mod - best_len;
 }
 
-int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
+int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, const double *pw) {
   Cells &C = c->cells;
   C.sg_ok = false;
   C.sg_cache_ok = false;
@@ -189,6 +189,8 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
   const int K = (npatch + 31) / 32, NPT = K * SG_T * 32;
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   const double ihx = 1.0 / hx, ihy = 1.0 / hy;
+  C.sg_npatch_active = 0;
+  for (int q = 0; q < npatch; q++) C.sg_npatch_active += (pw[q % C.nrad] != 0.0) ? 1 : 0;
   C.sg_ntl = ntl;
   C.sg_ntn = ntn;
   C.sg_ntiles = ntl * ntn;
@@ -223,7 +225,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
         const int i1m = ((i1 % m) + m) % m, j1m = ((j1 % n) + n) % n;
         ni1[(size_t)w * npatch + q] = i1m;
         nj1[(size_t)w * npatch + q] = j1m;
-        ui[i1m] = ui[(i1m + 1) % m] = 1;
+        if (pw[q % C.nrad] != 0.0) ui[i1m] = ui[(i1m + 1) % m] = 1;
       }
     }
     int ilo, ni;
@@ -237,6 +239,9 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG) {
     for (int w = 0; w < SG_T; w++) {
       if (row_tgt[(size_t)tl * SG_T + w] < 0) continue;
       for (int q = 0; q < npatch; q++) {
+        // patch points whose quadrature weight is exactly zero (the mask table vanishes on its last interval: the
+        // outermost radial node of every ray) contribute exactly zero: they are left out of the cached path
+        if (pw[q % C.nrad] == 0.0) continue;
         const int wi = (ni1[(size_t)w * npatch + q] - ilo + m) % m;
         const long long cellkey = (long long)nj1[(size_t)w * npatch + q] * ni + wi;
         // per-warp mode: target first, then spline cell; tile mode: spline cell first

@@ -282,6 +282,12 @@ class EwaldOperator:
     def set_pair_self(self, mode):
         check(self.lib.rbc3d_set_pair_self(self._h, int(mode)))
 
+    def sing_cache_info(self):
+        """(cached path active, patch points per target streamed from the cache)."""
+        a, b = C.c_int32(), C.c_int32()
+        check(self.lib.rbc3d_sing_cache_info(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), b.value
+
     def set_replicated_density(self, on=True):
         """host densities identical on all ranks: upload 1/nranks each, all-gather over NVLink (collective)."""
         check(self.lib.rbc3d_set_replicated_density(self._h, int(bool(on))))
