@@ -37,6 +37,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 C2_MATVEC = -1.0 / (4.0 * np.pi)
+GMRES_ITS_ASSUMED = 22     # iterations of the cell velocity solve at rtol 1e-11 (tests/test_gpu_gmres.py, 8 cells)
+C1_RHS = 1.0 / (4.0 * np.pi)
 FLOPS_DL_PAIR = 54.0      # flops per in-range double-layer pair (FMA = 2)
 FLOPS_SPLINE3 = 155.0     # one bicubic interpolation of 3 variables
 FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
@@ -328,6 +330,44 @@ def run_gpu(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t[0])
     clocks = sampler.stop()
+
+    # ---- the other half of BASELINE.json's metric: time-step rate of the boundary-integral part -----------------
+    # One mtube step evaluates, on a NEW geometry: SourceList_UpdateCoord (cell lists, geometry caches), Compute_Rhs
+    # (operator #1: c1 = 1/4pi, c2 = 0) and one GMRES solve (operator #2 x iterations).  Measured after the timed
+    # region above with host buffers (steady state: device buffers already allocated); the iteration count is the
+    # one the 8-cell parity solve takes at rtol 1e-11 (tests/test_gpu_gmres.py), stated as an assumption.
+    timestep = None
+    if not args.profile and not args.no_timestep:
+        try:
+            for arr in (sus.x, sus.a3, sus.spx, sus.spa3, sus.spdetj):   # the caller's arrays, pinned once
+                capi.check(lib.rbc3d_host_register(arr.ctypes.data, arr.nbytes), "rbc3d_host_register")
+            barrier()
+            t0 = time.perf_counter()
+            op.SourceList_UpdateCoord(sus.x, sus.a3, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize, sus.spx, sus.spa3,
+                                      sus.spdetj, active)
+            barrier()
+            t_geom = time.perf_counter() - t0
+            op.SourceList_UpdateDensity(f=g_host)          # any band-limited density times the RHS operator
+            t_rhs = []
+            for _ in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                op.SourceList_UpdateDensity(f=g_host)
+                op.apply_collect(C1_RHS, 0.0, v=v_host)
+                barrier()
+                t_rhs.append(time.perf_counter() - t0)
+            tt = torch.tensor([t_geom, min(t_rhs)], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_geom, t_rhs1 = float(tt[0]), float(tt[1])
+            its = GMRES_ITS_ASSUMED
+            timestep = {"geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
+                        "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations_assumed": its,
+                        "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its * e2e_s),
+                        "note": "boundary-integral part of one mtube step (membrane forces, SH transforms, GMRES "
+                                "vector algebra stay in the Fortran caller and are not included)"}
+        except Exception as exc:  # e.g. no room left for spline(f detJ) next to the caches
+            timestep = {"error": str(exc)[:200]}
     h2d = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0)
     d2h = v_host.nbytes * world    # whole job: every rank receives the complete v (CollectArray semantics);
                                    # h2d stays g_host.nbytes: every rank uploads 1/world of g (replicated density)
@@ -383,7 +423,7 @@ def run_gpu(args):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches),
            "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
-           "roofline": roof, "kernels": rows,
+           "roofline": roof, "kernels": rows, "timestep": timestep,
            "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "fp64_tflops": fp64_peak,
                      "fp64_source": "in-process DFMA micro-benchmark"},
            "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
@@ -415,6 +455,7 @@ def main():
                          "mesh cost, so a strided sample overstates the CPU time when extrapolated)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-timestep", action="store_true", help="skip the geometry-update / RHS-operator timing")
     ap.add_argument("--host-splines", action="store_true",
                     help="upload spline(g detJ) from the host every step instead of building it on the GPU")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: exact --warmup, no CPU leg, 1 e2e step")

@@ -356,6 +356,8 @@ __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
   const size_t off = (size_t)pt * a.npatch;
   for (int k = 0; k < a.K; k++) {
     const int q = k * 32 + lane;
+    const int sp = pos[(k * SG_T + w) * 32 + lane];
+    if (sp < 0) continue;  // beyond the patch, or a point with zero quadrature weight: not part of the cache
     double4 r = make_double4(0, 0, 0, 0);
     if (q < a.npatch) {
       const double th_j = __ldg(a.thG + off + q), phi_j = __ldg(a.phiG + off + q);
@@ -370,8 +372,7 @@ __global__ void __launch_bounds__(SG_T * 32) k_sing_cache_build(CacheArgs a) {
         r = make_double4(xx, yy, zz, EA * wq * (xx * nj[0] + yy * nj[1] + zz * nj[2]));
       }
     }
-    const int sp = pos[(k * SG_T + w) * 32 + lane];
-    if (sp >= 0) out[sp] = r;
+    out[sp] = r;
   }
 }
 
