@@ -339,12 +339,17 @@ def run_gpu(args):
     timestep = None
     if not args.profile and not args.no_timestep:
         try:
-            for arr in (sus.x, sus.a3, sus.spx, sus.spa3, sus.spdetj):   # the caller's arrays, pinned once
-                capi.check(lib.rbc3d_host_register(arr.ctypes.data, arr.nbytes), "rbc3d_host_register")
+            dev_geom = not args.host_splines
+            for arr in ((sus.x, sus.a3, sus.detj) if dev_geom else (sus.x, sus.a3, sus.spx, sus.spa3, sus.spdetj)):
+                capi.check(lib.rbc3d_host_register(arr.ctypes.data, arr.nbytes), "rbc3d_host_register")   # pinned once
             barrier()
             t0 = time.perf_counter()
-            op.SourceList_UpdateCoord(sus.x, sus.a3, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize, sus.spx, sus.spa3,
-                                      sus.spdetj, active)
+            if dev_geom:   # Rbc_BuildSurfaceSource(xFlag) on the device: x, a3, detJ cross PCIe, not their splines
+                op.SourceList_UpdateCoord_mesh(sus.x, sus.a3, sus.detj, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize,
+                                               active)
+            else:
+                op.SourceList_UpdateCoord(sus.x, sus.a3, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize, sus.spx,
+                                          sus.spa3, sus.spdetj, active)
             barrier()
             t_geom = time.perf_counter() - t0
             op.SourceList_UpdateDensity(f=g_host)          # any band-limited density times the RHS operator
@@ -361,7 +366,8 @@ def run_gpu(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_geom, t_rhs1 = float(tt[0]), float(tt[1])
             its = GMRES_ITS_ASSUMED
-            timestep = {"geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
+            timestep = {"geometry_splines": "device" if dev_geom else "host (uploaded)",
+                        "geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
                         "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations_assumed": its,
                         "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its * e2e_s),
                         "note": "boundary-integral part of one mtube step (membrane forces, SH transforms, GMRES "

@@ -64,6 +64,20 @@ module ModB200
       integer(c_int) :: active(*)
       integer(c_int) :: ierr
     end function
+    function rbc3d_cells_set_geometry_mesh(ctx, x, a3, detj, Acoef, Bcoef, area, meshSize, active) &
+      bind(C, name="rbc3d_cells_set_geometry_mesh") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: x(*), a3(*), detj(*), Acoef(*), Bcoef(*), area(*), meshSize(*)
+      integer(c_int) :: active(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_set_replicated_density(ctx, on) bind(C, name="rbc3d_set_replicated_density") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: on
+      integer(c_int) :: ierr
+    end function
     function rbc3d_cells_set_density(ctx, f, g, spF, spG) bind(C, name="rbc3d_cells_set_density") result(ierr)
       import
       type(c_ptr), value :: ctx

@@ -95,6 +95,12 @@ int rbc3d_cells_set_geometry(rbc3d_ctx *ctx, const double *x, const double *a3, 
                              const int32_t *active);
 int rbc3d_cells_set_density(rbc3d_ctx *ctx, const double *f, const double *g, const double *spF,
                             const double *spG);
+/* rbc3d_cells_set_geometry with Rbc_BuildSurfaceSource(xFlag) (ModRbc.F90:736-762) done on the device: the caller
+ * passes the mesh field detJ(Np) (rbc%detj, point order of x) instead of the splines of x, a3 and detJ, which are built
+ * with the same operator as the density splines.  Needs rbc3d_cells_enable_device_splines. */
+int rbc3d_cells_set_geometry_mesh(rbc3d_ctx *ctx, const double *x, const double *a3, const double *detj,
+                                  const double *Acoef_cell, const double *Bcoef_cell, const double *area,
+                                  const double *meshSize, const int32_t *active);
 /* Optional: Rbc_BuildSurfaceSource(fFlag/gFlag) on the device (ModRbc.F90:760-802: ShAnalGau + ShFilter(nlat0) +
  * ShSynthEqu + Spline_Build_on_Sphere, ModSpline.F90:121-142, FFT_Diff, ModFFT.F90:25-93).  After this call a
  * density passed to rbc3d_cells_set_density with a NULL spline gets its spline built on the GPU (instead of keeping
@@ -200,6 +206,8 @@ int rbc3d_wall_neighbor_signature(rbc3d_ctx *ctx, int tlist, int self_skip, int3
                                   int32_t *nduffy);
 /* device copy of a density spline in the ABI layout: which = 0 spline(f detJ), 1 spline(g detJ) */
 int rbc3d_cells_get_density_spline(rbc3d_ctx *ctx, int which, double *sp);
+/* device copy of the geometry splines (which = 0 x, 1 a3, 2 detJ) in the ABI layout */
+int rbc3d_cells_get_geometry_spline(rbc3d_ctx *ctx, int which, double *sp);
 int rbc3d_pme_get_grid(rbc3d_ctx *ctx, double *vv /* [3][Nz][Ny][Nx] */);
 int rbc3d_get_timings(rbc3d_ctx *ctx, float ms[RBC3D_T_COUNT]);
 int rbc3d_get_launch_count(rbc3d_ctx *ctx, long long *launches);

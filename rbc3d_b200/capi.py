@@ -37,9 +37,11 @@ SIGNATURES = {
     "rbc3d_ewald_coeff_dl": (C.c_int, [C.c_void_p, C.c_double, c_dp]),
     "rbc3d_cells_set_mesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "rbc3d_cells_set_geometry": (C.c_int, [C.c_void_p] + [c_dp] * 9 + [c_ip]),
+    "rbc3d_cells_set_geometry_mesh": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_ip]),
     "rbc3d_cells_set_density": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp]),
     "rbc3d_cells_enable_device_splines": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_cells_get_density_spline": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "rbc3d_cells_get_geometry_spline": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_walls_set": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip, c_dp, c_ip, c_dp, c_dp, c_ip]),
     "rbc3d_walls_set_traction": (C.c_int, [C.c_void_p, c_dp]),
     "rbc3d_wall_prepare_sing": (C.c_int, [C.c_void_p]),

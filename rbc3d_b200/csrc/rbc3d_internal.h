@@ -223,6 +223,7 @@ struct Cells {
   bool sb_ok = false;
   int sb_nlat0 = 0;
   dbuf<double> sb_M0, sb_M1, sb_cs;
+  dbuf<double> sb_detj;              // mesh detJ of rbc3d_cells_set_geometry_mesh (scratch)
   dbuf<int> sb_need;                 // several ranks: cells whose density spline this rank reads
 };
 
@@ -319,6 +320,7 @@ int combine(rbc3d_ctx *c, TargetList &t, double *v_dev, bool accumulate, const d
 // ---- density splines on the device (splinebuild.cu) ----
 int spline_builder_prepare(rbc3d_ctx *c, int nlat0);
 int spline_build_density(rbc3d_ctx *c, int which);
+int spline_build_geometry(rbc3d_ctx *c, const double *detj_dev);
 
 // ---- PME (pme.cu) ----
 int pme_block_edge();

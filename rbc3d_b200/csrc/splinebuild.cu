@@ -117,13 +117,15 @@ struct BuildArgs {
   double *sp_abi;       // [cell][4][3][nlon][2 nlat] or null
   double2 *sp_planes;   // [cell][6][nlon][2 nlat] or null
   const int *need;      // [cell] or null: build only flagged cells
+  int nvar;             // variables per cell of this field (3, or 1 for detJ)
+  int raw;              // 1: dens holds the mesh field itself (x, a3, detJ) -- no division by the Gauss weight
 };
 
 // one CTA per (cell, variable)
 __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
   extern __shared__ double sm[];
   const int nlat = a.nlat, nlon = a.nlon, M = 2 * nlat, m0 = a.nlat0;
-  const int cell = blockIdx.x / 3, var = blockIdx.x - 3 * cell;
+  const int cell = blockIdx.x / a.nvar, var = blockIdx.x - a.nvar * cell;
   if (a.need && !a.need[cell]) return;         // several ranks: only the cells this rank evaluates splines of
   double *s_gd = sm;                           // [nlon][nlat]
   double *s_cs = s_gd + (size_t)nlon * nlat;   // [m0][nlon][2]
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
   double *s_P = s_F + (size_t)2 * m0 * nlat;   // [4 arrays][2 (cos, sin coefficient)][m0][M]
   const int tid = threadIdx.x;
   const double *src = a.dens + (size_t)var * a.Np + (size_t)cell * a.npc;
-  for (int e = tid; e < nlon * nlat; e += blockDim.x) s_gd[e] = src[e] / a.w[e % nlat];  // g detJ = slist g / w
+  for (int e = tid; e < nlon * nlat; e += blockDim.x)
+    s_gd[e] = a.raw ? src[e] : src[e] / a.w[e % nlat];  // g detJ = slist g / w
   for (int e = tid; e < 2 * m0 * nlon; e += blockDim.x) s_cs[e] = a.cs[e];
   __syncthreads();
   // phi analysis (rfft convention): F_m(i) = sum_j gd(j,i) (cos - i sin)(m phi_j)
@@ -186,9 +189,9 @@ __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
       for (int q = 0; q < 4; q++) r[q] = fma(P[(2 * q) * st], cj, fma(P[(2 * q + 1) * st], sj, r[q]));
     }
     if (a.sp_abi) {
-      double *o = a.sp_abi + (size_t)cell * 12 * plane + (size_t)var * plane + e;  // [4][3][n][m]
+      double *o = a.sp_abi + (size_t)cell * 4 * a.nvar * plane + (size_t)var * plane + e;  // [4][nvar][n][m]
 #pragma unroll
-      for (int q = 0; q < 4; q++) o[(size_t)q * 3 * plane] = r[q];
+      for (int q = 0; q < 4; q++) o[(size_t)q * a.nvar * plane] = r[q];
     }
     if (a.sp_planes) {
       double2 *o = a.sp_planes + ((size_t)cell * 6 + 2 * var) * plane + e;
@@ -235,6 +238,8 @@ int spline_build_density(rbc3d_ctx *c, int which) {
   a.cs = C.sb_cs.p;
   a.sp_planes = nullptr;
   a.need = need;
+  a.nvar = 3;
+  a.raw = 0;
   if (which == 0) {
     RBC_TRY(C.spF.resize((size_t)C.ncell * 12 * plane));
     a.dens = C.f.p;
@@ -256,6 +261,40 @@ int spline_build_density(rbc3d_ctx *c, int which) {
   KERNEL_CHECK();
   c->launches++;
   if (which == 1 && a.sp_planes) C.spGi_valid = true;
+  return RBC3D_OK;
+}
+
+// Rbc_BuildSurfaceSource(xFlag) on the device (ModRbc.F90:736-762): splines of x, a3 and detJ from the mesh fields,
+// with the same operator as the density splines (ShAnalGau + ShFilter(nlat0) + ShSynthEqu + Spline_Build_On_Sphere)
+int spline_build_geometry(rbc3d_ctx *c, const double *detj_dev) {
+  Cells &C = c->cells;
+  if (!C.sb_ok) {
+    set_error("geometry splines on the device need rbc3d_cells_enable_device_splines first");
+    return RBC3D_ESTATE;
+  }
+  if (C.Np == 0) return RBC3D_OK;
+  const size_t plane = (size_t)2 * C.nlat * C.nlon;
+  RBC_TRY(C.spx.resize((size_t)C.ncell * 12 * plane));
+  RBC_TRY(C.spa3.resize((size_t)C.ncell * 12 * plane));
+  RBC_TRY(C.spdetj.resize((size_t)C.ncell * 4 * plane));
+  BuildArgs a;
+  a.ncell = C.ncell, a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.nlat0 = C.sb_nlat0, a.Np = C.Np;
+  a.w = C.w.p, a.M0 = C.sb_M0.p, a.M1 = C.sb_M1.p, a.cs = C.sb_cs.p;
+  a.sp_planes = nullptr, a.need = nullptr, a.raw = 1;
+  const int m0 = C.sb_nlat0, M = 2 * C.nlat;
+  const size_t smem = sizeof(double) * ((size_t)C.nlon * C.nlat + (size_t)2 * m0 * C.nlon + (size_t)2 * m0 * C.nlat +
+                                        (size_t)8 * m0 * M);
+  CUDA_TRY(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const double *src[3] = {C.x.p, C.a3.p, detj_dev};
+  double *dst[3] = {C.spx.p, C.spa3.p, C.spdetj.p};
+  for (int k = 0; k < 3; k++) {
+    a.dens = src[k];
+    a.sp_abi = dst[k];
+    a.nvar = k < 2 ? 3 : 1;
+    k_spline_build<<<C.ncell * a.nvar, 256, smem, c->stream>>>(a);
+    KERNEL_CHECK();
+    c->launches++;
+  }
   return RBC3D_OK;
 }
 

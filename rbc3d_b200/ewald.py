@@ -129,6 +129,22 @@ class EwaldOperator:
         act = i32(active)
         check(self.lib.rbc3d_cells_set_geometry(self._h, *[dp(a) for a in arrs], ip(act)), "rbc3d_cells_set_geometry")
 
+    def SourceList_UpdateCoord_mesh(self, x, a3, detj, Acoef, Bcoef, area, meshSize, active=None):
+        """SourceList_UpdateCoord with the geometry splines (Rbc_BuildSurfaceSource(xFlag)) built on the device from
+        the mesh fields; needs enable_device_splines."""
+        arrs = [f64(a) for a in (x, a3, detj, Acoef, Bcoef, area, meshSize)]
+        act = i32(active)
+        check(self.lib.rbc3d_cells_set_geometry_mesh(self._h, *[dp(a) for a in arrs], ip(act)),
+              "rbc3d_cells_set_geometry_mesh")
+
+    def get_geometry_spline(self, which="x"):
+        """device copy of spline(x) / spline(a3) / spline(detJ) in the ABI layout (tests)."""
+        nv = 1 if which == "detj" else 3
+        out = np.zeros((self.ncell, 4, nv, self.nlon, 2 * self.nlat))
+        check(self.lib.rbc3d_cells_get_geometry_spline(self._h, {"x": 0, "a3": 1, "detj": 2}[which], dp(out)),
+              "rbc3d_cells_get_geometry_spline")
+        return out
+
     def SourceList_UpdateDensity(self, f=None, g=None, spF=None, spG=None):
         """f, g: slist%f / slist%g (densities * detJ * w); spF, spG: splines of f*detJ, g*detJ."""
         f, g, spF, spG = f64(f), f64(g), f64(spF), f64(spG)

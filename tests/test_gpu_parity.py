@@ -372,6 +372,26 @@ def test_device_splines_follow_a_new_density(dev_spline_op, sus8, oracle_lib):
     dev_spline_op.SourceList_UpdateDensity(g=sus8.weighted(sus8.g))
 
 
+def test_geometry_splines_built_on_the_device(sus8, pair8):
+    """rbc3d_cells_set_geometry_mesh: Rbc_BuildSurfaceSource(xFlag) on the GPU (splines of x, a3, detJ from the mesh
+    fields) against the host-built splines, and the whole operator on that geometry against the oracle."""
+    from rbc3d_b200.ewald import EwaldOperator
+    _, orc = pair8
+    op = EwaldOperator(sus8.Lb)
+    op.set_mesh(sus8.ncell, sus8.nlat, sus8.nlon, sus8.th, sus8.phi, sus8.w)
+    op.enable_device_splines(sus8.nlat0)
+    op.SourceList_UpdateCoord_mesh(sus8.x, sus8.a3, sus8.detj, sus8.Acoef, sus8.Bcoef, sus8.area, sus8.meshSize)
+    for which, ref in (("x", sus8.spx), ("a3", sus8.spa3), ("detj", sus8.spdetj)):
+        sp = op.get_geometry_spline(which)
+        assert sp.shape == ref.shape
+        assert rel_l2(sp, ref) < 1e-12, which
+    op.SourceList_UpdateDensity(f=sus8.weighted(sus8.f), g=sus8.weighted(sus8.g))
+    for c1, c2 in [(0.0, C2_MATVEC), (C1_RHS, 0.0)]:
+        ref = orc.apply_cells(c1, c2, orc.cell_targets())
+        assert rel_l2(op.apply(c1, c2), ref) < TOL
+    op.close()
+
+
 def test_apply_assign_equals_zero_then_accumulate(pair8):
     op, _ = pair8
     v_acc = op.apply(0.0, C2_MATVEC)                       # caller zeroes v, operator accumulates
