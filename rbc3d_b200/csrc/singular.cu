@@ -499,8 +499,16 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
     for (int r = 0; r < R; r++) {
       const int2 ch = ch_next;
       double4 c4[SG_PC];
+      if (LR && SG_PC > 2) {
+        // no register room for a second set of cache entries: this round's entries are requested here and first used
+        // after the three density components have been interpolated (16 warps cover the rest of the latency)
 #pragma unroll
-      for (int p = 0; p < SG_PC; p++) c4[p] = c_next[p];
+        for (int p = 0; p < SG_PC; p++)
+          c4[p] = (p < (ch.x >> 18)) ? ld_stream4(cg + (size_t)tn * NPT + ch.y + p) : make_double4(0, 0, 0, 0);
+      } else {
+#pragma unroll
+        for (int p = 0; p < SG_PC; p++) c4[p] = c_next[p];
+      }
       {  // next round (of this tile or of the next tile of the row)
         int nr = r + 1, nt = tn;
         if (nr == R) {
@@ -509,10 +517,12 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
         }
         if (nt < a.ntn) {
           ch_next = ld_tab(chunk + nr * NTT);
-          const double4 *cgn = cg + (size_t)nt * NPT + ch_next.y;
-          const int cn = ch_next.x >> 18;
+          if (!(LR && SG_PC > 2)) {
+            const double4 *cgn = cg + (size_t)nt * NPT + ch_next.y;
+            const int cn = ch_next.x >> 18;
 #pragma unroll
-          for (int p = 0; p < SG_PC; p++) c_next[p] = (p < cn) ? ld_stream4(cgn + p) : make_double4(0, 0, 0, 0);
+            for (int p = 0; p < SG_PC; p++) c_next[p] = (p < cn) ? ld_stream4(cgn + p) : make_double4(0, 0, 0, 0);
+          }
         }
       }
       const int cnt = ch.x >> 18;
@@ -795,9 +805,9 @@ static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
     if (sg_lr() == 1 && PC_ == 2) {                                                                                            \
       CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, 2, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_sing_band<TS_, 2, 512, false, true><<<grid, 512, smem, c->stream>>>(a);                                               \
-    } else if (sg_lr() == 2 && PC_ == 2) {                                                                                     \
-      CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, 2, 512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      k_sing_band<TS_, 2, 512, true, true><<<grid, 512, smem, c->stream>>>(a);                                                \
+    } else if (sg_lr() == 2 && PC_ <= 4) {                                                                                     \
+      CUDA_TRY(cudaFuncSetAttribute(k_sing_band<TS_, PC_, 512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_sing_band<TS_, PC_, 512, true, true><<<grid, 512, smem, c->stream>>>(a);                                              \
     } else                                                      \
     if (sg_per_warp()) LAUNCH_BAND(TS_, PC_, SG_T * 32, true);  \
     else if (sg_nt() == 512) LAUNCH_BAND(TS_, PC_, 512, false); \
