@@ -374,15 +374,32 @@ def run_gpu(args):
                 op.apply_collect(C1_RHS, 0.0, v=v_host)
                 barrier()
                 t_rhs.append(time.perf_counter() - t0)
-            tt = torch.tensor([t_geom, min(t_rhs)], dtype=torch.float64, device="cuda")
+            # MyMatMult with the SH transforms and the Krylov vector on the device (rbc3d_solver_*):
+            # only 2 x dof doubles cross PCIe here, none inside rbc3d_solver_gmres
+            t_mm = float("nan")
+            if dev_geom:
+                op.solver_setup(sus.nlat0, sus.detj)
+                u = np.random.default_rng(args.seed).uniform(-1.0, 1.0, op.solver_dof)
+                op.solver_matmult(u)
+                tm = []
+                for _ in range(3):
+                    barrier()
+                    t0 = time.perf_counter()
+                    op.solver_matmult(u)
+                    barrier()
+                    tm.append(time.perf_counter() - t0)
+                t_mm = min(tm)
+            tt = torch.tensor([t_geom, min(t_rhs), t_mm], dtype=torch.float64, device="cuda")
             if dist is not None:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_geom, t_rhs1 = float(tt[0]), float(tt[1])
+            t_geom, t_rhs1, t_mm = float(tt[0]), float(tt[1]), float(tt[2])
             its = GMRES_ITS_ASSUMED
             timestep = {"geometry_splines": "device" if dev_geom else "host (uploaded)",
                         "geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
                         "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations_assumed": its,
                         "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its * e2e_s),
+                        "matmult_device_solver_ms": t_mm * 1e3,
+                        "bi_timesteps_per_s_device_solver": (1.0 / (t_geom + t_rhs1 + its * t_mm)) if t_mm == t_mm else None,
                         "note": "boundary-integral part of one mtube step (membrane forces, SH transforms, GMRES "
                                 "vector algebra stay in the Fortran caller and are not included)"}
         except Exception as exc:  # e.g. no room left for spline(f detJ) next to the caches

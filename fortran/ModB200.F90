@@ -72,6 +72,28 @@ module ModB200
       integer(c_int) :: active(*)
       integer(c_int) :: ierr
     end function
+    function rbc3d_solver_setup(ctx, nlat0, detj) bind(C, name="rbc3d_solver_setup") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nlat0
+      real(c_double) :: detj(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_solver_matmult(ctx, u, b) bind(C, name="rbc3d_solver_matmult") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: u(*), b(*)
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_solver_gmres(ctx, rhs, sol, rtol, restart, maxit, niter, history) &
+      bind(C, name="rbc3d_solver_gmres") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: rhs(*), sol(*), history(*)
+      real(c_double), value :: rtol
+      integer(c_int), value :: restart, maxit
+      integer(c_int) :: niter, ierr
+    end function
     function rbc3d_set_replicated_density(ctx, on) bind(C, name="rbc3d_set_replicated_density") result(ierr)
       import
       type(c_ptr), value :: ctx

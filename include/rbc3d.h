@@ -188,6 +188,21 @@ int rbc3d_set_replicated_density(rbc3d_ctx *ctx, int on);
  * 256-byte coefficient rows held (= bytes streamed per matvec / 256); either pointer may be NULL */
 int rbc3d_pair_cache_info(rbc3d_ctx *ctx, int32_t *cells_cached, int64_t *rows);
 
+/* ---- the cell velocity solve with Krylov vectors and SH transforms resident on the device ----
+ * rbc3d_solver_setup: once per geometry, after rbc3d_cells_set_geometry[_mesh] and
+ *   rbc3d_cells_enable_device_splines; nlat0 = SH truncation of the unknowns, detj = rbc%detj on the mesh (Np).
+ * rbc3d_solver_matmult: b = MyMatMult(u) (ModVelSolver.F90:523-601): Glob_Sph_Trans FOUR_TO_PHYS, operator #2
+ *   (c1 = 0, c2 = -1/4pi), + g, Glob_Sph_Trans PHYS_TO_FOUR; u, b host vectors of ncell*3*nlat0^2 doubles packed as
+ *   in Glob_Sph_Trans (ModVelSolver.F90:641-719).
+ * rbc3d_solver_gmres: KSPSolve of Solve_RBC_Vel (ModVelSolver.F90:74-116) with PETSc's GMRES defaults restated
+ *   (restart as given, classical Gram-Schmidt, no preconditioner, residual test rtol*||rhs||); sol: initial guess
+ *   in, solution out; history (maxit+1 doubles or NULL): residual norm after every iteration. */
+int rbc3d_solver_setup(rbc3d_ctx *ctx, int nlat0, const double *detj);
+int rbc3d_solver_dof(rbc3d_ctx *ctx, int64_t *dof);
+int rbc3d_solver_matmult(rbc3d_ctx *ctx, const double *u, double *b);
+int rbc3d_solver_gmres(rbc3d_ctx *ctx, const double *rhs, double *sol, double rtol, int restart, int maxit,
+                       int *niter, double *history);
+
 /* ---- introspection (tests, profiling) ---- */
 /* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,
  * ascending index inside a cell), start[Nc1*Nc2*Nc3+1]; any pointer may be NULL */

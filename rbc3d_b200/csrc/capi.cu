@@ -367,6 +367,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.ps_maskbits.release();
   C.ps_compact.release();
   C.ps_needmask.release();
+  solver_release(c);
   C.sb_need.release();
   C.sb_detj.release();
   C.pc_mask.release();

@@ -227,6 +227,17 @@ struct Cells {
   dbuf<int> sb_need;                 // several ranks: cells whose density spline this rank reads
 };
 
+// device-resident cell velocity solve (solver.cu)
+struct Solver {
+  bool ok = false;
+  int m0 = 0, dofc = 0;
+  size_t dof = 0;
+  long long nmatvec = 0;
+  dbuf<double> pb, pbw, cs, dsw, g_raw;
+  dbuf<int> ka, kb;
+  dbuf<double> V, w, part, h, u, b;
+};
+
 struct Pme {
   int Nx = 0, Ny = 0, Nz = 0, Nxh = 0;
   size_t G = 0, M = 0;
@@ -270,6 +281,7 @@ struct rbc3d_ctx {
   rbc3d::TargetList tl[3];
   rbc3d::Walls walls;
   rbc3d::Pme pme;
+  rbc3d::Solver solver;
   int skip_flags = 0;
   int pair_self_mode = 3;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel,
                             // 3 symmetric kernel streaming a per-geometry coefficient cache (double layer only)
@@ -344,6 +356,13 @@ int walls_min_dist_batch(rbc3d_ctx *c, int n, const double *xtar, const double *
 int walls_tri_int_batch(rbc3d_ctx *c, int n, const double *xtri, const double *ftri, const double *xtar,
                         const double *s0, const double *t0, double *rhs, double *lhs);
 void walls_release(rbc3d_ctx *c);
+
+// ---- cell velocity solve on the device (solver.cu) ----
+int solver_setup(rbc3d_ctx *c, int nlat0, const double *detj_host);
+int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev);
+int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter,
+                 double *history);
+void solver_release(rbc3d_ctx *c);
 
 // ---- multi-GPU (comm.cu) ----
 int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);

@@ -1,0 +1,427 @@
+// solver.cu -- SURVEY.md 8(f)-1: the cell velocity solve of ModVelSolver.F90 with everything resident on the device.
+//
+// Solve_RBC_Vel (ModVelSolver.F90:44-135) runs PETSc's GMRES on the spherical-harmonic coefficients of the surface
+// velocity; every iteration MyMatMult (:523-601) synthesises the double-layer density from the coefficients
+// (Glob_Sph_Trans FOUR_TO_PHYS, :641-719), applies the boundary-integral operator #2 and analyses v + g back
+// (PHYS_TO_FOUR).  Behind the drop-in boundary that costs two PCIe crossings of 24 B per point and matvec plus the
+// host transforms; here the Krylov vectors, the transforms and the operator stay on the GPU and only the Hessenberg
+// column (<= 31 doubles) returns to the host per iteration.
+//
+//   * k_sh_synth / k_sh_anal: ShSynthGau / ShAnalGau (ModSphpk.F90:74-105, 240-270) truncated to degree < nlat0 as
+//     dense per-cell operators (orthonormal associated Legendre table x DFT in phi), SPHEREPACK's shsgs convention:
+//     f = sum_n [ a(0,n)/2 Pbar_n^0 + sum_{m>=1} Pbar_n^m (a(m,n) cos m phi - b(m,n) sin m phi) ];
+//     packing of the unknowns as in Glob_Sph_Trans: a(m,n), n = m..nlat0-1, m = 0..; then b(m,n), m = 1..; the three
+//     components interleaved.
+//   * GMRES with the defaults the reference leaves untouched: restart 30, classical
+//     Gram-Schmidt without refinement, no preconditioner, test on the recurrence residual against rtol ||b||,
+//     non-zero initial guess.  Dot products are two-stage reductions in a fixed order (deterministic).
+// The host mirror of the same algorithm is rbc3d_b200/gmres.py; tests/test_gpu_gmres.py checks one against the other.
+#include <cmath>
+#include <vector>
+
+#include "device_math.cuh"
+#include "rbc3d_internal.h"
+
+namespace rbc3d {
+
+struct ShArgs {
+  int ncell, npc, nlat, nlon, m0, Np, dofc;
+  const double *pb;    // [m0][m0][nlat]  Pbar(m, n, i)            (synthesis)
+  const double *pbw;   // [m0][m0][nlat]  Pbar w_i 2/nlon           (analysis)
+  const double *cs;    // [m0][nlon][2]   cos, sin (m phi_j)
+  const int *ka, *kb;  // [m0][m0] packed index of a(m,n) / b(m,n), -1 where there is none
+  const double *dsw;   // [Np] detJ * w(ilat): raw density -> source-list density
+  const double *coef;  // packed coefficients (synthesis in / analysis out)
+  double *coef_out;
+  double *g_raw;       // SoA(3,Np) synthesised field
+  double *g_src;       // SoA(3,Np) field * detJ * w (slist%g)
+  const double *v;     // SoA(3,Np) operator result (analysis adds g_raw: the diagonal term of MyMatMult)
+};
+
+// one CTA per (cell, component)
+__global__ void __launch_bounds__(256) k_sh_synth(ShArgs a) {
+  extern __shared__ double sm[];
+  const int m0 = a.m0, nlat = a.nlat, nlon = a.nlon;
+  const int cell = blockIdx.x / 3, comp = blockIdx.x - 3 * cell;
+  double *s_a = sm, *s_b = s_a + m0 * m0, *s_A = s_b + m0 * m0, *s_B = s_A + m0 * nlat;
+  const double *c = a.coef + (size_t)cell * a.dofc + comp;
+  for (int e = threadIdx.x; e < m0 * m0; e += blockDim.x) {
+    const int ia = a.ka[e], ib = a.kb[e];
+    s_a[e] = ia >= 0 ? c[3 * ia] : 0.0;
+    s_b[e] = ib >= 0 ? c[3 * ib] : 0.0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < m0 * nlat; e += blockDim.x) {
+    const int m = e / nlat, i = e - m * nlat;
+    double A = 0, B = 0;
+    for (int n = m; n < m0; n++) {
+      const double p = a.pb[((size_t)m * m0 + n) * nlat + i];
+      A = fma(p, s_a[m * m0 + n], A);
+      B = fma(p, s_b[m * m0 + n], B);
+    }
+    s_A[e] = A;
+    s_B[e] = B;
+  }
+  __syncthreads();
+  const size_t base = (size_t)comp * a.Np + (size_t)cell * a.npc;
+  for (int e = threadIdx.x; e < nlon * nlat; e += blockDim.x) {
+    const int j = e / nlat, i = e - j * nlat;
+    double f = 0.5 * s_A[i];
+    for (int m = 1; m < m0; m++) {
+      const double cj = a.cs[(m * nlon + j) * 2], sj = a.cs[(m * nlon + j) * 2 + 1];
+      f = fma(s_A[m * nlat + i], cj, f);
+      f = fma(-s_B[m * nlat + i], sj, f);
+    }
+    a.g_raw[base + e] = f;
+    a.g_src[base + e] = f * a.dsw[(size_t)cell * a.npc + e];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sh_anal(ShArgs a) {
+  extern __shared__ double sm[];
+  const int m0 = a.m0, nlat = a.nlat, nlon = a.nlon;
+  const int cell = blockIdx.x / 3, comp = blockIdx.x - 3 * cell;
+  double *s_v = sm, *s_Fc = s_v + nlon * nlat, *s_Fs = s_Fc + m0 * nlat;
+  const size_t base = (size_t)comp * a.Np + (size_t)cell * a.npc;
+  for (int e = threadIdx.x; e < nlon * nlat; e += blockDim.x) s_v[e] = a.v[base + e] + a.g_raw[base + e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < m0 * nlat; e += blockDim.x) {
+    const int m = e / nlat, i = e - m * nlat;
+    double fc = 0, fs = 0;
+    for (int j = 0; j < nlon; j++) {
+      const double v = s_v[j * nlat + i];
+      fc = fma(v, a.cs[(m * nlon + j) * 2], fc);
+      fs = fma(-v, a.cs[(m * nlon + j) * 2 + 1], fs);
+    }
+    s_Fc[e] = fc;
+    s_Fs[e] = fs;
+  }
+  __syncthreads();
+  double *out = a.coef_out + (size_t)cell * a.dofc + comp;
+  for (int e = threadIdx.x; e < m0 * m0; e += blockDim.x) {
+    const int ia = a.ka[e], ib = a.kb[e];
+    if (ia < 0) continue;
+    const int m = e / m0;
+    double ca = 0, cb = 0;
+    for (int i = 0; i < nlat; i++) {
+      const double p = a.pbw[(size_t)e * nlat + i];
+      ca = fma(p, s_Fc[m * nlat + i], ca);
+      cb = fma(p, s_Fs[m * nlat + i], cb);
+    }
+    out[3 * ia] = ca;
+    if (ib >= 0) out[3 * ib] = cb;
+  }
+}
+
+// ---- vector kernels of the Krylov solver: fixed-order two-stage reductions ----
+constexpr int DOT_BLOCKS = 256, DOT_THREADS = 256;
+
+// part[i][blk] = partial sum of V_i . w over the block's slice; i < k
+__global__ void __launch_bounds__(DOT_THREADS) k_dots_partial(int n, int k, const double *__restrict__ V, size_t ldv,
+                                                               const double *__restrict__ w, double *__restrict__ part) {
+  __shared__ double s[DOT_THREADS / 32];
+  const int i = blockIdx.y;
+  const double *v = V + (size_t)i * ldv;
+  double acc = 0;
+  for (int e = blockIdx.x * DOT_THREADS + threadIdx.x; e < n; e += DOT_BLOCKS * DOT_THREADS) acc = fma(v[e], w[e], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int q = 0; q < DOT_THREADS / 32; q++) t += s[q];
+    part[(size_t)i * DOT_BLOCKS + blockIdx.x] = t;
+  }
+  (void)k;
+}
+__global__ void k_dots_final(int k, const double *__restrict__ part, double *__restrict__ h) {
+  const int i = blockIdx.x;
+  if (i >= k) return;
+  double v = 0;
+  for (int q = threadIdx.x; q < DOT_BLOCKS; q += 32) v += part[(size_t)i * DOT_BLOCKS + q];
+  v = warp_sum(v);
+  if (threadIdx.x == 0) h[i] = v;
+}
+// w -= sum_i h[i] V_i
+__global__ void k_gs_update(int n, int k, const double *__restrict__ V, size_t ldv, const double *__restrict__ h,
+                            double *__restrict__ w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double acc = w[e];
+  for (int i = 0; i < k; i++) acc = fma(-h[i], V[(size_t)i * ldv + e], acc);
+  w[e] = acc;
+}
+// w = b - w
+__global__ void k_residual(int n, const double *__restrict__ b, double *__restrict__ w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) w[e] = b[e] - w[e];
+}
+// y = alpha x (+ y if add)
+__global__ void k_axpy(int n, double alpha, const double *__restrict__ x, double *__restrict__ y, int add) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  y[e] = add ? fma(alpha, x[e], y[e]) : alpha * x[e];
+}
+
+static void pbar_table(int m0, int nlat, const double *th, std::vector<double> &pb) {
+  // orthonormal associated Legendre functions with the Condon-Shortley phase, int_{-1}^{1} Pbar^2 dx = 1
+  pb.assign((size_t)m0 * m0 * nlat, 0.0);
+  for (int i = 0; i < nlat; i++) {
+    const double x = cos(th[i]), s = sin(th[i]);
+    double pmm = sqrt(0.5);
+    for (int m = 0; m < m0; m++) {
+      if (m > 0) pmm *= -sqrt((2.0 * m + 1.0) / (2.0 * m)) * s;
+      double p2 = 0.0, p1 = pmm;
+      pb[((size_t)m * m0 + m) * nlat + i] = pmm;
+      for (int n = m + 1; n < m0; n++) {
+        const double an = sqrt((4.0 * n * n - 1.0) / ((double)n * n - (double)m * m));
+        const double bn = sqrt((((double)n - 1.0) * (n - 1.0) - (double)m * m) / (4.0 * (n - 1.0) * (n - 1.0) - 1.0));
+        const double p = an * (x * p1 - bn * p2);
+        pb[((size_t)m * m0 + n) * nlat + i] = p;
+        p2 = p1;
+        p1 = p;
+      }
+    }
+  }
+}
+
+int solver_setup(rbc3d_ctx *c, int nlat0, const double *detj_host) {
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  S.ok = false;
+  if (!C.geom_set || nlat0 < 1 || nlat0 > C.nlat) return RBC3D_EINVAL;
+  if (!C.sb_ok) {
+    set_error("rbc3d_solver_setup needs rbc3d_cells_enable_device_splines (the density splines are built on the device)");
+    return RBC3D_ESTATE;
+  }
+  const int nlat = C.nlat, nlon = C.nlon, m0 = nlat0;
+  S.m0 = m0;
+  S.dofc = 3 * m0 * m0;
+  S.dof = (size_t)C.ncell * S.dofc;
+  std::vector<double> pb, pbw((size_t)m0 * m0 * nlat), cs((size_t)m0 * nlon * 2);
+  pbar_table(m0, nlat, C.h_th.data(), pb);
+  const double wphi = RBC_TWO_PI / nlon;
+  for (int m = 0; m < m0; m++)
+    for (int n = 0; n < m0; n++)
+      for (int i = 0; i < nlat; i++)  // h_w = Gauss weight * 2 pi / nlon (ModRbc.F90:93-95)
+        pbw[((size_t)m * m0 + n) * nlat + i] = pb[((size_t)m * m0 + n) * nlat + i] * (C.h_w[i] / wphi) * (2.0 / nlon);
+  for (int m = 0; m < m0; m++)
+    for (int j = 0; j < nlon; j++) {
+      cs[((size_t)m * nlon + j) * 2] = cos(m * C.h_phi[j]);
+      cs[((size_t)m * nlon + j) * 2 + 1] = sin(m * C.h_phi[j]);
+    }
+  std::vector<int> ka(m0 * m0, -1), kb(m0 * m0, -1);
+  int k = 0;
+  for (int m = 0; m < m0; m++)
+    for (int n = m; n < m0; n++) ka[m * m0 + n] = k++;
+  for (int m = 1; m < m0; m++)
+    for (int n = m; n < m0; n++) kb[m * m0 + n] = k++;
+  auto up = [&](dbuf<double> &d, const std::vector<double> &h) -> int {
+    RBC_TRY(d.resize(h.size()));
+    CUDA_TRY(cudaMemcpyAsync(d.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, c->stream));
+    return RBC3D_OK;
+  };
+  RBC_TRY(up(S.pb, pb));
+  RBC_TRY(up(S.pbw, pbw));
+  RBC_TRY(up(S.cs, cs));
+  RBC_TRY(S.ka.resize(ka.size()));
+  RBC_TRY(S.kb.resize(kb.size()));
+  CUDA_TRY(cudaMemcpyAsync(S.ka.p, ka.data(), sizeof(int) * ka.size(), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(S.kb.p, kb.data(), sizeof(int) * kb.size(), cudaMemcpyHostToDevice, c->stream));
+  // detJ * w per point
+  std::vector<double> dsw((size_t)C.Np);
+  for (size_t p = 0; p < (size_t)C.Np; p++) dsw[p] = detj_host[p] * C.h_w[p % nlat];
+  RBC_TRY(up(S.dsw, dsw));
+  RBC_TRY(S.g_raw.resize(3 * (size_t)C.Np));
+  RBC_TRY(C.g.resize(3 * (size_t)C.Np));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  S.ok = true;
+  return RBC3D_OK;
+}
+
+static void sh_args(rbc3d_ctx *c, ShArgs &a) {
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  a.ncell = C.ncell, a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.m0 = S.m0, a.Np = C.Np, a.dofc = S.dofc;
+  a.pb = S.pb.p, a.pbw = S.pbw.p, a.cs = S.cs.p, a.ka = S.ka.p, a.kb = S.kb.p, a.dsw = S.dsw.p;
+  a.coef = nullptr, a.coef_out = nullptr, a.g_raw = S.g_raw.p, a.g_src = C.g.p, a.v = nullptr;
+}
+
+// b = MyMatMult(u), device vectors of length dof (ModVelSolver.F90:523-601, c1 = 0, c2 = -1/(4 pi))
+int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev) {
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  if (!S.ok) {
+    set_error("rbc3d_solver_setup has not been called for this geometry");
+    return RBC3D_ESTATE;
+  }
+  TargetList &t = c->tl[RBC3D_TL_CELLS];
+  ShArgs a;
+  sh_args(c, a);
+  a.coef = u_dev;
+  const size_t sm_s = sizeof(double) * (2 * (size_t)S.m0 * S.m0 + 2 * (size_t)S.m0 * C.nlat);
+  k_sh_synth<<<C.ncell * 3, 256, sm_s, c->stream>>>(a);  // Glob_Sph_Trans(g, u, FOUR_TO_PHYS) + SourceList_UpdateDensity
+  KERNEL_CHECK();
+  c->launches++;
+  C.g_set = true;
+  C.spGi_valid = false;
+  RBC_TRY(rbc3d_apply_resident(c, 0.0, -1.0 / (4.0 * RBC_PI), 1, 0, RBC3D_TL_CELLS));  // v (summed over ranks) in t.v
+  a.v = t.v.p;
+  a.coef_out = b_dev;
+  const size_t sm_a = sizeof(double) * ((size_t)C.nlon * C.nlat + 2 * (size_t)S.m0 * C.nlat);
+  CUDA_TRY(cudaFuncSetAttribute(k_sh_anal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+  k_sh_anal<<<C.ncell * 3, 256, sm_a, c->stream>>>(a);   // v = v + g; Glob_Sph_Trans(v, b, PHYS_TO_FOUR)
+  KERNEL_CHECK();
+  c->launches++;
+  S.nmatvec++;
+  return RBC3D_OK;
+}
+
+static int dots(rbc3d_ctx *c, int k, const double *V, size_t ldv, const double *w, double *h_host) {
+  Solver &S = c->solver;
+  const int n = (int)S.dof;
+  k_dots_partial<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>(n, k, V, ldv, w, S.part.p);
+  k_dots_final<<<k, 32, 0, c->stream>>>(k, S.part.p, S.h.p);
+  KERNEL_CHECK();
+  c->launches += 2;
+  CUDA_TRY(cudaMemcpyAsync(h_host, S.h.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+// KSPGMRES, PCNONE, classical Gram-Schmidt; x_dev in: initial guess, out: solution.  history[k] = residual norm after
+// k iterations (history[0] = ||b - A x0||), at most maxit + 1 entries.
+int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter,
+                 double *history) {
+  Solver &S = c->solver;
+  if (!S.ok) return RBC3D_ESTATE;
+  if (restart < 1 || restart > 200 || maxit < 0) return RBC3D_EINVAL;
+  const size_t n = S.dof;
+  const int nb = (int)((n + 255) / 256);
+  RBC_TRY(S.V.resize((size_t)(restart + 1) * n));
+  RBC_TRY(S.w.resize(n));
+  RBC_TRY(S.part.resize((size_t)(restart + 2) * DOT_BLOCKS));
+  RBC_TRY(S.h.resize(restart + 2));
+  std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), gv(restart + 1), hcol(restart + 2);
+  double bnorm2 = 0;
+  RBC_TRY(dots(c, 1, b_dev, n, b_dev, &bnorm2));
+  const double ttol = fmax(rtol * sqrt(bnorm2), 1e-50);
+  int it = 0, nh = 0;
+  for (;;) {
+    // r = b - A x (the reference sets KSPSetInitialGuessNonzero: the initial residual needs one matvec)
+    RBC_TRY(solver_matmult(c, x_dev, S.w.p));
+    k_residual<<<nb, 256, 0, c->stream>>>((int)n, b_dev, S.w.p);
+    double beta2 = 0;
+    RBC_TRY(dots(c, 1, S.w.p, n, S.w.p, &beta2));
+    const double beta = sqrt(beta2);
+    if (it == 0 && history) history[nh++] = beta;
+    if (beta < ttol || it >= maxit) break;
+    k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / beta, S.w.p, S.V.p, 0);
+    std::fill(H.begin(), H.end(), 0.0);
+    std::fill(gv.begin(), gv.end(), 0.0);
+    gv[0] = beta;
+    int k = 0;
+    double res = beta;
+    while (k < restart && it < maxit) {
+      RBC_TRY(solver_matmult(c, S.V.p + (size_t)k * n, S.w.p));
+      RBC_TRY(dots(c, k + 1, S.V.p, n, S.w.p, hcol.data()));            // all projections from the same w
+      k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, S.V.p, n, S.h.p, S.w.p);
+      double hn2 = 0;
+      RBC_TRY(dots(c, 1, S.w.p, n, S.w.p, &hn2));
+      const double hn = sqrt(hn2);
+      auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * restart + j]; };
+      for (int i = 0; i <= k; i++) Hm(i, k) = hcol[i];
+      Hm(k + 1, k) = hn;
+      for (int i = 0; i < k; i++) {  // previous rotations
+        const double t = cs[i] * Hm(i, k) + sn[i] * Hm(i + 1, k);
+        Hm(i + 1, k) = -sn[i] * Hm(i, k) + cs[i] * Hm(i + 1, k);
+        Hm(i, k) = t;
+      }
+      const double d = hypot(Hm(k, k), Hm(k + 1, k));
+      cs[k] = Hm(k, k) / d;
+      sn[k] = Hm(k + 1, k) / d;
+      Hm(k, k) = d;
+      Hm(k + 1, k) = 0.0;
+      gv[k + 1] = -sn[k] * gv[k];
+      gv[k] = cs[k] * gv[k];
+      it++;
+      k++;
+      res = fabs(gv[k]);
+      if (history) history[nh++] = res;
+      if (hn > 0.0) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / hn, S.w.p, S.V.p + (size_t)k * n, 0);
+      if (res < ttol || hn == 0.0) break;
+    }
+    // y = H^-1 g (upper triangular), x += V y
+    std::vector<double> y(k);
+    for (int i = k - 1; i >= 0; i--) {
+      double s = gv[i];
+      for (int j = i + 1; j < k; j++) s -= H[(size_t)i * restart + j] * y[j];
+      y[i] = s / H[(size_t)i * restart + i];
+    }
+    for (int i = 0; i < k; i++) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, y[i], S.V.p + (size_t)i * n, x_dev, 1);
+    KERNEL_CHECK();
+    c->launches += k + 3;
+    if (res < ttol || it >= maxit) break;
+  }
+  if (niter) *niter = it;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+void solver_release(rbc3d_ctx *c) {
+  Solver &S = c->solver;
+  for (dbuf<double> *b : {&S.pb, &S.pbw, &S.cs, &S.dsw, &S.g_raw, &S.V, &S.w, &S.part, &S.h, &S.u, &S.b}) b->release();
+  S.ka.release();
+  S.kb.release();
+  S.ok = false;
+}
+
+}  // namespace rbc3d
+
+using namespace rbc3d;
+
+extern "C" {
+
+int rbc3d_solver_setup(rbc3d_ctx *c, int nlat0, const double *detj) {
+  if (!c || !detj) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return solver_setup(c, nlat0, detj);
+}
+
+int rbc3d_solver_dof(rbc3d_ctx *c, int64_t *dof) {
+  if (!c || !dof || !c->solver.ok) return RBC3D_ESTATE;
+  *dof = (int64_t)c->solver.dof;
+  return RBC3D_OK;
+}
+
+int rbc3d_solver_matmult(rbc3d_ctx *c, const double *u, double *b) {
+  if (!c || !u || !b) return RBC3D_EINVAL;
+  if (!c->solver.ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Solver &S = c->solver;
+  RBC_TRY(S.u.resize(S.dof));
+  RBC_TRY(S.b.resize(S.dof));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, u, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(solver_matmult(c, S.u.p, S.b.p));
+  CUDA_TRY(cudaMemcpyAsync(b, S.b.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int rbc3d_solver_gmres(rbc3d_ctx *c, const double *rhs, double *sol, double rtol, int restart, int maxit, int *niter,
+                       double *history) {
+  if (!c || !rhs || !sol) return RBC3D_EINVAL;
+  if (!c->solver.ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Solver &S = c->solver;
+  RBC_TRY(S.u.resize(S.dof));
+  RBC_TRY(S.b.resize(S.dof));
+  CUDA_TRY(cudaMemcpyAsync(S.b.p, rhs, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(solver_gmres(c, S.b.p, S.u.p, rtol, restart, maxit, niter, history));
+  CUDA_TRY(cudaMemcpyAsync(sol, S.u.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+}  // extern "C"

@@ -298,6 +298,30 @@ class EwaldOperator:
     def set_pair_self(self, mode):
         check(self.lib.rbc3d_set_pair_self(self._h, int(mode)))
 
+    # -- cell velocity solve on the device --------------------------------------------------
+    def solver_setup(self, nlat0, detj):
+        check(self.lib.rbc3d_solver_setup(self._h, int(nlat0), dp(f64(detj))), "rbc3d_solver_setup")
+        n = C.c_int64()
+        check(self.lib.rbc3d_solver_dof(self._h, C.byref(n)))
+        self.solver_dof = int(n.value)
+
+    def solver_matmult(self, u):
+        """MyMatMult on the device: packed SH coefficients in, packed SH coefficients out."""
+        u = f64(u)
+        b = np.zeros(self.solver_dof)
+        check(self.lib.rbc3d_solver_matmult(self._h, dp(u), dp(b)), "rbc3d_solver_matmult")
+        return b
+
+    def solver_gmres(self, rhs, x0=None, rtol=1e-11, restart=30, maxit=200):
+        """-> (sol, niter, residual history)."""
+        rhs = f64(rhs)
+        sol = np.zeros(self.solver_dof) if x0 is None else np.array(x0, dtype=np.float64)
+        hist = np.full(maxit + 1, np.nan)
+        nit = C.c_int()
+        check(self.lib.rbc3d_solver_gmres(self._h, dp(rhs), dp(sol), float(rtol), int(restart), int(maxit), C.byref(nit),
+                                          dp(hist)), "rbc3d_solver_gmres")
+        return sol, nit.value, hist[:nit.value + 1]
+
     def sing_cache_info(self):
         """(cached path active, patch points per target streamed from the cache)."""
         a, b = C.c_int32(), C.c_int32()
