@@ -94,6 +94,19 @@ module ModB200
       integer(c_int), value :: restart, maxit
       integer(c_int) :: niter, ierr
     end function
+    function rbc3d_solver_rhs(ctx, vbkg, use_walls, rhs) bind(C, name="rbc3d_solver_rhs") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: vbkg(3), rhs(*)
+      integer(c_int), value :: use_walls
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_solver_velocity(ctx, sol, v) bind(C, name="rbc3d_solver_velocity") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      real(c_double) :: sol(*), v(*)
+      integer(c_int) :: ierr
+    end function
     function rbc3d_set_replicated_density(ctx, on) bind(C, name="rbc3d_set_replicated_density") result(ierr)
       import
       type(c_ptr), value :: ctx

@@ -202,6 +202,11 @@ int rbc3d_solver_dof(rbc3d_ctx *ctx, int64_t *dof);
 int rbc3d_solver_matmult(rbc3d_ctx *ctx, const double *u, double *b);
 int rbc3d_solver_gmres(rbc3d_ctx *ctx, const double *rhs, double *sol, double rtol, int restart, int maxit,
                        int *niter, double *history);
+/* rhs = Compute_Rhs (ModVelSolver.F90:455-515): operator #1 (c1 = 1/4pi, c2 = 0; walls' single layer too when
+ * use_walls) on the resident single-layer density, + 2 vBkg / Acoef, PHYS_TO_FOUR -- packed coefficients out */
+int rbc3d_solver_rhs(rbc3d_ctx *ctx, const double vbkg[3], int use_walls, double *rhs);
+/* v = Glob_Sph_Trans(sol, FOUR_TO_PHYS): the surface velocity of a solution (ModVelSolver.F90:124), host SoA(3,Np) */
+int rbc3d_solver_velocity(rbc3d_ctx *ctx, const double *sol, double *v);
 
 /* ---- introspection (tests, profiling) ---- */
 /* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,

@@ -67,6 +67,8 @@ SIGNATURES = {
     "rbc3d_solver_setup": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_solver_dof": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "rbc3d_solver_matmult": (C.c_int, [C.c_void_p, c_dp, c_dp]),
+    "rbc3d_solver_rhs": (C.c_int, [C.c_void_p, c_dp, C.c_int, c_dp]),
+    "rbc3d_solver_velocity": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "rbc3d_solver_gmres": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), c_dp]),
     "rbc3d_sing_cache_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rbc3d_set_replicated_density": (C.c_int, [C.c_void_p, C.c_int]),

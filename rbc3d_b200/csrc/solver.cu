@@ -36,6 +36,9 @@ struct ShArgs {
   double *g_raw;       // SoA(3,Np) synthesised field
   double *g_src;       // SoA(3,Np) field * detJ * w (slist%g)
   const double *v;     // SoA(3,Np) operator result (analysis adds g_raw: the diagonal term of MyMatMult)
+  int add_g;           // analysis: 1 = v + g_raw (MyMatMult), 0 = v + 2 vbkg / Acoef (Compute_Rhs)
+  double vbkg[3];
+  const double *Acell; // [ncell]
 };
 
 // one CTA per (cell, component)
@@ -83,7 +86,9 @@ __global__ void __launch_bounds__(256) k_sh_anal(ShArgs a) {
   const int cell = blockIdx.x / 3, comp = blockIdx.x - 3 * cell;
   double *s_v = sm, *s_Fc = s_v + nlon * nlat, *s_Fs = s_Fc + m0 * nlat;
   const size_t base = (size_t)comp * a.Np + (size_t)cell * a.npc;
-  for (int e = threadIdx.x; e < nlon * nlat; e += blockDim.x) s_v[e] = a.v[base + e] + a.g_raw[base + e];
+  const double bk = a.add_g ? 0.0 : 2.0 * a.vbkg[comp] / a.Acell[cell];  // ModVelSolver.F90:497-500
+  for (int e = threadIdx.x; e < nlon * nlat; e += blockDim.x)
+    s_v[e] = a.v[base + e] + (a.add_g ? a.g_raw[base + e] : bk);
   __syncthreads();
   for (int e = threadIdx.x; e < m0 * nlat; e += blockDim.x) {
     const int m = e / nlat, i = e - m * nlat;
@@ -245,6 +250,7 @@ static void sh_args(rbc3d_ctx *c, ShArgs &a) {
   a.ncell = C.ncell, a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.m0 = S.m0, a.Np = C.Np, a.dofc = S.dofc;
   a.pb = S.pb.p, a.pbw = S.pbw.p, a.cs = S.cs.p, a.ka = S.ka.p, a.kb = S.kb.p, a.dsw = S.dsw.p;
   a.coef = nullptr, a.coef_out = nullptr, a.g_raw = S.g_raw.p, a.g_src = C.g.p, a.v = nullptr;
+  a.add_g = 1, a.vbkg[0] = a.vbkg[1] = a.vbkg[2] = 0.0, a.Acell = C.A.p;
 }
 
 // b = MyMatMult(u), device vectors of length dof (ModVelSolver.F90:523-601, c1 = 0, c2 = -1/(4 pi))
@@ -274,6 +280,32 @@ int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev) {
   KERNEL_CHECK();
   c->launches++;
   S.nmatvec++;
+  return RBC3D_OK;
+}
+
+// rhs = Compute_Rhs (ModVelSolver.F90:455-515) for the cells alone: operator #1 (c1 = 1/(4 pi), c2 = 0) on the resident
+// single-layer density, + 2 vBkg / Acoef, Glob_Sph_Trans PHYS_TO_FOUR
+int solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs_dev) {
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  if (!S.ok) return RBC3D_ESTATE;
+  if (!C.f_set) {
+    set_error("rbc3d_solver_rhs: no single-layer density set");
+    return RBC3D_ESTATE;
+  }
+  TargetList &t = c->tl[RBC3D_TL_CELLS];
+  RBC_TRY(rbc3d_apply_resident(c, 1.0 / (4.0 * RBC_PI), 0.0, 1, use_walls, RBC3D_TL_CELLS));
+  ShArgs a;
+  sh_args(c, a);
+  a.v = t.v.p;
+  a.coef_out = rhs_dev;
+  a.add_g = 0;
+  for (int d = 0; d < 3; d++) a.vbkg[d] = vbkg[d];
+  const size_t sm_a = sizeof(double) * ((size_t)C.nlon * C.nlat + 2 * (size_t)S.m0 * C.nlat);
+  CUDA_TRY(cudaFuncSetAttribute(k_sh_anal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+  k_sh_anal<<<C.ncell * 3, 256, sm_a, c->stream>>>(a);
+  KERNEL_CHECK();
+  c->launches++;
   return RBC3D_OK;
 }
 
@@ -404,6 +436,41 @@ int rbc3d_solver_matmult(rbc3d_ctx *c, const double *u, double *b) {
   CUDA_TRY(cudaMemcpyAsync(S.u.p, u, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
   RBC_TRY(solver_matmult(c, S.u.p, S.b.p));
   CUDA_TRY(cudaMemcpyAsync(b, S.b.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int rbc3d_solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs) {
+  if (!c || !vbkg || !rhs) return RBC3D_EINVAL;
+  if (!c->solver.ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Solver &S = c->solver;
+  RBC_TRY(S.b.resize(S.dof));
+  RBC_TRY(solver_rhs(c, vbkg, use_walls, S.b.p));
+  CUDA_TRY(cudaMemcpyAsync(rhs, S.b.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+// surface velocity of the solution: Glob_Sph_Trans(v, sol, FOUR_TO_PHYS) (ModVelSolver.F90:124), host SoA(3,Np)
+int rbc3d_solver_velocity(rbc3d_ctx *c, const double *sol, double *v) {
+  if (!c || !sol || !v) return RBC3D_EINVAL;
+  if (!c->solver.ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  RBC_TRY(S.u.resize(S.dof));
+  RBC_TRY(S.w.resize(3 * (size_t)C.Np > S.dof ? 3 * (size_t)C.Np : S.dof));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  ShArgs a;
+  sh_args(c, a);
+  a.coef = S.u.p;
+  a.g_src = S.w.p;  // the weighted copy is not wanted here: scratch
+  const size_t sm_s = sizeof(double) * (2 * (size_t)S.m0 * S.m0 + 2 * (size_t)S.m0 * C.nlat);
+  k_sh_synth<<<C.ncell * 3, 256, sm_s, c->stream>>>(a);
+  KERNEL_CHECK();
+  c->launches++;
+  CUDA_TRY(cudaMemcpyAsync(v, S.g_raw.p, sizeof(double) * 3 * C.Np, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }

@@ -312,6 +312,18 @@ class EwaldOperator:
         check(self.lib.rbc3d_solver_matmult(self._h, dp(u), dp(b)), "rbc3d_solver_matmult")
         return b
 
+    def solver_rhs(self, vbkg=(1.0, 0.0, 0.0), walls=False):
+        """Compute_Rhs on the device (needs the single-layer density set): packed coefficients."""
+        rhs = np.zeros(self.solver_dof)
+        vb = f64(np.asarray(vbkg, dtype=np.float64))
+        check(self.lib.rbc3d_solver_rhs(self._h, dp(vb), int(walls), dp(rhs)), "rbc3d_solver_rhs")
+        return rhs
+
+    def solver_velocity(self, sol):
+        v = np.zeros((3, self.npoint))
+        check(self.lib.rbc3d_solver_velocity(self._h, dp(f64(sol)), dp(v)), "rbc3d_solver_velocity")
+        return v
+
     def solver_gmres(self, rhs, x0=None, rtol=1e-11, restart=30, maxit=200):
         """-> (sol, niter, residual history)."""
         rhs = f64(rhs)

@@ -84,8 +84,11 @@ def test_device_resident_solver_matches_host_harness():
     rng = np.random.default_rng(4)
     u = rng.uniform(-1, 1, host.T.dof)
     assert rel_l2(op.solver_matmult(u), host.matmult(u)) < 1e-11          # same transforms, same operator
+    op.SourceList_UpdateDensity(f=sus.weighted(sus.f))
+    assert rel_l2(op.solver_rhs((1.0, 0.0, 0.0)), rhs) < 1e-11              # Compute_Rhs on the device
     sol_h, v_h, it_h, hist_h = host.solve(rhs=rhs, rtol=1e-11)
     sol_d, it_d, hist_d = op.solver_gmres(rhs, rtol=1e-11)
+    assert rel_l2(op.solver_velocity(sol_d), v_h) < 1e-8                     # Glob_Sph_Trans(v, sol, FOUR_TO_PHYS)
     print(f"device-resident GMRES: {it_d} its, residual {hist_d[-1]:.3e}; host harness: {it_h} its, {hist_h[-1]:.3e}; "
           f"|sol_d - sol_h| / |sol_h| = {rel_l2(sol_d, sol_h):.2e}")
     assert it_d == it_h
