@@ -350,7 +350,8 @@ def run_gpu(args):
     # region above with host buffers (steady state: device buffers already allocated); the iteration count is the
     # one the 8-cell parity solve takes at rtol 1e-11 (tests/test_gpu_gmres.py), stated as an assumption.
     timestep = None
-    if not args.profile and not args.no_timestep:
+    if not args.profile and not args.no_timestep and world == 1:   # single GPU only: an exception on one rank of a
+        # multi-rank run would leave the others waiting in a collective
         try:
             dev_geom = not args.host_splines
             for arr in ((sus.x, sus.a3, sus.detj) if dev_geom else (sus.x, sus.a3, sus.spx, sus.spa3, sus.spdetj)):
