@@ -546,6 +546,7 @@ static int set_geometry_common(rbc3d_ctx *c, const double *x, const double *a3, 
                                const int32_t *active) {
   CUDA_TRY(cudaSetDevice(c->device));
   Cells &C = c->cells;
+  c->solver.ok = false;  // detJ * w of the device solver belongs to the previous geometry: rbc3d_solver_setup again
   const size_t Np = C.Np, nc = C.ncell;
   const size_t sp1 = (size_t)4 * 2 * C.nlat * C.nlon;
   RBC_TRY(upload(C.x, x, 3 * Np, c->stream));
