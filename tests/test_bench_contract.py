@@ -1,0 +1,42 @@
+"""bench.py contract checks that need no GPU: the reference arm (CPU restatement on the host cores) prints one JSON line
+with the agreed keys, ranks other than 0 leave without work, and the product arm refuses to run without a device."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT, env=e, capture_output=True,
+                          text=True, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = _run(["--impl", "reference", "--cells", "8", "--steps", "1", "--warmup", "0", "--ref-sample-cells", "4"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "Ewald BI matvecs/s" and line["unit"] == "matvecs/s"
+    assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["steps"] == 1
+    assert line["value"] > 0 and abs(line["value"] * line["ms_per_step"] / 1e3 - 1.0) < 1e-9
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "linear fit" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["config"]["cells"] == 8
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    r = _run(["--impl", "reference", "--cells", "8", "--steps", "1", "--warmup", "0"], env={"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_product_arm_refuses_to_run_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = _run(["--cells", "8", "--steps", "1", "--warmup", "0"])
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
