@@ -40,6 +40,7 @@ constexpr int SG_PC_DEFAULT = 2;  // patch points of one spline cell evaluated p
 // owns one target of the tile (register accumulation, no contribution buffer, no barriers in the tile loop).  Measured
 // at 512 cells: 7.8 ms vs 8.1 ms (profiles/r01_summary)
 static int sg_lr();
+static int sg_pitch_host(int ni);
 static int sg_per_warp() {
   static const int v = [] {
     const char *e = getenv("RBC3D_SING_PER_WARP");
@@ -295,7 +296,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   C.sg_ni_max = ni_max;
   C.sg_chunk_stride = CH;
   // shared memory: band of the spline (6 double2 planes x (n+1) phi columns x ni theta rows) + contribution buffer
-  const size_t smem = (size_t)12 * (ni_max | 1) * (n + 1) * sizeof(double) + (per_warp ? 0 : (size_t)3 * NPT * sizeof(double));
+  const size_t smem = (size_t)12 * sg_pitch_host(ni_max) * (n + 1) * sizeof(double) + (per_warp ? 0 : (size_t)3 * NPT * sizeof(double));
   if (smem > SG_SMEM_MAX || ni_max > 255) return RBC3D_OK;  // direct kernel only
   C.sg_smem = smem;
   RBC_TRY(C.sg_tile_tgt.resize(row_tgt.size()));
@@ -395,7 +396,29 @@ __global__ void __launch_bounds__(256) k_spline_interleave(int ncell, int plane,
   }
 }
 
+// pitch (in nodes) of a phi column of the shared-memory band: the smallest value >= ni with pitch = r (mod 8); the
+// residue decides which neighbouring spline cells share a 16-byte bank group (RBC3D_SING_PITCH_MOD, default 1 = odd)
+static int sg_pitch_mod() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_SING_PITCH_MOD");
+    const int q = e ? atoi(e) : 1;
+    return (q >= 0 && q < 8) ? q : 1;
+  }();
+  return v;
+}
+__host__ __device__ inline int sg_pitch(int ni, int r) {
+  if (r == 1) return ni | 1;
+  return ni + ((r - (ni & 7)) & 7);
+}
+
+static int sg_pitch_host(int ni) {  // worst case over the rows: the largest row decides the allocation
+  int worst = 0;
+  for (int k = 0; k <= 7 && ni - k > 0; k++) worst = worst > sg_pitch(ni - k, sg_pitch_mod()) ? worst : sg_pitch(ni - k, sg_pitch_mod());
+  return worst;
+}
+
 struct BandArgs {
+  int pitch_mod;
   int ncell, npc, nlat, nlon, ntl, ntn, Np, K, chunk_stride;
   const int *row_tgt;      // [tile row][T]: mesh point (ilon*nlat + ilat) of the targets of tile column 0, -1 = none
   const int *row_win;      // [tile row][2]: first theta row of the band, number of rows
@@ -441,7 +464,7 @@ __global__ void __launch_bounds__(NT, 1) k_sing_band(BandArgs a) {
   const int ilo = a.row_win[tl * 2 + 0], ni = a.row_win[tl * 2 + 1];
   const int m = 2 * a.nlat, n = a.nlon, plane = m * n;
   const int K = a.K, NPT = K * SG_T * 32;
-  const int nip = ni | 1;                            // odd pitch of a phi column: neighbouring columns fall into
+  const int nip = sg_pitch(ni, a.pitch_mod);         // odd pitch of a phi column: neighbouring columns fall into
                                                      // different 16-byte bank groups
   const int wn = nip * (n + 1);                      // node slots of the band
   double2 *sP = reinterpret_cast<double2 *>(smem);   // [6][n+1][nip]
@@ -765,6 +788,7 @@ int singular_density_prepare(rbc3d_ctx *c) {
 static int singular_apply_cached(rbc3d_ctx *c, TargetList &t, double c2) {
   Cells &C = c->cells;
   BandArgs a;
+  a.pitch_mod = sg_pitch_mod();
   a.ncell = C.ncell;
   a.npc = C.npc;
   a.nlat = C.nlat;
