@@ -98,9 +98,10 @@ def build_splines(sus: Suspension, builder: "sphere.SurfaceSplines", which=("x",
 def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: int = 161269,
                     visc_ratio: float = 5.0, jitter: float = 0.2, L: float | None = None,
                     spacing_scale: float = 1.0, with_f: bool = True, with_g: bool = True,
-                    centers: np.ndarray | None = None) -> Suspension:
+                    centers: np.ndarray | None = None, rotate: bool = True) -> Suspension:
     """Build an n_side^3-cell suspension.  ``spacing_scale`` < 1 packs the lattice tighter (used by the
-    tests to force near-singular cell-cell pairs); ``centers`` overrides the lattice (cells, 3)."""
+    tests to force near-singular cell-cell pairs); ``centers`` overrides the lattice (cells, 3); ``rotate=False``
+    keeps every cell in the orientation of RBC_MakeBiConcave (axis along z), as the example init programs do."""
     rng = np.random.Generator(np.random.PCG64(seed))
     builder = sphere.SurfaceSplines(nlat0, dealias)
     nlat, nlon = builder.nlat, builder.nlon
@@ -114,6 +115,8 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
     centers = np.asarray(centers, dtype=float)
     ncell = centers.shape[0]
     R = sphere.rotation_matrices(rng, ncell)
+    if not rotate:
+        R = np.broadcast_to(np.eye(3), (ncell, 3, 3)).copy()
 
     xu, a1u, a2u = sphere.biconcave_unit(th, phi, 1.0)          # (3, nlon, nlat)
     x = np.einsum("cij,jlk->cilk", R, xu) + centers[:, :, None, None]
