@@ -55,7 +55,7 @@ def minicase(mesh_path: str, nlat0: int = 12, dealias: int = 3, seed: int = 1612
     x, e2v = read_wall_mesh(mesh_path)
     actlen, lengtube, tube_rad = 13.33, 8.0, 5.0
     th = np.arctan2(x[0], x[1])                                   # ATAN2(wall%x(i,1), wall%x(i,2)), minit.F90:53
-    xw = np.stack([tube_rad * np.cos(th), tube_rad * np.sin(th), np.float32(lengtube) / np.float32(actlen) * x[2]])
+    xw = np.stack([tube_rad * np.cos(th), tube_rad * np.sin(th), lengtube / actlen * x[2]])
     Lb = np.array([xw[0].max() - xw[0].min() + 0.5, 0.0, xw[2].max() - xw[2].min()])
     Lb[1] = Lb[0]
     centers = np.array([[-0.5, -0.5, 4.0], [0.5, 0.5, 1.0]])      # minit.F90:80-96

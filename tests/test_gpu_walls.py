@@ -220,3 +220,30 @@ def test_partial_active_rows(two_walls):
     op.set_walls(W)
     op.PrepareSingIntOnWall()
     orc.prepare_sing_int_on_walls()
+
+
+def test_noslip_wall_solve(one_wall):
+    """NoSlipWall (ModNoSlip.F90:44-149) around the boundary: operator #3 for the right-hand side, operator #4 per
+    GMRES iteration (rtol = eps_Ewd = 1e-3, at most 60 iterations), through the C ABI and on the oracle -- same
+    iteration count (north_star: same or fewer), same residual history, same tractions."""
+    import copy
+    from rbc3d_b200 import noslip
+    op, orc, _, W = one_wall
+    f_keep = W.f.copy()
+    vbkg = np.array([0.0, 0.0, 8.0])
+    out = []
+    for backend in (noslip.oracle_backend(orc, vbkg), noslip.library_backend(op, vbkg)):
+        Wc = copy.copy(W)
+        Wc.f = f_keep.copy()
+        s = noslip.WallNoSlipSolver(Wc, LB, *backend)
+        out.append(s.solve(rtol=1e-3, maxit=60))
+    (f_o, it_o, h_o, slip_o), (f_g, it_g, h_g, slip_g) = out
+    assert 0 < it_g <= it_o <= 60
+    n = min(len(h_o), len(h_g))
+    assert np.allclose(h_g[:n], h_o[:n], rtol=1e-6, atol=1e-9 * h_o[0])
+    assert h_g[-1] < 1e-3 * h_g[0]
+    if it_g == it_o:
+        assert rel_l2(f_g, f_o) < 1e-6        # a first-kind equation: tractions are conditioned worse than velocities
+        assert np.abs(slip_g - slip_o).max() < 1e-7 * np.abs(vbkg).max()
+    op.set_wall_traction(f_keep)
+    orc.set_wall_traction(f_keep)
