@@ -466,11 +466,84 @@ def run_gpu(args):
            "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
     if cb is not None:
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
     op.close()
+    if world == 1 and not args.profile and not args.no_mtube:
+        # the other half of the metric on BASELINE.json configs[0]; a child process, after this one released the GPU
+        out["mtube"] = mtube_child(args)
+    print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def run_mtube(args):
+    """BASELINE.json configs[0] ("examples/minicase: a few RBCs in a periodic tube"): the boundary-integral work of one
+    TimeInt_Euler step (rbc3d_b200/mtube.py: geometry update, Compute_Rhs with cells + wall, NoSlipWall = operator #3
+    twice + operator #4 per wall-GMRES iteration) through the C ABI with host buffers, and the same steps on the CPU
+    oracle on the box's host cores.  Tractions carry over from step to step as in a run.  Prints one JSON object; run
+    as a child process of the main bench so that a failure here cannot cost the headline line."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mtube-only: no CUDA device; the product has no CPU path")
+    from rbc3d_b200 import mtube
+    from rbc3d_b200.ewald import EwaldOperator
+    nsteps = max(2, args.mtube_steps)
+    sus, W = mtube.minicase_like(seed=args.seed)
+    op = EwaldOperator(sus.Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
+    step = mtube.LibraryStep(op, sus, W)
+    l0 = op.launch_count()
+    runs = [mtube.bi_timestep(step) for _ in range(1 + nsteps)]          # first step = warm-up (allocations, cuFFT plans)
+    launches = op.launch_count() - l0
+    Nb = list(op.Nb)
+    op.close()
+    gpu = runs[1:]
+    out = {"workload": "examples/minicase-like: 2 RBCs (36x72 pts/cell, lambda = 1) in a periodic tube of radius 5, box "
+                       "10.5x10.5x8, generated tube mesh %d vertices / %d triangles (the reference's Exodus mesh: "
+                       "1328 / 2404), vBkg = (0,0,8), PME grid %s" % (W.NV, W.NE, "x".join(str(n) for n in Nb)),
+           "step": "geometry update + operator #1 (RHS, cells+wall -> cells) + NoSlipWall (operator #3 x 2 + operator #4 "
+                   "per wall-GMRES iteration, rtol = eps_Ewd = 1e-3, <= 60); host buffers through the C ABI",
+           "steps": nsteps,
+           "bi_timesteps_per_s": nsteps / sum(r["seconds"]["total"] for r in gpu),
+           "ms_per_step": [r["seconds"]["total"] * 1e3 for r in gpu],
+           "ms_geometry_rhs_noslip": [[r["seconds"][k] * 1e3 for k in ("geometry", "rhs", "noslip")] for r in gpu],
+           "wall_gmres_iterations": [r["wall_iterations"] for r in runs],
+           "operator_applications": [r["operator_applications"] for r in gpu],
+           "gpu_launches": int(launches)}
+    if not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        sus2, W2 = mtube.minicase_like(seed=args.seed)
+        ostep = mtube.OracleStep(oracle.Oracle(sus2.Lb), sus2, W2)
+        cruns = [mtube.bi_timestep(ostep) for _ in range(1 + nsteps)]
+        cpu = cruns[1:]
+        rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+        out["cpu_baseline"] = {"value": nsteps / sum(r["seconds"]["total"] for r in cpu), "unit": "timesteps/s",
+                               "cores": os.cpu_count(), "kind": "port",
+                               "sample": "the same %d steps in full on the CPU oracle (OpenMP, all host cores)" % nsteps,
+                               "ms_per_step": [r["seconds"]["total"] * 1e3 for r in cpu],
+                               "wall_gmres_iterations": [r["wall_iterations"] for r in cruns]}
+        out["parity_vs_oracle"] = {"rel_l2_cell_velocity": [rel(a["v_cells"], b["v_cells"]) for a, b in zip(runs, cruns)],
+                                   "rel_l2_wall_traction": [rel(a["f_wall"], b["f_wall"]) for a, b in zip(runs, cruns)],
+                                   "same_iterations": [a["wall_iterations"] == b["wall_iterations"]
+                                                       for a, b in zip(runs, cruns)]}
+    print(json.dumps({"mtube": out}))
+    return 0
+
+
+def mtube_child(args):
+    """Run --mtube-only in a child process (after the main operator has released the GPU) and return its object."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--mtube-only", "--seed", str(args.seed), "--mtube-steps",
+           str(args.mtube_steps)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR",
+                                                            "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)["mtube"]
+        return {"error": ("rc=%d " % r.returncode) + r.stderr.strip()[-300:]}
+    except Exception as exc:
+        return {"error": str(exc)[:300]}
 
 
 def world_value(v):
@@ -496,7 +569,12 @@ def main():
     ap.add_argument("--host-splines", action="store_true",
                     help="upload spline(g detJ) from the host every step instead of building it on the GPU")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: exact --warmup, no CPU leg, 1 e2e step")
+    ap.add_argument("--no-mtube", action="store_true", help="skip the minicase time-step block (configs[0])")
+    ap.add_argument("--mtube-only", action="store_true", help="only the minicase time-step block, one JSON object")
+    ap.add_argument("--mtube-steps", type=int, default=4)
     args = ap.parse_args()
+    if args.mtube_only:
+        return run_mtube(args)
     if args.warmup < 3 and args.impl == "b200" and not args.profile:
         args.warmup = 3   # timing hygiene: at least 3 warm-up steps
     if args.profile:

@@ -1,0 +1,104 @@
+"""The boundary-integral work of one ``TimeInt_Euler`` step of examples/minicase/mtube (ModTimeInt.F90:108-176), composed
+from the boundary's entry points -- harness code used by bench.py (``mtube`` block: BASELINE.json "mtube timesteps/s")
+and by the tests; the same composition runs on the CUDA library (C ABI) and on the CPU oracle.
+
+    Compute_Rbc_Vel   SourceList_UpdateCoord / UpdateDensity(f) on the moved cells         ModTimeInt.F90:127, ModVelSolver.F90:44-93
+                      Compute_Rhs = operator #1: c1 = 1/(4 pi), c2 = 0, cells + walls -> cell points, + 2 vBkg / A   :455-515
+                      viscRat = 1 in every shipped tube.in: sol = rhs, no cell GMRES                                   :104-105
+    NoSlipWall        operator #3 (rhs), operator #4 x wall-GMRES iterations, operator #3 (monitor)                  ModNoSlip.F90:44-149
+
+Membrane forces, spherical-harmonic filtering, volume constraint and repulsion are outside SURVEY.md section 8 and are
+not part of the timed step; the traction ``f`` of the cells is a band-limited stand-in (synth.make_suspension).
+``PrepareSingIntOnWall`` runs once at start-up (TimeInt_Init, ModTimeInt.F90:87), not per step.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import noslip, synth
+
+C1 = 1.0 / (4.0 * np.pi)
+VBKG = (0.0, 0.0, 8.0)                                       # examples/minicase/Input/tube.in via mtube.F90
+
+
+def minicase_like(nlat0: int = 12, dealias: int = 3, seed: int = 161269, ntheta: int = 48, nz: int = 26):
+    """examples/minicase with a generated tube mesh (the Exodus file is not on the GPU box): box 10.5 x 10.5 x 8, tube
+    radius 5 (minit.F90:39-70), two unrotated biconcave cells at the init program's positions (:80-96), lambda = 1.
+    48 x 26 gives 1296 vertices / 2496 triangles against the file's 1328 / 2404."""
+    Lb = np.array([10.5, 10.5, 8.0])
+    centers = np.array([[-0.5, -0.5, 4.0], [0.5, 0.5, 1.0]]) + np.array([0.5 * Lb[0], 0.5 * Lb[1], 0.0])
+    sus = synth.make_suspension(1, nlat0=nlat0, dealias=dealias, seed=seed, L=1.0, centers=centers, rotate=False,
+                                visc_ratio=1.0)
+    sus.Lb = Lb
+    W = synth.make_walls(Lb, [dict(radius=5.0, ntheta=ntheta, nz=nz)])
+    W.f[:] = 0.0                                             # minit.F90 writes zero wall tractions into the restart file
+    return sus, W
+
+
+class OracleStep:
+    """One step's operators on the CPU oracle (bench.py cpu_baseline / --impl reference, tests)."""
+
+    def __init__(self, orc, sus, W, vbkg=VBKG):
+        self.orc, self.sus, self.W, self.vbkg = orc, sus, W, np.asarray(vbkg, dtype=float)
+        orc.set_cells(sus)
+        orc.set_walls(W)
+        orc.prepare_sing_int_on_walls()                      # TimeInt_Init
+
+    def update_geometry(self):
+        self.orc.set_cells(self.sus)                         # SourceList_UpdateCoord + UpdateDensity, TargetList_Update
+        self.orc.set_wall_traction(self.W.f)
+
+    def compute_rhs(self):
+        sus = self.sus
+        v = self.orc.apply(C1, 0.0, self.orc.cell_targets(), cells=True, walls=True)
+        A = np.repeat(sus.Acoef, sus.nlat * sus.nlon)
+        return v + 2.0 * self.vbkg[:, None] / A[None, :]
+
+    def noslip_backend(self):
+        return noslip.oracle_backend(self.orc, self.vbkg)
+
+
+class LibraryStep:
+    """The same on the CUDA library through the C ABI (rbc3d_b200.ewald.EwaldOperator)."""
+
+    def __init__(self, op, sus, W, vbkg=VBKG):
+        self.op, self.sus, self.W, self.vbkg = op, sus, W, np.asarray(vbkg, dtype=float)
+        op.set_suspension(sus)
+        op.set_walls(W)
+        op.PrepareSingIntOnWall()
+
+    def update_geometry(self):
+        sus, op = self.sus, self.op
+        op.SourceList_UpdateCoord(sus.x, sus.a3, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize, sus.spx, sus.spa3, sus.spdetj)
+        op.SourceList_UpdateDensity(sus.weighted(sus.f), sus.weighted(sus.g), sus.spF, sus.spG)
+        op.set_wall_traction(self.W.f)
+
+    def compute_rhs(self):
+        from .capi import TL_CELLS
+        sus = self.sus
+        v = self.op.apply(C1, 0.0, TL_CELLS, cells=True, walls=True)
+        A = np.repeat(sus.Acoef, sus.nlat * sus.nlon)
+        return v + 2.0 * self.vbkg[:, None] / A[None, :]
+
+    def noslip_backend(self):
+        return noslip.library_backend(self.op, self.vbkg)
+
+
+def bi_timestep(step, rtol: float = 1e-3, maxit: int = 60):
+    """Run the step's boundary-integral work once.  -> dict(v_cells, f_wall, wall_iterations, history, slip, seconds{})."""
+    t = {}
+    t0 = time.perf_counter()
+    step.update_geometry()
+    t["geometry"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    v = step.compute_rhs()
+    t["rhs"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    s = noslip.WallNoSlipSolver(step.W, step.sus.Lb, *step.noslip_backend())
+    f, niter, hist, slip = s.solve(rtol=rtol, maxit=maxit)
+    t["noslip"] = time.perf_counter() - t0
+    t["total"] = t["geometry"] + t["rhs"] + t["noslip"]
+    return {"v_cells": v, "f_wall": f, "wall_iterations": niter, "history": hist, "slip": slip, "seconds": t,
+            "operator_applications": 1 + 2 + s.nmatvec}

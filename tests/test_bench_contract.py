@@ -40,3 +40,21 @@ def test_product_arm_refuses_to_run_without_a_device():
         pytest.skip("a GPU is present")
     r = _run(["--cells", "8", "--steps", "1", "--warmup", "0"])
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_mtube_block_refuses_without_a_device_and_the_parent_survives_it():
+    """--mtube-only is the child process of the main bench (BASELINE.json configs[0] time-step block): without a device
+    it refuses like the product arm, and the parent turns a failing child into {"error": ...} instead of dying."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = _run(["--mtube-only"])
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    out = bench.mtube_child(argparse.Namespace(seed=1, mtube_steps=2, no_cpu_baseline=True))
+    assert set(out) == {"error"} and "no CUDA device" in out["error"]
