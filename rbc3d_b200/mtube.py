@@ -13,11 +13,12 @@ not part of the timed step; the traction ``f`` of the cells is a band-limited st
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
 
-from . import noslip, synth
+from . import noslip, sphere, synth
 
 C1 = 1.0 / (4.0 * np.pi)
 VBKG = (0.0, 0.0, 8.0)                                       # examples/minicase/Input/tube.in via mtube.F90
@@ -34,6 +35,43 @@ def minicase_like(nlat0: int = 12, dealias: int = 3, seed: int = 161269, ntheta:
     sus.Lb = Lb
     W = synth.make_walls(Lb, [dict(radius=5.0, ntheta=ntheta, nz=nz)])
     W.f[:] = 0.0                                             # minit.F90 writes zero wall tractions into the restart file
+    return sus, W
+
+
+GOLDEN_SICKLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "ref_sickle_cell.npz")
+
+
+def import_read_rbc(x_file: np.ndarray, xc) -> np.ndarray:
+    """ImportReadRBC (ModIO.F90:668-681): the exported cell recentred by (5.25, 5.25, 5/7), then moved to xc.
+    x_file (3, nlon, nlat) as parsed from SickleCell.dat (scripts/make_golden_sickle.py)."""
+    off = np.array([5.25, 5.25, 5.0 / 7.0])
+    return x_file - off[:, None, None] + np.asarray(xc, dtype=float)[:, None, None]
+
+
+def case_like(nrbc: int = 8, sickles: bool = True, seed: int = 161269, ntheta: int = 48, nz: int = 36,
+              visc_ratio: float = 1.0, sickle_x: np.ndarray | None = None):
+    """examples/case (initcond.F90:42-110) and examples/case_sickles (sickle_initcond.F90:50-110) with a generated tube
+    mesh: tube radius 5, length nrbc / 0.7, box 10.5 x 10.5 x length, the cells on the axis at z = (iz - 1/2) length /
+    nrbc, all biconcave (case) or every second one the imported sickle cell (case_sickles; shape from the committed
+    fixture tests/golden/ref_sickle_cell.npz = the reference's SickleCell.dat).  BASELINE.json configs[1] / configs[3]."""
+    length = nrbc / 0.7
+    Lb = np.array([10.5, 10.5, length])
+    spacing = length / nrbc
+    th, phi, _ = sphere.gauss_grid(36, 72)
+    xb, _, _ = sphere.biconcave_unit(th, phi, 1.0)
+    if sickles and sickle_x is None:
+        sickle_x = np.load(GOLDEN_SICKLE)["x"]
+    xs = []
+    for iz in range(1, nrbc + 1):
+        xc = np.array([0.5 * Lb[0], 0.5 * Lb[1], spacing * (iz - 0.5)])          # after Recenter_Cells_and_Walls
+        if sickles and iz % 2 == 0:
+            xs.append(import_read_rbc(sickle_x, xc))
+        else:
+            xs.append(xb + xc[:, None, None])
+    sus = synth.suspension_from_shapes(np.stack(xs), Lb, nlat0=12, dealias=3, visc_ratio=visc_ratio, seed=seed)
+    W = synth.make_walls(Lb, [dict(radius=5.0, ntheta=ntheta, nz=nz)])
+    W.f[:] = 0.0
     return sus, W
 
 

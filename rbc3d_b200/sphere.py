@@ -133,6 +133,46 @@ def biconcave_unit(th: np.ndarray, phi: np.ndarray, rad: float = 1.0):
     return x, a1, a2
 
 
+def _dpbar_dth(nmax: int, th: np.ndarray) -> np.ndarray:
+    """d Pbar_n^m(cos th) / d th for 0 <= m <= n < nmax at colatitudes th (no pole among them):
+    sin(th) dP_n^m/dth = n cos(th) P_n^m - (n + m) P_{n-1}^m, carried over to the orthonormal functions."""
+    x, s = np.cos(th), np.sin(th)
+    out = np.zeros((nmax, nmax, th.size))
+    for m in range(nmax):
+        for n in range(m, nmax):
+            lognorm = 0.5 * (np.log(2 * n + 1.0) - np.log(2.0) + gammaln(n - m + 1) - gammaln(n + m + 1))
+            pn = lpmv(m, n, x)
+            pn1 = lpmv(m, n - 1, x) if n - 1 >= m else np.zeros_like(x)
+            out[m, n] = np.exp(lognorm) * (n * x * pn - (n + m) * pn1) / s
+    return out
+
+
+class SphereGradient:
+    """ShAnalGau + ShGradGau (ModSphpk.F90:74-105, 377-417; SPHEREPACK shags + gradgs, then the sin(th) factor put
+    back): scalar fields on the nlat x nlon Gauss grid -> (d/d theta, d/d phi), all degrees n < nlat kept."""
+
+    def __init__(self, nlat: int, nlon: int):
+        self.nlat, self.nlon = nlat, nlon
+        self.th, self.phi, w = gauss_grid(nlat, nlon)
+        wg = w / (TWO_PI / nlon)
+        mmax = min(nlat, nlon // 2 + 1)
+        pb = _pbar(nlat, np.cos(self.th))[:mmax]                   # (m, n, nlat)
+        dpb = _dpbar_dth(nlat, self.th)[:mmax]
+        self.mmax = mmax
+        self.D = np.einsum("mno,mni->moi", dpb, pb * wg[None, None, :])   # values -> d/dth, per zonal wavenumber
+
+    def __call__(self, f: np.ndarray):
+        """f (..., nlon, nlat) -> f_theta, f_phi (..., nlon, nlat)."""
+        F = np.fft.rfft(f, axis=-2)
+        G = np.zeros_like(F)
+        G[..., :self.mmax, :] = np.einsum("moi,...mi->...mo", self.D, F[..., :self.mmax, :])
+        m = np.arange(F.shape[-2])
+        Fp = 1j * m[:, None] * F
+        if self.nlon % 2 == 0:
+            Fp[..., -1, :] = 0.0
+        return np.fft.irfft(G, n=self.nlon, axis=-2), np.fft.irfft(Fp, n=self.nlon, axis=-2)
+
+
 def surface_geometry(a1: np.ndarray, a2: np.ndarray, th: np.ndarray):
     """a3 (unit normal) and detJ = |a1 x a2| / sin(theta) -- ModRbc.F90:431-455.
     a1, a2 (..., 3, nlon, nlat)."""

@@ -122,6 +122,14 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
     x = np.einsum("cij,jlk->cilk", R, xu) + centers[:, :, None, None]
     a1 = np.einsum("cij,jlk->cilk", R, a1u)
     a2 = np.einsum("cij,jlk->cilk", R, a2u)
+    return _assemble(rng, builder, Lb, nlat0, x, a1, a2, np.full(ncell, float(visc_ratio)), centers, with_f, with_g)
+
+
+def _assemble(rng, builder, Lb, nlat0, x, a1, a2, visc_ratio, centers, with_f, with_g) -> Suspension:
+    """x, a1, a2 (ncell, 3, nlon, nlat) -> Suspension with normals, Jacobians, densities, coefficients and splines."""
+    nlat, nlon = builder.nlat, builder.nlon
+    th, phi, w = sphere.gauss_grid(nlat, nlon)
+    ncell = x.shape[0]
     a3, detj = sphere.surface_geometry(a1, a2, th)
     ds = detj * w                                             # (ncell, nlon, nlat)
     area = ds.sum(axis=(1, 2))
@@ -132,8 +140,8 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
         f = _flat(sphere.random_bandlimited_field(rng, ncell, 3, nlat0, th, nlon))
     if with_g:
         g = _flat(sphere.random_bandlimited_field(rng, ncell, 3, nlat0, th, nlon))
-    A = np.full(ncell, 1.0 + visc_ratio)
-    B = np.full(ncell, 1.0 - visc_ratio)
+    A = 1.0 + np.asarray(visc_ratio, dtype=float)              # initCOEFs: A = 1 + lambda, B = 1 - lambda
+    B = 1.0 - np.asarray(visc_ratio, dtype=float)
     sus = Suspension(Lb=Lb, nlat0=nlat0, nlat=nlat, nlon=nlon, ncell=ncell, th=th, phi=phi, w=w,
                      x=_flat(x), a3=_flat(a3), detj=np.ascontiguousarray(detj.reshape(-1)), f=f, g=g,
                      Acoef=A, Bcoef=B, area=area, meshSize=meshSize, spx=None, spa3=None, spdetj=None,
@@ -141,6 +149,22 @@ def make_suspension(n_side: int = 4, nlat0: int = 12, dealias: int = 3, seed: in
     build_splines(sus, builder)
     sus._builder = builder
     return sus
+
+
+def suspension_from_shapes(x: np.ndarray, Lb, nlat0: int = 12, dealias: int = 3, visc_ratio=1.0, seed: int = 161269,
+                           with_f: bool = True, with_g: bool = True) -> Suspension:
+    """Cells given by their mesh coordinates x (ncell, 3, nlon, nlat) -- imported shapes (ImportReadRBC) next to analytic
+    ones: tangent vectors by spectral differentiation as RBC_ComputeGeometry does (ModRbc.F90:419-456: ShAnalGau +
+    ShGradGau over all degrees of the nlat x nlon grid).  ``visc_ratio``: scalar or one value per cell."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    builder = sphere.SurfaceSplines(nlat0, dealias)
+    x = np.ascontiguousarray(x, dtype=float)
+    ncell = x.shape[0]
+    assert x.shape == (ncell, 3, builder.nlon, builder.nlat)
+    a1, a2 = sphere.SphereGradient(builder.nlat, builder.nlon)(x)
+    lam = np.broadcast_to(np.asarray(visc_ratio, dtype=float), (ncell,)).copy()
+    Lb = np.asarray(Lb, dtype=float) * np.ones(3)
+    return _assemble(rng, builder, Lb, nlat0, x, a1, a2, lam, x.mean(axis=(2, 3)), with_f, with_g)
 
 
 # ---------------------------------------------------------------------------------------------------------

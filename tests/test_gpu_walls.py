@@ -268,3 +268,31 @@ def test_mtube_time_step(oracle_lib):
         if a["wall_iterations"] == b["wall_iterations"]:
             assert rel_l2(a["f_wall"], b["f_wall"]) < 1e-6
     op.close()
+
+
+@pytest.mark.parametrize("sickles", [False, True])
+def test_case_and_case_sickles_configurations(oracle_lib, sickles):
+    """BASELINE.json configs[1] / configs[3]: 8 cells on the axis of the vessel (examples/case), every second one the
+    sickle cell imported from the reference's SickleCell.dat (examples/case_sickles; tests/golden/ref_sickle_cell.npz),
+    lambda = 5 so that the matvec operator exists; operators #1 (RHS), #2 (matvec) and #3 (wall residual)."""
+    from rbc3d_b200 import mtube
+    from rbc3d_b200.capi import TL_CELLS, TL_WALLS
+    from rbc3d_b200.ewald import EwaldOperator
+    sus, W = mtube.case_like(8, sickles=sickles, ntheta=32, nz=24, visc_ratio=5.0)
+    rng = np.random.default_rng(11)
+    W.f = rng.normal(size=W.f.shape)
+    op = EwaldOperator(sus.Lb)
+    op.set_suspension(sus)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    orc.set_walls(W)
+    orc.prepare_sing_int_on_walls()
+    assert list(op.Nb) == [48, 48, 52] and np.array_equal(op.cell_list()[1], orc.cell_ids(sus.x))
+    for c1, c2, kind, tl, walls in ((C1_RHS, 0.0, TL_CELLS, orc.cell_targets(), True),
+                                    (0.0, C2_MATVEC, TL_CELLS, orc.cell_targets(), False),
+                                    (C1_RHS, C1_RHS, TL_WALLS, orc.wall_targets(), True)):
+        v = op.apply(c1, c2, kind, cells=True, walls=walls)
+        ref = orc.apply(c1, c2, tl, cells=True, walls=walls)
+        assert rel_l2(v, ref) < TOL
+    op.close()
