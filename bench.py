@@ -39,6 +39,7 @@ if ROOT not in sys.path:
 C2_MATVEC = -1.0 / (4.0 * np.pi)
 GMRES_ITS_ASSUMED = 22     # iterations of the cell velocity solve at rtol 1e-11 (tests/test_gpu_gmres.py, 8 cells)
 C1_RHS = 1.0 / (4.0 * np.pi)
+MTUBE_WARM_STEPS = 5       # mtube block: untimed steps until the wall-GMRES iteration count settles (~21 per step)
 FLOPS_DL_PAIR = 54.0      # flops per in-range double-layer pair (FMA = 2)
 FLOPS_SPLINE3 = 155.0     # one bicubic interpolation of 3 variables
 FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
@@ -204,8 +205,30 @@ def run_reference(args):
            "cpu_baseline": cb,
            "e2e": {"value": val, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_mtube:
+        out["mtube"] = cpu_mtube(args)
     print(json.dumps(out))
     return 0
+
+
+def cpu_mtube(args):
+    """configs[0] on the CPU restatement alone: the boundary-integral work of mtube time steps (rbc3d_b200/mtube.py) on the
+    oracle, all host cores (the reference's own CPU-runnable case; the GPU arm reports the same block under "mtube")."""
+    try:
+        from oracle import oracle
+        from rbc3d_b200 import mtube
+        oracle.build()
+        nsteps = max(2, args.mtube_steps)
+        sus, W = mtube.minicase_like(seed=args.seed)
+        step = mtube.OracleStep(oracle.Oracle(sus.Lb), sus, W)
+        runs = [mtube.bi_timestep(step, advect=True) for _ in range(MTUBE_WARM_STEPS + nsteps)]
+        cpu = runs[MTUBE_WARM_STEPS:]
+        return {"bi_timesteps_per_s": nsteps / sum(r["seconds"]["total"] for r in cpu), "steps": nsteps,
+                "ms_per_step": [r["seconds"]["total"] * 1e3 for r in cpu], "cores": os.cpu_count(), "kind": "port",
+                "wall_gmres_iterations": [r["wall_iterations"] for r in runs],
+                "workload": "examples/minicase-like: 2 RBCs in a periodic tube, %d wall vertices / %d triangles" % (W.NV, W.NE)}
+    except Exception as exc:
+        return {"error": str(exc)[:300]}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -492,14 +515,17 @@ def run_mtube(args):
     op = EwaldOperator(sus.Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
     step = mtube.LibraryStep(op, sus, W)
     l0 = op.launch_count()
-    runs = [mtube.bi_timestep(step) for _ in range(1 + nsteps)]          # first step = warm-up (allocations, cuFFT plans)
+    warm = MTUBE_WARM_STEPS      # start-up transient of the wall tractions (3, 19, 60, 42 iterations), allocations, plans
+    runs = [mtube.bi_timestep(step, advect=True) for _ in range(warm + nsteps)]
     launches = op.launch_count() - l0
     Nb = list(op.Nb)
     op.close()
-    gpu = runs[1:]
+    gpu = runs[warm:]
     out = {"workload": "examples/minicase-like: 2 RBCs (36x72 pts/cell, lambda = 1) in a periodic tube of radius 5, box "
                        "10.5x10.5x8, generated tube mesh %d vertices / %d triangles (the reference's Exodus mesh: "
                        "1328 / 2404), vBkg = (0,0,8), PME grid %s" % (W.NV, W.NE, "x".join(str(n) for n in Nb)),
+           "between_steps": "cells translated by Ts = 0.0008 times their mean surface velocity (stand-in for the membrane "
+                            "update, untimed); %d untimed start-up steps" % warm,
            "step": "geometry update + operator #1 (RHS, cells+wall -> cells) + NoSlipWall (operator #3 x 2 + operator #4 "
                    "per wall-GMRES iteration, rtol = eps_Ewd = 1e-3, <= 60); host buffers through the C ABI",
            "steps": nsteps,
@@ -514,8 +540,8 @@ def run_mtube(args):
         oracle.build()
         sus2, W2 = mtube.minicase_like(seed=args.seed)
         ostep = mtube.OracleStep(oracle.Oracle(sus2.Lb), sus2, W2)
-        cruns = [mtube.bi_timestep(ostep) for _ in range(1 + nsteps)]
-        cpu = cruns[1:]
+        cruns = [mtube.bi_timestep(ostep, advect=True) for _ in range(warm + nsteps)]
+        cpu = cruns[warm:]
         rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
         out["cpu_baseline"] = {"value": nsteps / sum(r["seconds"]["total"] for r in cpu), "unit": "timesteps/s",
                                "cores": os.cpu_count(), "kind": "port",

@@ -75,6 +75,25 @@ def case_like(nrbc: int = 8, sickles: bool = True, seed: int = 161269, ntheta: i
     return sus, W
 
 
+TS = 0.0008                                                  # examples/minicase/Input/tube.in: Ts
+
+
+def advect_rigid(sus, v_cells: np.ndarray, Ts: float = TS) -> None:
+    """Stand-in for ``rbc%x = rbc%x + Ts*rbc%v`` (ModTimeInt.F90:136-141) + ReboxRbcs that needs no membrane solver: every
+    cell is translated by Ts times its mean surface velocity, so x and spline(x) move and every other geometric field
+    (a3, detJ, their splines, the densities) is unchanged.  Gives each time step of the harness a NEW geometry, which
+    is what makes the cell lists, the geometry caches and the wall solve's right-hand side change from step to step."""
+    npc = sus.nlat * sus.nlon
+    for c in range(sus.ncell):
+        d = Ts * v_cells[:, c * npc:(c + 1) * npc].mean(axis=1)
+        ctr = sus.centers[c] + d
+        wrap = -np.floor(ctr / sus.Lb) * sus.Lb              # ReboxRbcs: keep the centre inside the box
+        d = d + wrap
+        sus.centers[c] = sus.centers[c] + d
+        sus.x[:, c * npc:(c + 1) * npc] += d[:, None]
+        sus.spx[c, 0] += d[:, None, None]                    # spline values u; derivatives u1, u2, u12 do not change
+
+
 class OracleStep:
     """One step's operators on the CPU oracle (bench.py cpu_baseline / --impl reference, tests)."""
 
@@ -124,8 +143,8 @@ class LibraryStep:
         return noslip.library_backend(self.op, self.vbkg)
 
 
-def bi_timestep(step, rtol: float = 1e-3, maxit: int = 60):
-    """Run the step's boundary-integral work once.  -> dict(v_cells, f_wall, wall_iterations, history, slip, seconds{})."""
+def bi_timestep(step, rtol: float = 1e-3, maxit: int = 60, advect: bool = False):
+    """Run the step's boundary-integral work once (advect: then move the cells for the next step, untimed).  -> dict(v_cells, f_wall, wall_iterations, history, slip, seconds{})."""
     t = {}
     t0 = time.perf_counter()
     step.update_geometry()
@@ -138,5 +157,7 @@ def bi_timestep(step, rtol: float = 1e-3, maxit: int = 60):
     f, niter, hist, slip = s.solve(rtol=rtol, maxit=maxit)
     t["noslip"] = time.perf_counter() - t0
     t["total"] = t["geometry"] + t["rhs"] + t["noslip"]
+    if advect:
+        advect_rigid(step.sus, v)                            # untimed: the caller's position update
     return {"v_cells": v, "f_wall": f, "wall_iterations": niter, "history": hist, "slip": slip, "seconds": t,
             "operator_applications": 1 + 2 + s.nmatvec}

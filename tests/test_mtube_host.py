@@ -52,3 +52,20 @@ def test_one_step_reference_mesh(oracle_lib):
     ndup = int((v2v > 0).sum())
     assert ndup == 126 and r["f_wall"].shape == (3, 1328)
     assert np.array_equal(r["f_wall"][:, v2v > 0], r["f_wall"][:, v2v[v2v > 0] - 1])
+
+
+def test_rigid_advection_keeps_the_splines_consistent():
+    from rbc3d_b200 import synth
+    sus, _ = mtube.minicase_like(nlat0=6)
+    rng = np.random.default_rng(2)
+    v = rng.normal(size=(3, sus.npoint)) + np.array([0.0, 0.0, 9000.0])[:, None]      # far enough to leave the box in z
+    x0, c0 = sus.x.copy(), sus.centers.copy()
+    mtube.advect_rigid(sus, v)
+    d = sus.centers - c0
+    assert np.all(sus.centers >= 0) and np.all(sus.centers < sus.Lb)                  # ReboxRbcs
+    npc = sus.nlat * sus.nlon
+    for c in range(sus.ncell):
+        assert np.allclose(sus.x[:, c * npc:(c + 1) * npc] - x0[:, c * npc:(c + 1) * npc], d[c][:, None], atol=1e-12)
+    moved = sus.spx.copy()
+    synth.build_splines(sus, sus._builder, which=("x",))                              # Rbc_BuildSurfaceSource(xFlag) afresh
+    assert np.abs(moved - sus.spx).max() < 1e-11
