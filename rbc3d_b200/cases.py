@@ -70,3 +70,23 @@ def minicase(mesh_path: str, nlat0: int = 12, dealias: int = 3, seed: int = 1612
                     np.ascontiguousarray(e2v), None, None, np.zeros_like(xw))
     W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
     return sus, W, np.array([0.0, 0.0, 8.0])
+
+
+def carotid_web_walls(input_dir: str):
+    """-> (walls, Lb) of examples/carotid_web (carotid_initcond.F90:47-70, 118-138): carotid.e + web.e, shifted so that
+    the first wall's coordinates start at 0 (recenterWalls), Lb = (max x + 0.5, max y + 0.5, 30)."""
+    import os
+    xs, es = [], []
+    for name in ("carotid.e", "web.e"):
+        x, e = read_wall_mesh(os.path.join(input_dir, name))
+        xs.append(x)
+        es.append(e)
+    off = -xs[0].min(axis=1)
+    xs = [x + off[:, None] for x in xs]
+    Lb = np.array([xs[0][0].max() + 0.5, xs[0][1].max() + 0.5, 30.0])
+    x = np.ascontiguousarray(np.concatenate(xs, axis=1))
+    e2v = np.ascontiguousarray(np.concatenate(es, axis=1))
+    W = synth.Walls(np.array([a.shape[1] for a in xs], np.int32), np.array([a.shape[1] for a in es], np.int32), x, e2v,
+                    None, None, np.zeros_like(x))
+    W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
+    return W, Lb

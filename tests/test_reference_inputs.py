@@ -52,3 +52,45 @@ def test_minicase_configuration_and_oracle_operator(oracle_lib):
     # by symmetry of the (unrotated) configuration about the tube axis only weakly broken by the two cells, the axial
     # component dominates
     assert np.abs(v[2]).mean() > 5 * np.abs(v[0]).mean()
+
+
+CAROTID = "/root/reference/examples/carotid_web/Input"
+
+
+@pytest.mark.skipif(not os.path.isdir(CAROTID), reason="reference tree not mounted")
+def test_carotid_web_walls_on_the_oracle(oracle_lib):
+    """BASELINE.json configs[4] (wall-dominated operator): the two real wall meshes through the wall matvec of the
+    no-slip solve (operator #4) on the oracle."""
+    from rbc3d_b200 import cases, noslip
+    W, Lb = cases.carotid_web_walls(CAROTID)
+    assert list(W.nvert) == [14550, 2903] and list(W.nele) == [28948, 5682]
+    assert np.allclose(Lb, [10.5, 10.5, 30.0], atol=2e-3)
+    orc = oracle_lib.Oracle(Lb)
+    assert orc.Nb == [48, 48, 136] and orc.Nc == [8, 8, 25]
+    orc.set_walls(W, ncell=0)
+    orc.prepare_sing_int_on_walls()
+    # the vessel is periodic in z: its end rings are duplicated vertices; the web has none
+    vo = W.voff()
+    v2v0 = noslip.wall_build_v2v(W.x[:, vo[0]:vo[1]], Lb)
+    v2v1 = noslip.wall_build_v2v(W.x[:, vo[1]:vo[2]], Lb)
+    assert (v2v0 > 0).sum() > 50 and (v2v1 > 0).sum() == 0
+    # self-interaction matrix: every vertex row is populated; SingIntOnWall = matrix times traction
+    rng = np.random.default_rng(4)
+    W.f = rng.normal(size=W.f.shape)
+    orc.set_wall_traction(W.f)
+    for w in range(2):
+        rowptr, col, val = orc.wall_matrix(w)
+        assert np.all(np.diff(rowptr) > 0) and np.all(np.isfinite(val))
+        f = W.f[:, vo[w]:vo[w + 1]]
+        v = orc.sing_int_on_wall(0.3, w)
+        rows = np.repeat(np.arange(W.nvert[w]), np.diff(rowptr))
+        ref = np.zeros_like(v)
+        np.add.at(ref.T, rows, np.einsum("bij,bj->bi", val, f.T[col]))
+        assert np.abs(v - 0.3 * ref).max() < 1e-12 * np.abs(ref).max()
+    # a few GMRES iterations of the wall solve on a uniform slip reduce the residual monotonically
+    W.f[:] = 0.0
+    rv, mv, st = noslip.oracle_backend(orc, [0.0, 0.0, 8.0], cells=False)
+    s = noslip.WallNoSlipSolver(W, Lb, rv, mv, st)
+    assert s.dof == 3 * (W.NV - int((v2v0 > 0).sum()))
+    _, niter, hist, _ = s.solve(rtol=1e-3, maxit=8)
+    assert niter == 8 and np.all(np.diff(hist) < 0) and hist[-1] < 0.5 * hist[0]
