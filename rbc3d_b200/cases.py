@@ -90,3 +90,91 @@ def carotid_web_walls(input_dir: str):
                     None, None, np.zeros_like(x))
     W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
     return W, Lb
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Binary restart files (ModIO.F90:742-784 WriteRestart, :792-921 ReadRestart): Fortran unformatted sequential records
+# (gfortran: 4-byte length before and after each record), real(WP) = float64, default integer = int32, arrays in Fortran
+# element order -- rbc%x(nlat, nlon, 3) is (3, nlon, nlat) in C order, wall%x(nvert, 3) is (3, nvert), e2v(nele, 3) is
+# (3, nele): exactly the SoA layouts of the boundary.
+def write_restart(path: str, Lb, lt: int, time: float, vbkg, cells, walls) -> None:
+    """cells: list of dicts(nlat0, nlon0, nlat, nlon, celltype, starting_area, x (3, nlon, nlat));
+    walls: list of dicts(x (3, nvert), f (3, nvert), e2v (3, nele) int32 1-based)."""
+    from scipy.io import FortranFile
+    f = FortranFile(path, "w")
+    try:
+        f.write_record(np.asarray(Lb, dtype=np.float64))
+        f.write_record(np.array([lt], dtype=np.int32))
+        f.write_record(np.array([time], dtype=np.float64))
+        f.write_record(np.asarray(vbkg, dtype=np.float64))
+        f.write_record(np.array([len(cells)], dtype=np.int32))
+        for c in cells:
+            f.write_record(np.array([c["nlat0"], c["nlon0"]], dtype=np.int32))
+            f.write_record(np.array([c["nlat"], c["nlon"]], dtype=np.int32))
+            f.write_record(np.array([c["celltype"]], dtype=np.int32))
+            f.write_record(np.array([c["starting_area"]], dtype=np.float64))
+            x = np.ascontiguousarray(c["x"], dtype=np.float64)
+            assert x.shape == (3, c["nlon"], c["nlat"])
+            f.write_record(x)
+        f.write_record(np.array([len(walls)], dtype=np.int32))
+        for w in walls:
+            x = np.ascontiguousarray(w["x"], dtype=np.float64)
+            e2v = np.ascontiguousarray(w["e2v"], dtype=np.int32)
+            f.write_record(np.array([x.shape[1], e2v.shape[1]], dtype=np.int32))
+            f.write_record(x)
+            f.write_record(np.ascontiguousarray(w["f"], dtype=np.float64))
+            f.write_record(e2v)
+    finally:
+        f.close()
+
+
+def read_restart(path: str) -> dict:
+    """-> dict(Lb, Nt0, time0, vBkg, cells=[...], walls=[...]) with the array layouts of write_restart."""
+    from scipy.io import FortranFile
+    f = FortranFile(path, "r")
+    try:
+        out = {"Lb": f.read_reals(np.float64), "Nt0": int(f.read_ints(np.int32)[0]),
+               "time0": float(f.read_reals(np.float64)[0]), "vBkg": f.read_reals(np.float64), "cells": [], "walls": []}
+        for _ in range(int(f.read_ints(np.int32)[0])):
+            nlat0, nlon0 = (int(v) for v in f.read_ints(np.int32))
+            nlat, nlon = (int(v) for v in f.read_ints(np.int32))
+            celltype = int(f.read_ints(np.int32)[0])
+            area0 = float(f.read_reals(np.float64)[0])
+            x = f.read_reals(np.float64)
+            if x.size != 3 * nlat * nlon:
+                raise ValueError("invalid array dimension")                      # ModIO.F90:867-875
+            out["cells"].append(dict(nlat0=nlat0, nlon0=nlon0, nlat=nlat, nlon=nlon, celltype=celltype,
+                                     starting_area=area0, x=x.reshape(3, nlon, nlat)))
+        for _ in range(int(f.read_ints(np.int32)[0])):
+            nvert, nele = (int(v) for v in f.read_ints(np.int32))
+            x = f.read_reals(np.float64).reshape(3, nvert)
+            fw = f.read_reals(np.float64).reshape(3, nvert)
+            e2v = f.read_ints(np.int32).reshape(3, nele)
+            out["walls"].append(dict(x=x, f=fw, e2v=e2v))
+    finally:
+        f.close()
+    return out
+
+
+def state_from_restart(rst: dict, visc_ratio=1.0, seed: int = 161269):
+    """restart contents -> (Suspension, Walls | None, vBkg): geometry by RBC_ComputeGeometry's spectral tangents
+    (synth.suspension_from_shapes); all cells must share one mesh size, as they do in every shipped example."""
+    cells = rst["cells"]
+    sus = None
+    if cells:
+        c0 = cells[0]
+        if any((c["nlat"], c["nlon"], c["nlat0"]) != (c0["nlat"], c0["nlon"], c0["nlat0"]) for c in cells):
+            raise ValueError("cells with different mesh sizes are not supported by the harness")
+        x = np.stack([c["x"] for c in cells])
+        sus = synth.suspension_from_shapes(x, rst["Lb"], nlat0=c0["nlat0"], dealias=c0["nlat"] // c0["nlat0"],
+                                           visc_ratio=visc_ratio, seed=seed)
+    W = None
+    if rst["walls"]:
+        ws = rst["walls"]
+        x = np.ascontiguousarray(np.concatenate([w["x"] for w in ws], axis=1))
+        e2v = np.ascontiguousarray(np.concatenate([w["e2v"] for w in ws], axis=1))
+        fw = np.ascontiguousarray(np.concatenate([w["f"] for w in ws], axis=1))
+        W = synth.Walls(np.array([w["x"].shape[1] for w in ws], np.int32), np.array([w["e2v"].shape[1] for w in ws], np.int32),
+                        x, e2v, None, None, fw)
+        W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
+    return sus, W, np.asarray(rst["vBkg"], dtype=float)
