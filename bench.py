@@ -505,14 +505,15 @@ def run_mtube(args):
     twice + operator #4 per wall-GMRES iteration) through the C ABI with host buffers, and the same steps on the CPU
     oracle on the box's host cores.  Tractions carry over from step to step as in a run.  Prints one JSON object; run
     as a child process of the main bench so that a failure here cannot cost the headline line."""
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --mtube-only: no CUDA device; the product has no CPU path")
     from rbc3d_b200 import mtube
+    from rbc3d_b200.capi import Rbc3dError
     from rbc3d_b200.ewald import EwaldOperator
     nsteps = max(2, args.mtube_steps)
     sus, W = mtube.minicase_like(seed=args.seed)
-    op = EwaldOperator(sus.Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
+    try:          # no torch in this child (its import costs more than the block): the library itself refuses without a GPU
+        op = EwaldOperator(sus.Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
+    except Rbc3dError as exc:
+        raise SystemExit("bench.py --mtube-only: no CUDA device; the product has no CPU path (%s)" % str(exc)[:160])
     step = mtube.LibraryStep(op, sus, W)
     l0 = op.launch_count()
     warm = MTUBE_WARM_STEPS      # start-up transient of the wall tractions (3, 19, 60, 42 iterations), allocations, plans

@@ -58,3 +58,64 @@ def test_mtube_block_refuses_without_a_device_and_the_parent_survives_it():
     spec.loader.exec_module(bench)
     out = bench.mtube_child(argparse.Namespace(seed=1, mtube_steps=2, no_cpu_baseline=True))
     assert set(out) == {"error"} and "no CUDA device" in out["error"]
+
+
+def test_mtube_block_python_path_with_a_stand_in_library(monkeypatch, capsys, oracle_lib):
+    """run_mtube end to end on a machine without a GPU: EwaldOperator replaced by a stand-in that answers the same calls
+    from the oracle, so that the block's own logic (steps, warm-up, JSON keys, parity record) is exercised here."""
+    import argparse
+    import importlib.util
+    import numpy as np
+    from rbc3d_b200 import ewald
+    from rbc3d_b200.capi import TL_CELLS, TL_WALLS
+
+    class StandIn:
+        def __init__(self, Lb, device=-1):
+            self.orc = oracle_lib.Oracle(Lb)
+            self.Nb = self.orc.Nb
+            self.n = 0
+
+        def set_suspension(self, sus):
+            self.sus = sus
+            self.orc.set_cells(sus)
+
+        def SourceList_UpdateCoord(self, *a):
+            self.orc.set_cells(self.sus)
+
+        def SourceList_UpdateDensity(self, *a):
+            pass
+
+        def set_walls(self, W):
+            self.orc.set_walls(W)
+
+        def PrepareSingIntOnWall(self):
+            self.orc.prepare_sing_int_on_walls()
+
+        def set_wall_traction(self, f):
+            self.orc.set_wall_traction(f)
+
+        def apply(self, c1, c2, tlist, cells=True, walls=False):
+            self.n += 1
+            tl = self.orc.cell_targets() if tlist == TL_CELLS else self.orc.wall_targets()
+            assert tlist in (TL_CELLS, TL_WALLS)
+            return self.orc.apply(c1, c2, tl, cells=cells, walls=walls)
+
+        def launch_count(self):
+            return 10 * self.n
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(ewald, "EwaldOperator", StandIn)
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "MTUBE_WARM_STEPS", 2)
+    assert bench.run_mtube(argparse.Namespace(seed=161269, mtube_steps=2, no_cpu_baseline=False)) == 0
+    m = json.loads(capsys.readouterr().out.strip().splitlines()[-1])["mtube"]
+    assert m["steps"] == 2 and len(m["ms_per_step"]) == 2 and m["bi_timesteps_per_s"] > 0 and m["gpu_launches"] > 0
+    assert len(m["wall_gmres_iterations"]) == 4 and m["wall_gmres_iterations"][0] == 3
+    cb = m["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["unit"] == "timesteps/s" and cb["wall_gmres_iterations"] == m["wall_gmres_iterations"]
+    par = m["parity_vs_oracle"]
+    assert all(par["same_iterations"]) and max(par["rel_l2_cell_velocity"]) < 1e-12      # the stand-in IS the oracle
