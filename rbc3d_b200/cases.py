@@ -178,3 +178,39 @@ def state_from_restart(rst: dict, visc_ratio=1.0, seed: int = 161269):
                         x, e2v, None, None, fw)
         W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
     return sus, W, np.asarray(rst["vBkg"], dtype=float)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tecplot output of the reference (ModIO.F90:180-227 WriteManyRBCs, :389-423 WriteManyWalls), so that states stepped by
+# the harness can be looked at with the reference's own visualisation recipe (docs/visualization.md).
+def write_many_rbcs(path: str, sus) -> None:
+    """x_<step>.dat: every cell filtered to degree < nlat0 and synthesised on nlat + 1 equally spaced colatitudes
+    0..pi (ShAnalGau + ShFilter + ShSynthEqu), one ZONE per cell, the first meridian repeated to close the surface."""
+    from . import sphere
+    nlat, nlon, nc = sus.nlat, sus.nlon, sus.ncell
+    if nc <= 0:
+        return
+    proj = sphere.SphereProjector(nlat, nlon, sus.nlat0, np.linspace(0.0, np.pi, nlat + 1))
+    x = proj(np.ascontiguousarray(sus.x.reshape(3, nc, nlon, nlat).transpose(1, 0, 2, 3)))    # (nc, 3, nlon, nlat + 1)
+    with open(path, "w") as fh:
+        fh.write("VARIABLES = X, Y, Z\n")
+        for c in range(nc):
+            fh.write("ZONE I=%9d  J=%9d  F=POINT\n" % (nlat + 1, nlon + 1))
+            for j in list(range(nlon)) + [0]:
+                for i in range(nlat + 1):
+                    fh.write("%20.10f%20.10f%20.10f\n" % tuple(x[c, :, j, i]))
+
+
+def write_many_walls(path: str, W) -> None:
+    """wall_<step>.dat: FEPOINT / TRIANGLE zones, vertex numbers local to each wall (1-based)."""
+    if W is None or W.nwall <= 0:
+        return
+    vo, eo = W.voff(), W.eoff()
+    with open(path, "w") as fh:
+        fh.write("VARIABLES = X, Y, Z\n")
+        for w in range(W.nwall):
+            fh.write("ZONE N = %9d E = %9d F=FEPOINT ET=TRIANGLE\n" % (W.nvert[w], W.nele[w]))
+            for v in range(vo[w], vo[w + 1]):
+                fh.write("%20.10f%20.10f%20.10f\n" % tuple(W.x[:, v]))
+            for e in range(eo[w], eo[w + 1]):
+                fh.write("%9d%9d%9d\n" % tuple(W.e2v[:, e]))

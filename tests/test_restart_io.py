@@ -55,3 +55,26 @@ def test_round_trip_and_state(tmp_path, oracle_lib):
     W2.f[:] = 0.0
     r = mtube.bi_timestep(mtube.OracleStep(oracle_lib.Oracle(sus2.Lb), sus2, W2, vbkg))
     assert 0 < r["wall_iterations"] <= 60 and r["history"][-1] < 1e-3 * r["history"][0]
+
+
+def test_tecplot_writers(tmp_path):
+    """WriteManyRBCs / WriteManyWalls (ModIO.F90:180-227, 389-423): zone headers, point counts, closed surfaces."""
+    sus, W = mtube.minicase_like(nlat0=6)
+    pc, pw = str(tmp_path / "x000000000.dat"), str(tmp_path / "wall000000000.dat")
+    cases.write_many_rbcs(pc, sus)
+    cases.write_many_walls(pw, W)
+    lines = open(pc).read().splitlines()
+    nlat, nlon = sus.nlat, sus.nlon
+    per = 1 + (nlat + 1) * (nlon + 1)
+    assert lines[0] == "VARIABLES = X, Y, Z" and len(lines) == 1 + sus.ncell * per
+    assert lines[1] == "ZONE I=%9d  J=%9d  F=POINT" % (nlat + 1, nlon + 1)
+    zone = np.array([[float(t) for t in ln.split()] for ln in lines[2:1 + per]]).reshape(nlon + 1, nlat + 1, 3)
+    assert np.array_equal(zone[0], zone[-1])                              # the first meridian closes the surface
+    # equally spaced colatitudes include the poles: one point per pole, the same on every meridian
+    assert np.abs(zone[:, 0] - zone[0, 0]).max() < 1e-9 and np.abs(zone[:, -1] - zone[0, -1]).max() < 1e-9
+    # the biconcave cell: poles on the axis through the centre, at half the dimple thickness 0.5 * 1.3858189 * 0.207
+    assert np.allclose(zone[0, 0, :2], sus.centers[0][:2], atol=1e-9)
+    assert abs(abs(zone[0, 0, 2] - sus.centers[0][2]) - 0.5 * 1.3858189 * 0.207) < 1e-9
+    wl = open(pw).read().splitlines()
+    assert wl[1] == "ZONE N = %9d E = %9d F=FEPOINT ET=TRIANGLE" % (W.NV, W.NE) and len(wl) == 2 + W.NV + W.NE
+    assert [int(t) for t in wl[2 + W.NV].split()] == list(W.e2v[:, 0])
