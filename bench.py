@@ -129,13 +129,15 @@ def cpu_operator_sample(sus, sample_cells: int, spread_stride: int = 1, threads:
     npc = sus.nlat * sus.nlon
     ns = min(sample_cells, sus.ncell)
 
+    keep = {}
+
     def realspace(ncells_sample):
         act = np.zeros(sus.npoint, np.int32)
         # a compact block of cells (neighbouring lattice sites) so that the sample sees typical neighbourhoods
         act[:ncells_sample * npc] = 1
         tl_ = orc.cell_targets(active=act)
         t0_ = time.perf_counter()
-        orc.add_int_on_rbcs(0.0, C2_MATVEC, tl_)
+        keep["v"] = orc.add_int_on_rbcs(0.0, C2_MATVEC, tl_)
         return time.perf_counter() - t0_, tl_
 
     # two sample sizes: the call has a cost that does not depend on the number of targets (cell list of all sources),
@@ -158,7 +160,7 @@ def cpu_operator_sample(sus, sample_cells: int, spread_stride: int = 1, threads:
     orc.pme_transform()
     t_fft = time.perf_counter() - t0
     t0 = time.perf_counter()
-    orc.pme_interp(tl)
+    orc.pme_interp(tl, keep["v"])      # keep["v"]: the complete operator at the sample's targets (when the spread was full)
     t_interp = time.perf_counter() - t0
     scale = sus.ncell / ns
     total = t_fixed + per_cell * sus.ncell + t_interp * scale + t_spread + t_fft
@@ -166,6 +168,8 @@ def cpu_operator_sample(sus, sample_cells: int, spread_stride: int = 1, threads:
               "t_realspace_sample_s": t_real, "t_realspace_small_sample_s": t_small,
               "t_realspace_fixed_s": t_fixed, "t_realspace_per_cell_s": per_cell, "t_interp_sample_s": t_interp,
               "t_spread_full_s": t_spread, "t_transform_full_s": t_fft, "extrapolated_matvec_s": total}
+    if spread_stride == 1:
+        detail["_v_sample"] = keep["v"][:, :ns * npc].copy()     # popped by the callers before the JSON line
     return total, detail
 
 
@@ -193,6 +197,7 @@ def run_reference(args):
         t, detail = cpu_operator_sample(sus, args.ref_sample_cells, args.ref_spread_stride)
         if it >= args.warmup:
             times.append(t)
+    detail.pop("_v_sample", None)
     sec = float(np.mean(times))
     val = 1.0 / sec
     cb = {"value": val, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
@@ -366,6 +371,25 @@ def run_gpu(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t[0])
     clocks = sampler.stop()
+    v_e2e = v_host.copy()              # operator #2 applied to g: compared with the oracle's sample below (full size)
+
+    # ---- size-independent property at the full size: linearity in the density (after the timed regions) -----------
+    full_size = None
+    if world == 1 and not args.profile and not args.host_splines:
+        try:
+            npc_ = sus.nlat * sus.nlon
+            g2 = np.ascontiguousarray(np.roll(g_host, 3 * npc_ + 17, axis=1)[::-1])    # another band-unlimited density
+            a_, b_ = 0.5, -2.0
+            op.SourceList_UpdateDensity(g=g2)
+            v2 = op.apply_collect(0.0, C2_MATVEC).copy()
+            op.SourceList_UpdateDensity(g=np.ascontiguousarray(a_ * g_host + b_ * g2))
+            v3 = op.apply_collect(0.0, C2_MATVEC)
+            lin = a_ * v_e2e + b_ * v2
+            full_size = {"linearity_rel_l2": float(np.linalg.norm(v3 - lin) / np.linalg.norm(lin)),
+                         "linearity": "||A(0.5 g - 2 g2) - (0.5 A g - 2 A g2)|| / ||.|| over all %d targets" % N}
+            op.SourceList_UpdateDensity(g=g_host)
+        except Exception as exc:
+            full_size = {"error": str(exc)[:200]}
 
     # ---- the other half of BASELINE.json's metric: time-step rate of the boundary-integral part -----------------
     # One mtube step evaluates, on a NEW geometry: SourceList_UpdateCoord (cell lists, geometry caches), Compute_Rhs
@@ -462,6 +486,13 @@ def run_gpu(args):
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         tcpu, detail = cpu_operator_sample(sus, args.cpu_sample_cells)
+        vs = detail.pop("_v_sample", None)
+        if vs is not None:   # the oracle as the checker at the FULL size: complete operator at the sample's targets
+            ref_n = float(np.linalg.norm(vs))
+            full_size = dict(full_size or {})
+            full_size["oracle_sample_rel_l2"] = float(np.linalg.norm(v_e2e[:, :vs.shape[1]] - vs) / ref_n)
+            full_size["oracle_sample"] = "all %d targets of the first %d cells, every cell a source, PME in full" % (
+                vs.shape[1], detail["sample_cells"])
         cb = {"value": 1.0 / tcpu, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
               "sample": sample_text(detail, sus.ncell), "detail": detail}
 
@@ -483,7 +514,7 @@ def run_gpu(args):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches),
            "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
-           "roofline": roof, "kernels": rows, "timestep": timestep,
+           "roofline": roof, "kernels": rows, "timestep": timestep, "parity_full_size": full_size,
            "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "fp64_tflops": fp64_peak,
                      "fp64_source": "in-process DFMA micro-benchmark"},
            "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
