@@ -435,6 +435,32 @@ class Oracle:
         lib().orc_pme_distrib_walls(self.pme(), C.byref(self.prm), C.c_double(c1), C.c_double(c2), C.byref(self.walls),
                                     C.c_int(1 if accumulate else 0))
 
+    # ---- ModRepulsion (closest-neighbour queries on the path's cell lists) ---------------------------
+    def closest_neighbors(self, x, surf_id, eps_dist):
+        """Closest_Neighbor_Cell / Closest_Neighbor_Wall for points x (3, n) lying on surfaces surf_id (n,):
+        -> dist_cell, x0_cell, dist_wall, x0_wall (distances are inf where no neighbour is in the 27 list cells)."""
+        x = _f64(x)
+        n = x.shape[1]
+        sid = np.ascontiguousarray(surf_id, dtype=np.int32)
+        dc, dw = np.zeros(n), np.zeros(n)
+        xc, xw = np.zeros((3, n)), np.zeros((3, n))
+        W = C.byref(self.walls) if getattr(self, "walls", None) is not None else None
+        lib().orc_closest_neighbors(C.byref(self.prm), C.byref(self.cells), W, C.c_int(n), _dp(x), _ip(sid),
+                                    C.c_double(eps_dist), _dp(dc), _dp(xc), _dp(dw), _dp(xw))
+        return dc, xc, dw, xw
+
+    def inter_cell_repulsion(self, eps_dist, active=None):
+        """InterCellRepulsion up to the displacement: -> dx (3, Np), number of moved points, min separation."""
+        n = self.sus.npoint
+        dx = np.zeros((3, n))
+        dmin = C.c_double()
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
+        W = C.byref(self.walls) if getattr(self, "walls", None) is not None else None
+        lib().orc_inter_cell_repulsion.restype = C.c_int
+        cnt = lib().orc_inter_cell_repulsion(C.byref(self.prm), C.byref(self.cells), W, _ip(act), C.c_double(eps_dist),
+                                             _dp(dx), C.byref(dmin))
+        return dx, int(cnt), dmin.value
+
     def apply(self, c1, c2, tl, cells=True, walls=False, v=None):
         """v += AddIntOnRbcs + AddIntOnWalls + PME over the chosen source sets (the composition of
         ModVelSolver.F90:473-493 / ModNoSlip.F90:172-191, 284-299)."""

@@ -181,6 +181,13 @@ void orc_wall_neighbor_signature(const orc_params *prm, const orc_walls *W, cons
 void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, double c2, const orc_walls *W,
                            int accumulate);
 
+/* ---- ModRepulsion.F90: Closest_Neighbor_Cell / _Wall (:480-613), InterCellRepulsion (:270-402) ---- */
+void orc_closest_neighbors(const orc_params *prm, const orc_cells *C, const orc_walls *W, int n, const double *x,
+                           const int *surfId, double epsDist, double *dist_cell, double *x0_cell, double *dist_wall,
+                           double *x0_wall);
+int orc_inter_cell_repulsion(const orc_params *prm, const orc_cells *C, const orc_walls *W, const int *active,
+                             double epsDist, double *dx, double *dist_min);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

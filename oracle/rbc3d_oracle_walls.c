@@ -532,3 +532,148 @@ void orc_pme_distrib_walls(orc_pme *pme, const orc_params *prm, double c1, doubl
   free(ft);
   wall_lists_free(&L);
 }
+
+/* ====================================================================== */
+/* ModRepulsion.F90: closest-neighbour queries on the cell lists of the path's own source
+ * lists, and the displacement InterCellRepulsion derives from them.  Lives here because it needs both the
+ * cell source list and the wall element list. */
+
+/* ModRepulsion.F90:480-546 Closest_Neighbor_Cell for one point.  hoc/next: cell list of all cell points
+ * (slist_rbc).  Returns dist0 (HUGE when no other cell has a point in the 27 neighbouring list cells). */
+static double closest_neighbor_cell(const orc_params *prm, const orc_cells *C, const int *hoc, const int *next,
+                                    const double xi[3], int surfId_i, double epsDist, double x0[3]) {
+  const int *Nc = prm->Nc;
+  const int n1 = Nc[0] + 2, n2 = Nc[1] + 2;
+  const int nlat = C->nlat, nlon = C->nlon, npc = nlat * nlon;
+  const size_t Np = (size_t)C->ncell * npc;
+  double dist0 = HUGE_VAL;
+  if (C->ncell == 0) return dist0;
+  int i1, i2, i3, j0 = -1;
+  orc_hash_index(prm, xi, &i1, &i2, &i3);
+  FOR_NEIGHBOUR_CELLS {
+    for (int j = hoc[j1 + (size_t)n1 * (j2 + (size_t)n2 * j3)]; j >= 0; j = next[j]) {
+      if (j / npc + 1 == surfId_i) continue; /* :507 */
+      double xx[3], rr = 0;
+      for (int d = 0; d < 3; d++) {
+        xx[d] = xi[d] - C->x[d * Np + j];
+        xx[d] = xx[d] - wnint(xx[d] * prm->iLb[d]) * prm->Lb[d];
+        rr += xx[d] * xx[d];
+      }
+      rr = sqrt(rr);
+      if (rr < dist0) dist0 = rr, j0 = j;
+    }
+  }
+  if (dist0 <= 2 * epsDist) { /* :525-542: refine by projecting on the neighbour's spline surface */
+    const int jc = j0 / npc, ilon0 = (j0 % npc) / nlat, ilat0 = (j0 % npc) % nlat;
+    double th0 = C->th[ilat0], phi0 = C->phi[ilon0], xtar[3], xx[3];
+    for (int d = 0; d < 3; d++) {
+      x0[d] = C->x[d * Np + j0];
+      xx[d] = xi[d] - x0[d];
+      xx[d] = xx[d] - wnint(xx[d] * prm->iLb[d]) * prm->Lb[d];
+      xtar[d] = x0[d] + xx[d];
+    }
+    const size_t sp3 = (size_t)4 * 3 * nlon * 2 * nlat;
+    orc_spline_find_projection(C->spx + sp3 * jc, 2 * nlat, nlon, xtar, &th0, &phi0, x0);
+    dist0 = 0;
+    for (int d = 0; d < 3; d++) dist0 += (xtar[d] - x0[d]) * (xtar[d] - x0[d]);
+    dist0 = sqrt(dist0);
+  }
+  return dist0;
+}
+
+/* ModRepulsion.F90:556-613 Closest_Neighbor_Wall for one point */
+static double closest_neighbor_wall(const orc_params *prm, const orc_walls *W, const wall_lists *Lp, const double xi[3],
+                                    int surfId_i, double x0[3]) {
+  const wall_lists L = *Lp;
+  const int *Nc = prm->Nc;
+  const int n1 = Nc[0] + 2, n2 = Nc[1] + 2;
+  double dist0 = HUGE_VAL;
+  if (W->nwall == 0) return dist0;
+  int i1, i2, i3;
+  orc_hash_index(prm, xi, &i1, &i2, &i3);
+  FOR_NEIGHBOUR_CELLS {
+    for (int j = HOC3(j1, j2, j3); j >= 0; j = L.next[j]) {
+      if (W->id0 + L.ewall[j] == surfId_i) continue; /* :582 */
+      const int w = L.ewall[j];
+      double xele[9], xtar[3], xj[3], s0, t0;
+      for (int l = 0; l < 3; l++) {
+        int iv = L.voff[w] + W->e2v[(size_t)l * L.NE + j] - 1;
+        for (int d = 0; d < 3; d++) xele[3 * l + d] = W->x[(size_t)d * L.NV + iv];
+      }
+      for (int d = 0; d < 3; d++) { /* :593-595: translate xi as close to the triangle as possible */
+        double xx = xi[d] - xele[d];
+        xx = xx - wnint(xx * prm->iLb[d]) * prm->Lb[d];
+        xtar[d] = xele[d] + xx;
+      }
+      double rr = orc_min_dist_to_tri(xtar, xele, &s0, &t0, xj);
+      if (rr < dist0) {
+        dist0 = rr;
+        for (int d = 0; d < 3; d++) x0[d] = xj[d];
+      }
+    }
+  }
+  return dist0;
+}
+
+/* Both queries for a list of points: x SoA(3,n), surfId [n]; outputs dist_cell/dist_wall [n] (HUGE_VAL =
+ * none), x0_cell/x0_wall SoA(3,n) (undefined where the distance is HUGE_VAL).  W may be NULL. */
+void orc_closest_neighbors(const orc_params *prm, const orc_cells *C, const orc_walls *W, int n, const double *x,
+                           const int *surfId, double epsDist, double *dist_cell, double *x0_cell, double *dist_wall,
+                           double *x0_wall) {
+  const int n1 = prm->Nc[0] + 2, n2 = prm->Nc[1] + 2, n3 = prm->Nc[2] + 2;
+  const size_t Np = (size_t)C->ncell * C->nlat * C->nlon;
+  int *hoc = (int *)malloc(sizeof(int) * (size_t)n1 * n2 * n3), *next = (int *)malloc(sizeof(int) * (Np > 0 ? Np : 1));
+  orc_hash_build(prm, (int)Np, C->x, hoc, next);
+  wall_lists L;
+  const int have_walls = W && W->nwall > 0;
+  if (have_walls) wall_lists_init(prm, W, &L);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < n; i++) {
+    const double xi[3] = {x[i], x[(size_t)n + i], x[2 * (size_t)n + i]};
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    dist_cell[i] = closest_neighbor_cell(prm, C, hoc, next, xi, surfId[i], epsDist, a);
+    dist_wall[i] = have_walls ? closest_neighbor_wall(prm, W, &L, xi, surfId[i], b) : HUGE_VAL;
+    for (int d = 0; d < 3; d++) x0_cell[(size_t)d * n + i] = a[d], x0_wall[(size_t)d * n + i] = b[d];
+  }
+  if (have_walls) wall_lists_free(&L);
+  free(hoc), free(next);
+}
+
+/* ModRepulsion.F90:270-402 InterCellRepulsion up to the displacement field: for every active cell point the
+ * closer of the two neighbours; if it is closer than epsDist the point is pushed away by half the deficit,
+ * dx = 0.5 xx (epsDist - rr) / rr with xx the minimum image of xi - xj (:317-325).  dx SoA(3,Np) (zero rows for
+ * points that do not move); returns the number of moved points, *dist_min = smallest separation seen.  The
+ * caller adds dx to rbc%x (:350) -- cells below viscRatThresh; the rigid-cell branch (:352-385) averages dx. */
+int orc_inter_cell_repulsion(const orc_params *prm, const orc_cells *C, const orc_walls *W, const int *active,
+                             double epsDist, double *dx, double *dist_min) {
+  const int npc = C->nlat * C->nlon;
+  const int Np = C->ncell * npc;
+  double *dc = (double *)malloc(sizeof(double) * (Np > 0 ? Np : 1)), *dw = (double *)malloc(sizeof(double) * (Np > 0 ? Np : 1));
+  double *xc = (double *)malloc(sizeof(double) * 3 * (Np > 0 ? Np : 1)), *xw = (double *)malloc(sizeof(double) * 3 * (Np > 0 ? Np : 1));
+  int *sid = (int *)calloc(Np > 0 ? Np : 1, sizeof(int));
+  for (int i = 0; i < Np; i++) sid[i] = i / npc + 1;
+  orc_closest_neighbors(prm, C, W, Np, C->x, sid, epsDist, dc, xc, dw, xw);
+  int cnt = 0;
+  double dmin = HUGE_VAL;
+  memset(dx, 0, sizeof(double) * 3 * (size_t)Np);
+  for (int i = 0; i < Np; i++) {
+    if (active && !active[i]) continue;
+    const double *x0 = dc[i] < dw[i] ? xc : xw; /* :304-310 */
+    const double dist = dc[i] < dw[i] ? dc[i] : dw[i];
+    if (dist < dmin) dmin = dist;
+    if (dist < epsDist) {
+      double xx[3], rr = 0;
+      for (int d = 0; d < 3; d++) {
+        xx[d] = C->x[(size_t)d * Np + i] - x0[(size_t)d * Np + i];
+        xx[d] = xx[d] - wnint(xx[d] * prm->iLb[d]) * prm->Lb[d];
+        rr += xx[d] * xx[d];
+      }
+      rr = sqrt(rr);
+      cnt++;
+      for (int d = 0; d < 3; d++) dx[(size_t)d * Np + i] = 0.5 * xx[d] * (epsDist - rr) / rr;
+    }
+  }
+  *dist_min = dmin;
+  free(dc), free(dw), free(xc), free(xw), free(sid);
+  return cnt;
+}
