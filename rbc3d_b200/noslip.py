@@ -103,31 +103,36 @@ class WallNoSlipSolver:
         return f_new, niter, hist, self.residual_vel()
 
 
-def oracle_backend(orc, vbkg, cells: bool = True):
+def oracle_backend(orc, vbkg, cells: bool = True, active=None, collect=None):
     """(residual_vel, wall_matvec, set_traction) on the CPU oracle (tests, cpu_baseline).  Needs orc.set_cells /
-    set_walls / prepare_sing_int_on_walls done."""
-    tl = orc.wall_targets()
+    set_walls / prepare_sing_int_on_walls done.  Several ranks: ``active`` = this rank's flags of the wall target list
+    (SetActiveFlag), ``collect`` = TargetList_CollectArray (sum over ranks); the background velocity is added after the
+    sum, as in Compute_Wall_Residual_Vel (ModNoSlip.F90:186-191)."""
+    tl = orc.wall_targets(active)
     vb = np.asarray(vbkg, dtype=float)[:, None]
+    collect = collect or (lambda v: v)
 
     def residual_vel():
-        return orc.apply(C1_WALL, C1_WALL, tl, cells=cells, walls=True) + vb
+        return collect(orc.apply(C1_WALL, C1_WALL, tl, cells=cells, walls=True)) + vb
 
     def wall_matvec(_f):
-        return orc.apply(C1_WALL, 0.0, tl, cells=False, walls=True)
+        return collect(orc.apply(C1_WALL, 0.0, tl, cells=False, walls=True))
 
     return residual_vel, wall_matvec, orc.set_wall_traction
 
 
-def library_backend(op, vbkg, cells: bool = True):
+def library_backend(op, vbkg, cells: bool = True, collect: bool = False):
     """The same three callables on the CUDA library through the C ABI (rbc3d_b200.ewald.EwaldOperator with
-    set_suspension / set_walls / PrepareSingIntOnWall done)."""
+    set_suspension / set_walls / PrepareSingIntOnWall done).  ``collect``: several ranks -- rbc3d_apply_collect sums the
+    rows over the ranks on the devices (the contexts were given their ``active`` flags in set_walls)."""
     from .capi import TL_WALLS
     vb = np.asarray(vbkg, dtype=float)[:, None]
+    apply = op.apply_collect if collect else op.apply
 
     def residual_vel():
-        return op.apply(C1_WALL, C1_WALL, TL_WALLS, cells=cells, walls=True) + vb
+        return apply(C1_WALL, C1_WALL, TL_WALLS, cells=cells, walls=True) + vb
 
     def wall_matvec(_f):
-        return op.apply(C1_WALL, 0.0, TL_WALLS, cells=False, walls=True)
+        return apply(C1_WALL, 0.0, TL_WALLS, cells=False, walls=True)
 
     return residual_vel, wall_matvec, op.set_wall_traction

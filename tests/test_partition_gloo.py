@@ -71,3 +71,48 @@ def test_two_rank_sum_equals_single_rank(tmp_path, oracle_lib, mode):
     act = (np.arange(sus.npoint) % 7 == 0).astype(np.int32)
     ref = orc.apply_cells(0.0, util.C2_MATVEC, orc.cell_targets(active=act))
     assert util.rel_l2(v2, ref) < 1e-13
+
+
+def _noslip_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    from rbc3d_b200 import mtube, noslip
+    oracle.lib().orc_set_num_threads(2)
+    sus, W = mtube.minicase_like(nlat0=6, ntheta=24, nz=12)
+    act = partition.zslab_active(W.x, sus.Lb, world, rank)      # SetActiveFlag on tlist_wall
+    orc = oracle.Oracle(sus.Lb).set_cells(sus)
+    orc.set_walls(W)
+    orc.prepare_sing_int_on_walls(active=act)                   # rows of this rank's vertices only
+
+    def collect(v):
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        dist.all_reduce(t)                                      # TargetList_CollectArray(tlist_wall, 3, v)
+        return t.numpy()
+
+    s = noslip.WallNoSlipSolver(W, sus.Lb, *noslip.oracle_backend(orc, mtube.VBKG, active=act, collect=collect))
+    f, niter, hist, slip = s.solve()                            # GMRES runs redundantly on every rank (PETSC_COMM_SELF)
+    np.savez(out % rank, f=f, niter=niter, hist=np.array(hist), slip=slip)
+    dist.destroy_process_group()
+
+
+def test_two_rank_wall_noslip_solve_equals_single_rank(tmp_path, oracle_lib):
+    """NoSlipWall with the wall targets split by z-slab over two ranks (ModNoSlip.F90 + SetActiveFlag + CollectArray)."""
+    from rbc3d_b200 import mtube, noslip
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "r%d.npz")
+    mp.spawn(_noslip_worker, args=(2, port, out), nprocs=2, join=True)
+    r0, r1 = np.load(out % 0), np.load(out % 1)
+    assert int(r0["niter"]) == int(r1["niter"]) and np.array_equal(r0["f"], r1["f"])      # redundant solves agree bit for bit
+    sus, W = mtube.minicase_like(nlat0=6, ntheta=24, nz=12)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    orc.set_walls(W)
+    orc.prepare_sing_int_on_walls()
+    f, niter, hist, slip = noslip.WallNoSlipSolver(W, sus.Lb, *noslip.oracle_backend(orc, mtube.VBKG)).solve()
+    assert niter == int(r0["niter"])
+    assert np.allclose(r0["hist"], hist, rtol=1e-9)
+    assert np.linalg.norm(r0["f"] - f) < 1e-9 * np.linalg.norm(f)
+    assert np.abs(r0["slip"] - slip).max() < 1e-10
