@@ -84,3 +84,28 @@ def test_gmres_against_scipy_iteration_history():
     assert k >= 5
     # scipy reports the relative preconditioned residual after every inner iteration
     assert np.allclose(np.array(hist[1:k + 1]) / np.linalg.norm(b), res[:k], rtol=1e-6)
+
+
+def test_gmres_restatement_against_scipy():
+    """Independent implementation: scipy.sparse.linalg.gmres (restart 30, no preconditioner) must produce the same
+    residual history and solution as the KSPGMRES restatement -- in exact arithmetic the history does not depend on the
+    orthogonalisation, so classical Gram-Schmidt (PETSc's default, ours) and SciPy's agree to round-off on a
+    well-conditioned second-kind operator; the restart boundary (30) is crossed."""
+    from scipy.sparse.linalg import LinearOperator, gmres as sp_gmres
+    from rbc3d_b200.gmres import gmres
+    rng = np.random.default_rng(5)
+    n = 300
+    K = rng.normal(size=(n, n)) / np.sqrt(n)
+    A = np.eye(n) + 0.9 * K                       # spectrum in a disc of radius ~0.9 around 1: slow enough to restart
+    b = rng.normal(size=n)
+    x, it, hist = gmres(lambda u: A @ u, b, rtol=1e-10, restart=30, maxit=200)
+    assert it > 30                                # crossed a restart
+    res = []
+    xs, info = sp_gmres(LinearOperator((n, n), matvec=lambda u: A @ u), b, rtol=1e-10, atol=0.0, restart=30,
+                        maxiter=20, callback=lambda r: res.append(r), callback_type="pr_norm")
+    assert info == 0
+    res = np.array(res) * np.linalg.norm(b)       # SciPy reports ||r|| / ||b||
+    m = min(len(res), len(hist) - 1)
+    assert m >= it - 1
+    assert np.allclose(res[:m], hist[1:m + 1], rtol=1e-6)
+    assert np.linalg.norm(x - xs) < 1e-8 * np.linalg.norm(x)
