@@ -317,3 +317,62 @@ def test_spline_interp_reproduces_mesh(orc_mod):
         xs = orc_mod.Oracle.spline_interp(sus.spx[0], sus.th[ilat], sus.phi[ilon])
         # band-limited shape: the spline (built from the SH-filtered surface) passes close to the mesh point
         assert np.linalg.norm(xs - sus.x[:, p]) < 2e-3
+
+
+# ---- A.6 (7b): the same jump for a rigid-body ROTATION density (tests the tensor structure, not only its trace) ---
+def test_double_layer_rigid_rotation_density_jump(orc_mod):
+    """For any rigid-body field g = U + Omega x (x - xc) on a closed surface the double layer is -8 pi c2 B g inside,
+    0 outside and half the jump on the surface (the stresslet of a rigid motion carries no net flux: with xc the
+    centroid, int x (g.n) dS = int g dV = 0, so AddLinearInt adds nothing)."""
+    L = 6.0
+    sus = synth.make_suspension(1, L=L, centers=np.array([[3.1, 2.9, 3.0]]), seed=5)
+    om = np.array([0.4, -0.3, 0.8])
+    xc = (sus.x * sus.dS()[None, :]).sum(1) / sus.dS().sum()             # surface centroid ~ volume centroid (symmetric cell)
+    g_of = lambda x: np.cross(om, (x - xc[:, None]).T).T                 # noqa: E731
+    sus.g = np.ascontiguousarray(g_of(sus.x))
+    synth.build_splines(sus, sus._builder, which=("G",))
+    orc = orc_mod.Oracle(sus.Lb).set_cells(sus)
+    c2 = C2_MATVEC
+    B, A = sus.Bcoef[0], sus.Acoef[0]
+    idx = np.arange(50, sus.npoint, 397)
+    scale = 8 * PI * abs(c2 * B) * np.abs(sus.g).max()
+    x_out = sus.x[:, idx] + 0.4 * sus.a3[:, idx]
+    v_out = orc.apply_cells(0.0, c2, orc.make_targets(x_out)) * 2.0
+    assert np.abs(v_out).max() < 3e-3 * scale
+    x_in = sus.x[:, idx] - 0.12 * sus.a3[:, idx]
+    v_in = orc.apply_cells(0.0, c2, orc.make_targets(x_in)) * 2.0
+    assert np.abs(v_in + 8 * PI * c2 * B * g_of(x_in)).max() < 5e-3 * scale
+    act = np.zeros(sus.npoint, np.int32)
+    act[idx] = 1
+    v_on = orc.apply_cells(0.0, c2, orc.cell_targets(active=act))[:, idx] * A
+    assert np.abs(v_on + 0.5 * 8 * PI * c2 * B * sus.g[:, idx]).max() < 5e-3 * scale
+
+
+# ---- reciprocity: the single-layer operator is self-adjoint in the surface inner product ---------------------------
+def test_single_layer_reciprocity(orc_mod):
+    """int f1 . S[f2] dS = int f2 . S[f1] dS over all surfaces (Lorentz reciprocity of the periodic Stokeslet); in the
+    discretisation pair sum, singular / near-singular quadrature and PME must combine to a symmetric form up to the
+    quadrature error.  Two cells, one close to the other, band-limited random tractions."""
+    sus = util.close_pair_suspension(gap=0.25, seed=9)
+    orc = orc_mod.Oracle(sus.Lb)
+    rng = np.random.default_rng(1)
+    th = sus.th
+    f1 = synth._flat(sphere_field(rng, sus, th))
+    f2 = synth._flat(sphere_field(rng, sus, th))
+    out = []
+    for f in (f1, f2):
+        sus.f = f
+        synth.build_splines(sus, sus._builder, which=("F",))
+        orc.set_cells(sus)
+        out.append(orc.apply_cells(C1_RHS, 0.0, orc.cell_targets()) * np.repeat(sus.Acoef, sus.nlat * sus.nlon))
+    dS = sus.dS()
+    a = (f1 * out[1] * dS).sum()
+    b = (f2 * out[0] * dS).sum()
+    scale = np.sqrt((f1 * out[0] * dS).sum() * (f2 * out[1] * dS).sum())     # energy norms (S is positive)
+    assert (f1 * out[0] * dS).sum() > 0 and (f2 * out[1] * dS).sum() > 0
+    assert abs(a - b) < 2e-3 * scale
+
+
+def sphere_field(rng, sus, th):
+    from rbc3d_b200 import sphere
+    return sphere.random_bandlimited_field(rng, sus.ncell, 3, sus.nlat0, th, sus.nlon)
