@@ -520,10 +520,13 @@ def run_gpu(args):
            "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
     if cb is not None:
         out["cpu_baseline"] = cb
-    op.close()
-    if world == 1 and not args.profile and not args.no_mtube:
-        # the other half of the metric on BASELINE.json configs[0]; a child process, after this one released the GPU
-        out["mtube"] = mtube_child(args)
+    try:
+        op.close()
+        if world == 1 and not args.profile and not args.no_mtube:
+            # the other half of the metric on BASELINE.json configs[0]; a child process, after this one released the GPU
+            out["mtube"] = mtube_child(args)
+    except Exception as exc:   # nothing after the timed regions may cost the line
+        out.setdefault("mtube", {"error": str(exc)[:300]})
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
