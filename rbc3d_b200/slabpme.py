@@ -167,6 +167,28 @@ class PmeModel:
         return np.stack([(w * vv[d].reshape(-1)[flat]).sum(axis=(1, 2, 3)) for d in range(3)])
 
 
+    def interp_slab(self, x, vslab, zlo: int, zhi: int):
+        """Interp_Vel on a rank that holds only the planes zlo - P .. zhi - 1 of the velocity mesh (its z-slab plus the P
+        planes received from the -z neighbour, Update_Buff_Vel, ModPME.F90:354-396): vslab (3, P + zhi - zlo, Ny, Nx),
+        plane 0 = mesh plane zlo - P (periodic).  Valid for the targets the rank owns, floor(z Nb3 / Lb3) mod Nb3 in
+        [zlo, zhi) (SetActiveFlag); the index arithmetic is the one of ModPME.F90:470-473."""
+        Nx, Ny, Nz = self.Nb
+        P = self.P
+        ih = np.array(self.Nb) / self.Lb
+        im, wx = bspline_func(x[0] * ih[0], P)
+        jm, wy = bspline_func(x[1] * ih[1], P)
+        km, wz = bspline_func(x[2] * ih[2], P)
+        ar = np.arange(P)
+        i, j = np.mod(im[:, None] + ar, Nx), np.mod(jm[:, None] + ar, Ny)
+        lb = zlo - P                                                    # lbound(vv, 3)
+        k = lb + np.mod(km[:, None] + ar - lb, Nz)
+        ok = k <= zhi - 1                                               # "if (k > ubound(vv,3)) cycle"
+        kk = np.where(ok, k - lb, 0)
+        w = wx[:, None, None, :] * wy[:, None, :, None] * (wz * ok)[:, :, None, None]
+        flat = (kk[:, :, None, None] * Ny + j[:, None, :, None]) * Nx + i[:, None, None, :]
+        return np.stack([(w * vslab[d].reshape(-1)[flat]).sum(axis=(1, 2, 3)) for d in range(3)])
+
+
 class SlabRank:
     """One rank of the slab-decomposed transform.  ``exchange(blocks, shapes)``: blocks[s] goes to rank s, returns the
     list of blocks received from every rank, shapes[s] being the shape of the block rank s sends here (an all-to-all:

@@ -70,6 +70,25 @@ def test_slab_transform_in_process(R):
     assert np.array_equal(ts[:, lo:hi], tt[:, lo:hi])
 
 
+def test_slab_interpolation_with_the_halo_of_the_lower_neighbour():
+    """Interp_Vel on a z-slab + P planes from the -z neighbour (Update_Buff_Vel) = interpolation on the full mesh for the
+    targets the slab owns; a target of another slab is NOT reproduced (it needs planes the rank does not hold)."""
+    Nb, P, R = [20, 18, 24], 6, 3
+    m = slabpme.PmeModel(LB, Nb, 0.3, P)
+    rng = np.random.default_rng(4)
+    vv = rng.normal(size=(3, Nb[2], Nb[1], Nb[0]))
+    x = rng.uniform(-0.5, 1.5, size=(3, 400)) * LB[:, None]
+    ref = m.interp(x, vv)
+    kown = np.mod(np.floor(x[2] * Nb[2] / LB[2]).astype(int), Nb[2])
+    for r, (lo, hi) in enumerate(slabpme.slab_chunks(Nb[2], R)):
+        planes = np.arange(lo - P, hi) % Nb[2]                           # halo wraps around the period for rank 0
+        mine = (kown >= lo) & (kown < hi)
+        got = m.interp_slab(x[:, mine], vv[:, planes], lo, hi)
+        assert mine.sum() > 50 and util.rel_l2(got, ref[:, mine]) < 1e-14
+        other = m.interp_slab(x[:, ~mine], vv[:, planes], lo, hi)
+        assert util.rel_l2(other, ref[:, ~mine]) > 1e-3
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
