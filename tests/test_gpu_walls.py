@@ -296,3 +296,42 @@ def test_case_and_case_sickles_configurations(oracle_lib, sickles):
         ref = orc.apply(c1, c2, tl, cells=True, walls=walls)
         assert rel_l2(v, ref) < TOL
     op.close()
+
+
+def test_wall_dominated_operator_at_carotid_size(oracle_lib):
+    """BASELINE.json configs[4] (wall-dominated operator) at the size of examples/carotid_web -- 14 550 + 2 903 vertices,
+    28 948 + 5 682 triangles in a 10.5 x 10.5 x 30 box -- with generated walls of the same counts' order (the Exodus
+    meshes are not on the GPU box; the real ones run on the oracle in tests/test_reference_inputs.py): self-interaction
+    matrices (pattern bit-exact), operator #4 with the wall-wall direct loop, and a second traction."""
+    from rbc3d_b200.capi import TL_WALLS
+    from rbc3d_b200.ewald import EwaldOperator
+    Lb = np.array([10.5, 10.5, 30.0])
+    W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02)
+    assert W.NV == 121 * 120 + 61 * 48 and W.NE == 2 * 120 * 120 + 2 * 60 * 48
+    op = EwaldOperator(Lb)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc = oracle_lib.Oracle(Lb)
+    orc.set_walls(W, ncell=0)
+    orc.prepare_sing_int_on_walls()
+    assert list(op.Nb) == orc.Nb == [48, 48, 136]
+    rowptr, col, val = op.wall_matrix()
+    vo = W.voff()
+    for w in range(2):
+        rrow, rcol, rval = orc.wall_matrix(w)
+        lo, hi = rowptr[vo[w]], rowptr[vo[w + 1]]
+        assert np.array_equal(rowptr[vo[w]:vo[w + 1] + 1] - lo, rrow)
+        assert np.array_equal(col[lo:hi] - vo[w], rcol)
+        assert rel_l2(val[lo:hi], rval) < TOL
+    tl = orc.wall_targets()
+    cnt, sig, nd = op.wall_neighbor_signature(TL_WALLS)
+    rcnt, rsig, rnd = orc.wall_neighbor_signature(tl)
+    assert np.array_equal(cnt, rcnt) and np.array_equal(sig, rsig) and np.array_equal(nd, rnd)
+    assert cnt.sum() > 100000                              # the two walls are 0.9 < rc apart: the direct loop has work
+    for f in (W.f, np.random.default_rng(8).normal(size=W.f.shape)):
+        op.set_wall_traction(f)
+        orc.set_wall_traction(f)
+        v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+        ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+        assert rel_l2(v, ref) < TOL
+    op.close()
