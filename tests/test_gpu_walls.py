@@ -335,3 +335,25 @@ def test_wall_dominated_operator_at_carotid_size(oracle_lib):
         ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
         assert rel_l2(v, ref) < TOL
     op.close()
+
+
+def test_device_glob_sph_trans_reproduces_the_reference_exported_cell():
+    """Golden vector FROM THE REFERENCE on the device: SickleCell.dat (tests/golden/ref_sickle_cell.npz, a cell written by
+    the reference after its SPHEREPACK filter) is carried exactly by 3 x 12^2 packed coefficients, so
+    Glob_Sph_Trans(FOUR_TO_PHYS) on the GPU (rbc3d_solver_velocity, solver.cu k_sh_synth) must give back the file's
+    coordinates -- for the imported cells and the analytic biconcave ones of the case_sickles configuration alike."""
+    from rbc3d_b200 import gmres, mtube
+    from rbc3d_b200.ewald import EwaldOperator
+    sus, _ = mtube.case_like(8, sickles=True, ntheta=24, nz=12, visc_ratio=5.0)
+    op = EwaldOperator(sus.Lb)
+    op.set_mesh(sus.ncell, sus.nlat, sus.nlon, sus.th, sus.phi, sus.w)
+    op.enable_device_splines(sus.nlat0)
+    op.SourceList_UpdateCoord_mesh(sus.x, sus.a3, sus.detj, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize)
+    op.SourceList_UpdateDensity(f=sus.weighted(sus.f), g=sus.weighted(sus.g))
+    op.solver_setup(sus.nlat0, sus.detj)
+    T = gmres.GlobSphTrans(sus.ncell, sus.nlat, sus.nlon, sus.nlat0)
+    coef = T.phys_to_four(sus.x)
+    assert coef.size == op.solver_dof == 8 * 3 * 144
+    v = op.solver_velocity(coef)
+    assert np.abs(v - sus.x).max() < 1e-11 * np.abs(sus.x).max()
+    op.close()
