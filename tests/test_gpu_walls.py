@@ -222,6 +222,69 @@ def test_partial_active_rows(two_walls):
     orc.prepare_sing_int_on_walls()
 
 
+# ---- added after round 1's GPU budget was spent (not yet run on a device), most basic first; kept at the end of the
+# ---- last GPU file so that `pytest -x` cannot hide tests that have run ------------------------------------------
+def test_device_glob_sph_trans_reproduces_the_reference_exported_cell():
+    """Golden vector FROM THE REFERENCE on the device: SickleCell.dat (tests/golden/ref_sickle_cell.npz, a cell written by
+    the reference after its SPHEREPACK filter) is carried exactly by 3 x 12^2 packed coefficients, so
+    Glob_Sph_Trans(FOUR_TO_PHYS) on the GPU (rbc3d_solver_velocity, solver.cu k_sh_synth) must give back the file's
+    coordinates -- for the imported cells and the analytic biconcave ones of the case_sickles configuration alike."""
+    from rbc3d_b200 import gmres, mtube
+    from rbc3d_b200.ewald import EwaldOperator
+    sus, _ = mtube.case_like(8, sickles=True, ntheta=24, nz=12, visc_ratio=5.0)
+    op = EwaldOperator(sus.Lb)
+    op.set_mesh(sus.ncell, sus.nlat, sus.nlon, sus.th, sus.phi, sus.w)
+    op.enable_device_splines(sus.nlat0)
+    op.SourceList_UpdateCoord_mesh(sus.x, sus.a3, sus.detj, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize)
+    op.SourceList_UpdateDensity(f=sus.weighted(sus.f), g=sus.weighted(sus.g))
+    op.solver_setup(sus.nlat0, sus.detj)
+    T = gmres.GlobSphTrans(sus.ncell, sus.nlat, sus.nlon, sus.nlat0)
+    coef = T.phys_to_four(sus.x)
+    assert coef.size == op.solver_dof == 8 * 3 * 144
+    v = op.solver_velocity(coef)
+    assert np.abs(v - sus.x).max() < 1e-11 * np.abs(sus.x).max()
+    op.close()
+
+
+def test_wall_dominated_operator_at_carotid_size(oracle_lib):
+    """BASELINE.json configs[4] (wall-dominated operator) at the size of examples/carotid_web -- 14 550 + 2 903 vertices,
+    28 948 + 5 682 triangles in a 10.5 x 10.5 x 30 box -- with generated walls of the same counts' order (the Exodus
+    meshes are not on the GPU box; the real ones run on the oracle in tests/test_reference_inputs.py): self-interaction
+    matrices (pattern bit-exact), operator #4 with the wall-wall direct loop, and a second traction."""
+    from rbc3d_b200.capi import TL_WALLS
+    from rbc3d_b200.ewald import EwaldOperator
+    Lb = np.array([10.5, 10.5, 30.0])
+    W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02)
+    assert W.NV == 121 * 120 + 61 * 48 and W.NE == 2 * 120 * 120 + 2 * 60 * 48
+    op = EwaldOperator(Lb)
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    orc = oracle_lib.Oracle(Lb)
+    orc.set_walls(W, ncell=0)
+    orc.prepare_sing_int_on_walls()
+    assert list(op.Nb) == orc.Nb == [48, 48, 136]
+    rowptr, col, val = op.wall_matrix()
+    vo = W.voff()
+    for w in range(2):
+        rrow, rcol, rval = orc.wall_matrix(w)
+        lo, hi = rowptr[vo[w]], rowptr[vo[w + 1]]
+        assert np.array_equal(rowptr[vo[w]:vo[w + 1] + 1] - lo, rrow)
+        assert np.array_equal(col[lo:hi] - vo[w], rcol)
+        assert rel_l2(val[lo:hi], rval) < TOL
+    tl = orc.wall_targets()
+    cnt, sig, nd = op.wall_neighbor_signature(TL_WALLS)
+    rcnt, rsig, rnd = orc.wall_neighbor_signature(tl)
+    assert np.array_equal(cnt, rcnt) and np.array_equal(sig, rsig) and np.array_equal(nd, rnd)
+    assert cnt.sum() > 100000                              # the two walls are 0.9 < rc apart: the direct loop has work
+    for f in (W.f, np.random.default_rng(8).normal(size=W.f.shape)):
+        op.set_wall_traction(f)
+        orc.set_wall_traction(f)
+        v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+        ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+        assert rel_l2(v, ref) < TOL
+    op.close()
+
+
 def test_noslip_wall_solve(one_wall):
     """NoSlipWall (ModNoSlip.F90:44-149) around the boundary: operator #3 for the right-hand side, operator #4 per
     GMRES iteration (rtol = eps_Ewd = 1e-3, at most 60 iterations), through the C ABI and on the oracle -- same
@@ -295,65 +358,4 @@ def test_case_and_case_sickles_configurations(oracle_lib, sickles):
         v = op.apply(c1, c2, kind, cells=True, walls=walls)
         ref = orc.apply(c1, c2, tl, cells=True, walls=walls)
         assert rel_l2(v, ref) < TOL
-    op.close()
-
-
-def test_wall_dominated_operator_at_carotid_size(oracle_lib):
-    """BASELINE.json configs[4] (wall-dominated operator) at the size of examples/carotid_web -- 14 550 + 2 903 vertices,
-    28 948 + 5 682 triangles in a 10.5 x 10.5 x 30 box -- with generated walls of the same counts' order (the Exodus
-    meshes are not on the GPU box; the real ones run on the oracle in tests/test_reference_inputs.py): self-interaction
-    matrices (pattern bit-exact), operator #4 with the wall-wall direct loop, and a second traction."""
-    from rbc3d_b200.capi import TL_WALLS
-    from rbc3d_b200.ewald import EwaldOperator
-    Lb = np.array([10.5, 10.5, 30.0])
-    W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02)
-    assert W.NV == 121 * 120 + 61 * 48 and W.NE == 2 * 120 * 120 + 2 * 60 * 48
-    op = EwaldOperator(Lb)
-    op.set_walls(W)
-    op.PrepareSingIntOnWall()
-    orc = oracle_lib.Oracle(Lb)
-    orc.set_walls(W, ncell=0)
-    orc.prepare_sing_int_on_walls()
-    assert list(op.Nb) == orc.Nb == [48, 48, 136]
-    rowptr, col, val = op.wall_matrix()
-    vo = W.voff()
-    for w in range(2):
-        rrow, rcol, rval = orc.wall_matrix(w)
-        lo, hi = rowptr[vo[w]], rowptr[vo[w + 1]]
-        assert np.array_equal(rowptr[vo[w]:vo[w + 1] + 1] - lo, rrow)
-        assert np.array_equal(col[lo:hi] - vo[w], rcol)
-        assert rel_l2(val[lo:hi], rval) < TOL
-    tl = orc.wall_targets()
-    cnt, sig, nd = op.wall_neighbor_signature(TL_WALLS)
-    rcnt, rsig, rnd = orc.wall_neighbor_signature(tl)
-    assert np.array_equal(cnt, rcnt) and np.array_equal(sig, rsig) and np.array_equal(nd, rnd)
-    assert cnt.sum() > 100000                              # the two walls are 0.9 < rc apart: the direct loop has work
-    for f in (W.f, np.random.default_rng(8).normal(size=W.f.shape)):
-        op.set_wall_traction(f)
-        orc.set_wall_traction(f)
-        v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
-        ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
-        assert rel_l2(v, ref) < TOL
-    op.close()
-
-
-def test_device_glob_sph_trans_reproduces_the_reference_exported_cell():
-    """Golden vector FROM THE REFERENCE on the device: SickleCell.dat (tests/golden/ref_sickle_cell.npz, a cell written by
-    the reference after its SPHEREPACK filter) is carried exactly by 3 x 12^2 packed coefficients, so
-    Glob_Sph_Trans(FOUR_TO_PHYS) on the GPU (rbc3d_solver_velocity, solver.cu k_sh_synth) must give back the file's
-    coordinates -- for the imported cells and the analytic biconcave ones of the case_sickles configuration alike."""
-    from rbc3d_b200 import gmres, mtube
-    from rbc3d_b200.ewald import EwaldOperator
-    sus, _ = mtube.case_like(8, sickles=True, ntheta=24, nz=12, visc_ratio=5.0)
-    op = EwaldOperator(sus.Lb)
-    op.set_mesh(sus.ncell, sus.nlat, sus.nlon, sus.th, sus.phi, sus.w)
-    op.enable_device_splines(sus.nlat0)
-    op.SourceList_UpdateCoord_mesh(sus.x, sus.a3, sus.detj, sus.Acoef, sus.Bcoef, sus.area, sus.meshSize)
-    op.SourceList_UpdateDensity(f=sus.weighted(sus.f), g=sus.weighted(sus.g))
-    op.solver_setup(sus.nlat0, sus.detj)
-    T = gmres.GlobSphTrans(sus.ncell, sus.nlat, sus.nlon, sus.nlat0)
-    coef = T.phys_to_four(sus.x)
-    assert coef.size == op.solver_dof == 8 * 3 * 144
-    v = op.solver_velocity(coef)
-    assert np.abs(v - sus.x).max() < 1e-11 * np.abs(sus.x).max()
     op.close()
