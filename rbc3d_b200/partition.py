@@ -28,3 +28,44 @@ def zslab_active(x: np.ndarray, Lb, nranks: int, rank: int) -> np.ndarray:
     """The reference's point-wise z-slab ownership (SetActiveFlag, ModTargetList.F90:221-222)."""
     iz = np.floor(x[2] * (1.0 / Lb[2]) * nranks).astype(np.int64)
     return (np.mod(iz, nranks) == rank).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's SOURCE filter per rank (ModConf.F90:412-515): with spatial slabs a rank needs only the sources within
+# its slab plus a buffer of max(rc, P L3 / Nb3) on either side.  Not used by this round's CUDA path (sources are
+# replicated, DESIGN.md section 6); restated for the slab-decomposed path of the next round and checked for
+# completeness in tests/test_partition_gloo.py.
+def domain_decomp(Lb, rc: float, P: int, Nb3: int, nranks: int, rank: int):
+    """DomainDecomp -> (nodeZmin, nodeZmax, nodeZminBuf, nodeZmaxBuf)."""
+    hz = Lb[2] / nranks
+    hbuf = max(0.0, rc, P * Lb[2] / Nb3)
+    zmin, zmax = rank * hz, (rank + 1) * hz
+    return zmin, zmax, zmin - hbuf, zmax + hbuf
+
+
+def is_source(z: np.ndarray, dd, Lb, nranks: int) -> np.ndarray:
+    """Is_Source for points with z coordinates ``z`` (ModConf.F90:441-463)."""
+    if nranks == 1:
+        return np.ones(np.shape(z), dtype=bool)
+    _, _, zlo, zhi = dd
+    zz = np.asarray(z, dtype=float) - zlo
+    zz = zz - np.floor(zz * (1.0 / Lb[2])) * Lb[2]
+    return zz < zhi - zlo + 1.0e-5
+
+
+def cell_has_source(z_cell: np.ndarray, dd, Lb, nranks: int) -> bool:
+    """Cell_Has_Source for one cell given the z coordinates of its mesh points (ModConf.F90:467-493)."""
+    if nranks == 1:
+        return True
+    _, _, zlo, zhi = dd
+    iL = 1.0 / Lb[2]
+    zmin = float(np.min(z_cell)) - zlo
+    zmin = zmin - np.floor(zmin * iL) * Lb[2]
+    zmax = float(np.max(z_cell)) - zlo
+    zmax = zmax - np.floor(zmax * iL) * Lb[2]
+    return bool(zmin < zhi - zlo + 1.0e-5 or zmax < zmin)
+
+
+def tri_has_source(z_tri: np.ndarray, dd, Lb, nranks: int) -> np.ndarray:
+    """Tri_Has_Source: all three vertices must pass Is_Source (ModConf.F90:499-515).  z_tri (3 corners, nele)."""
+    return is_source(z_tri, dd, Lb, nranks).all(axis=0)

@@ -116,3 +116,37 @@ def test_two_rank_wall_noslip_solve_equals_single_rank(tmp_path, oracle_lib):
     assert np.allclose(r0["hist"], hist, rtol=1e-9)
     assert np.linalg.norm(r0["f"] - f) < 1e-9 * np.linalg.norm(f)
     assert np.abs(r0["slip"] - slip).max() < 1e-10
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_source_filter_is_complete_for_the_slab_targets(nranks):
+    """Cell_Has_Source (ModConf.F90:467-493) keeps every cell that has a point within rc of a target of the rank's z-slab
+    (real-space sum) or whose B-spline support reaches the slab's mesh planes (PME spreading), and drops the others."""
+    from rbc3d_b200.ewald import SetEwaldPrms
+    from tests import util
+    sus = util.small_suspension(3, nlat0=4)                      # 27 small cells in a periodic box
+    rc, Nb = SetEwaldPrms(sus.Lb, nranks=nranks)
+    npc = sus.nlat * sus.nlon
+    P = 8
+    kept_any_dropped = False
+    for r in range(nranks):
+        dd = partition.domain_decomp(sus.Lb, rc, P, Nb[2], nranks, r)
+        keep = np.array([partition.cell_has_source(sus.x[2, c * npc:(c + 1) * npc], dd, sus.Lb, nranks)
+                         for c in range(sus.ncell)])
+        kept_any_dropped |= not keep.all()
+        act = partition.zslab_active(sus.x, sus.Lb, nranks, r).astype(bool)
+        xt = sus.x[:, act]
+        for c in np.nonzero(~keep)[0]:                           # a dropped cell must be out of reach of every slab target
+            xs = sus.x[:, c * npc:(c + 1) * npc]
+            d = xt[:, :, None] - xs[:, None, :]
+            d -= np.rint(d / sus.Lb[:, None, None]) * sus.Lb[:, None, None]
+            assert np.sqrt((d ** 2).sum(0)).min() > rc
+            # and its B-spline support (P planes below floor(z Nb3 / L3)) misses the slab's planes
+            k = np.floor(xs[2] * Nb[2] / sus.Lb[2]).astype(int)
+            planes = np.mod(k[:, None] - np.arange(P)[None, :], Nb[2])
+            lo, hi = r * Nb[2] // nranks, (r + 1) * Nb[2] // nranks
+            assert not ((planes >= lo) & (planes < hi)).any()
+        # Is_Source point-wise is implied by the cell test for every point inside the buffer
+        pts = partition.is_source(sus.x[2], dd, sus.Lb, nranks)
+        assert np.all(keep[np.nonzero(pts)[0] // npc])
+    assert kept_any_dropped or nranks < 4                        # with 4 slabs the filter does drop cells in this box
