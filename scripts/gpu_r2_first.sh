@@ -6,7 +6,8 @@ for t in "tests/test_gpu_walls.py::test_noslip_wall_solve" \
          "tests/test_gpu_walls.py::test_mtube_time_step" \
          "tests/test_gpu_walls.py::test_case_and_case_sickles_configurations" \
          "tests/test_gpu_walls.py::test_wall_dominated_operator_at_carotid_size" \
-         "tests/test_gpu_walls.py::test_device_glob_sph_trans_reproduces_the_reference_exported_cell"; do
+         "tests/test_gpu_walls.py::test_device_glob_sph_trans_reproduces_the_reference_exported_cell" \
+         "tests/test_gpu_walls.py::test_edge_cases_empty_inactive_and_zero_inputs"; do
   echo "=== $t" >> gpurun_out/r2a_newtests.log
   timeout 600 python -m pytest "$t" -q -m gpu 2>&1 | tail -25 >> gpurun_out/r2a_newtests.log
 done

@@ -359,3 +359,31 @@ def test_case_and_case_sickles_configurations(oracle_lib, sickles):
         ref = orc.apply(c1, c2, tl, cells=True, walls=walls)
         assert rel_l2(v, ref) < TOL
     op.close()
+
+
+def test_edge_cases_empty_inactive_and_zero_inputs(oracle_lib):
+    """The edge cases of tests/test_oracle_edge_cases.py through the C ABI: an empty raw target list, an all-inactive
+    target list (rows untouched), zero densities (zero out), c1 = c2 = 0."""
+    from rbc3d_b200.capi import TL_CELLS, TL_RAW
+    from rbc3d_b200.ewald import EwaldOperator
+    sus = util.small_suspension(2, nlat0=4)
+    op = EwaldOperator(sus.Lb)
+    act = np.zeros(sus.npoint, np.int32)
+    op.set_suspension(sus, active=act)
+    v0 = np.full((3, sus.npoint), 3.25)
+    v = op.apply(C1_RHS, C2_MATVEC, TL_CELLS, v=v0.copy())
+    assert np.array_equal(v, v0)
+    op.set_suspension(sus)
+    assert not op.apply(0.0, 0.0, TL_CELLS).any()
+    op.SourceList_UpdateDensity(f=np.zeros((3, sus.npoint)), g=np.zeros((3, sus.npoint)), spF=np.zeros_like(sus.spF),
+                                spG=np.zeros_like(sus.spG))
+    assert not op.apply(C1_RHS, C2_MATVEC, TL_CELLS).any()
+    op.set_suspension(sus)
+    x0 = sus.x[:, [17, 300]].copy()                      # raw targets on top of source points: r = 0 is skipped
+    op.TargetList_CreateFromRaw(x0)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    ref = orc.apply_cells(C1_RHS, C2_MATVEC, orc.make_targets(x0))
+    assert rel_l2(op.apply(C1_RHS, C2_MATVEC, TL_RAW), ref) < TOL
+    op.TargetList_CreateFromRaw(np.zeros((3, 0)))
+    assert op.apply(C1_RHS, C2_MATVEC, TL_RAW).shape == (3, 0)
+    op.close()
