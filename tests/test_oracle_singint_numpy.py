@@ -276,3 +276,133 @@ def test_nearsing_int_equals_the_oracle(setup, oracle_lib, c1, c2):
                 assert not ref.any() and not mine.any()
             else:
                 assert np.linalg.norm(mine - ref) < 1e-10 * np.linalg.norm(ref)
+
+
+# ---- Spline_FindProjection (ModSpline.F90:203-269) and the whole of AddIntOnRbcs (ModIntOnRbcs.F90:25-201) ----------
+def polar_patch_map(th0, phi0, dth, dphi):
+    s1 = np.array([np.cos(th0) * np.cos(phi0), np.cos(th0) * np.sin(phi0), -np.sin(th0)])
+    s2 = np.array([-np.sin(phi0), np.cos(phi0), 0.0])
+    x0 = np.array([np.sin(th0) * np.cos(phi0), np.sin(th0) * np.sin(phi0), np.cos(th0)])
+    x = np.sin(dth) * np.cos(dphi) * s1 + np.sin(dth) * np.sin(dphi) * s2 + np.cos(dth) * x0
+    x = x / np.sqrt(x @ x)
+    th = np.arccos(max(-1.0, min(1.0, x[2])))
+    phi = np.arctan2(x[1], x[0])
+    return th, phi + 2 * PI if phi < 0 else phi
+
+
+def find_projection(spx, xtar, th0, phi0):
+    nth, nphi = 2, 8
+    m, n = spx.shape[3], spx.shape[2]
+    x0 = spline_interp(spx, th0, phi0)
+    h = max(2 * PI / m, 2 * PI / n)
+    for _ in range(3):
+        thL = np.array([(i + 1) * h / nth for i in range(nth)])
+        phL = np.arange(nphi) * 2 * PI / nphi
+        thP, phP = polar_patch_build(th0, phi0, thL, phL)
+        xy = [(0.0, 0.0)]
+        d2 = [((spline_interp(spx, th0, phi0) - xtar) ** 2).sum()]
+        for iphi in range(nphi):
+            for ith in range(nth):
+                xy.append((thL[ith] * np.cos(phL[iphi]), thL[ith] * np.sin(phL[iphi])))
+                d2.append(((spline_interp(spx, thP[ith, iphi], phP[ith, iphi]) - xtar) ** 2).sum())
+        xy, d2 = np.array(xy), np.array(d2)
+        U = np.stack([np.ones(len(xy)), xy[:, 0], xy[:, 1], xy[:, 0] ** 2, xy[:, 0] * xy[:, 1], xy[:, 1] ** 2], axis=1)
+        a0, a1, a2, a11, a12, a22 = np.linalg.solve(U.T @ U, U.T @ d2)          # QuadFit_2D: normal equations (dposv)
+        det = 4 * a11 * a22 - a12 * a12                                            # Min_Quad_2D
+        xm = np.array([(2 * a22 * (-a1) - a12 * (-a2)) / det, (-a12 * (-a1) + 2 * a11 * (-a2)) / det]) if det > 0 \
+            else np.zeros(2)
+        thMin, phiMin = polar_patch_map(th0, phi0, np.sqrt(xm @ xm), np.arctan2(xm[1], xm[0]))
+        xMin = spline_interp(spx, thMin, phiMin)
+        if ((xMin - xtar) ** 2).sum() > d2[0]:
+            break
+        th0, phi0, x0, h = thMin, phiMin, xMin, 0.5 * h
+    return th0, phi0, x0
+
+
+def add_int_on_rbcs_target(sus, tabs, c1, c2, xi, A_i, cell_i=None, ilat_i=None, ilon_i=None):
+    """One target of AddIntOnRbcs without the linear term; cell_i None = raw target (indx = -1)."""
+    npc = sus.nlat * sus.nlon
+    radius = PI / np.sqrt(float(sus.nlat))
+    fw = sus.weighted(sus.f) if c1 != 0 else None
+    gw = sus.weighted(sus.g) if c2 != 0 else None
+    d = sus.x - xi[:, None]
+    d = d - np.rint(d / sus.Lb[:, None]) * sus.Lb[:, None]
+    r = np.sqrt((d ** 2).sum(0))
+    v = np.zeros(3)
+    nbr = {}                                                            # NbrRbcList: other cell -> (dist, point)
+    for j in np.nonzero(r <= tabs.rc)[0]:
+        cj, pj = divmod(j, npc)
+        ilon_j, ilat_j = divmod(pj, sus.nlat)
+        xx, rr = d[:, j], r[j]
+        if cell_i is not None and cj == cell_i:
+            mask = mask_func(dist_on_sphere(sus.th[ilat_i], sus.phi[ilon_i], sus.th[ilat_j], sus.phi[ilon_j]) / radius)
+        else:
+            mask = 0.0
+            if cj not in nbr or rr < nbr[cj][0]:
+                nbr[cj] = (rr, j)
+        if c1 != 0:
+            EA, EB = tabs.sl(rr)
+            v = v + (1.0 - mask) * c1 / A_i * (EA * xx * (xx @ fw[:, j]) + EB * fw[:, j])
+        if c2 != 0:
+            v = v + (1.0 - mask) * c2 * sus.Bcoef[cj] / A_i * (tabs.dl(rr) * xx * (xx @ gw[:, j]) * (xx @ sus.a3[:, j]))
+    if cell_i is not None:
+        v = v + sing_int(sus, tabs, c1, c2 * sus.Bcoef[cell_i], cell_i, ilat_i, ilon_i) / A_i
+    for cj, (_, j) in nbr.items():
+        pj = j % npc
+        ilon0, ilat0 = divmod(pj, sus.nlat)
+        x0 = sus.x[:, j]
+        xx = xi - x0
+        xt = x0 + (xx - np.rint(xx / sus.Lb) * sus.Lb)
+        th0, phi0, x0p = find_projection(sus.spx[cj], xt, sus.th[ilat0], sus.phi[ilon0])
+        v = v + nearsing_int(sus, tabs, c1, c2 * sus.Bcoef[cj], cj, xt, x0p, th0, phi0) / A_i
+    return v
+
+
+def linear_int(sus, c2):
+    if c2 == 0:
+        return np.zeros(3)
+    npc = sus.nlat * sus.nlon
+    vn = (sus.g * sus.a3).sum(0) * sus.dS()
+    xv = (np.repeat(sus.Bcoef, npc)[None, :] * sus.x * vn[None, :]).sum(1)
+    return c2 * (-8 * PI * np.prod(1.0 / sus.Lb) * xv)
+
+
+def test_find_projection_equals_the_oracle(setup, oracle_lib):
+    sus, orc, _ = setup
+    rng = np.random.default_rng(2)
+    for cell, ilat0, ilon0 in ((0, 5, 9), (4, 30, 50), (6, 0, 3)):
+        p = cell * sus.nlat * sus.nlon + ilon0 * sus.nlat + ilat0
+        xtar = sus.x[:, p] + 0.1 * sus.a3[:, p] + 0.03 * rng.normal(size=3)
+        th, ph, x0 = find_projection(sus.spx[cell], xtar, sus.th[ilat0], sus.phi[ilon0])
+        th_o, ph_o, x0_o = oracle_lib.Oracle.find_projection(sus.spx[cell], xtar, sus.th[ilat0], sus.phi[ilon0])
+        assert abs(th - th_o) < 1e-9 and abs(ph - ph_o) < 1e-9 and np.abs(x0 - np.asarray(x0_o)).max() < 1e-9
+
+
+@pytest.mark.parametrize("c1,c2", [(C1_RHS, 0.0), (0.0, C2_MATVEC), (C1_RHS, C1_RHS)])
+def test_add_int_on_rbcs_equals_the_oracle(oracle_lib, c1, c2):
+    """The whole of AddIntOnRbcs for a handful of targets of two nearly touching cells (pair sum with masks, singular,
+    neighbour list + projection + near-singular incl. the jump branch, linear term) and for raw targets next to a
+    surface -- second restatement vs the C oracle."""
+    sus = util.close_pair_suspension(gap=0.004, seed=7)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    tabs = Tables(orc.alpha, orc.rc)
+    npc = sus.nlat * sus.nlon
+    # the points of cell 0 closest to cell 1, plus two ordinary ones
+    d = sus.x[:, :npc, None] - sus.x[:, None, npc::7]
+    close = np.argsort(np.sqrt((d ** 2).sum(0)).min(1))[:3]
+    idx = np.concatenate([close, [100, npc + 777]])
+    act = np.zeros(sus.npoint, np.int32)
+    act[idx] = 1
+    ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(active=act))
+    lin = linear_int(sus, c2)
+    for i in idx:
+        cell, p = divmod(i, npc)
+        ilon, ilat = divmod(p, sus.nlat)
+        A = sus.Acoef[cell]
+        mine = add_int_on_rbcs_target(sus, tabs, c1, c2, sus.x[:, i], A, cell, ilat, ilon) + lin / A
+        assert np.linalg.norm(mine - ref[:, i]) < 1e-9 * np.linalg.norm(ref[:, i])
+    xr = sus.x[:, close[:2]] + 0.002 * sus.a3[:, close[:2]]             # raw targets just outside cell 0 (and near cell 1)
+    ref = orc.add_int_on_rbcs(c1, c2, orc.make_targets(xr))
+    for k in range(xr.shape[1]):
+        mine = add_int_on_rbcs_target(sus, tabs, c1, c2, xr[:, k], 2.0) + lin / 2.0
+        assert np.linalg.norm(mine - ref[:, k]) < 1e-9 * np.linalg.norm(ref[:, k])
