@@ -10,8 +10,14 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
  * this path and cannot be compiled in this image (no
  * Fortran compiler, MPI, PETSc, FFTW).  The restatement is validated by physics
- * identities (tests/test_oracle_identities.py) and by an independent NumPy mirror
- * of the closed-form pieces inside the tests; nothing here was checked against an
+ * identities (tests/test_oracle_identities.py) and by a second restatement written
+ * separately in NumPy, straight from the Fortran, that agrees with this one to
+ * round-off (singular / near-singular integrals, projection and the whole of
+ * AddIntOnRbcs per target: tests/test_oracle_singint_numpy.py; Duffy rule and the
+ * wall loop: tests/test_oracle_walls_numpy.py; PME: rbc3d_b200/slabpme.py +
+ * tests/test_slab_pme.py).  The one output of the reference that its tree ships,
+ * SickleCell.dat, pins the Gauss grid, the point order and the SH truncation
+ * (tests/test_reference_golden.py).  Nothing here was checked against an
  * execution of the reference binary.
  *
  * Every function cites the reference file:line it follows (paths relative to
