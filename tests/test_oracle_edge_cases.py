@@ -56,3 +56,26 @@ def test_walls_without_cells_and_zero_traction(oracle_lib):
     # c1 = 0: nothing is spread, nothing is integrated (flag_sing_lay = |c1| > 1e-10, ModPME.F90:71)
     orc.set_wall_traction(W.f)
     assert not orc.apply(0.0, 0.0, tl, cells=False, walls=True).any()
+
+
+def test_set_ewald_prms_three_ways(oracle_lib):
+    """SetEwaldPrms (ModConf.F90:348-408) restated in the oracle (C), in the library's host arithmetic
+    (rbc3d_set_ewald_prms) and here in NumPy from the Fortran; the box sizes of BASELINE.json's configurations."""
+    from rbc3d_b200.ewald import SetEwaldPrms
+    for Lb, nranks in (((10.5, 10.5, 8.0), 1), ((10.5, 10.5, 8.0), 2), ((10.5, 10.5, 8 / 0.7), 1), ((10.5, 10.5, 30.0), 8),
+                       ((57.2589, 57.2589, 57.2589), 8), ((3.0, 2.5, 2.0), 3)):
+        Lb = np.array(Lb)
+        alpha, eps, P = 0.44, 1e-3, 8
+        s = 1.0
+        for _ in range(10):
+            s = 0.75 * np.sqrt(np.pi) * eps / (s ** 3 + 1.5 * s + 0.75 / s)
+            s = np.sqrt(-np.log(s))
+        rc = min((Lb / 3.001).min(), np.sqrt(alpha / np.pi) * s)
+        Nb = (2 * np.ceil(np.sqrt(-np.log(eps) / (np.pi * alpha)) * Lb)).astype(int)
+        Nb[2] = max(Nb[2], nranks * P)
+        Nb[2] = int(np.ceil(Nb[2] / nranks)) * nranks
+        orc = oracle_lib.Oracle(Lb, alpha, eps, P, nranks=nranks)
+        rc_lib, Nb_lib = SetEwaldPrms(Lb, alpha, eps, P, nranks=nranks)
+        assert abs(orc.rc - rc) < 1e-15 and abs(rc_lib - rc) < 1e-15
+        assert orc.Nb == list(Nb) == list(Nb_lib)
+        assert orc.Nc == [max(int(np.floor(L / rc)), 3) for L in Lb]      # HashTable_ComputeNumBlocks
