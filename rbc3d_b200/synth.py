@@ -167,6 +167,23 @@ def suspension_from_shapes(x: np.ndarray, Lb, nlat0: int = 12, dealias: int = 3,
     return _assemble(rng, builder, Lb, nlat0, x, a1, a2, lam, x.mean(axis=(2, 3)), with_f, with_g)
 
 
+def subset(sus: Suspension, cells) -> Suspension:
+    """The suspension restricted to the given cells (in the given order) -- what a rank holds after the reference's
+    source filter (Cell_Has_Source, ModConf.F90:467-493; rbc3d_b200/partition.py)."""
+    cells = np.asarray(cells, dtype=np.int64)
+    npc = sus.nlat * sus.nlon
+    pts = (cells[:, None] * npc + np.arange(npc)[None, :]).reshape(-1)
+    pick = lambda a: None if a is None else np.ascontiguousarray(a[..., pts])      # noqa: E731
+    cpick = lambda a: None if a is None else np.ascontiguousarray(a[cells])        # noqa: E731
+    out = Suspension(Lb=sus.Lb, nlat0=sus.nlat0, nlat=sus.nlat, nlon=sus.nlon, ncell=len(cells), th=sus.th, phi=sus.phi,
+                     w=sus.w, x=pick(sus.x), a3=pick(sus.a3), detj=pick(sus.detj), f=pick(sus.f), g=pick(sus.g),
+                     Acoef=cpick(sus.Acoef), Bcoef=cpick(sus.Bcoef), area=cpick(sus.area), meshSize=cpick(sus.meshSize),
+                     spx=cpick(sus.spx), spa3=cpick(sus.spa3), spdetj=cpick(sus.spdetj), spF=cpick(sus.spF),
+                     spG=cpick(sus.spG), centers=cpick(sus.centers))
+    out._builder = getattr(sus, "_builder", None)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Walls: triangulated tubes like the vessel of examples/minicase and examples/case (a cylinder along z whose end
 # rings sit on z = 0 and z = Lb3 as duplicated vertices, the way the reference's Exodus meshes close the period).

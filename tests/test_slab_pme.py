@@ -139,3 +139,58 @@ def test_slab_transform_two_gloo_ranks(tmp_path):
     x, f, g, a3, B = point_sources()
     ref = m.transform(*m.spread(x, 0.7, -0.4, f=f, g=g, a3=a3, Bcoef=B))
     assert util.rel_l2(np.load(out), ref) < 1e-13
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_slab_decomposed_operator_equals_single_rank(oracle_lib, R):
+    """The reference's whole decomposition on CPU: every rank keeps the cells that pass Cell_Has_Source,
+    owns the targets of its z-slab (SetActiveFlag), evaluates the real-space sums from its kept cells alone, spreads its
+    kept sources onto its own mesh planes only (no mesh reduction at all), takes part in the z-slab <-> y-slab transform,
+    interpolates from its slab plus the halo of the lower neighbour, and contributes its cells' share of the linear
+    term (one 3-number all-reduce).  The disjoint rows of all ranks together = the single-rank operator."""
+    from rbc3d_b200 import partition, synth
+    from tests.util import C1_RHS
+    sus = util.small_suspension(3, nlat0=4)
+    orc = oracle_lib.Oracle(sus.Lb, nranks=R)                           # Nb(3) a multiple of R
+    orc.set_cells(sus)
+    c1, c2 = C1_RHS, -0.5 * C1_RHS
+    ref = orc.apply_cells(c1, c2, orc.cell_targets())
+    m = slabpme.PmeModel(sus.Lb, orc.Nb, orc.alpha, orc.P)
+    npc = sus.nlat * sus.nlon
+    zs = slabpme.slab_chunks(orc.Nb[2], R)
+    ranks = []
+    ff = np.zeros((3, orc.Nb[2], orc.Nb[1], orc.Nb[0]))
+    tt = np.zeros((9,) + ff.shape[1:])
+    xvint = np.zeros(3)
+    for r in range(R):
+        dd = partition.domain_decomp(sus.Lb, orc.rc, orc.P, orc.Nb[2], R, r)
+        keep = [c for c in range(sus.ncell) if partition.cell_has_source(sus.x[2, c * npc:(c + 1) * npc], dd, sus.Lb, R)]
+        sub = synth.subset(sus, keep)
+        act = partition.zslab_active(sub.x, sus.Lb, R, r)
+        o = oracle_lib.Oracle(sus.Lb, nranks=R).set_cells(sub)
+        v = o.add_int_on_rbcs(c1, c2, o.cell_targets(active=act), flags=o.FLAG_NO_LINEAR)
+        lo, hi = zs[r]
+        fs, ts = m.spread(sub.x, c1, c2, f=sub.weighted(sub.f), g=sub.weighted(sub.g), a3=sub.a3,
+                          Bcoef=np.repeat(sub.Bcoef, npc), zrange=(lo, hi))
+        ff[:, lo:hi], tt[:, lo:hi] = fs[:, lo:hi], ts[:, lo:hi]         # the rank's own planes; nothing is summed
+        own = range(*partition.cell_block(sus.ncell, R, r))              # its share of the linear term (AddLinearInt)
+        for c in own:
+            sl = slice(c * npc, (c + 1) * npc)
+            xvint += sus.Bcoef[c] * (sus.x[:, sl] * ((sus.g[:, sl] * sus.a3[:, sl]).sum(0) * sus.dS()[sl])[None, :]).sum(1)
+        ranks.append((keep, sub, act, v, lo, hi))
+    xvint = -8 * np.pi * np.prod(1.0 / sus.Lb) * xvint                   # after the all-reduce
+    vv = slabpme.run_slabs_in_process(m, R, ff, tt)
+    total = np.zeros_like(ref)
+    owned = np.zeros(sus.npoint, int)
+    for keep, sub, act, v, lo, hi in ranks:
+        planes = np.arange(lo - m.P, hi) % orc.Nb[2]
+        on = act.astype(bool)
+        A = np.repeat(sub.Acoef, npc)
+        v[:, on] += m.interp_slab(sub.x[:, on], vv[:, planes], lo, hi) / A[on]
+        v[:, on] += c2 * xvint[:, None] / A[on]
+        glob = (np.asarray(keep)[:, None] * npc + np.arange(npc)[None, :]).reshape(-1)
+        total[:, glob[on]] += v[:, on]
+        owned[glob[on]] += 1
+        assert not v[:, ~on].any()
+    assert (owned == 1).all()
+    assert util.rel_l2(total, ref) < 1e-12
