@@ -225,7 +225,8 @@ def cpu_mtube(args):
         oracle.build()
         nsteps = max(2, args.mtube_steps)
         sus, W = mtube.minicase_like(seed=args.seed)
-        step = mtube.OracleStep(oracle.Oracle(sus.Lb), sus, W)
+        from oracle import harness
+        step = harness.OracleStep(oracle.Oracle(sus.Lb), sus, W)
         runs = [mtube.bi_timestep(step, advect=True) for _ in range(MTUBE_WARM_STEPS + nsteps)]
         cpu = runs[MTUBE_WARM_STEPS:]
         return {"bi_timesteps_per_s": nsteps / sum(r["seconds"]["total"] for r in cpu), "steps": nsteps,
@@ -574,7 +575,8 @@ def run_mtube(args):
         from oracle import oracle
         oracle.build()
         sus2, W2 = mtube.minicase_like(seed=args.seed)
-        ostep = mtube.OracleStep(oracle.Oracle(sus2.Lb), sus2, W2)
+        from oracle import harness
+        ostep = harness.OracleStep(oracle.Oracle(sus2.Lb), sus2, W2)
         cruns = [mtube.bi_timestep(ostep, advect=True) for _ in range(warm + nsteps)]
         cpu = cruns[warm:]
         rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731

@@ -1,6 +1,7 @@
 """The boundary-integral work of one ``TimeInt_Euler`` step of examples/minicase/mtube (ModTimeInt.F90:108-176), composed
 from the boundary's entry points -- harness code used by bench.py (``mtube`` block: BASELINE.json "mtube timesteps/s")
-and by the tests; the same composition runs on the CUDA library (C ABI) and on the CPU oracle.
+and by the tests; the same composition runs on the CUDA library (C ABI, ``LibraryStep``) and, for checking and for the
+CPU baseline, on the oracle (``oracle/harness.py``: ``OracleStep``).
 
     Compute_Rbc_Vel   SourceList_UpdateCoord / UpdateDensity(f) on the moved cells         ModTimeInt.F90:127, ModVelSolver.F90:44-93
                       Compute_Rhs = operator #1: c1 = 1/(4 pi), c2 = 0, cells + walls -> cell points, + 2 vBkg / A   :455-515
@@ -92,29 +93,6 @@ def advect_rigid(sus, v_cells: np.ndarray, Ts: float = TS) -> None:
         sus.centers[c] = sus.centers[c] + d
         sus.x[:, c * npc:(c + 1) * npc] += d[:, None]
         sus.spx[c, 0] += d[:, None, None]                    # spline values u; derivatives u1, u2, u12 do not change
-
-
-class OracleStep:
-    """One step's operators on the CPU oracle (bench.py cpu_baseline / --impl reference, tests)."""
-
-    def __init__(self, orc, sus, W, vbkg=VBKG):
-        self.orc, self.sus, self.W, self.vbkg = orc, sus, W, np.asarray(vbkg, dtype=float)
-        orc.set_cells(sus)
-        orc.set_walls(W)
-        orc.prepare_sing_int_on_walls()                      # TimeInt_Init
-
-    def update_geometry(self):
-        self.orc.set_cells(self.sus)                         # SourceList_UpdateCoord + UpdateDensity, TargetList_Update
-        self.orc.set_wall_traction(self.W.f)
-
-    def compute_rhs(self):
-        sus = self.sus
-        v = self.orc.apply(C1, 0.0, self.orc.cell_targets(), cells=True, walls=True)
-        A = np.repeat(sus.Acoef, sus.nlat * sus.nlon)
-        return v + 2.0 * self.vbkg[:, None] / A[None, :]
-
-    def noslip_backend(self):
-        return noslip.oracle_backend(self.orc, self.vbkg)
 
 
 class LibraryStep:

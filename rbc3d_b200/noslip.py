@@ -11,8 +11,8 @@ finds the duplicated boundary rings, ``indxVertGlb`` (ModData.F90:50-63) numbers
 ``AssembleArray`` (ModNoSlip.F90:362-384) moves between the two numberings -- duplicates are overwritten in vertex
 order going to 1-D, so the last duplicate wins, exactly as the reference's loop does.
 
-The solver is written against two callables so that the same code runs on the CPU oracle (tests) and on the CUDA library
-through the C ABI (GPU tests, bench.py): ``residual_vel() -> v (3, NV)`` and ``wall_matvec(f (3, NV)) -> v (3, NV)``.
+The solver is written against callables so that the same code runs on the CUDA library through the C ABI
+(``library_backend``; GPU tests, bench.py) and, for the tests and the CPU baseline, on the oracle (``oracle/harness.py``): ``residual_vel() -> v (3, NV)`` and ``wall_matvec(f (3, NV)) -> v (3, NV)``.
 """
 from __future__ import annotations
 
@@ -101,24 +101,6 @@ class WallNoSlipSolver:
         self.set_traction(f_new)
         W.f = f_new
         return f_new, niter, hist, self.residual_vel()
-
-
-def oracle_backend(orc, vbkg, cells: bool = True, active=None, collect=None):
-    """(residual_vel, wall_matvec, set_traction) on the CPU oracle (tests, cpu_baseline).  Needs orc.set_cells /
-    set_walls / prepare_sing_int_on_walls done.  Several ranks: ``active`` = this rank's flags of the wall target list
-    (SetActiveFlag), ``collect`` = TargetList_CollectArray (sum over ranks); the background velocity is added after the
-    sum, as in Compute_Wall_Residual_Vel (ModNoSlip.F90:186-191)."""
-    tl = orc.wall_targets(active)
-    vb = np.asarray(vbkg, dtype=float)[:, None]
-    collect = collect or (lambda v: v)
-
-    def residual_vel():
-        return collect(orc.apply(C1_WALL, C1_WALL, tl, cells=cells, walls=True)) + vb
-
-    def wall_matvec(_f):
-        return collect(orc.apply(C1_WALL, 0.0, tl, cells=False, walls=True))
-
-    return residual_vel, wall_matvec, orc.set_wall_traction
 
 
 def library_backend(op, vbkg, cells: bool = True, collect: bool = False):

@@ -53,7 +53,8 @@ def main():
         e3 = util.rel_l2(v3, orc.apply(noslip.C1_WALL, noslip.C1_WALL, tl, cells=True, walls=True))
         e4 = util.rel_l2(v4, orc.apply(noslip.C1_WALL, 0.0, tl, cells=False, walls=True))
         W2.f = np.zeros_like(f_rand)
-        fo, no, ho, so = noslip.WallNoSlipSolver(W2, sus2.Lb, *noslip.oracle_backend(orc, mtube.VBKG)).solve()
+        from oracle import harness
+        fo, no, ho, so = noslip.WallNoSlipSolver(W2, sus2.Lb, *harness.noslip_backend(orc, mtube.VBKG)).solve()
         ef = util.rel_l2(f, fo)
         print(f"multi-gpu walls {world} ranks: operator #3 err {e3:.2e}, operator #4 err {e4:.2e}, "
               f"no-slip iterations {niter} (oracle {no}), traction err {ef:.2e}")

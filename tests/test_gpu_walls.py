@@ -295,7 +295,8 @@ def test_noslip_wall_solve(one_wall):
     f_keep = W.f.copy()
     vbkg = np.array([0.0, 0.0, 8.0])
     out = []
-    for backend in (noslip.oracle_backend(orc, vbkg), noslip.library_backend(op, vbkg)):
+    from oracle import harness
+    for backend in (harness.noslip_backend(orc, vbkg), noslip.library_backend(op, vbkg)):
         Wc = copy.copy(W)
         Wc.f = f_keep.copy()
         s = noslip.WallNoSlipSolver(Wc, LB, *backend)
@@ -321,7 +322,8 @@ def test_mtube_time_step(oracle_lib):
     sus2, W2 = mtube.minicase_like(nlat0=6, ntheta=32, nz=16)
     op = EwaldOperator(sus.Lb)
     lstep = mtube.LibraryStep(op, sus, W)
-    ostep = mtube.OracleStep(oracle_lib.Oracle(sus2.Lb), sus2, W2)
+    from oracle import harness
+    ostep = harness.OracleStep(oracle_lib.Oracle(sus2.Lb), sus2, W2)
     for _ in range(2):
         a, b = mtube.bi_timestep(lstep), mtube.bi_timestep(ostep)
         assert rel_l2(a["v_cells"], b["v_cells"]) < TOL

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+from oracle import harness
 from rbc3d_b200 import mtube
 
 MESH = "/root/reference/examples/minicase/Input/new_cyl_D6_L13_33.e"
@@ -24,7 +25,7 @@ def check_step(r, sus, first):
 
 def test_two_steps_generated_mesh(oracle_lib):
     sus, W = mtube.minicase_like(nlat0=6)
-    step = mtube.OracleStep(oracle_lib.Oracle(sus.Lb), sus, W)
+    step = harness.OracleStep(oracle_lib.Oracle(sus.Lb), sus, W)
     r1 = mtube.bi_timestep(step)
     check_step(r1, sus, True)
     slip0 = r1["history"][0]
@@ -42,7 +43,7 @@ def test_two_steps_generated_mesh(oracle_lib):
 def test_one_step_reference_mesh(oracle_lib):
     from rbc3d_b200 import cases
     sus, W, vbkg = cases.minicase(MESH, nlat0=6)
-    step = mtube.OracleStep(oracle_lib.Oracle(sus.Lb), sus, W, vbkg)
+    step = harness.OracleStep(oracle_lib.Oracle(sus.Lb), sus, W, vbkg)
     r = mtube.bi_timestep(step)
     check_step(r, sus, True)
     # 1328 vertices / 2404 triangles: an open cylinder has 2 V - F = 252 boundary vertices = two end rings of 126 that

@@ -66,7 +66,8 @@ def test_noslip_solve_on_the_oracle(oracle_lib, with_cells):
     orc.set_walls(W)
     orc.prepare_sing_int_on_walls()
     vbkg = np.array([0.0, 0.0, 8.0])                                                         # minicase, mtube.F90
-    rv, mv, st = noslip.oracle_backend(orc, vbkg, cells=with_cells)
+    from oracle import harness
+    rv, mv, st = harness.noslip_backend(orc, vbkg, cells=with_cells)
     s = noslip.WallNoSlipSolver(W, LB, rv, mv, st)
     slip0 = rv()
     f, niter, hist, slip = s.solve(rtol=1e-3, maxit=60)

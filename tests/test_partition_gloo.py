@@ -90,7 +90,8 @@ def _noslip_worker(rank, world, port, out):
         dist.all_reduce(t)                                      # TargetList_CollectArray(tlist_wall, 3, v)
         return t.numpy()
 
-    s = noslip.WallNoSlipSolver(W, sus.Lb, *noslip.oracle_backend(orc, mtube.VBKG, active=act, collect=collect))
+    from oracle import harness
+    s = noslip.WallNoSlipSolver(W, sus.Lb, *harness.noslip_backend(orc, mtube.VBKG, active=act, collect=collect))
     f, niter, hist, slip = s.solve()                            # GMRES runs redundantly on every rank (PETSC_COMM_SELF)
     np.savez(out % rank, f=f, niter=niter, hist=np.array(hist), slip=slip)
     dist.destroy_process_group()
@@ -111,7 +112,8 @@ def test_two_rank_wall_noslip_solve_equals_single_rank(tmp_path, oracle_lib):
     orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
     orc.set_walls(W)
     orc.prepare_sing_int_on_walls()
-    f, niter, hist, slip = noslip.WallNoSlipSolver(W, sus.Lb, *noslip.oracle_backend(orc, mtube.VBKG)).solve()
+    from oracle import harness
+    f, niter, hist, slip = noslip.WallNoSlipSolver(W, sus.Lb, *harness.noslip_backend(orc, mtube.VBKG)).solve()
     assert niter == int(r0["niter"])
     assert np.allclose(r0["hist"], hist, rtol=1e-9)
     assert np.linalg.norm(r0["f"] - f) < 1e-9 * np.linalg.norm(f)

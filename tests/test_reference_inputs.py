@@ -89,7 +89,8 @@ def test_carotid_web_walls_on_the_oracle(oracle_lib):
         assert np.abs(v - 0.3 * ref).max() < 1e-12 * np.abs(ref).max()
     # a few GMRES iterations of the wall solve on a uniform slip reduce the residual monotonically
     W.f[:] = 0.0
-    rv, mv, st = noslip.oracle_backend(orc, [0.0, 0.0, 8.0], cells=False)
+    from oracle import harness
+    rv, mv, st = harness.noslip_backend(orc, [0.0, 0.0, 8.0], cells=False)
     s = noslip.WallNoSlipSolver(W, Lb, rv, mv, st)
     assert s.dof == 3 * (W.NV - int((v2v0 > 0).sum()))
     _, niter, hist, _ = s.solve(rtol=1e-3, maxit=8)

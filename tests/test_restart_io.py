@@ -53,7 +53,8 @@ def test_round_trip_and_state(tmp_path, oracle_lib):
     assert np.abs(sus2.spx - sus.spx).max() < 1e-9
     # and runs: one time step's boundary-integral work from the restart
     W2.f[:] = 0.0
-    r = mtube.bi_timestep(mtube.OracleStep(oracle_lib.Oracle(sus2.Lb), sus2, W2, vbkg))
+    from oracle import harness
+    r = mtube.bi_timestep(harness.OracleStep(oracle_lib.Oracle(sus2.Lb), sus2, W2, vbkg))
     assert 0 < r["wall_iterations"] <= 60 and r["history"][-1] < 1e-3 * r["history"][0]
 
 
