@@ -14,7 +14,7 @@
  * separately in NumPy, straight from the Fortran, that agrees with this one to
  * round-off (singular / near-singular integrals, projection and the whole of
  * AddIntOnRbcs per target: tests/test_oracle_singint_numpy.py; Duffy rule and the
- * wall loop: tests/test_oracle_walls_numpy.py; PME: rbc3d_b200/slabpme.py +
+ * wall loop: tests/test_oracle_walls_numpy.py; PME: oracle/slabpme.py +
  * tests/test_slab_pme.py).  The one output of the reference that its tree ships,
  * SickleCell.dat, pins the Gauss grid, the point order and the SH truncation
  * (tests/test_reference_golden.py).  Nothing here was checked against an

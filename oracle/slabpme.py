@@ -1,8 +1,10 @@
-"""NumPy model of the PME part of the operator with the SLAB-DECOMPOSED transform of the reference:
+"""TEST INFRASTRUCTURE / DESIGN MODEL, NOT PRODUCT CODE (lives under oracle/ with the other CPU restatements).
+
+NumPy model of the PME part of the operator with the SLAB-DECOMPOSED transform of the reference:
 the executable specification of the multi-GPU PME transpose path (next round: cuFFT 2-D per z-slab + all-to-all over
 NVLink + 1-D FFT per y-slab), checked on CPU against the oracle and, over two gloo ranks, against the single-rank
 result (tests/test_slab_pme.py).  The CUDA library of this round sums full meshes with one all-reduce and transforms
-redundantly on every rank; this module is harness / design code, not on the product path.
+redundantly on every rank; nothing under rbc3d_b200/ imports this module.
 
 Restated here, each citing the reference:
 * ``bspline_func``        BSplineFunc, ModBasicMath.F90:392-417 (vectorised over points)

@@ -1,5 +1,5 @@
 """The slab-decomposed PME transform of the reference (ModPFFTW.F90: z-slabs -> all-to-all -> y-slabs and back) as an
-executable NumPy specification (rbc3d_b200/slabpme.py) -- SURVEY.md 8(e) (3), the multi-GPU transpose path planned for the
+executable NumPy specification (oracle/slabpme.py) -- SURVEY.md 8(e) (3), the multi-GPU transpose path planned for the
 next round.  Checked here against the oracle's PME (single rank) and, slab-decomposed, in process and over two gloo
 ranks, against the single-rank transform."""
 import os
@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from rbc3d_b200 import slabpme
+from oracle import slabpme
 from tests import util
 
 LB = np.array([3.0, 2.5, 2.0])
