@@ -368,7 +368,7 @@ def test_edge_cases_empty_inactive_and_zero_inputs(oracle_lib):
     target list (rows untouched), zero densities (zero out), c1 = c2 = 0."""
     from rbc3d_b200.capi import TL_CELLS, TL_RAW
     from rbc3d_b200.ewald import EwaldOperator
-    sus = util.small_suspension(2, nlat0=4)
+    sus = util.small_suspension(2, nlat0=6)          # 18 x 36 mesh: a size the GPU suite has run
     op = EwaldOperator(sus.Lb)
     act = np.zeros(sus.npoint, np.int32)
     op.set_suspension(sus, active=act)
