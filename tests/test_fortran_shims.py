@@ -1,0 +1,63 @@
+"""The ISO_C_BINDING shims under fortran/ cannot be compiled in this image (no Fortran compiler), so their interface
+blocks are checked statically against include/rbc3d.h: every bind(C) name is a declared entry point, the argument counts
+agree, and an argument is passed by VALUE in Fortran exactly where the C prototype takes a scalar (type(c_ptr) handles by value
+where it takes a pointer)."""
+import glob
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def c_prototypes():
+    txt = open(os.path.join(ROOT, "include", "rbc3d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(rbc3d_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        args = [] if args in ([""], ["void"]) else args
+        out[m.group(1)] = ["*" in a or "[" in a for a in args]            # True = pointer / array parameter
+    return out
+
+
+def fortran_interfaces():
+    out = {}
+    for fn in sorted(glob.glob(os.path.join(ROOT, "fortran", "*.F90"))):
+        src = open(fn).read()
+        src = re.sub(r"&\s*\n\s*&?", " ", src)                           # join continuation lines
+        for m in re.finditer(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)\s*result\((\w+)\)(.*?)end function",
+                             src, flags=re.S | re.I):
+            args = [a.strip().lower() for a in m.group(2).split(",") if a.strip()]
+            body = m.group(5)
+            byval, cptr = set(), set()
+            for line in body.splitlines():
+                line = line.split("!")[0]
+                if "::" not in line:
+                    continue
+                decl, names = line.split("::")[0], line.split("::")[1]
+                names = [re.sub(r"\(.*", "", n).strip().lower() for n in re.split(r",(?![^()]*\))", names)]
+                if re.search(r",\s*value\b", decl, flags=re.I):
+                    byval.update(names)
+                if re.search(r"type\(c_ptr\)", decl, flags=re.I):
+                    cptr.update(names)
+            out[m.group(3)] = (os.path.basename(fn), args, byval, cptr)
+    return out
+
+
+def test_interfaces_match_the_header():
+    protos, ifaces = c_prototypes(), fortran_interfaces()
+    assert len(protos) >= 55 and len(ifaces) >= 30
+    for cname, (fn, args, byval, cptr) in ifaces.items():
+        assert cname in protos, f"{fn}: {cname} is not declared in include/rbc3d.h"
+        ptr = protos[cname]
+        assert len(args) == len(ptr), f"{fn}: {cname} has {len(args)} arguments, the header {len(ptr)}"
+        for a, is_ptr in zip(args, ptr):
+            # a C pointer is either a Fortran array / scalar passed by reference, or a type(c_ptr) passed by value
+            # (an opaque handle or a host address); a C scalar is a Fortran scalar with the VALUE attribute
+            f_ptr = (a not in byval) or (a in cptr)
+            assert f_ptr == is_ptr, f"{fn}: {cname}({a}): by value = {a in byval}, c_ptr = {a in cptr}, C pointer = {is_ptr}"
+    # the operator entry points the replaced modules forward to must all be bound
+    for need in ("rbc3d_add_int_on_rbcs", "rbc3d_add_int_on_walls", "rbc3d_pme_distrib_source", "rbc3d_pme_transform",
+                 "rbc3d_pme_add_interp_vel", "rbc3d_cells_set_geometry", "rbc3d_cells_set_density", "rbc3d_walls_set",
+                 "rbc3d_wall_prepare_sing", "rbc3d_sing_int_on_wall", "rbc3d_ctx_create", "rbc3d_ctx_destroy"):
+        assert need in ifaces, need
