@@ -280,6 +280,29 @@ module ModB200
       import
       type(c_ptr) :: msg
     end function
+    ! Pin host arrays that are passed every matvec (slist_rbc%g, v, ...): call once with c_loc(array) and its size in
+    ! bytes, e.g. ierr = rbc3d_host_register(c_loc(slist_rbc%g), int(8*size(slist_rbc%g), c_size_t))
+    function rbc3d_host_register(ptr, bytes) bind(C, name="rbc3d_host_register") result(ierr)
+      import
+      type(c_ptr), value :: ptr
+      integer(c_size_t), value :: bytes
+      integer(c_int) :: ierr
+    end function
+    function rbc3d_host_unregister(ptr) bind(C, name="rbc3d_host_unregister") result(ierr)
+      import
+      type(c_ptr), value :: ptr
+      integer(c_int) :: ierr
+    end function
+    ! SetEwaldPrms (ModConf.F90:348-408) as the library derives it (host arithmetic): rc and Nb for a box
+    function rbc3d_set_ewald_prms(Lb, alpha, eps, P, nranks, rc, Nb) bind(C, name="rbc3d_set_ewald_prms") result(ierr)
+      import
+      real(c_double) :: Lb(3)
+      real(c_double), value :: alpha, eps
+      integer(c_int), value :: P, nranks
+      real(c_double) :: rc
+      integer(c_int) :: Nb(3)
+      integer(c_int) :: ierr
+    end function
   end interface
 
 contains
