@@ -61,3 +61,28 @@ def test_interfaces_match_the_header():
                  "rbc3d_pme_add_interp_vel", "rbc3d_cells_set_geometry", "rbc3d_cells_set_density", "rbc3d_walls_set",
                  "rbc3d_wall_prepare_sing", "rbc3d_sing_int_on_wall", "rbc3d_ctx_create", "rbc3d_ctx_destroy"):
         assert need in ifaces, need
+
+
+def test_ctypes_signatures_match_the_header():
+    """rbc3d_b200/capi.py SIGNATURES (the ctypes stub INTEGRATION.md points other host languages at): same set of
+    entry points as the header, same argument counts, pointer types exactly where the prototype has a pointer, double
+    vs integer scalars as declared."""
+    import ctypes as C
+    from rbc3d_b200 import capi
+    txt = open(os.path.join(ROOT, "include", "rbc3d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(rbc3d_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if args in ([""], ["void"]) else args
+    assert set(protos) == set(capi.SIGNATURES)
+    for name, (_, argtypes) in capi.SIGNATURES.items():
+        cargs = protos[name]
+        assert len(argtypes) == len(cargs), name
+        for t, a in zip(argtypes, cargs):
+            is_ptr = "*" in a or "[" in a
+            t_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer)
+            assert t_ptr == is_ptr, (name, a, t)
+            if not is_ptr:
+                want = C.c_double if a.startswith("double") else (C.c_size_t if a.startswith("size_t") else C.c_int)
+                assert t is want, (name, a, t)
