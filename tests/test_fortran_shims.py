@@ -40,14 +40,14 @@ def fortran_interfaces():
                     byval.update(names)
                 if re.search(r"type\(c_ptr\)", decl, flags=re.I):
                     cptr.update(names)
-            out[m.group(3)] = (os.path.basename(fn), args, byval, cptr)
+            out[m.group(1).lower()] = (os.path.basename(fn), args, byval, cptr, m.group(3))
     return out
 
 
 def test_interfaces_match_the_header():
     protos, ifaces = c_prototypes(), fortran_interfaces()
     assert len(protos) >= 55 and len(ifaces) >= 30
-    for cname, (fn, args, byval, cptr) in ifaces.items():
+    for fname, (fn, args, byval, cptr, cname) in ifaces.items():
         assert cname in protos, f"{fn}: {cname} is not declared in include/rbc3d.h"
         ptr = protos[cname]
         assert len(args) == len(ptr), f"{fn}: {cname} has {len(args)} arguments, the header {len(ptr)}"
@@ -60,7 +60,7 @@ def test_interfaces_match_the_header():
     for need in ("rbc3d_add_int_on_rbcs", "rbc3d_add_int_on_walls", "rbc3d_pme_distrib_source", "rbc3d_pme_transform",
                  "rbc3d_pme_add_interp_vel", "rbc3d_cells_set_geometry", "rbc3d_cells_set_density", "rbc3d_walls_set",
                  "rbc3d_wall_prepare_sing", "rbc3d_sing_int_on_wall", "rbc3d_ctx_create", "rbc3d_ctx_destroy"):
-        assert need in ifaces, need
+        assert need in {v[4] for v in ifaces.values()}, need
 
 
 def test_ctypes_signatures_match_the_header():
@@ -86,3 +86,32 @@ def test_ctypes_signatures_match_the_header():
             if not is_ptr:
                 want = C.c_double if a.startswith("double") else (C.c_size_t if a.startswith("size_t") else C.c_int)
                 assert t is want, (name, a, t)
+
+
+def test_shim_calls_have_the_interface_arity():
+    """every call of an rbc3d_* function in the shim procedures passes as many arguments as its interface declares"""
+    ifaces = fortran_interfaces()
+    ncalls = 0
+    for fn in sorted(glob.glob(os.path.join(ROOT, "fortran", "*.F90"))):
+        src = open(fn).read()
+        src = re.sub(r"&\s*\n\s*&?", " ", src)
+        src = "\n".join(line.split("!")[0] if "bind(C" not in line else "" for line in src.splitlines())
+        for m in re.finditer(r"=\s*(rbc3d_\w+)\s*\(", src):
+            name = m.group(1).lower()
+            depth, i, nargs, any_char = 1, m.end(), 1, False
+            while depth:
+                ch = src[i]
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    nargs += 1
+                elif not ch.isspace():
+                    any_char = True
+                i += 1
+            nargs = nargs if any_char else 0
+            assert name in ifaces, (os.path.basename(fn), name)
+            assert nargs == len(ifaces[name][1]), (os.path.basename(fn), name, nargs, len(ifaces[name][1]))
+            ncalls += 1
+    assert ncalls >= 25
