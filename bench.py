@@ -526,6 +526,7 @@ def run_gpu(args):
         if world == 1 and not args.profile and not args.no_mtube:
             # the other half of the metric on BASELINE.json configs[0]; a child process, after this one released the GPU
             out["mtube"] = mtube_child(args)
+            out["walls"] = child_block(args, "--walls-only", "walls")       # configs[4], wall-dominated operator
     except Exception as exc:   # nothing after the timed regions may cost the line
         out.setdefault("mtube", {"error": str(exc)[:300]})
     print(json.dumps(out))
@@ -593,9 +594,10 @@ def run_mtube(args):
     return 0
 
 
-def mtube_child(args):
-    """Run --mtube-only in a child process (after the main operator has released the GPU) and return its object."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--mtube-only", "--seed", str(args.seed), "--mtube-steps",
+def child_block(args, flag, key):
+    """Run a side block (--mtube-only / --walls-only) in a child process, after the main operator has released the GPU,
+    and return its object; a failure there becomes {"error": ...} instead of costing the headline line."""
+    cmd = [sys.executable, os.path.abspath(__file__), flag, "--seed", str(args.seed), "--mtube-steps",
            str(args.mtube_steps)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR",
                                                             "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
@@ -603,10 +605,80 @@ def mtube_child(args):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
         for line in reversed(r.stdout.strip().splitlines()):
             if line.startswith("{"):
-                return json.loads(line)["mtube"]
+                return json.loads(line)[key]
         return {"error": ("rc=%d " % r.returncode) + r.stderr.strip()[-300:]}
     except Exception as exc:
         return {"error": str(exc)[:300]}
+
+
+def mtube_child(args):
+    return child_block(args, "--mtube-only", "mtube")
+
+
+def run_walls(args):
+    """BASELINE.json configs[4] ("large complex wall mesh ... wall-dominated operator") at the size of
+    examples/carotid_web with generated walls (17 448 vertices / 34 560 triangles in two interacting tubes, box
+    10.5 x 10.5 x 30, PME grid 48 x 48 x 136; the Exodus meshes are not on the GPU box): the wall matvec of the no-slip
+    solve (operator #4: c1 = 1/4pi, wall tractions -> wall vertices; self-interaction matrices + wall-wall direct loop +
+    PME) through the C ABI with host buffers, the CPU oracle beside it, and their agreement.  Child process of the bench."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.capi import TL_WALLS, Rbc3dError
+    from rbc3d_b200.ewald import EwaldOperator
+    Lb = np.array([10.5, 10.5, 30.0])
+    W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02,
+                         seed=args.seed)
+    try:
+        op = EwaldOperator(Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
+    except Rbc3dError as exc:
+        raise SystemExit("bench.py --walls-only: no CUDA device; the product has no CPU path (%s)" % str(exc)[:160])
+    t0 = time.perf_counter()
+    op.set_walls(W)
+    op.PrepareSingIntOnWall()
+    t_prep = time.perf_counter() - t0
+    rng = np.random.default_rng(args.seed)
+    fs = [rng.normal(size=W.f.shape) for _ in range(4)]
+    nrep = 5
+    for f in fs[:2]:                                            # warm-up: pair lists, cuFFT plans
+        op.set_wall_traction(f)
+        v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+    l0 = op.launch_count()
+    t0 = time.perf_counter()
+    for k in range(nrep * len(fs)):
+        op.set_wall_traction(fs[k % len(fs)])                   # wall%f = f of every GMRES iteration (ModNoSlip.F90:273-278)
+        v = op.apply(C1_RHS, 0.0, TL_WALLS, cells=False, walls=True)
+    t_gpu = (time.perf_counter() - t0) / (nrep * len(fs))
+    launches = op.launch_count() - l0
+    rowptr, _, _ = op.wall_matrix()
+    Nb = list(op.Nb)
+    op.close()
+    out = {"workload": "wall-dominated operator at the size of examples/carotid_web: %d + %d vertices, %d + %d triangles "
+                       "(generated tubes of radius 4.9 and 4.0, 0.9 < rc apart), box 10.5x10.5x30, PME grid %s"
+                       % (W.nvert[0], W.nvert[1], W.nele[0], W.nele[1], "x".join(str(n) for n in Nb)),
+           "step": "operator #4 of the wall no-slip solve (set traction + AddIntOnWalls + PME, host buffers through the C ABI)",
+           "wall_matvecs_per_s": 1.0 / t_gpu, "ms_per_matvec": t_gpu * 1e3, "matrix_blocks_3x3": int(rowptr[-1]),
+           "prepare_sing_int_on_wall_ms": t_prep * 1e3, "gpu_launches": int(launches), "steps": nrep * len(fs)}
+    if not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        orc = oracle.Oracle(Lb)
+        orc.set_walls(W, ncell=0)
+        t0 = time.perf_counter()
+        orc.prepare_sing_int_on_walls()
+        t_prep_cpu = time.perf_counter() - t0
+        tl = orc.wall_targets()
+        orc.set_wall_traction(fs[0])
+        orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+        t0 = time.perf_counter()
+        for f in fs:
+            orc.set_wall_traction(f)
+            ref = orc.apply(C1_RHS, 0.0, tl, cells=False, walls=True)
+        t_cpu = (time.perf_counter() - t0) / len(fs)
+        out["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "wall matvecs/s", "ms_per_matvec": t_cpu * 1e3,
+                               "prepare_sing_int_on_wall_ms": t_prep_cpu * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "the same operator in full on the CPU oracle (OpenMP, all host cores)"}
+        out["parity_vs_oracle"] = {"rel_l2_velocity": float(np.linalg.norm(v - ref) / np.linalg.norm(ref))}
+    print(json.dumps({"walls": out}))
+    return 0
 
 
 def world_value(v):
@@ -635,9 +707,12 @@ def main():
     ap.add_argument("--no-mtube", action="store_true", help="skip the minicase time-step block (configs[0])")
     ap.add_argument("--mtube-only", action="store_true", help="only the minicase time-step block, one JSON object")
     ap.add_argument("--mtube-steps", type=int, default=4)
+    ap.add_argument("--walls-only", action="store_true", help="only the wall-dominated operator block, one JSON object")
     args = ap.parse_args()
     if args.mtube_only:
         return run_mtube(args)
+    if args.walls_only:
+        return run_walls(args)
     if args.warmup < 3 and args.impl == "b200" and not args.profile:
         args.warmup = 3   # timing hygiene: at least 3 warm-up steps
     if args.profile:

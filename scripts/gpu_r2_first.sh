@@ -15,6 +15,7 @@ done
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2a_pytest.log
 # 3+4. the mtube block alone (child process of the bench), then the bench with parity_full_size and mtube in its line
 timeout 600 python bench.py --mtube-only > gpurun_out/r2a_mtube.json 2> gpurun_out/r2a_mtube.err
+timeout 600 python bench.py --walls-only > gpurun_out/r2a_walls.json 2> gpurun_out/r2a_walls.err
 timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/r2a_bench_4096.json 2> gpurun_out/r2a_bench_4096.err
 # 5. (with gpurun --gpus 2) the wall paths over two ranks:
 #    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \

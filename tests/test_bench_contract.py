@@ -119,3 +119,53 @@ def test_mtube_block_python_path_with_a_stand_in_library(monkeypatch, capsys, or
     assert cb["kind"] == "port" and cb["unit"] == "timesteps/s" and cb["wall_gmres_iterations"] == m["wall_gmres_iterations"]
     par = m["parity_vs_oracle"]
     assert all(par["same_iterations"]) and max(par["rel_l2_cell_velocity"]) < 1e-12      # the stand-in IS the oracle
+
+
+def test_walls_block_python_path_with_a_stand_in_library(monkeypatch, capsys, oracle_lib):
+    """run_walls (configs[4], wall-dominated operator) end to end without a GPU: the library replaced by an
+    oracle-backed stand-in, so that the block's own logic and JSON keys are exercised here."""
+    import argparse
+    import importlib.util
+    import numpy as np
+    from rbc3d_b200 import ewald
+
+    class StandIn:
+        def __init__(self, Lb, device=-1):
+            self.orc = oracle_lib.Oracle(Lb)
+            self.Nb = self.orc.Nb
+            self.n = 0
+
+        def set_walls(self, W):
+            self.W = W
+            self.orc.set_walls(W, ncell=0)
+
+        def PrepareSingIntOnWall(self):
+            self.orc.prepare_sing_int_on_walls()
+
+        def set_wall_traction(self, f):
+            self.orc.set_wall_traction(f)
+
+        def apply(self, c1, c2, tlist, cells=True, walls=False):
+            self.n += 1
+            return self.orc.apply(c1, c2, self.orc.wall_targets(), cells=cells, walls=walls)
+
+        def wall_matrix(self):
+            n = sum(len(self.orc.wall_matrix(w)[1]) for w in range(self.W.nwall))
+            return np.array([0, n]), None, None
+
+        def launch_count(self):
+            return 7 * self.n
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(ewald, "EwaldOperator", StandIn)
+    spec = importlib.util.spec_from_file_location("bench_mod3", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.run_walls(argparse.Namespace(seed=161269, no_cpu_baseline=False)) == 0
+    w = json.loads(capsys.readouterr().out.strip().splitlines()[-1])["walls"]
+    assert w["wall_matvecs_per_s"] > 0 and w["steps"] == 20 and w["gpu_launches"] == 140
+    assert w["matrix_blocks_3x3"] > 1_000_000 and "17448" not in w["workload"] and "14520 + 2928" in w["workload"]
+    assert w["cpu_baseline"]["kind"] == "port" and w["cpu_baseline"]["value"] > 0
+    assert w["parity_vs_oracle"]["rel_l2_velocity"] < 1e-12              # the stand-in IS the oracle
