@@ -32,21 +32,46 @@ def read_wall_mesh(path: str):
 
 
 def read_tube_in(path: str) -> dict:
-    """Leading entries of tube.in (one value per line, '!' starts a comment)."""
-    vals = []
+    """Input/tube.in as ReadConfig consumes it (ModConf.F90:239-273): list-directed reads, one READ statement per
+    record -- a scalar takes the first value of the next non-blank record ('!' ends the data of a line), an array of
+    nCellTypes values (viscRat, refRad) takes as many values as it needs, over several records if necessary."""
+    recs = []
     with open(path) as fh:
         for line in fh:
-            t = line.split("!")[0].strip()
+            t = line.split("!")[0].replace(",", " ").split()
             if t:
-                vals.append(t)
-    it = iter(vals)
-    out = {"alpha_Ewd": float(next(it).replace("D", "E")), "eps_Ewd": float(next(it).replace("D", "E")),
-           "PBspln_Ewd": int(next(it))}
-    ntypes = int(next(it))
-    out["nCellTypes"] = ntypes
-    out["viscRat"] = [float(next(it).replace("D", "E")) for _ in range(ntypes)]
-    out["refRad"] = float(next(it).replace("D", "E"))
-    out["Deflate"] = next(it).lower().startswith(".t")
+                recs.append(t)
+    it = iter(recs)
+
+    def num(tok):
+        return float(tok.upper().replace("D", "E"))
+
+    def logical(tok):
+        return tok.strip(".").lower().startswith("t")
+
+    def scalar(conv):
+        return conv(next(it)[0])
+
+    def array(n, conv):
+        vals = []
+        while len(vals) < n:
+            vals += next(it)
+        return [conv(v) for v in vals[:n]]
+
+    out = {"alpha_Ewd": scalar(num), "eps_Ewd": scalar(num), "PBspln_Ewd": scalar(lambda t: int(num(t)))}
+    n = out["nCellTypes"] = scalar(lambda t: int(num(t)))
+    out["viscRat"] = array(n, num)
+    out["refRad"] = array(n, num)
+    out["Deflate"] = scalar(logical)
+    out["pGradTar"] = [scalar(num) for _ in range(3)]
+    out["Nt"] = scalar(lambda t: int(num(t)))
+    out["Ts"] = scalar(num)
+    for k in ("cell_out", "wall_out", "pgrad_out", "flow_out", "ftot_out", "restart_out"):
+        out[k] = scalar(lambda t: int(num(t)))
+    out["restart_file"] = scalar(lambda t: t.strip("'\""))
+    out["epsDist"], out["ForceCoef"], out["viscRatThresh"] = scalar(num), scalar(num), scalar(num)
+    out["rigidsep"] = scalar(logical)
+    out["fmags"] = scalar(num)
     return out
 
 

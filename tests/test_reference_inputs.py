@@ -13,7 +13,9 @@ def test_tube_in_and_wall_mesh_readers():
     from rbc3d_b200 import cases
     cfg = cases.read_tube_in(os.path.join(REF, "tube.in"))
     assert cfg["alpha_Ewd"] == 0.44 and cfg["eps_Ewd"] == 1e-3 and cfg["PBspln_Ewd"] == 8
-    assert cfg["nCellTypes"] == 1 and cfg["viscRat"] == [1.0] and cfg["Deflate"] is False
+    assert cfg["nCellTypes"] == 1 and cfg["viscRat"] == [1.0] and cfg["refRad"] == [1.0] and cfg["Deflate"] is False
+    assert cfg["Nt"] == 10000 and cfg["Ts"] == 0.0008 and cfg["epsDist"] == 0.02 and cfg["rigidsep"] is False
+    assert cfg["restart_file"] == "D/restart.LATEST.dat"
     x, e2v = cases.read_wall_mesh(os.path.join(REF, "new_cyl_D6_L13_33.e"))
     assert x.shape == (3, 1328) and e2v.shape == (3, 2404)
     assert e2v.min() == 1 and e2v.max() == 1328
@@ -95,3 +97,24 @@ def test_carotid_web_walls_on_the_oracle(oracle_lib):
     assert s.dof == 3 * (W.NV - int((v2v0 > 0).sum()))
     _, niter, hist, _ = s.solve(rtol=1e-3, maxit=8)
     assert niter == 8 and np.all(np.diff(hist) < 0) and hist[-1] < 0.5 * hist[0]
+
+
+def test_every_shipped_tube_in_and_wall_mesh_reads():
+    """all example inputs of the reference parse: tube.in heads (alpha = 0.44, eps = 1e-3, P = 8 everywhere)
+    and every Tri3 Exodus wall mesh under examples/ and sample_files/."""
+    import glob
+    from rbc3d_b200 import cases
+    tubes = sorted(glob.glob("/root/reference/examples/*/Input/tube.in"))
+    assert len(tubes) >= 5
+    for t in tubes:
+        cfg = cases.read_tube_in(t)
+        assert (cfg["alpha_Ewd"], cfg["eps_Ewd"], cfg["PBspln_Ewd"]) == (0.44, 1e-3, 8), t
+        assert cfg["nCellTypes"] == len(cfg["viscRat"]) >= 1 and all(v == 1.0 for v in cfg["viscRat"]), t
+    meshes = sorted(set(glob.glob("/root/reference/examples/*/Input/*.e") + glob.glob("/root/reference/sample_files/*/*/*.e")))
+    assert len(meshes) >= 10
+    for m in meshes:
+        x, e2v = cases.read_wall_mesh(m)
+        assert x.shape[0] == 3 and e2v.shape[0] == 3 and e2v.min() == 1 and e2v.max() == x.shape[1], m
+        xe = x[:, e2v - 1]
+        area = 0.5 * np.linalg.norm(np.cross((xe[:, 1] - xe[:, 0]).T, (xe[:, 2] - xe[:, 0]).T), axis=1)
+        assert np.all(area > 0), m                                       # no degenerate triangles
