@@ -46,6 +46,11 @@ FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
 FLOPS_PATCH_CACHED = 110.0  # cached matvec path: one 3-variable bicubic (96) + 7 FMAs per patch point
 
 
+PARTITION_TEXT = ("targets, singular/pair work, geometry caches and PME spreading by owned cell block; densities uploaded "
+                  "1/world per rank + ncclAllGather; meshes and velocities summed with ncclAllReduce; the PME chain "
+                  "overlaps the real-space kernels on a second stream (stage_ms overlap)")
+
+
 def n_side_of(cells: int) -> int:
     n = round(cells ** (1.0 / 3.0))
     if n ** 3 != cells:
@@ -122,8 +127,7 @@ def cpu_operator_sample(sus, sample_cells: int, spread_stride: int = 1, threads:
     reference MPI rank works on its slab); both are extrapolated linearly.
     Returns (seconds per full matvec, detail dict)."""
     from oracle import oracle  # the one place bench.py runs oracle/: cpu_baseline and --impl reference
-    if threads:
-        oracle.lib().orc_set_num_threads(int(threads))
+    oracle.lib().orc_set_num_threads(int(threads or host_threads()))   # torchrun exports OMP_NUM_THREADS=1
     cores = int(oracle.lib().orc_num_threads())
     orc = oracle.Oracle(sus.Lb).set_cells(sus)
     npc = sus.nlat * sus.nlon
@@ -182,35 +186,84 @@ def sample_text(d, ncell):
             f"{ncell}); {cpu_s:.1f} s of CPU work per sample")
 
 
+REF_CACHE_DIR = os.path.join(ROOT, "oracle", "_cache")
+
+
+def ref_cache_path(cells, seed):
+    return os.path.join(REF_CACHE_DIR, "ref_matvec_c%d_s%d.npy" % (cells, seed))
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def bench_config(sus, Nb, alpha, eps, P, rc, Nc, seed):
+    """The workload description both arms print (the driver compares them key by key)."""
+    return {"workload": workload_name(sus.ncell, Nb), "cells": sus.ncell, "points": sus.npoint, "alpha": alpha,
+            "eps": eps, "P": P, "rc": rc, "Nc": [int(v) for v in Nc], "visc_ratio": 5.0, "seed": seed}
+
+
 def run_reference(args):
+    """The CPU arm: ONE complete application of operator #2 at the full size (all targets of all cells) on the CPU
+    restatement of the reference (oracle/, "port": the Fortran + MPI + PETSc + FFTW reference cannot be built in this
+    image), every host thread, timed per stage with the wall clock.  Nothing is extrapolated: ``steps`` is the number of
+    applications actually run (1; 0 warm-up) and ``ms_per_step`` their measured time.  The product library is not loaded
+    in this process (parameters come from the oracle's own SetEwaldPrms).  The result is kept under oracle/_cache/ so
+    that the GPU arm that follows on the same box can check ALL its targets against it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from rbc3d_b200 import synth
-    from rbc3d_b200.ewald import SetEwaldPrms
+    from oracle import oracle
+    from rbc3d_b200 import synth          # NumPy only: does not load librbc3d_b200.so
+    oracle.build()
+    threads = host_threads()              # torchrun exports OMP_NUM_THREADS=1: set the team size explicitly
+    oracle.lib().orc_set_num_threads(int(threads))
+    cores = int(oracle.lib().orc_num_threads())
     n_side = n_side_of(args.cells)
     sus = synth.make_suspension(n_side, seed=args.seed, with_f=False)
-    _, Nb = SetEwaldPrms(sus.Lb)
-    times = []
-    detail = None
-    for it in range(args.warmup + args.steps):
-        t, detail = cpu_operator_sample(sus, args.ref_sample_cells, args.ref_spread_stride)
-        if it >= args.warmup:
-            times.append(t)
-    detail.pop("_v_sample", None)
-    sec = float(np.mean(times))
+    orc = oracle.Oracle(sus.Lb).set_cells(sus)
+    npc = sus.nlat * sus.nlon
+    stage = {}
+
+    def timed(name, fn):
+        t0 = time.perf_counter()
+        r = fn()
+        stage[name] = time.perf_counter() - t0
+        return r
+
+    tl = orc.cell_targets()
+    wall0 = time.perf_counter()
+    v = timed("add_int_on_rbcs(cell list, pairs, singular, near-singular, linear)",
+              lambda: orc.add_int_on_rbcs(0.0, C2_MATVEC, tl))
+    gw, Bp = sus.weighted(sus.g), np.repeat(sus.Bcoef, npc)
+    timed("pme_distrib_source", lambda: orc.pme_distrib(0.0, C2_MATVEC, sus.x, None, gw, sus.a3, Bp))
+    timed("pme_transform(9 fwd + 3 inv FFT, scaling)", orc.pme_transform)
+    timed("pme_add_interp_vel", lambda: orc.pme_interp(tl, v))
+    sec = time.perf_counter() - wall0
+    try:
+        os.makedirs(REF_CACHE_DIR, exist_ok=True)
+        np.save(ref_cache_path(sus.ncell, args.seed), v)
+        with open(ref_cache_path(sus.ncell, args.seed) + ".json", "w") as fh:
+            json.dump({"seconds": sec, "cores": cores, "stage_s": stage}, fh)
+    except Exception:
+        pass
     val = 1.0 / sec
-    cb = {"value": val, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
-          "sample": sample_text(detail, sus.ncell), "detail": detail}
+    sample = ("one complete matvec: all %d targets of all %d cells, every cell a source, PME in full; nothing "
+              "extrapolated" % (sus.npoint, sus.ncell))
+    cb = {"value": val, "unit": "matvecs/s", "cores": cores, "kind": "port", "sample": sample,
+          "stage_s": stage}
     out = {"impl": "reference", "metric": "Ewald BI matvecs/s", "value": val, "unit": "matvecs/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+           "n_gpus": args.gpus, "steps": 1, "warmup": 0, "steps_requested": args.steps,
+           "warmup_requested": args.warmup, "ms_per_step": sec * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(sus.ncell, Nb), "cells": sus.ncell, "points": sus.npoint,
-                      "seed": args.seed},
+           "config": bench_config(sus, orc.Nb, orc.alpha, orc.eps, orc.P, orc.rc, orc.Nc, args.seed),
            "cpu_baseline": cb,
            "e2e": {"value": val, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
-    if not args.no_mtube:
+           "gpu_launches": 0, "extrapolated": False}
+    if args.ref_mtube:
         out["mtube"] = cpu_mtube(args)
     print(json.dumps(out))
     return 0
@@ -426,6 +479,7 @@ def run_gpu(args):
             # MyMatMult with the SH transforms and the Krylov vector on the device (rbc3d_solver_*):
             # only 2 x dof doubles cross PCIe here, none inside rbc3d_solver_gmres
             t_mm = float("nan")
+            its, t_solve, resid = None, float("nan"), None
             if dev_geom:
                 op.solver_setup(sus.nlat0, sus.detj)
                 u = np.random.default_rng(args.seed).uniform(-1.0, 1.0, op.solver_dof)
@@ -438,19 +492,31 @@ def run_gpu(args):
                     barrier()
                     tm.append(time.perf_counter() - t0)
                 t_mm = min(tm)
-            tt = torch.tensor([t_geom, min(t_rhs), t_mm], dtype=torch.float64, device="cuda")
+                # a REAL cell velocity solve at this size (Solve_RBC_Vel, ModVelSolver.F90:74-116: GMRES(30), rtol 1e-11,
+                # zero initial guess = the first step of a run): its iteration count replaces any assumption
+                op.SourceList_UpdateDensity(f=g_host)
+                rhs = op.solver_rhs((0.0, 0.0, 8.0))
+                barrier()
+                t0 = time.perf_counter()
+                _, its, hist = op.solver_gmres(rhs, rtol=1e-11)
+                barrier()
+                t_solve = time.perf_counter() - t0
+                resid = float(hist[-1] / hist[0]) if len(hist) and hist[0] > 0 else None
+            tt = torch.tensor([t_geom, min(t_rhs), t_mm, t_solve], dtype=torch.float64, device="cuda")
             if dist is not None:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_geom, t_rhs1, t_mm = float(tt[0]), float(tt[1]), float(tt[2])
-            its = GMRES_ITS_ASSUMED
+            t_geom, t_rhs1, t_mm, t_solve = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
+            its_used = its if its is not None else GMRES_ITS_ASSUMED
             timestep = {"geometry_splines": "device" if dev_geom else "host (uploaded)",
                         "geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
-                        "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations_assumed": its,
-                        "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its * e2e_s),
+                        "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations": its_used,
+                        "gmres_iterations_measured": its is not None, "gmres_relative_residual": resid,
+                        "gmres_solve_ms": t_solve * 1e3 if t_solve == t_solve else None,
+                        "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its_used * e2e_s),
                         "matmult_device_solver_ms": t_mm * 1e3,
-                        "bi_timesteps_per_s_device_solver": (1.0 / (t_geom + t_rhs1 + its * t_mm)) if t_mm == t_mm else None,
-                        "note": "boundary-integral part of one mtube step (membrane forces, SH transforms, GMRES "
-                                "vector algebra stay in the Fortran caller and are not included)"}
+                        "bi_timesteps_per_s_device_solver": (1.0 / (t_geom + t_rhs1 + t_solve)) if t_solve == t_solve else None,
+                        "note": "boundary-integral part of one mtube step (membrane forces stay in the Fortran caller); "
+                                "device_solver: rbc3d_solver_gmres, SH transforms and Krylov vectors on the GPU"}
         except Exception as exc:  # e.g. no room left for spline(f detJ) next to the caches
             timestep = {"error": str(exc)[:200]}
     h2d = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0)
@@ -484,38 +550,74 @@ def run_gpu(args):
                 "algorithmic_bytes_per_launch": (dom.get("gbs") or 0.0) * 1e9 * dom["ms"] * 1e-3,
                 "frac_fp64": dom.get("frac_fp64")}
 
+    # ---- parity at the benchmark's own size (the oracle as the checker, after every timed region) -----------------
+    # (1) when the CPU arm (--impl reference) ran before on this box, its complete result is under oracle/_cache/:
+    #     ALL targets are compared; (2) otherwise the complete operator at the targets of a sample of cells.
     cb = None
-    if world == 1 and not args.no_cpu_baseline:
-        tcpu, detail = cpu_operator_sample(sus, args.cpu_sample_cells)
+    parity = dict(full_size or {})
+    ref_full = None
+    try:
+        pth = ref_cache_path(sus.ncell, args.seed)
+        if os.path.exists(pth) and not args.profile:
+            ref_full = np.load(pth, mmap_mode="r")
+            if ref_full.shape != v_e2e.shape:
+                ref_full = None
+    except Exception:
+        ref_full = None
+    if ref_full is not None:
+        num = den = 0.0
+        worst = 0.0
+        step_ = 64 * sus.nlat * sus.nlon
+        for lo in range(0, N, step_):
+            r_ = np.asarray(ref_full[:, lo:lo + step_])
+            d_ = v_e2e[:, lo:lo + step_] - r_
+            n2, d2 = float((d_ * d_).sum()), float((r_ * r_).sum())
+            num, den = num + n2, den + d2
+            worst = max(worst, (n2 / d2) ** 0.5 if d2 > 0 else 0.0)
+        parity["oracle_rel_l2"] = (num / den) ** 0.5
+        parity["oracle_rel_l2_worst_64_cell_block"] = worst
+        parity["oracle_targets"] = int(N)
+        parity["oracle_source"] = "complete CPU matvec of the --impl reference run on this box (oracle/_cache)"
+        try:
+            with open(ref_cache_path(sus.ncell, args.seed) + ".json") as fh:
+                parity["oracle_full_matvec_s"] = json.load(fh).get("seconds")
+        except Exception:
+            pass
+    need_sample = (world == 1 and not args.no_cpu_baseline) or (ref_full is None and not args.no_cpu_baseline
+                                                                and not args.profile)
+    if need_sample:
+        ns_ = args.cpu_sample_cells if world == 1 else min(8, args.cpu_sample_cells)
+        tcpu, detail = cpu_operator_sample(sus, ns_)
         vs = detail.pop("_v_sample", None)
         if vs is not None:   # the oracle as the checker at the FULL size: complete operator at the sample's targets
             ref_n = float(np.linalg.norm(vs))
-            full_size = dict(full_size or {})
-            full_size["oracle_sample_rel_l2"] = float(np.linalg.norm(v_e2e[:, :vs.shape[1]] - vs) / ref_n)
-            full_size["oracle_sample"] = "all %d targets of the first %d cells, every cell a source, PME in full" % (
-                vs.shape[1], detail["sample_cells"])
-        cb = {"value": 1.0 / tcpu, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
-              "sample": sample_text(detail, sus.ncell), "detail": detail}
+            parity["oracle_sample_rel_l2"] = float(np.linalg.norm(v_e2e[:, :vs.shape[1]] - vs) / ref_n)
+            parity["oracle_sample_targets"] = int(vs.shape[1])
+        if world == 1:
+            cb = {"value": 1.0 / tcpu, "unit": "matvecs/s", "cores": detail["cores"], "kind": "port",
+                  "sample": sample_text(detail, sus.ncell), "extrapolated": True, "detail": detail}
+            if "oracle_full_matvec_s" in parity and parity["oracle_full_matvec_s"]:
+                cb["measured_full_matvec_s_of_reference_arm"] = parity["oracle_full_matvec_s"]
+    parity["n_gpus"] = world
+    parity["tolerance"] = 1e-10
+    vals_ = [parity[k] for k in ("oracle_rel_l2", "oracle_sample_rel_l2", "linearity_rel_l2") if parity.get(k) is not None]
+    parity["ok"] = bool(vals_) and all(v_ <= 1e-10 for v_ in vals_)
 
     out = {"metric": "Ewald BI matvecs/s", "value": world_value(1e3 / dev_ms), "unit": "matvecs/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
            "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(sus.ncell, op.Nb), "cells": sus.ncell, "points": N,
-                      "alpha": op.alpha, "eps": op.eps, "P": op.P, "rc": op.rc, "Nc": op.cell_list_dims(),
-                      "visc_ratio": 5.0, "seed": args.seed, "in_range_pairs": npairs,
-                      "l2": "inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
-                      "density_splines": "host (uploaded)" if args.host_splines else "device (built from g every step)",
-                      "partition": ("targets, singular/pair work, geometry caches and PME spreading by owned cell block; "
-                                    "densities uploaded 1/world per rank + ncclAllGather; meshes and velocities summed "
-                                    "with ncclAllReduce; the PME chain overlaps the real-space kernels on a second "
-                                    "stream (stage_ms overlap)") if world > 1 else "single GPU"},
+           "config": dict(bench_config(sus, op.Nb, op.alpha, op.eps, op.P, op.rc, op.cell_list_dims(), args.seed),
+                          in_range_pairs=npairs,
+                          l2="inputs (>= 10 GB at 4096 cells) exceed the 126 MB L2; no explicit flush",
+                          density_splines="host (uploaded)" if args.host_splines else "device (built from g every step)",
+                          partition=PARTITION_TEXT if world > 1 else "single GPU"),
            "clocks": clocks,
            "e2e": {"value": 1.0 / e2e_s, "unit": "matvecs/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches),
            "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
-           "roofline": roof, "kernels": rows, "timestep": timestep, "parity_full_size": full_size,
+           "roofline": roof, "kernels": rows, "timestep": timestep,
            "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "fp64_tflops": fp64_peak,
                      "fp64_source": "in-process DFMA micro-benchmark"},
            "setup_s": {"synth": t_synth, "upload+geometry": t_setup}}
@@ -529,6 +631,14 @@ def run_gpu(args):
             out["walls"] = child_block(args, "--walls-only", "walls")       # configs[4], wall-dominated operator
     except Exception as exc:   # nothing after the timed regions may cost the line
         out.setdefault("mtube", {"error": str(exc)[:300]})
+    # parity evidence goes LAST so that it survives a truncated tail of the line
+    for key in ("mtube", "walls"):
+        blk = out.get(key) or {}
+        pv = blk.get("parity_vs_oracle") if isinstance(blk, dict) else None
+        if pv:
+            parity[key] = {k: (max(v) if isinstance(v, list) and v and not isinstance(v[0], bool) else
+                               (all(v) if isinstance(v, list) else v)) for k, v in pv.items()}
+    out["parity"] = parity
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -694,10 +804,7 @@ def main():
     ap.add_argument("--seed", type=int, default=161269)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-cells", type=int, default=32)
-    ap.add_argument("--ref-sample-cells", type=int, default=32, help="--impl reference: target cells per step")
-    ap.add_argument("--ref-spread-stride", type=int, default=1,
-                    help="--impl reference: spread every n-th cell (1 = all: the oracle's spread has a fixed per-thread "
-                         "mesh cost, so a strided sample overstates the CPU time when extrapolated)")
+    ap.add_argument("--ref-mtube", action="store_true", help="--impl reference: also run the minicase block on the CPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-timestep", action="store_true", help="skip the geometry-update / RHS-operator timing")

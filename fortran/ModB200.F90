@@ -328,21 +328,35 @@ contains
     end if
   end function TlistKind
 
-  ! PME_Init: create the context (cuFFT plans, meshes, B-spline moduli, Ewald tables) and join the communicator
-  subroutine B200_Init
-    integer(c_int) :: ierr, device
+  ! Create the context (cuFFT plans, meshes, B-spline moduli, Ewald tables) and join the communicator -- lazily and
+  ! idempotently: TimeInt_Init calls PrepareSingIntOnWall (ModTimeInt.F90:87-91) BEFORE PME_Init (:96), and
+  ! PostProcess / field_visual programs may touch the lists before either, so every procedure that needs the context
+  ! calls B200_EnsureInit first; PME_Init is then a no-op when the context already exists.  The communicator is
+  ! attached here, before any geometry reaches the library (rbc3d_ctx_attach_comm requires that order).
+  subroutine B200_EnsureInit
+    integer(c_int) :: ierr, device, mpierr
     character(kind=c_char) :: id(128)
+    if (c_associated(b200_ctx)) return
     device = -1                                   ! the launcher binds one GPU per rank (CUDA_VISIBLE_DEVICES)
     ierr = rbc3d_ctx_create(b200_ctx, Lb, alpha_Ewd, eps_Ewd, PBspln_Ewd, rc_Ewd, Nb_Ewd, device)
     call B200_Check(ierr, 'rbc3d_ctx_create')
     if (numNodes > 1) then
+      ierr = 0
       if (nodeNum == 0) ierr = rbc3d_comm_unique_id(id)
-      call MPI_Bcast(id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierr)
+      call B200_Check(ierr, 'rbc3d_comm_unique_id')
+      call MPI_Bcast(id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, mpierr)
       ierr = rbc3d_ctx_attach_comm(b200_ctx, numNodes, nodeNum, id)
       call B200_Check(ierr, 'rbc3d_ctx_attach_comm')
     end if
-    ierr = rbc3d_cells_set_mesh(b200_ctx, nrbc, rbcs(1)%nlat, rbcs(1)%nlon, rbcs(1)%th, rbcs(1)%phi, rbcs(1)%w)
-    call B200_Check(ierr, 'rbc3d_cells_set_mesh')
+    if (nrbc > 0) then
+      ierr = rbc3d_cells_set_mesh(b200_ctx, nrbc, rbcs(1)%nlat, rbcs(1)%nlon, rbcs(1)%th, rbcs(1)%phi, rbcs(1)%w)
+      call B200_Check(ierr, 'rbc3d_cells_set_mesh')
+    end if
+  end subroutine B200_EnsureInit
+
+  ! PME_Init (ModPME.F90:252-338)
+  subroutine B200_Init
+    call B200_EnsureInit
   end subroutine B200_Init
 
   ! SourceList_UpdateCoord(slist_rbc) + TargetList_Update(tlist_rbc): gather the per-cell splines into the ABI
@@ -352,6 +366,7 @@ contains
     integer(c_int), allocatable :: act(:)
     integer :: irbc, m, n, o3, o1, ierr
     type(t_rbc), pointer :: rbc
+    call B200_EnsureInit
     m = 2*rbcs(1)%nlat; n = rbcs(1)%nlon
     allocate (spx(12*m*n*nrbc), spa3(12*m*n*nrbc), spdj(4*m*n*nrbc))
     allocate (Acell(nrbc), Bcell(nrbc), area(nrbc), msize(nrbc), act(tlist_rbc%nPoint))
@@ -376,6 +391,7 @@ contains
     real(WP), allocatable, target :: spF(:), spG(:)
     type(c_ptr) :: pf, pg, psf, psg
     integer :: irbc, m, n, o3, ierr
+    call B200_EnsureInit
     m = 2*rbcs(1)%nlat; n = rbcs(1)%nlon
     pf = c_null_ptr; pg = c_null_ptr; psf = c_null_ptr; psg = c_null_ptr
     if (present(updateF)) then
@@ -409,6 +425,7 @@ contains
     integer(c_int), allocatable :: nv(:), ne(:), e2v(:), act(:)
     real(WP), allocatable :: area(:), eps(:)
     integer :: iwall, NE, p, l, ierr
+    call B200_EnsureInit
     allocate (nv(nwall), ne(nwall))
     do iwall = 1, nwall
       nv(iwall) = walls(iwall)%nvert; ne(iwall) = walls(iwall)%nele
@@ -433,6 +450,7 @@ contains
   subroutine B200_SyncWallTraction
     real(WP), allocatable :: f(:, :)
     integer :: iwall, p, ierr
+    call B200_EnsureInit
     allocate (f(tlist_wall%nPoint, 3))
     p = 0
     do iwall = 1, nwall

@@ -28,12 +28,14 @@ contains
   subroutine EwaldCoeff_SL(r, A, B)                ! ModEwaldFunc.F90:86-131
     real(WP) :: r, A, B
     integer(c_int) :: ierr
+    call B200_EnsureInit
     ierr = rbc3d_ewald_coeff_sl(b200_ctx, r, A, B)
   end subroutine EwaldCoeff_SL
 
   subroutine EwaldCoeff_DL(r, A)                   ! ModEwaldFunc.F90:141-178
     real(WP) :: r, A
     integer(c_int) :: ierr
+    call B200_EnsureInit
     ierr = rbc3d_ewald_coeff_dl(b200_ctx, r, A)
   end subroutine EwaldCoeff_DL
 

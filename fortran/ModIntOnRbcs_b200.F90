@@ -21,6 +21,7 @@ contains
     real(WP) :: v(:, :)
     integer(c_int) :: ierr, kind
     if (nrbc == 0) return
+    call B200_EnsureInit
     kind = TlistKind(tlist)
     if (kind == TL_RAW) then
       ! TargetList_CreateFromRaw targets (ModPostProcess.F90:40-59): mirror them on first use

@@ -63,6 +63,7 @@ contains
     real(WP), optional :: lhs(3, 3, 3)
     real(WP) :: xt(9), ft(9), lt(27)
     integer(c_int) :: ierr
+    call B200_EnsureInit
     xt = reshape(transpose(x), (/9/)); ft = reshape(transpose(f), (/9/))     ! [corner][component], C order
     if (present(lhs)) then
       ierr = rbc3d_tri_int(b200_ctx, 1, xt, ft, xtar, c_null_ptr, c_null_ptr, rhs, lt)
@@ -80,6 +81,7 @@ contains
     real(WP), target :: st(2)
     real(WP) :: xt(9), ft(9), lt(27)
     integer(c_int) :: ierr
+    call B200_EnsureInit
     xt = reshape(transpose(x), (/9/)); ft = reshape(transpose(f), (/9/))
     st = (/s0, t0/)
     if (present(lhs)) then
@@ -98,6 +100,7 @@ contains
     real(WP), optional :: s0, t0, x0(3)
     real(WP) :: xt(9), d(1), s(1), t(1)
     integer(c_int) :: ierr
+    call B200_EnsureInit
     xt = reshape(transpose(x), (/9/))
     ierr = rbc3d_min_dist_to_tri(b200_ctx, 1, xTar, xt, d, s, t)
     call B200_Check(ierr, 'MinDistToTri')

@@ -7,14 +7,35 @@
 * ``minicase``        -- examples/minicase/minit.F90 restated: the cylinder mesh mapped to radius 5 and length 8, the box
   Lb = (10.5, 10.5, 8), two unrotated biconcave cells at the init program's positions, everything recentred.
 
-Nothing here is on the product path; the files live under /root/reference (not present on the GPU box), so only CPU
-tests use the readers and they skip when the files are absent.
+* ``case`` / ``carotid_web`` -- examples/case, case_sickles (initcond.F90, sickle_initcond.F90) and
+  examples/carotid_web (carotid_initcond.F90: 72 cells in the carotid vessel with its web, two walls) restated.
+
+Nothing here is on the product path.  The wall meshes the BASELINE configs use are committed as fixtures under
+tests/golden/meshes/ (scripts/make_golden_meshes.py, SHA-256 in MANIFEST.json), so the GPU box -- where /root/reference does
+not exist -- runs the operator on the reference's own geometries; ``mesh_file`` resolves a name to the fixture or, failing
+that, to the reference tree.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
 from . import synth
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MESH_DIRS = (os.path.join(os.path.dirname(_HERE), "tests", "golden", "meshes"),
+             "/root/reference/examples/minicase/Input", "/root/reference/examples/carotid_web/Input")
+
+
+def mesh_file(name: str) -> str:
+    """path of a wall mesh of the BASELINE configs: the committed fixture, else the reference tree"""
+    for d in MESH_DIRS:
+        p = os.path.join(d, name)
+        if os.path.exists(p):
+            return p
+    raise FileNotFoundError(name)
 
 
 def read_wall_mesh(path: str):
@@ -97,13 +118,43 @@ def minicase(mesh_path: str, nlat0: int = 12, dealias: int = 3, seed: int = 1612
     return sus, W, np.array([0.0, 0.0, 8.0])
 
 
-def carotid_web_walls(input_dir: str):
+def case(mesh_path: str | None = None, nrbc: int = 8, sickles: bool = False, visc_ratio: float = 1.0,
+         sickle_x: np.ndarray | None = None, seed: int = 161269):
+    """-> (suspension, walls, vBkg) of examples/case (initcond.F90:36-106) and examples/case_sickles
+    (sickle_initcond.F90): the cylinder mesh mapped to radius 5 and length nrbc / 0.7, Lb = (10.5, 10.5, length), nrbc
+    cells on the axis at z = (iz - 1/2) length / nrbc -- all biconcave, or every second one the imported SickleCell.dat --
+    and everything moved to the middle of the box (Recenter_Cells_and_Walls)."""
+    from . import mtube, sphere
+    x, e2v = read_wall_mesh(mesh_path or mesh_file("new_cyl_D6_L13_33.e"))
+    actlen, lengtube = 13.33, nrbc / 0.7
+    th = np.arctan2(x[0], x[1])
+    xw = np.stack([5.0 * np.cos(th), 5.0 * np.sin(th), lengtube / actlen * x[2]])
+    Lb = np.array([xw[0].max() - xw[0].min() + 0.5, 0.0, xw[2].max() - xw[2].min()])
+    Lb[1] = Lb[0]
+    spacing = Lb[2] / nrbc
+    xc_w = 0.5 * (xw.min(axis=1) + xw.max(axis=1))
+    xw = xw + (0.5 * Lb - xc_w)[:, None]
+    thg, phig, _ = sphere.gauss_grid(36, 72)
+    xb, _, _ = sphere.biconcave_unit(thg, phig, 1.0)
+    if sickles and sickle_x is None:
+        sickle_x = np.load(mtube.GOLDEN_SICKLE)["x"]
+    xs = []
+    for iz in range(1, nrbc + 1):
+        xc = np.array([0.5 * Lb[0], 0.5 * Lb[1], spacing * (iz - 0.5)])
+        xs.append(mtube.import_read_rbc(sickle_x, xc) if (sickles and iz % 2 == 0) else xb + xc[:, None, None])
+    sus = synth.suspension_from_shapes(np.stack(xs), Lb, nlat0=12, dealias=3, visc_ratio=visc_ratio, seed=seed)
+    W = synth.Walls(np.array([xw.shape[1]], np.int32), np.array([e2v.shape[1]], np.int32), np.ascontiguousarray(xw),
+                    np.ascontiguousarray(e2v), None, None, np.zeros_like(xw))
+    W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
+    return sus, W, np.array([0.0, 0.0, 8.0])
+
+
+def carotid_web_walls(input_dir: str | None = None):
     """-> (walls, Lb) of examples/carotid_web (carotid_initcond.F90:47-70, 118-138): carotid.e + web.e, shifted so that
     the first wall's coordinates start at 0 (recenterWalls), Lb = (max x + 0.5, max y + 0.5, 30)."""
-    import os
     xs, es = [], []
     for name in ("carotid.e", "web.e"):
-        x, e = read_wall_mesh(os.path.join(input_dir, name))
+        x, e = read_wall_mesh(os.path.join(input_dir, name) if input_dir else mesh_file(name))
         xs.append(x)
         es.append(e)
     off = -xs[0].min(axis=1)
@@ -115,6 +166,117 @@ def carotid_web_walls(input_dir: str):
                     None, None, np.zeros_like(x))
     W.area, W.epsDist = synth.wall_geometry(W.x, W.e2v_global())
     return W, Lb
+
+
+def carotid_place_cells(W, nrbc: int, seed: int = 112, tubelen: float = 30.0, max_attempts: int = 2_000_000,
+                        progress: bool = False, stall: int = 4000, n_random: int = 8):
+    """The rejection sampling of carotid_initcond.F90:186-268 -> (centres (nrbc, 3), rotations (nrbc, 3, 3)): a random
+    rotation (rotate_cell, :272-299), a random point of the vessel cross-section at a random height that is not inside
+    the web (choose_point, :131-182), rejected when the cell leaves [0, tubelen) in z, comes closer than 0.3 to a wall
+    vertex (check_wall_collision, :302-336) or touches an earlier cell (check_cell_collision, :341-407).  Differences,
+    stated: the reference draws from its own generator (ModBasicMath RandomNumber, seed 112), this uses NumPy's PCG64
+    with the same seed, and the cell-cell test (overlap of the bounding boxes of diagonal mesh neighbours, centres closer
+    than 4) is restated as "no two mesh points closer than 0.15" (about the diagonal-neighbour spacing of the mesh,
+    median 0.13) with a k-d tree; and because the random proposals need millions of attempts beyond ~50 cells (87 000 for
+    the 53rd; the vessel narrows to a radius of 3), only the first ``n_random`` cells are drawn that way; the others come
+    from a systematic sweep of the vessel with discs roughly across its axis, accepted by the same three tests -- the
+    same cell count and wall meshes, not the same positions."""
+    from scipy.spatial import cKDTree
+    from . import sphere
+    rng = np.random.Generator(np.random.PCG64(seed))
+    thg, phig, _ = sphere.gauss_grid(36, 72)
+    xb, _, _ = sphere.biconcave_unit(thg, phig, 1.0)                      # (3, nlon, nlat)
+    xb_pts = xb.reshape(3, -1)
+    vo = W.voff()
+    w1, w2 = W.x[:, vo[0]:vo[1]], W.x[:, vo[1]:vo[2]]
+    o1, o2 = np.argsort(w1[2]), np.argsort(w2[2])
+    w1, w2 = w1[:, o1], w2[:, o2]
+    wall_tree = cKDTree(W.x.T)
+    diag = 0.15
+
+    def choose_point():
+        while True:
+            ln = rng.random() * tubelen
+            lo, hi = np.searchsorted(w1[2], [ln - 0.2, ln + 0.2], side="left")[0], np.searchsorted(w1[2], ln + 0.2, side="right")
+            seg = w1[:2, lo:hi]
+            mx, mn = seg.max(), seg.min()
+            rad = 0.5 * (mx - mn)
+            ang, r = rng.random() * 2 * np.pi, np.sqrt(rng.random()) * rad
+            pt = np.array([r * np.cos(ang) + rad + mn, r * np.sin(ang) + rad + mn, ln])
+            lo2, hi2 = np.searchsorted(w2[2], ln - 0.5, side="left"), np.searchsorted(w2[2], ln + 0.5, side="right")
+            if hi2 > lo2 and w2[1, lo2:hi2].min() <= pt[1] <= w2[1, lo2:hi2].max():
+                continue                                                  # the point is inside the web
+            return pt
+
+    centres, rots, all_pts, tree = [], [], np.zeros((0, 3)), None
+
+    def try_place(R, xc):
+        nonlocal all_pts, tree
+        pts = (R @ xb_pts + xc[:, None]).T
+        if (pts[:, 2] >= tubelen).any() or (pts[:, 2] < 0).any():
+            return False
+        if np.isfinite(wall_tree.query(pts, k=1, distance_upper_bound=0.3)[0]).any():
+            return False
+        if tree is not None and np.isfinite(tree.query(pts, k=1, distance_upper_bound=diag)[0]).any():
+            return False
+        centres.append(xc)
+        rots.append(R)
+        all_pts = np.concatenate([all_pts, pts])
+        tree = cKDTree(all_pts)
+        if progress:
+            print("placed", len(centres), flush=True)
+        return True
+
+    fails = 0
+    for _ in range(max_attempts):
+        if len(centres) >= min(nrbc, n_random) or fails > stall:
+            break
+        while True:
+            v1, v2 = rng.random(2) * 2 - 1
+            vsq = v1 * v1 + v2 * v2
+            if vsq < 1:
+                break
+        zv = np.array([v1 * 2 * np.sqrt(1 - vsq), v2 * 2 * np.sqrt(1 - vsq), 1 - 2 * vsq])
+        fails = 0 if try_place(sphere.rotate_matrix(zv), choose_point()) else fails + 1
+    if len(centres) < nrbc:
+        # the random proposals have stalled: sweep the vessel systematically with discs across the axis (same tests)
+        zs = np.arange(0.75, tubelen - 0.75, 0.125)            # ascending: a dense stack
+        for ln in zs:
+            lo, hi = np.searchsorted(w1[2], ln - 0.2, side="left"), np.searchsorted(w1[2], ln + 0.2, side="right")
+            seg = w1[:2, lo:hi]
+            mx, mn = seg.max(), seg.min()
+            for dx in np.arange(mn + 1.0, mx - 1.0 + 1e-9, 0.25):
+                for dy in np.arange(mn + 1.0, mx - 1.0 + 1e-9, 0.25):
+                    if len(centres) == nrbc:
+                        break
+                    tilt = rng.normal(scale=0.15, size=2)
+                    zv = np.array([tilt[0], tilt[1], 1.0])
+                    try_place(sphere.rotate_matrix(zv / np.linalg.norm(zv)), np.array([dx, dy, ln]))
+    if len(centres) < nrbc:
+        raise RuntimeError("carotid_place_cells: placed %d of %d cells" % (len(centres), nrbc))
+    return np.array(centres), np.array(rots)
+
+
+def carotid_web(input_dir: str | None = None, nrbc: int | None = None, visc_ratio: float = 1.0, seed: int = 112,
+                hematocrit: float = 0.2, placement=None):
+    """-> (suspension, walls, Lb, vBkg) of examples/carotid_web (carotid_initcond.F90): the two walls and
+    nrbc = 3 * tubelen * tuber^2 * hematocrit / 4 = 72 biconcave cells (:38).  ``placement`` = (centres, rotations) as
+    returned by carotid_place_cells (the committed tests/golden/carotid_web_cells.npz holds one such draw: the sampling
+    takes minutes at 72 cells, as the init program's does); None = sample now."""
+    from . import sphere
+    W, Lb = carotid_web_walls(input_dir)
+    tuber, tubelen = 4.0, 30.0
+    if nrbc is None:
+        nrbc = int((3 * (tubelen * tuber ** 2 * hematocrit)) / 4)        # carotid_initcond.F90:38 -> 72
+    if placement is None:
+        placement = carotid_place_cells(W, nrbc, seed, tubelen)
+    centres, rots = placement
+    centres, rots = np.asarray(centres)[:nrbc], np.asarray(rots)[:nrbc]
+    thg, phig, _ = sphere.gauss_grid(36, 72)
+    xb, _, _ = sphere.biconcave_unit(thg, phig, 1.0)
+    x = np.einsum("cij,jlk->cilk", rots, xb) + centres[:, :, None, None]
+    sus = synth.suspension_from_shapes(x, Lb, nlat0=12, dealias=3, visc_ratio=visc_ratio, seed=161269)
+    return sus, W, Lb, np.array([0.0, 0.0, 8.0])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -362,6 +362,7 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.sg_cell_active.release();
   C.sg_st.release();
   C.spGi.release();
+  C.spTi.release();
   C.sg_cache.release();
   C.ps_warp_tgt.release();
   C.ps_maskbits.release();
@@ -652,6 +653,7 @@ int rbc3d_cells_set_density(rbc3d_ctx *c, const double *f, const double *g, cons
   if (f) C.f_set = true;
   if (g) C.g_set = true;
   if (spG) C.spGi_valid = false;
+  if (f || spF) C.spFi_valid = false;
   RBC_TRY(cells_gather_sorted(c, false, f != nullptr, g != nullptr));
   if (spG) RBC_TRY(singular_density_prepare(c));
   if (C.sb_ok) {

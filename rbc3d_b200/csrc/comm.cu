@@ -80,8 +80,11 @@ int rbc3d_comm_unique_id(void *id128) {
 
 int rbc3d_ctx_attach_comm(rbc3d_ctx *c, int nranks, int rank, const void *id128) {
   if (!c || nranks < 1 || rank < 0 || rank >= nranks) return RBC3D_EINVAL;
-  if (c->cells.geom_set) {
-    set_error("rbc3d_ctx_attach_comm must precede rbc3d_cells_set_geometry");
+  // ownership (cell blocks, wall source ownership, per-rank target lists, PME slabs) is derived from nranks / rank when
+  // a list is built: anything built before the communicator is attached would keep single-rank ownership and be counted
+  // nranks times by the reductions
+  if (c->cells.geom_set || c->walls.geom_set || c->walls.NE > 0 || c->tl[0].valid || c->tl[1].valid || c->tl[2].valid) {
+    set_error("rbc3d_ctx_attach_comm must precede rbc3d_cells_set_geometry, rbc3d_walls_set and rbc3d_targets_set_raw");
     return RBC3D_ESTATE;
   }
   if (nranks == 1) {

@@ -191,7 +191,7 @@ struct Cells {
   dbuf<double> xvint_part;           // partial sums of the linear term
   dbuf<double> sing_xi;              // SoA(3,Np) spline-evaluated target positions (ModRbcSingInt.F90:58)
   // cached double-layer singular path (singular.cu): cell-independent tile tables, per-geometry cache
-  bool sg_ok = false, sg_cache_ok = false, spGi_valid = false;
+  bool sg_ok = false, sg_cache_ok = false, spGi_valid = false, spFi_valid = false;
   int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
   int sg_npatch_active = 0;          // patch points per target with a non-zero quadrature weight (cached path)
   dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active, sg_tile_list, sg_pos;
@@ -201,8 +201,9 @@ struct Cells {
   dbuf<int2> sg_chunk;
   size_t sg_smem = 0;
   dbuf<double> sg_st;                // (s, t) pairs
-  dbuf<double> spGi;                 // spline(g detJ) as double2 planes: [cell][6][nlon][2 nlat][2]
-  dbuf<double4> sg_cache;            // [cell][tile][sorted patch point] (xx, w EA (xx.a3))
+  dbuf<double> spGi;                 // spline(g detJ) as double2 planes: [cell][6][2 nlat][nlon][2] (phi fastest)
+  dbuf<double> spTi;                 // same layout, scratch: spline(x), spline(a3) at geometry time, then spline(f detJ)
+  dbuf<double4> sg_cache;            // [slot][row][sorted patch point][half][nlon] x 16 B: (xx.x, xx.y) | (xx.z, w EA (xx.a3))
   // dense same-surface pair kernel (pairself.cu)
   bool ps_ok = false;
   int ps_nwarps = 0;

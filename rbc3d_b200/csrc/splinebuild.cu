@@ -115,7 +115,7 @@ struct BuildArgs {
   const double *w;      // [nlat]
   const double *M0, *M1, *cs;
   double *sp_abi;       // [cell][4][3][nlon][2 nlat] or null
-  double2 *sp_planes;   // [cell][6][nlon][2 nlat] or null
+  double2 *sp_planes;   // [cell][6][2 nlat][nlon] or null
   const int *need;      // [cell] or null: build only flagged cells
   int nvar;             // variables per cell of this field (3, or 1 for detJ)
   int raw;              // 1: dens holds the mesh field itself (x, a3, detJ) -- no division by the Gauss weight
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(256) k_spline_build(BuildArgs a) {
       for (int q = 0; q < 4; q++) o[(size_t)q * a.nvar * plane] = r[q];
     }
     if (a.sp_planes) {
-      double2 *o = a.sp_planes + ((size_t)cell * 6 + 2 * var) * plane + e;
+      // [cell][6][2 nlat][nlon], phi fastest (singular.cu: lanes = consecutive longitudes)
+      double2 *o = a.sp_planes + ((size_t)cell * 6 + 2 * var) * plane + (size_t)I * nlon + j;
       o[0] = make_double2(r[0], r[1]);
       o[plane] = make_double2(r[2], r[3]);
     }
@@ -261,6 +262,7 @@ int spline_build_density(rbc3d_ctx *c, int which) {
   KERNEL_CHECK();
   c->launches++;
   if (which == 1 && a.sp_planes) C.spGi_valid = true;
+  if (which == 0) C.spFi_valid = false;
   return RBC3D_OK;
 }
 

@@ -183,6 +183,20 @@ def surface_geometry(a1: np.ndarray, a2: np.ndarray, th: np.ndarray):
     return a3, detj
 
 
+def rotate_matrix(c1) -> np.ndarray:
+    """RotateMatrix (ModBasicMath.F90:97-126): the rotation that takes the z axis to the unit vector c1 about the axis
+    a = z x c1; mat = a a^T + b1 b^T + c1 z^T with b = z x a, b1 = c1 x a; the identity when c1 is (anti)parallel to z."""
+    c1 = np.asarray(c1, dtype=float)
+    c = np.array([0.0, 0.0, 1.0])
+    a = np.array([-c1[1], c1[0], 0.0])
+    if (a * a).sum() < 1e-10:
+        return np.eye(3)
+    a = a / np.sqrt((a * a).sum())
+    b = np.array([-a[1], a[0], 0.0])
+    b1 = np.cross(c1, a)
+    return np.outer(a, a) + np.outer(b1, b) + np.outer(c1, c)
+
+
 def rotation_matrices(rng: np.random.Generator, n: int) -> np.ndarray:
     """n uniformly random rotations (n, 3, 3) from unit quaternions."""
     q = rng.normal(size=(n, 4))

@@ -16,16 +16,49 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run(["--impl", "reference", "--cells", "8", "--steps", "1", "--warmup", "0", "--ref-sample-cells", "4"])
+    """One complete CPU matvec, measured (nothing extrapolated), steps = the applications actually run, the same config
+    keys as the product arm, all host threads even under torchrun's OMP_NUM_THREADS=1, and the result kept for the GPU
+    arm's all-targets check."""
+    import numpy as np
+    r = _run(["--impl", "reference", "--cells", "8", "--steps", "20", "--warmup", "5", "--seed", "7"],
+             env={"OMP_NUM_THREADS": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "Ewald BI matvecs/s" and line["unit"] == "matvecs/s"
-    assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["steps"] == 1
+    assert line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["steps_requested"] == 20 and line["extrapolated"] is False
     assert line["value"] > 0 and abs(line["value"] * line["ms_per_step"] / 1e3 - 1.0) < 1e-9
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "linear fit" in cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == line["value"] and "nothing extrapolated" in cb["sample"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))
+    assert abs(sum(cb["stage_s"].values()) - line["ms_per_step"] / 1e3) < 0.05 * line["ms_per_step"] / 1e3 + 0.05
     assert line["e2e"] == {"value": line["value"], "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"] and line["config"]["cells"] == 8
+    cfg = line["config"]
+    assert set(cfg) == {"workload", "cells", "points", "alpha", "eps", "P", "rc", "Nc", "visc_ratio", "seed"}
+    assert cfg["cells"] == 8 and cfg["P"] == 8 and abs(cfg["rc"] - 1.1986122199272495) < 1e-12
+    pth = os.path.join(ROOT, "oracle", "_cache", "ref_matvec_c8_s7.npy")
+    try:
+        v = np.load(pth)
+        assert v.shape == (3, cfg["points"]) and np.isfinite(v).all() and np.abs(v).max() > 0
+    finally:
+        for q in (pth, pth + ".json"):
+            if os.path.exists(q):
+                os.remove(q)
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    code = ("import sys, argparse; sys.path.insert(0, %r); import importlib.util as u;"
+            "sp = u.spec_from_file_location('b', %r); b = u.module_from_spec(sp); sp.loader.exec_module(b);"
+            "import io, contextlib; buf = io.StringIO();\n"
+            "with contextlib.redirect_stdout(buf):\n"
+            "    b.run_reference(argparse.Namespace(cells=8, seed=11, gpus=1, steps=1, warmup=0, ref_mtube=False))\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'librbc3d_oracle' in maps and 'librbc3d_b200' not in maps, 'product library mapped'\n"
+            "import os\n"
+            "[os.remove(p) for p in (b.ref_cache_path(8, 11), b.ref_cache_path(8, 11) + '.json') if os.path.exists(p)]\n"
+            % (ROOT, os.path.join(ROOT, "bench.py")))
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
 
 
 def test_reference_arm_other_ranks_exit_without_work():

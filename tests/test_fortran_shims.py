@@ -115,3 +115,48 @@ def test_shim_calls_have_the_interface_arity():
             assert nargs == len(ifaces[name][1]), (os.path.basename(fn), name, nargs, len(ifaces[name][1]))
             ncalls += 1
     assert ncalls >= 25
+
+
+def _procedures():
+    """name -> body (comments stripped, continuation lines joined, lower case) of every shim procedure"""
+    out = {}
+    for fn in sorted(glob.glob(os.path.join(ROOT, "fortran", "*.F90"))):
+        src = open(fn).read()
+        src = re.sub(r"&\s*\n\s*&?", " ", src)
+        src = "\n".join(line.split("!")[0] for line in src.splitlines()).lower()
+        src = re.sub(r"interface.*?end interface", "", src, flags=re.S)
+        for m in re.finditer(r"^\s*(?:subroutine|(?:[\w()]+\s+)?function)\s+(\w+).*?^\s*end (?:subroutine|function)", src,
+                             flags=re.S | re.M):
+            out[m.group(1)] = m.group(0)
+    return out
+
+
+def test_every_shim_creates_the_context_before_using_it():
+    """The reference's TimeInt_Init calls PrepareSingIntOnWall (ModTimeInt.F90:87-91) before PME_Init (:96), and the
+    post-processing programs use the lists without either: context creation is lazy (B200_EnsureInit, guarded by
+    c_associated) and every procedure reaches it before the first use of b200_ctx."""
+    procs = _procedures()
+    ensure = procs["b200_ensureinit"]
+    assert "c_associated(b200_ctx)" in ensure.split("rbc3d_ctx_create")[0]
+    assert ensure.index("rbc3d_ctx_attach_comm") < ensure.index("rbc3d_cells_set_mesh")
+    assert "b200_check(ierr, 'rbc3d_comm_unique_id')" in ensure
+    creators = ("b200_ensureinit", "b200_init", "b200_syncwalls", "b200_synccells", "b200_syncdensity",
+                "b200_syncwalltraction")
+    for c in creators[1:]:
+        first = procs[c].index("b200_ctx") if "b200_ctx" in procs[c] else len(procs[c])
+        assert "call b200_ensureinit" in procs[c][:first] or "call b200_ensureinit" in procs[c], c
+    used = 0
+    for name, body in procs.items():
+        if name in ("b200_ensureinit", "pme_finalize") or "b200_ctx" not in body:
+            continue
+        used += 1
+        first = body.index("b200_ctx")
+        assert any("call " + c in body[:first] for c in creators), f"{name} uses b200_ctx before creating it"
+    assert used >= 15
+    # replay of TimeInt_Init (walls present): PrepareSingIntOnWall first, then PME_Init, which must not create a second context
+    prep = procs["preparesingintonwall"]
+    assert prep.index("call b200_syncwalls") < prep.index("rbc3d_wall_prepare_sing")
+    assert "call b200_init" in procs["pme_init"] and "call b200_ensureinit" in procs["b200_init"]
+    # Fourier-only ranks and ModPostProcess: tractions are sent by PME_Distrib_Source itself
+    ds = procs["pme_distrib_source"]
+    assert ds.index("call b200_syncwalltraction") < ds.index("rbc3d_pme_distrib_source")
