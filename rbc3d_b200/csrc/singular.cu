@@ -154,15 +154,17 @@ static void cyclic_cover(const std::vector<char> &used, int mod, int &lo, int &l
 // row kernel: tables (host, once per rbc3d_cells_set_mesh)
 
 constexpr int SR_TPW = 31;        // targets per warp; lane nt (<= 31) holds the right-hand column of the last target
-constexpr int SR_PF = 3;          // cache records in flight per lane
+constexpr int SR_PF = 3;          // cache records in flight per lane (registers)
+constexpr int SR_L2PF = 20;       // patch points ahead of which the records are prefetched into L2
 constexpr int SR_TABW = 10;       // doubles per table entry: cx[4], cy[4], quadrature weight, code
-constexpr int SR_NT = 384;        // threads per CTA at most (launch bound: 168 registers)
-constexpr int SR_FRESH = 1 << 16, SR_SLIDE = 1 << 17;
+constexpr int SR_NT = 384;        // consumer threads per CTA at most (+ one producer warp; launch bound: 157 registers)
+constexpr int SR_FRESH = 1 << 16;
 constexpr int SR_RI = 16;         // ints per row-info record: ilo, ni, npts, stream bounds [0..NS]
 constexpr size_t SR_SMEM_MAX = 227 * 1024;
 enum { SR_BUILD_X = 0, SR_BUILD_N = 1, SR_DL = 2, SR_SL = 3 };
 
 static int sr_groups(int nlon) { return (nlon + SR_TPW - 1) / SR_TPW; }
+static int sr_tpw(int nlon) { return (nlon + sr_groups(nlon) - 1) / sr_groups(nlon); }  // balanced groups: 72 -> 3 x 24
 static int sr_streams(int nlon) {
   const int g = sr_groups(nlon);
   return std::max(1, std::min(4, (SR_NT / 32) / g));
@@ -220,15 +222,13 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
       if (a.wi != b.wi) return a.wi < b.wi;
       return a.q < b.q;
     });
-    // codes: FRESH = load both theta nodes of the lane's column, SLIDE = the lower node becomes the upper one
+    // code FRESH: first point of a spline cell = load both theta nodes of the lane's column
     std::vector<int> code(npts, 0);
     std::vector<double> cost(npts + 1, 0.0);
     for (int k = 0; k < npts; k++) {
-      int f = 0;
-      if (k == 0 || pts[k].j1 != pts[k - 1].j1 || pts[k].wi != pts[k - 1].wi)
-        f = (k > 0 && pts[k].j1 == pts[k - 1].j1 && pts[k].wi == pts[k - 1].wi + 1) ? SR_SLIDE : SR_FRESH;
+      const int f = (k == 0 || pts[k].j1 != pts[k - 1].j1 || pts[k].wi != pts[k - 1].wi) ? SR_FRESH : 0;
       code[k] = pts[k].wi | (pts[k].j1 << 8) | f;
-      cost[k + 1] = cost[k] + 11.0 + (f == SR_FRESH ? 48.0 : f == SR_SLIDE ? 24.0 : 0.0);
+      cost[k + 1] = cost[k] + 90.0 + (f ? 14.0 : 0.0);  // instructions per point; node loads at the first point of a spline cell
     }
     // NS streams of contiguous points with about equal cost, cut at spline-cell boundaries
     int *ri = rowinfo.data() + (size_t)row * SR_RI;
@@ -239,7 +239,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
       int best = ri[3 + s - 1];
       double bd = 1e300;
       for (int k = ri[3 + s - 1]; k <= npts; k++) {
-        if (k < npts && !(code[k] & (SR_FRESH | SR_SLIDE))) continue;
+        if (k < npts && !(code[k] & SR_FRESH)) continue;
         const double d = fabs(cost[k] - want);
         if (d < bd) bd = d, best = k;
       }
@@ -247,7 +247,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
     }
     ri[3 + NS] = npts;
     for (int s = 1; s < NS; s++)
-      if (ri[3 + s] < npts) code[ri[3 + s]] = (code[ri[3 + s]] & ~SR_SLIDE) | SR_FRESH;  // a stream starts with a full load
+      if (ri[3 + s] < npts) code[ri[3 + s]] |= SR_FRESH;  // a stream starts with a node load
     for (int k = 0; k < npts; k++) {
       double *te = tab.data() + ((size_t)row * npts + k) * SR_TABW;
       const double s = pts[k].s, t = pts[k].t;
@@ -268,7 +268,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   // shared memory: barriers, the row's tables, the cross-stream reduction buffer, one or two bands
   const size_t band = (size_t)6 * ni_max * n * sizeof(double2);
-  const size_t fixed = 64 + (size_t)npts * SR_TABW * sizeof(double) + (size_t)(SR_NT / 32) * 3 * 32 * sizeof(double);
+  const size_t fixed = 64 + (size_t)npts * SR_TABW * sizeof(double) + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW * sizeof(double);
   if (fixed + band > SR_SMEM_MAX) return RBC3D_OK;  // direct kernel only
   C.sg_K = (fixed + 2 * band <= SR_SMEM_MAX) ? 2 : 1;  // band buffers
   C.sg_smem = fixed + C.sg_K * band;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_spline_planes(int ncell, int m, int n, 
 // ---------------------------------------------------------------------------------------------------------
 struct RowArgs {
   Params prm;
-  int npc, nlat, nlon, Np, npts, ni_max, nslot, ngrp, NS, reps, nbuf;
+  int npc, nlat, nlon, Np, npts, ni_max, nslot, ngrp, NS, tpw, reps, nbuf;
   const double *tab;        // [row][npts][SR_TABW]
   const int *rowinfo;       // [row][SR_RI]
   const double2 *planes;    // [cell][6][m][n] of the interpolated field (x, a3, g detJ or f detJ)
@@ -325,6 +325,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// contiguous bytes (a multiple of 16) on their way from HBM to L2, no register, no shared memory
+__device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile(
@@ -362,99 +369,113 @@ __device__ __forceinline__ void st_stream2(double2 *p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
-// One persistent CTA per (latitude row, replica): warps = target groups x point streams.
+// One persistent CTA per (latitude row, replica): consumer warps = target groups x point streams, plus one producer warp
+// that keeps the spline bands coming (full / empty mbarriers per band buffer: a consumer warp never waits for another
+// one except for its own group's 4 streams when their sums are combined).
 template <int MODE>
-__global__ void __launch_bounds__(SR_NT, 1) k_sing_row(RowArgs a) {
+__global__ void __maxnreg__(152) k_sing_row(RowArgs a) {  // 13 warps x 152 registers fit the register file
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.nlon, m = 2 * a.nlat, npts = a.npts, NS = a.NS;
   const int row = blockIdx.x % a.nlat, rep = blockIdx.x / a.nlat;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int grp = warp / NS, strm = warp - grp * NS;
-  const int jt0 = grp * SR_TPW, nt = min(SR_TPW, n - jt0);  // this warp's targets jt0 .. jt0 + nt - 1
-  const bool on = lane <= nt, is_t = lane < nt;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncons = a.ngrp * NS;                                        // consumer warps; warp ncons = producer
+  unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem_raw);   // [2]
+  unsigned long long *bar_empty = bar_full + 2;                                          // [2]
   double *s_tab = reinterpret_cast<double *>(smem_raw + 64);
-  double *s_red = s_tab + (size_t)npts * SR_TABW;                      // [warp][3][32]
-  double2 *s_band = reinterpret_cast<double2 *>(s_red + (size_t)(SR_NT / 32) * 96);
+  double *s_red = s_tab + (size_t)npts * SR_TABW;                       // [2][consumer warp][3][tpw]
+  const int tpw = a.tpw;
+  double2 *s_band = reinterpret_cast<double2 *>(s_red + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW);
   const int *ri = a.rowinfo + (size_t)row * SR_RI;
   const int ilo = ri[0], ni = ri[1];
-  const int pbeg = ri[3 + strm], pend = ri[4 + strm];
-  const size_t band_n = (size_t)6 * a.ni_max * n;                      // double2 per buffer
-  const int wpl = ni * n;                                              // double2 per plane of the band
-  const unsigned band_bytes = (unsigned)(6 * wpl * sizeof(double2));
-  // ---- prologue: tables of the row, barriers, first band ----
+  const int wpl = a.ni_max * n;                                         // double2 per plane of a band buffer (uniform)
+  const size_t band_n = (size_t)6 * wpl;
+  const int nbuf = a.nbuf;
+  // ---- prologue: tables of the row, barriers ----
   for (int e = threadIdx.x; e < npts * SR_TABW; e += blockDim.x) s_tab[e] = a.tab[(size_t)row * npts * SR_TABW + e];
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar + 1, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(bar_full + b, 1);
+      mbar_init(bar_empty + b, ncons);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue_band = [&](int slot, int buf) {  // thread 0 only
-    const int cell = a.active_list[slot];
-    mbar_expect_tx(bar + buf, band_bytes);
-    const int n1 = min(ni, m - ilo);  // rows before the cyclic wrap
-    for (int q = 0; q < 6; q++) {
-      const double2 *src = a.planes + ((size_t)cell * 6 + q) * m * n;
-      double2 *dst = s_band + (size_t)buf * band_n + (size_t)q * wpl;
-      bulk_g2s(dst, src + (size_t)ilo * n, (unsigned)(n1 * n * sizeof(double2)), bar + buf);
-      if (n1 < ni) bulk_g2s(dst + (size_t)n1 * n, src, (unsigned)((ni - n1) * n * sizeof(double2)), bar + buf);
+  if (warp == ncons) {
+    // ---- producer: one lane streams the band of every item into the buffer ring ----
+    if (lane == 0) {
+      const unsigned band_bytes = (unsigned)(6 * ni * n * sizeof(double2));
+      const int n1 = min(ni, m - ilo);  // rows before the cyclic wrap
+      int it = 0;
+      for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
+        const int buf = it % nbuf, use = it / nbuf;
+        if (use > 0) mbar_wait(bar_empty + buf, (unsigned)((use - 1) & 1));  // every consumer warp has left the buffer
+        const int cell = a.active_list[slot];
+        mbar_expect_tx(bar_full + buf, band_bytes);
+        for (int q = 0; q < 6; q++) {
+          const double2 *src = a.planes + ((size_t)cell * 6 + q) * m * n;
+          double2 *dst = s_band + (size_t)buf * band_n + (size_t)q * wpl;
+          bulk_g2s(dst, src + (size_t)ilo * n, (unsigned)(n1 * n * sizeof(double2)), bar_full + buf);
+          if (n1 < ni) bulk_g2s(dst + (size_t)n1 * n, src, (unsigned)((ni - n1) * n * sizeof(double2)), bar_full + buf);
+        }
+      }
     }
-  };
-  if (threadIdx.x == 0 && rep < a.nslot) issue_band(rep, 0);
+    return;
+  }
+  const int grp = warp / NS, strm = warp - grp * NS;
+  const int jt0 = grp * tpw, nt = min(tpw, n - jt0);  // this warp's targets jt0 .. jt0 + nt - 1
+  const bool on = lane <= nt, is_t = lane < nt;
+  const int pbeg = ri[3 + strm], pend = ri[4 + strm];
   const unsigned long long pol = l2_evict_first_policy();
+  const size_t rstep = (size_t)2 * n;  // double2 per patch point of an item
   int it = 0;
   for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
-    const int buf = a.nbuf == 2 ? (it & 1) : 0;
-    if (a.nbuf == 2 && threadIdx.x == 0 && slot + a.reps < a.nslot) issue_band(slot + a.reps, buf ^ 1);
+    const int buf = it % nbuf, use = it / nbuf;
     const int cell = a.active_list[slot];
-    const int ti = cell * a.npc + (jt0 + lane) * a.nlat + row;  // this lane's target (valid when is_t)
-    double2 *rec = a.cache + (((size_t)slot * a.nlat + row) * npts) * 2 * n + (jt0 + lane);
+    double2 *rec = a.cache + (((size_t)slot * a.nlat + row) * npts) * rstep + (jt0 + lane);
     double xi0 = 0, xi1 = 0, xi2 = 0;
     if (MODE == SR_BUILD_X && is_t) {
       double xi[3];
       spline_interp<3>(a.spx + (size_t)12 * m * n * cell, m, n, a.th[row], a.phi[jt0 + lane], xi);  // ModRbcSingInt.F90:58
       xi0 = xi[0], xi1 = xi[1], xi2 = xi[2];
     }
-    // records in flight before the band is waited for
+    // records: SR_PF points in flight in registers, SR_L2PF points ahead on their way from HBM to L2
     double2 ra[SR_PF], rb[SR_PF];
 #pragma unroll
     for (int k = 0; k < SR_PF; k++) {
       ra[k] = rb[k] = make_double2(0, 0);
       if (MODE != SR_BUILD_X && is_t && pbeg + k < pend) {
-        ra[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * 2 * n) : ld_stream2(rec + (size_t)(pbeg + k) * 2 * n, pol);
-        rb[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * 2 * n + n) : ld_stream2(rec + (size_t)(pbeg + k) * 2 * n + n, pol);
+        ra[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * rstep) : ld_stream2(rec + (size_t)(pbeg + k) * rstep, pol);
+        rb[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * rstep + n) : ld_stream2(rec + (size_t)(pbeg + k) * rstep + n, pol);
       }
     }
-    mbar_wait(bar + buf, (unsigned)((a.nbuf == 2 ? (it >> 1) : it) & 1));
+    if (MODE != SR_BUILD_X && lane < 2) {
+      const unsigned pfb = (unsigned)(nt * sizeof(double2));
+      for (int k = SR_PF; k < SR_L2PF && pbeg + k < pend; k++) l2_prefetch(rec - lane + (size_t)(pbeg + k) * rstep + lane * n, pfb);
+    }
+    mbar_wait(bar_full + buf, (unsigned)(use & 1));
     const double2 *band = s_band + (size_t)buf * band_n;
     double2 top[6], bot[6];
 #pragma unroll
     for (int q = 0; q < 6; q++) top[q] = bot[q] = make_double2(0, 0);
     double pv0 = 0, pv1 = 0, pv2 = 0;
+    const double *te = s_tab + (size_t)pbeg * SR_TABW;
+    double2 *rp = rec + (size_t)pbeg * rstep;  // records of the current point
     for (int p = pbeg; p < pend; p += SR_PF) {
 #pragma unroll
       for (int k = 0; k < SR_PF; k++) {
         const int pk = p + k;
         if (pk < pend) {  // warp uniform
-          const double *te = s_tab + (size_t)pk * SR_TABW;
           const int code = *reinterpret_cast<const int *>(te + 9);
-          if (code & (SR_FRESH | SR_SLIDE)) {
+          if (code & SR_FRESH) {  // first point of a spline cell: the two theta nodes of this lane's phi column
             int col = ((code >> 8) & 255) + jt0 + lane;
             if (col >= n) col -= n;
             const double2 *nb = band + (code & 255) * n + col;
-            if (code & SR_FRESH) {
-              if (on) {
-#pragma unroll
-                for (int q = 0; q < 6; q++) top[q] = nb[(size_t)q * wpl];
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 6; q++) top[q] = bot[q];
-            }
             if (on) {
 #pragma unroll
-              for (int q = 0; q < 6; q++) bot[q] = nb[(size_t)q * wpl + n];
+              for (int q = 0; q < 6; q++) {
+                top[q] = nb[q * wpl];
+                bot[q] = nb[q * wpl + n];
+              }
             }
           }
           const double2 cx01 = *reinterpret_cast<const double2 *>(te), cx23 = *reinterpret_cast<const double2 *>(te + 2);
@@ -473,8 +494,8 @@ __global__ void __launch_bounds__(SR_NT, 1) k_sing_row(RowArgs a) {
           const double2 A2 = ra[k], B2 = rb[k];
           if (MODE == SR_BUILD_X) {
             if (is_t) {
-              st_stream2(rec + (size_t)pk * 2 * n, make_double2(g[0] - xi0, g[1] - xi1));
-              st_stream2(rec + (size_t)pk * 2 * n + n, make_double2(g[2] - xi2, 0.0));
+              st_stream2(rp, make_double2(g[0] - xi0, g[1] - xi1));
+              st_stream2(rp + n, make_double2(g[2] - xi2, 0.0));
             }
           } else if (MODE == SR_BUILD_N) {
             const double xx = A2.x, yy = A2.y, zz = B2.x;
@@ -482,7 +503,7 @@ __global__ void __launch_bounds__(SR_NT, 1) k_sing_row(RowArgs a) {
             double w = 0.0;
             if (rr < a.prm.rc)  // ModRbcSingInt.F90:69
               w = ewald_dl(a.tab_dl, a.prm, rr) * te[8] * (xx * g[0] + yy * g[1] + zz * g[2]);
-            if (is_t) st_stream2(rec + (size_t)pk * 2 * n + n, make_double2(zz, w));
+            if (is_t) st_stream2(rp + n, make_double2(zz, w));
           } else if (MODE == SR_DL) {
             const double qd = B2.y * (A2.x * g[0] + A2.y * g[1] + B2.x * g[2]);
             pv0 = fma(qd, A2.x, pv0);
@@ -502,36 +523,40 @@ __global__ void __launch_bounds__(SR_NT, 1) k_sing_row(RowArgs a) {
               pv2 += xf * zz + EB * f2;
             }
           }
-          if (MODE != SR_BUILD_X && is_t && pk + SR_PF < pend) {
-            ra[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pk + SR_PF) * 2 * n) : ld_stream2(rec + (size_t)(pk + SR_PF) * 2 * n, pol);
-            rb[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pk + SR_PF) * 2 * n + n) : ld_stream2(rec + (size_t)(pk + SR_PF) * 2 * n + n, pol);
+          if (MODE != SR_BUILD_X) {
+            if (is_t && pk + SR_PF < pend) {
+              ra[k] = MODE == SR_BUILD_N ? ld_plain2(rp + SR_PF * rstep) : ld_stream2(rp + SR_PF * rstep, pol);
+              rb[k] = MODE == SR_BUILD_N ? ld_plain2(rp + SR_PF * rstep + n) : ld_stream2(rp + SR_PF * rstep + n, pol);
+            }
+            if (lane < 2 && pk + SR_L2PF < pend) l2_prefetch(rp - lane + SR_L2PF * rstep + lane * n, (unsigned)(nt * sizeof(double2)));
           }
+          te += SR_TABW;
+          rp += rstep;
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + buf);  // this warp has read its last node of the band
     if (MODE == SR_DL || MODE == SR_SL) {
-      // fixed order: a lane's points in stream order, then the streams -- one writer per target, no atomics
-      double *sr = s_red + (size_t)warp * 96 + lane;
-      sr[0] = pv0, sr[32] = pv1, sr[64] = pv2;
-      __syncthreads();
-      if (threadIdx.x < n) {
-        const int j = threadIdx.x, g2 = j / SR_TPW, l2 = j - g2 * SR_TPW;
-        const int tj = cell * a.npc + j * a.nlat + row;
+      // fixed order: a lane's points in stream order, then the streams -- one writer per target, no atomics.  Only the NS
+      // warps of a target group meet here (named barrier 1 + grp); the buffer alternates with the item's parity.
+      double *sr = s_red + ((size_t)(it & 1) * (SR_NT / 32) + warp) * 3 * SR_TPW + lane;
+      if (is_t) sr[0] = pv0, sr[SR_TPW] = pv1, sr[2 * SR_TPW] = pv2;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NS * 32) : "memory");
+      if (strm == 0 && is_t) {
+        const int tj = cell * a.npc + (jt0 + lane) * a.nlat + row;
         if (a.active[tj]) {
           const double cm = MODE == SR_DL ? a.coef * a.Bcell[cell] : a.coef;  // c2Mod, ModIntOnRbcs.F90:116
+          const double *s0 = s_red + ((size_t)(it & 1) * (SR_NT / 32) + grp * NS) * 3 * SR_TPW + lane;
 #pragma unroll
           for (int d = 0; d < 3; d++) {
             double s = 0;
-            for (int q = 0; q < NS; q++) s += s_red[(size_t)(g2 * NS + q) * 96 + d * 32 + l2];
+            for (int q = 0; q < NS; q++) s += s0[(size_t)q * 3 * SR_TPW + d * SR_TPW];
             a.acc[(size_t)d * a.Np + tj] += cm * s;
           }
         }
       }
     }
-    (void)ti;
-    (void)nwarps;
-    __syncthreads();  // every warp has left this band buffer (and s_red) before it is refilled
-    if (a.nbuf == 1 && threadIdx.x == 0 && slot + a.reps < a.nslot) issue_band(slot + a.reps, 0);
   }
 }
 
@@ -586,7 +611,7 @@ static int launch_row(rbc3d_ctx *c, TargetList &t, const double *planes, double 
   a.prm = c->prm;
   a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.Np = C.Np;
   a.npts = C.sg_npatch_active, a.ni_max = C.sg_ni_max, a.nslot = C.sg_nactive;
-  a.ngrp = sr_groups(C.nlon), a.NS = sr_streams(C.nlon);
+  a.ngrp = sr_groups(C.nlon), a.NS = sr_streams(C.nlon), a.tpw = sr_tpw(C.nlon);
   a.reps = std::max(1, std::min(c->sm_count / C.nlat, C.sg_nactive));
   a.nbuf = C.sg_K;
   a.tab = C.sg_st.p, a.rowinfo = C.sg_idx.p;
@@ -598,7 +623,7 @@ static int launch_row(rbc3d_ctx *c, TargetList &t, const double *planes, double 
   a.coef = coef;
   a.acc = t.acc.p;
   CUDA_TRY(cudaFuncSetAttribute(k_sing_row<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.sg_smem));
-  k_sing_row<MODE><<<C.nlat * a.reps, a.ngrp * a.NS * 32, C.sg_smem, c->stream>>>(a);
+  k_sing_row<MODE><<<C.nlat * a.reps, a.ngrp * a.NS * 32 + 32, C.sg_smem, c->stream>>>(a);
   KERNEL_CHECK();
   c->launches++;
   return RBC3D_OK;
