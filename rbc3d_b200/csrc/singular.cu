@@ -154,7 +154,7 @@ static void cyclic_cover(const std::vector<char> &used, int mod, int &lo, int &l
 // row kernel: tables (host, once per rbc3d_cells_set_mesh)
 
 constexpr int SR_TPW = 31;        // targets per warp; lane nt (<= 31) holds the right-hand column of the last target
-constexpr int SR_PF = 3;          // cache records in flight per lane (registers)
+constexpr int SR_PF = 2;          // cache records in flight per lane (registers)
 constexpr int SR_L2PF = 20;       // patch points ahead of which the records are prefetched into L2
 constexpr int SR_TABW = 10;       // doubles per table entry: cx[4], cy[4], quadrature weight, code
 constexpr int SR_NT = 384;        // consumer threads per CTA at most (+ one producer warp; launch bound: 157 registers)
@@ -373,7 +373,7 @@ __device__ __forceinline__ void st_stream2(double2 *p, double2 v) {
 // that keeps the spline bands coming (full / empty mbarriers per band buffer: a consumer warp never waits for another
 // one except for its own group's 4 streams when their sums are combined).
 template <int MODE>
-__global__ void __maxnreg__(152) k_sing_row(RowArgs a) {  // 13 warps x 152 registers fit the register file
+__global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 warps: 4 on one scheduler -> 128 registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.nlon, m = 2 * a.nlat, npts = a.npts, NS = a.NS;
   const int row = blockIdx.x % a.nlat, rep = blockIdx.x / a.nlat;
