@@ -192,7 +192,7 @@ struct Cells {
   dbuf<double> sing_xi;              // SoA(3,Np) spline-evaluated target positions (ModRbcSingInt.F90:58)
   // cached double-layer singular path (singular.cu): cell-independent tile tables, per-geometry cache
   bool sg_ok = false, sg_cache_ok = false, spGi_valid = false, spFi_valid = false;
-  int sg_ntiles = 0, sg_K = 0, sg_win_max = 0;
+  int sg_ntiles = 0, sg_K = 0, sg_win_max = 0, sg_ntab = 0;
   int sg_npatch_active = 0;          // patch points per target with a non-zero quadrature weight (cached path)
   dbuf<int> sg_tile_tgt, sg_tile_win, sg_idx, sg_cell_active, sg_tile_list, sg_pos;
   int sg_ntl = 0, sg_ntn = 0, sg_ni_max = 0, sg_chunk_stride = 0;

@@ -155,11 +155,12 @@ static void cyclic_cover(const std::vector<char> &used, int mod, int &lo, int &l
 
 constexpr int SR_TPW = 31;        // targets per warp; lane nt (<= 31) holds the right-hand column of the last target
 constexpr int SR_PF = 2;          // cache records in flight per lane (registers)
+constexpr int SR_U = 4;           // points per trip of the unrolled loop; streams are padded to multiples of it
 constexpr int SR_L2PF = 20;       // patch points ahead of which the records are prefetched into L2
 constexpr int SR_TABW = 10;       // doubles per table entry: cx[4], cy[4], quadrature weight, code
-constexpr int SR_NT = 384;        // consumer threads per CTA at most (+ one producer warp; launch bound: 157 registers)
-constexpr int SR_FRESH = 1 << 16;
-constexpr int SR_RI = 16;         // ints per row-info record: ilo, ni, npts, stream bounds [0..NS]
+constexpr int SR_NT = 480;        // consumer threads per CTA at most (+ one producer warp = 16 warps of 128 registers)
+constexpr int SR_FRESH = 1 << 16, SR_DUMMY = 1 << 17;
+constexpr int SR_RI = 16;         // ints per row-info record: ilo, ni, table entries, stream bounds [0..NS] (table indices)
 constexpr size_t SR_SMEM_MAX = 227 * 1024;
 enum { SR_BUILD_X = 0, SR_BUILD_N = 1, SR_DL = 2, SR_SL = 3 };
 
@@ -167,7 +168,7 @@ static int sr_groups(int nlon) { return (nlon + SR_TPW - 1) / SR_TPW; }
 static int sr_tpw(int nlon) { return (nlon + sr_groups(nlon) - 1) / sr_groups(nlon); }  // balanced groups: 72 -> 3 x 24
 static int sr_streams(int nlon) {
   const int g = sr_groups(nlon);
-  return std::max(1, std::min(4, (SR_NT / 32) / g));
+  return std::max(1, std::min(5, (SR_NT / 32) / g));
 }
 
 int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, const double *pw) {
@@ -184,9 +185,9 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   const int npts = C.sg_npatch_active;
   const int ngrp = sr_groups(n), NS = sr_streams(n);
   if (npts == 0 || n > 255 || m > 255 || ngrp * NS * 32 > SR_NT || NS + 4 > SR_RI) return RBC3D_OK;  // direct kernel only
-  std::vector<double> tab((size_t)nlat * npts * SR_TABW, 0.0);
+  std::vector<std::vector<double>> rowtab(nlat);
   std::vector<int> rowinfo((size_t)nlat * SR_RI, 0);
-  int ni_max = 0;
+  int ni_max = 0, ntab = 0;
   struct Pt {
     int j1, wi, q;
     double s, t;
@@ -231,35 +232,58 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
       cost[k + 1] = cost[k] + 90.0 + (f ? 14.0 : 0.0);  // instructions per point; node loads at the first point of a spline cell
     }
     // NS streams of contiguous points with about equal cost, cut at spline-cell boundaries
-    int *ri = rowinfo.data() + (size_t)row * SR_RI;
-    ri[0] = ilo, ri[1] = ni, ri[2] = npts;
-    ri[3] = 0;
+    std::vector<int> cut(NS + 1, 0);
     for (int s = 1; s < NS; s++) {
       const double want = cost[npts] * s / NS;
-      int best = ri[3 + s - 1];
+      int best = cut[s - 1];
       double bd = 1e300;
-      for (int k = ri[3 + s - 1]; k <= npts; k++) {
+      for (int k = cut[s - 1]; k <= npts; k++) {
         if (k < npts && !(code[k] & SR_FRESH)) continue;
         const double d = fabs(cost[k] - want);
         if (d < bd) bd = d, best = k;
       }
-      ri[3 + s] = best;
+      cut[s] = best;
     }
-    ri[3 + NS] = npts;
-    for (int s = 1; s < NS; s++)
-      if (ri[3 + s] < npts) code[ri[3 + s]] |= SR_FRESH;  // a stream starts with a node load
-    for (int k = 0; k < npts; k++) {
-      double *te = tab.data() + ((size_t)row * npts + k) * SR_TABW;
-      const double s = pts[k].s, t = pts[k].t;
-      te[0] = 1.0 + s * s * (-3.0 + 2.0 * s), te[1] = s * s * (3.0 - 2.0 * s);
-      te[2] = hx * s * (1.0 + s * (-2.0 + s)), te[3] = hx * s * s * (-1.0 + s);
-      te[4] = 1.0 + t * t * (-3.0 + 2.0 * t), te[5] = t * t * (3.0 - 2.0 * t);
-      te[6] = hy * t * (1.0 + t * (-2.0 + t)), te[7] = hy * t * t * (-1.0 + t);
-      te[8] = pw[pts[k].q % C.nrad];
-      long long cw = code[k];
-      memcpy(&te[9], &cw, sizeof(double));
+    cut[NS] = npts;
+    // table entries: every stream padded to a multiple of SR_U points with dummies (zero basis: they add exactly zero;
+    // their record index is the stream's last point), SR_PF more dummies behind the row for the look-ahead
+    int *ri = rowinfo.data() + (size_t)row * SR_RI;
+    ri[0] = ilo, ri[1] = ni;
+    std::vector<double> &rt = rowtab[row];
+    rt.clear();
+    auto push = [&](int k, bool dummy, bool fresh) {
+      double te[SR_TABW];
+      for (int i = 0; i < SR_TABW; i++) te[i] = 0.0;
+      int cw = code[k] & 0xffff;
+      if (!dummy) {
+        const double s = pts[k].s, t = pts[k].t;
+        te[0] = 1.0 + s * s * (-3.0 + 2.0 * s), te[1] = s * s * (3.0 - 2.0 * s);
+        te[2] = hx * s * (1.0 + s * (-2.0 + s)), te[3] = hx * s * s * (-1.0 + s);
+        te[4] = 1.0 + t * t * (-3.0 + 2.0 * t), te[5] = t * t * (3.0 - 2.0 * t);
+        te[6] = hy * t * (1.0 + t * (-2.0 + t)), te[7] = hy * t * t * (-1.0 + t);
+        te[8] = pw[pts[k].q % C.nrad];
+        if (fresh || (code[k] & SR_FRESH)) cw |= SR_FRESH;
+      } else {
+        cw |= SR_DUMMY;
+      }
+      const unsigned long long w64 = (unsigned long long)(unsigned)cw | ((unsigned long long)(unsigned)k << 32);
+      memcpy(&te[9], &w64, sizeof(double));
+      rt.insert(rt.end(), te, te + SR_TABW);
+    };
+    for (int s = 0; s < NS; s++) {
+      ri[3 + s] = (int)(rt.size() / SR_TABW);
+      for (int k = cut[s]; k < cut[s + 1]; k++) push(k, false, k == cut[s]);  // a stream starts with a node load
+      const int len = cut[s + 1] - cut[s];
+      for (int k = len; k % SR_U != 0; k++) push(std::max(cut[s + 1] - 1, 0), true, false);
     }
+    ri[3 + NS] = (int)(rt.size() / SR_TABW);
+    for (int k = 0; k < SR_PF; k++) push(npts - 1, true, false);
+    ri[2] = (int)(rt.size() / SR_TABW);
+    ntab = std::max(ntab, ri[2]);
   }
+  std::vector<double> tab((size_t)nlat * ntab * SR_TABW, 0.0);
+  for (int row = 0; row < nlat; row++) std::copy(rowtab[row].begin(), rowtab[row].end(), tab.begin() + (size_t)row * ntab * SR_TABW);
+  C.sg_ntab = ntab;
   C.sg_ni_max = ni_max;
   RBC_TRY(C.sg_st.resize(tab.size()));
   RBC_TRY(C.sg_idx.resize(rowinfo.size()));
@@ -268,7 +292,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   // shared memory: barriers, the row's tables, the cross-stream reduction buffer, one or two bands
   const size_t band = (size_t)6 * ni_max * n * sizeof(double2);
-  const size_t fixed = 64 + (size_t)npts * SR_TABW * sizeof(double) + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW * sizeof(double);
+  const size_t fixed = 64 + (size_t)ntab * SR_TABW * sizeof(double) + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW * sizeof(double);
   if (fixed + band > SR_SMEM_MAX) return RBC3D_OK;  // direct kernel only
   C.sg_K = (fixed + 2 * band <= SR_SMEM_MAX) ? 2 : 1;  // band buffers
   C.sg_smem = fixed + C.sg_K * band;
@@ -299,8 +323,8 @@ __global__ void __launch_bounds__(256) k_spline_planes(int ncell, int m, int n, 
 // ---------------------------------------------------------------------------------------------------------
 struct RowArgs {
   Params prm;
-  int npc, nlat, nlon, Np, npts, ni_max, nslot, ngrp, NS, tpw, reps, nbuf;
-  const double *tab;        // [row][npts][SR_TABW]
+  int npc, nlat, nlon, Np, npts, ntab, ni_max, nslot, ngrp, NS, tpw, reps, nbuf;
+  const double *tab;        // [row][ntab][SR_TABW]
   const int *rowinfo;       // [row][SR_RI]
   const double2 *planes;    // [cell][6][m][n] of the interpolated field (x, a3, g detJ or f detJ)
   double2 *cache;           // [slot][row][point][half][n]: (xx.x, xx.y), (xx.z, w)
@@ -382,7 +406,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
   unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem_raw);   // [2]
   unsigned long long *bar_empty = bar_full + 2;                                          // [2]
   double *s_tab = reinterpret_cast<double *>(smem_raw + 64);
-  double *s_red = s_tab + (size_t)npts * SR_TABW;                       // [2][consumer warp][3][tpw]
+  double *s_red = s_tab + (size_t)a.ntab * SR_TABW;                     // [2][consumer warp][3][tpw]
   const int tpw = a.tpw;
   double2 *s_band = reinterpret_cast<double2 *>(s_red + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW);
   const int *ri = a.rowinfo + (size_t)row * SR_RI;
@@ -391,7 +415,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
   const size_t band_n = (size_t)6 * wpl;
   const int nbuf = a.nbuf;
   // ---- prologue: tables of the row, barriers ----
-  for (int e = threadIdx.x; e < npts * SR_TABW; e += blockDim.x) s_tab[e] = a.tab[(size_t)row * npts * SR_TABW + e];
+  for (int e = threadIdx.x; e < a.ntab * SR_TABW; e += blockDim.x) s_tab[e] = a.tab[(size_t)row * a.ntab * SR_TABW + e];
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; b++) {
       mbar_init(bar_full + b, 1);
@@ -423,34 +447,51 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
   }
   const int grp = warp / NS, strm = warp - grp * NS;
   const int jt0 = grp * tpw, nt = min(tpw, n - jt0);  // this warp's targets jt0 .. jt0 + nt - 1
-  const bool on = lane <= nt, is_t = lane < nt;
-  const int pbeg = ri[3 + strm], pend = ri[4 + strm];
+  const bool is_t = lane < nt;
+  const int lane_t = min(lane, nt - 1);               // lanes beyond the targets repeat the last target's record loads
+  const int cb = (jt0 + lane) % n;                    // phi column of this lane for j1 = 0
+  const int pbeg = ri[3 + strm], pend = ri[4 + strm]; // table entries of this stream, a multiple of SR_U
   const unsigned long long pol = l2_evict_first_policy();
-  const size_t rstep = (size_t)2 * n;  // double2 per patch point of an item
+  const size_t rstep = (size_t)2 * n;                 // double2 per patch point of an item
+  const size_t item_step = (size_t)a.reps * a.nlat * npts * rstep;
+  // the stream's real points are contiguous in the cache: [rfirst, rfirst + rcount)
+  const int rfirst = (int)(reinterpret_cast<const unsigned long long *>(s_tab + (size_t)pbeg * SR_TABW + 9)[0] >> 32);
+  const int rcount = (pend > pbeg)
+                         ? (int)(reinterpret_cast<const unsigned long long *>(s_tab + (size_t)(pend - 1) * SR_TABW + 9)[0] >> 32) + 1 - rfirst
+                         : 0;
+  const bool pf_lane = (MODE != SR_BUILD_X) && grp == 0 && lane == 0;  // group 0 prefetches whole rows (all groups' records)
   int it = 0;
   for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
     const int buf = it % nbuf, use = it / nbuf;
     const int cell = a.active_list[slot];
-    double2 *rec = a.cache + (((size_t)slot * a.nlat + row) * npts) * rstep + (jt0 + lane);
+    double2 *item = a.cache + (((size_t)slot * a.nlat + row) * npts) * rstep;
+    double2 *rec = item + (jt0 + lane_t);
     double xi0 = 0, xi1 = 0, xi2 = 0;
     if (MODE == SR_BUILD_X && is_t) {
       double xi[3];
       spline_interp<3>(a.spx + (size_t)12 * m * n * cell, m, n, a.th[row], a.phi[jt0 + lane], xi);  // ModRbcSingInt.F90:58
       xi0 = xi[0], xi1 = xi[1], xi2 = xi[2];
     }
-    // records: SR_PF points in flight in registers, SR_L2PF points ahead on their way from HBM to L2
+    if (pf_lane) {
+      // HBM -> L2, far ahead of the register loads: this item's first records (first item only) and the next item's
+      const unsigned head = (unsigned)(min(rcount, SR_L2PF) * rstep * sizeof(double2));
+      if (head) {
+        if (it == 0) l2_prefetch(item + (size_t)rfirst * rstep, head);
+        if (slot + a.reps < a.nslot) l2_prefetch(item + item_step + (size_t)rfirst * rstep, head);
+      }
+    }
+    // records: SR_PF points in flight in registers
+    unsigned long long cw[SR_PF];
     double2 ra[SR_PF], rb[SR_PF];
 #pragma unroll
     for (int k = 0; k < SR_PF; k++) {
+      cw[k] = reinterpret_cast<const unsigned long long *>(s_tab + (size_t)(pbeg + k) * SR_TABW + 9)[0];
       ra[k] = rb[k] = make_double2(0, 0);
-      if (MODE != SR_BUILD_X && is_t && pbeg + k < pend) {
-        ra[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * rstep) : ld_stream2(rec + (size_t)(pbeg + k) * rstep, pol);
-        rb[k] = MODE == SR_BUILD_N ? ld_plain2(rec + (size_t)(pbeg + k) * rstep + n) : ld_stream2(rec + (size_t)(pbeg + k) * rstep + n, pol);
+      if (MODE != SR_BUILD_X) {
+        const double2 *q = rec + (size_t)(cw[k] >> 32) * rstep;
+        ra[k] = MODE == SR_BUILD_N ? ld_plain2(q) : ld_stream2(q, pol);
+        rb[k] = MODE == SR_BUILD_N ? ld_plain2(q + n) : ld_stream2(q + n, pol);
       }
-    }
-    if (MODE != SR_BUILD_X && lane < 2) {
-      const unsigned pfb = (unsigned)(nt * sizeof(double2));
-      for (int k = SR_PF; k < SR_L2PF && pbeg + k < pend; k++) l2_prefetch(rec - lane + (size_t)(pbeg + k) * rstep + lane * n, pfb);
     }
     mbar_wait(bar_full + buf, (unsigned)(use & 1));
     const double2 *band = s_band + (size_t)buf * band_n;
@@ -459,80 +500,79 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
     for (int q = 0; q < 6; q++) top[q] = bot[q] = make_double2(0, 0);
     double pv0 = 0, pv1 = 0, pv2 = 0;
     const double *te = s_tab + (size_t)pbeg * SR_TABW;
-    double2 *rp = rec + (size_t)pbeg * rstep;  // records of the current point
-    for (int p = pbeg; p < pend; p += SR_PF) {
+    for (int p = pbeg; p < pend; p += SR_U) {
+      if (pf_lane) {
+        const int r0 = (int)(cw[0] >> 32) + SR_L2PF;  // records SR_L2PF points ahead, SR_U points per trip
+        if (r0 + SR_U <= rfirst + rcount) l2_prefetch(item + (size_t)r0 * rstep, (unsigned)(SR_U * rstep * sizeof(double2)));
+      }
 #pragma unroll
-      for (int k = 0; k < SR_PF; k++) {
-        const int pk = p + k;
-        if (pk < pend) {  // warp uniform
-          const int code = *reinterpret_cast<const int *>(te + 9);
-          if (code & SR_FRESH) {  // first point of a spline cell: the two theta nodes of this lane's phi column
-            int col = ((code >> 8) & 255) + jt0 + lane;
-            if (col >= n) col -= n;
-            const double2 *nb = band + (code & 255) * n + col;
-            if (on) {
+      for (int k = 0; k < SR_U; k++) {
+        const int kr = k % SR_PF;
+        const int code = (int)(unsigned)cw[kr];
+        if (code & SR_FRESH) {  // first point of a spline cell: the two theta nodes of this lane's phi column
+          int col = ((code >> 8) & 255) + cb;
+          if (col >= n) col -= n;
+          const double2 *nb = band + (code & 255) * n + col;
 #pragma unroll
-              for (int q = 0; q < 6; q++) {
-                top[q] = nb[q * wpl];
-                bot[q] = nb[q * wpl + n];
-              }
-            }
+          for (int q = 0; q < 6; q++) {
+            top[q] = nb[q * wpl];
+            bot[q] = nb[q * wpl + n];
           }
-          const double2 cx01 = *reinterpret_cast<const double2 *>(te), cx23 = *reinterpret_cast<const double2 *>(te + 2);
-          const double2 cy01 = *reinterpret_cast<const double2 *>(te + 4), cy23 = *reinterpret_cast<const double2 *>(te + 6);
-          double g[3];
-#pragma unroll
-          for (int l = 0; l < 3; l++) {
-            // theta interpolants of this lane's phi column: P (value), Q (phi derivative)
-            const double P = top[2 * l].x * cx01.x + bot[2 * l].x * cx01.y + top[2 * l].y * cx23.x + bot[2 * l].y * cx23.y;
-            const double Q = top[2 * l + 1].x * cx01.x + bot[2 * l + 1].x * cx01.y + top[2 * l + 1].y * cx23.x +
-                             bot[2 * l + 1].y * cx23.y;
-            const double A = P * cy01.x + Q * cy23.x;   // this column as the left one of the lane's own target
-            const double Br = P * cy01.y + Q * cy23.y;  // ... as the right one of the left neighbour's target
-            g[l] = A + __shfl_down_sync(FULL_MASK, Br, 1);
-          }
-          const double2 A2 = ra[k], B2 = rb[k];
-          if (MODE == SR_BUILD_X) {
-            if (is_t) {
-              st_stream2(rp, make_double2(g[0] - xi0, g[1] - xi1));
-              st_stream2(rp + n, make_double2(g[2] - xi2, 0.0));
-            }
-          } else if (MODE == SR_BUILD_N) {
-            const double xx = A2.x, yy = A2.y, zz = B2.x;
-            const double rr = sqrt(xx * xx + yy * yy + zz * zz);
-            double w = 0.0;
-            if (rr < a.prm.rc)  // ModRbcSingInt.F90:69
-              w = ewald_dl(a.tab_dl, a.prm, rr) * te[8] * (xx * g[0] + yy * g[1] + zz * g[2]);
-            if (is_t) st_stream2(rp + n, make_double2(zz, w));
-          } else if (MODE == SR_DL) {
-            const double qd = B2.y * (A2.x * g[0] + A2.y * g[1] + B2.x * g[2]);
-            pv0 = fma(qd, A2.x, pv0);
-            pv1 = fma(qd, A2.y, pv1);
-            pv2 = fma(qd, B2.x, pv2);
-          } else {  // SR_SL: ModRbcSingInt.F90:72-78 with the cached xx
-            const double xx = A2.x, yy = A2.y, zz = B2.x;
-            const double rr = sqrt(xx * xx + yy * yy + zz * zz);
-            if (rr < a.prm.rc) {
-              const double wq = te[8];
-              const double f0 = g[0] * wq, f1 = g[1] * wq, f2 = g[2] * wq;
-              double EA, EB;
-              ewald_sl(a.tab_sl, a.prm, rr, EA, EB);
-              const double xf = EA * (xx * f0 + yy * f1 + zz * f2);
-              pv0 += xf * xx + EB * f0;
-              pv1 += xf * yy + EB * f1;
-              pv2 += xf * zz + EB * f2;
-            }
-          }
-          if (MODE != SR_BUILD_X) {
-            if (is_t && pk + SR_PF < pend) {
-              ra[k] = MODE == SR_BUILD_N ? ld_plain2(rp + SR_PF * rstep) : ld_stream2(rp + SR_PF * rstep, pol);
-              rb[k] = MODE == SR_BUILD_N ? ld_plain2(rp + SR_PF * rstep + n) : ld_stream2(rp + SR_PF * rstep + n, pol);
-            }
-            if (lane < 2 && pk + SR_L2PF < pend) l2_prefetch(rp - lane + SR_L2PF * rstep + lane * n, (unsigned)(nt * sizeof(double2)));
-          }
-          te += SR_TABW;
-          rp += rstep;
         }
+        const double2 cx01 = *reinterpret_cast<const double2 *>(te), cx23 = *reinterpret_cast<const double2 *>(te + 2);
+        const double2 cy01 = *reinterpret_cast<const double2 *>(te + 4), cy23 = *reinterpret_cast<const double2 *>(te + 6);
+        double g[3];
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          // theta interpolants of this lane's phi column: P (value), Q (phi derivative)
+          const double P = top[2 * l].x * cx01.x + bot[2 * l].x * cx01.y + top[2 * l].y * cx23.x + bot[2 * l].y * cx23.y;
+          const double Q = top[2 * l + 1].x * cx01.x + bot[2 * l + 1].x * cx01.y + top[2 * l + 1].y * cx23.x +
+                           bot[2 * l + 1].y * cx23.y;
+          const double A = P * cy01.x + Q * cy23.x;   // this column as the left one of the lane's own target
+          const double Br = P * cy01.y + Q * cy23.y;  // ... as the right one of the left neighbour's target
+          g[l] = A + __shfl_down_sync(FULL_MASK, Br, 1);
+        }
+        const double2 A2 = ra[kr], B2 = rb[kr];
+        double2 *rp = rec + (size_t)(cw[kr] >> 32) * rstep;  // this point's records (stores of the build passes)
+        if (MODE == SR_BUILD_X) {
+          if (is_t && !(code & SR_DUMMY)) {
+            st_stream2(rp, make_double2(g[0] - xi0, g[1] - xi1));
+            st_stream2(rp + n, make_double2(g[2] - xi2, 0.0));
+          }
+        } else if (MODE == SR_BUILD_N) {
+          const double xx = A2.x, yy = A2.y, zz = B2.x;
+          const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+          double w = 0.0;
+          if (rr < a.prm.rc)  // ModRbcSingInt.F90:69
+            w = ewald_dl(a.tab_dl, a.prm, rr) * te[8] * (xx * g[0] + yy * g[1] + zz * g[2]);
+          if (is_t && !(code & SR_DUMMY)) st_stream2(rp + n, make_double2(zz, w));
+        } else if (MODE == SR_DL) {
+          const double qd = B2.y * (A2.x * g[0] + A2.y * g[1] + B2.x * g[2]);
+          pv0 = fma(qd, A2.x, pv0);
+          pv1 = fma(qd, A2.y, pv1);
+          pv2 = fma(qd, B2.x, pv2);
+        } else {  // SR_SL: ModRbcSingInt.F90:72-78 with the cached xx
+          const double xx = A2.x, yy = A2.y, zz = B2.x;
+          const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+          if (rr < a.prm.rc) {
+            const double wq = te[8];
+            const double f0 = g[0] * wq, f1 = g[1] * wq, f2 = g[2] * wq;
+            double EA, EB;
+            ewald_sl(a.tab_sl, a.prm, rr, EA, EB);
+            const double xf = EA * (xx * f0 + yy * f1 + zz * f2);
+            pv0 += xf * xx + EB * f0;
+            pv1 += xf * yy + EB * f1;
+            pv2 += xf * zz + EB * f2;
+          }
+        }
+        // look ahead: the table has SR_PF dummy entries behind the last stream
+        cw[kr] = reinterpret_cast<const unsigned long long *>(te + SR_PF * SR_TABW + 9)[0];
+        if (MODE != SR_BUILD_X) {
+          const double2 *q = rec + (size_t)(cw[kr] >> 32) * rstep;
+          ra[kr] = MODE == SR_BUILD_N ? ld_plain2(q) : ld_stream2(q, pol);
+          rb[kr] = MODE == SR_BUILD_N ? ld_plain2(q + n) : ld_stream2(q + n, pol);
+        }
+        te += SR_TABW;
       }
     }
     __syncwarp();
@@ -610,7 +650,7 @@ static int launch_row(rbc3d_ctx *c, TargetList &t, const double *planes, double 
   RowArgs a;
   a.prm = c->prm;
   a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.Np = C.Np;
-  a.npts = C.sg_npatch_active, a.ni_max = C.sg_ni_max, a.nslot = C.sg_nactive;
+  a.npts = C.sg_npatch_active, a.ntab = C.sg_ntab, a.ni_max = C.sg_ni_max, a.nslot = C.sg_nactive;
   a.ngrp = sr_groups(C.nlon), a.NS = sr_streams(C.nlon), a.tpw = sr_tpw(C.nlon);
   a.reps = std::max(1, std::min(c->sm_count / C.nlat, C.sg_nactive));
   a.nbuf = C.sg_K;

@@ -99,8 +99,9 @@ def test_carotid_web_72_cells_and_two_walls(oracle_lib):
     assert sus.ncell == 72 and sus.npoint == 186624 and list(W.nvert) == [14550, 2903] and list(W.nele) == [28948, 5682]
     op = EwaldOperator(Lb)
     orc = oracle_lib.Oracle(Lb)
-    assert list(op.Nb) == orc.Nb == [48, 48, 136] and op.cell_list_dims() == orc.Nc == [8, 8, 25]
+    assert list(op.Nb) == orc.Nb == [48, 48, 136] and orc.Nc == [8, 8, 25]
     _check_all(op, orc, sus, W)
+    assert op.cell_list_dims() == [8, 8, 25]
     # a few iterations of the wall solve with the cells present: identical residual history
     import copy
     from oracle import harness
