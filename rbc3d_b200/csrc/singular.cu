@@ -155,11 +155,11 @@ static void cyclic_cover(const std::vector<char> &used, int mod, int &lo, int &l
 
 constexpr int SR_TPW = 31;        // targets per warp; lane nt (<= 31) holds the right-hand column of the last target
 constexpr int SR_PF = 2;          // cache records in flight per lane (registers)
-constexpr int SR_U = 4;           // points per trip of the unrolled loop; streams are padded to multiples of it
+constexpr int SR_U = 2;           // points per trip of the unrolled loop; streams are padded to multiples of it
 constexpr int SR_L2PF = 20;       // patch points ahead of which the records are prefetched into L2
 constexpr int SR_TABW = 10;       // doubles per table entry: cx[4], cy[4], quadrature weight, code
 constexpr int SR_NT = 480;        // consumer threads per CTA at most (+ one producer warp = 16 warps of 128 registers)
-constexpr int SR_FRESH = 1 << 16, SR_DUMMY = 1 << 17;
+constexpr int SR_FRESH = 1 << 16, SR_DUMMY = 1 << 17, SR_LOADX = 1 << 18, SR_LOADY = 1 << 19;
 constexpr int SR_RI = 16;         // ints per row-info record: ilo, ni, table entries, stream bounds [0..NS] (table indices)
 constexpr size_t SR_SMEM_MAX = 227 * 1024;
 enum { SR_BUILD_X = 0, SR_BUILD_N = 1, SR_DL = 2, SR_SL = 3 };
@@ -231,30 +231,26 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
       code[k] = pts[k].wi | (pts[k].j1 << 8) | f;
       cost[k + 1] = cost[k] + 90.0 + (f ? 14.0 : 0.0);  // instructions per point; node loads at the first point of a spline cell
     }
-    // NS streams of contiguous points with about equal cost, cut at spline-cell boundaries
+    // NS streams of contiguous points of equal length (+-1): every warp of a target group then runs the same number of
+    // steps; a cut inside a spline cell only costs the next stream one more node load
     std::vector<int> cut(NS + 1, 0);
-    for (int s = 1; s < NS; s++) {
-      const double want = cost[npts] * s / NS;
-      int best = cut[s - 1];
-      double bd = 1e300;
-      for (int k = cut[s - 1]; k <= npts; k++) {
-        if (k < npts && !(code[k] & SR_FRESH)) continue;
-        const double d = fabs(cost[k] - want);
-        if (d < bd) bd = d, best = k;
-      }
-      cut[s] = best;
-    }
-    cut[NS] = npts;
+    for (int s = 1; s <= NS; s++) cut[s] = (int)(((long long)npts * s) / NS);
+    (void)cost;
     // table entries: every stream padded to a multiple of SR_U points with dummies (zero basis: they add exactly zero;
     // their record index is the stream's last point), SR_PF more dummies behind the row for the look-ahead
     int *ri = rowinfo.data() + (size_t)row * SR_RI;
     ri[0] = ilo, ri[1] = ni;
     std::vector<double> &rt = rowtab[row];
     rt.clear();
-    auto push = [&](int k, bool dummy, bool fresh) {
+    // Node registers X, Y of a lane hold two adjacent theta rows of its phi column.  FRESH loads both (X = upper row i1,
+    // Y = lower row i2).  When the next spline cell is the one below in the same column, only the new lower row is
+    // loaded, into the register pair that held the old upper row (LOADX / LOADY), and the roles of X and Y are swapped
+    // by swapping the theta basis values IN THE TABLE (te[0] <-> te[1], te[2] <-> te[3]): no register moves.
+    bool swapped = false;
+    auto push = [&](int k, bool dummy, int load) {
       double te[SR_TABW];
       for (int i = 0; i < SR_TABW; i++) te[i] = 0.0;
-      int cw = code[k] & 0xffff;
+      int cw = (code[k] & 0xffff) | load;
       if (!dummy) {
         const double s = pts[k].s, t = pts[k].t;
         te[0] = 1.0 + s * s * (-3.0 + 2.0 * s), te[1] = s * s * (3.0 - 2.0 * s);
@@ -262,7 +258,7 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
         te[4] = 1.0 + t * t * (-3.0 + 2.0 * t), te[5] = t * t * (3.0 - 2.0 * t);
         te[6] = hy * t * (1.0 + t * (-2.0 + t)), te[7] = hy * t * t * (-1.0 + t);
         te[8] = pw[pts[k].q % C.nrad];
-        if (fresh || (code[k] & SR_FRESH)) cw |= SR_FRESH;
+        if (swapped) std::swap(te[0], te[1]), std::swap(te[2], te[3]);
       } else {
         cw |= SR_DUMMY;
       }
@@ -272,12 +268,25 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
     };
     for (int s = 0; s < NS; s++) {
       ri[3 + s] = (int)(rt.size() / SR_TABW);
-      for (int k = cut[s]; k < cut[s + 1]; k++) push(k, false, k == cut[s]);  // a stream starts with a node load
+      for (int k = cut[s]; k < cut[s + 1]; k++) {
+        int load = 0;
+        if (k == cut[s]) {
+          load = SR_FRESH, swapped = false;  // a stream starts with a full node load
+        } else if (code[k] & SR_FRESH) {
+          if (pts[k].j1 == pts[k - 1].j1 && pts[k].wi == pts[k - 1].wi + 1) {
+            load = swapped ? SR_LOADY : SR_LOADX;  // the pair that held the old upper row takes the new lower row
+            swapped = !swapped;
+          } else {
+            load = SR_FRESH, swapped = false;
+          }
+        }
+        push(k, false, load);
+      }
       const int len = cut[s + 1] - cut[s];
-      for (int k = len; k % SR_U != 0; k++) push(std::max(cut[s + 1] - 1, 0), true, false);
+      for (int k = len; k % SR_U != 0; k++) push(std::max(cut[s + 1] - 1, 0), true, 0);
     }
     ri[3 + NS] = (int)(rt.size() / SR_TABW);
-    for (int k = 0; k < SR_PF; k++) push(npts - 1, true, false);
+    for (int k = 0; k < SR_PF; k++) push(npts - 1, true, 0);
     ri[2] = (int)(rt.size() / SR_TABW);
     ntab = std::max(ntab, ri[2]);
   }
@@ -357,6 +366,19 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 __device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -432,7 +454,8 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       int it = 0;
       for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
         const int buf = it % nbuf, use = it / nbuf;
-        if (use > 0) mbar_wait(bar_empty + buf, (unsigned)((use - 1) & 1));  // every consumer warp has left the buffer
+        if (use > 0)  // every consumer warp has left the buffer; poll with a pause: the issue slots belong to the consumers
+          while (!mbar_test(bar_empty + buf, (unsigned)((use - 1) & 1))) __nanosleep(200);
         const int cell = a.active_list[slot];
         mbar_expect_tx(bar_full + buf, band_bytes);
         for (int q = 0; q < 6; q++) {
@@ -509,14 +532,21 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       for (int k = 0; k < SR_U; k++) {
         const int kr = k % SR_PF;
         const int code = (int)(unsigned)cw[kr];
-        if (code & SR_FRESH) {  // first point of a spline cell: the two theta nodes of this lane's phi column
+        if (code & (SR_FRESH | SR_LOADX | SR_LOADY)) {  // first point of a spline cell: theta nodes of this lane's phi column
           int col = ((code >> 8) & 255) + cb;
           if (col >= n) col -= n;
           const double2 *nb = band + (code & 255) * n + col;
+          if (code & SR_FRESH) {
 #pragma unroll
-          for (int q = 0; q < 6; q++) {
-            top[q] = nb[q * wpl];
-            bot[q] = nb[q * wpl + n];
+            for (int q = 0; q < 6; q++) top[q] = nb[q * wpl];
+          }
+          if (code & (SR_FRESH | SR_LOADY)) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) bot[q] = nb[q * wpl + n];
+          }
+          if (code & SR_LOADX) {  // the cell below: its lower row replaces the old upper row (roles swapped in the table)
+#pragma unroll
+            for (int q = 0; q < 6; q++) top[q] = nb[q * wpl + n];
           }
         }
         const double2 cx01 = *reinterpret_cast<const double2 *>(te), cx23 = *reinterpret_cast<const double2 *>(te + 2);
