@@ -301,7 +301,8 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   // shared memory: barriers, the row's tables, the cross-stream reduction buffer, one or two bands
   const size_t band = (size_t)6 * ni_max * n * sizeof(double2);
-  const size_t fixed = 64 + (size_t)ntab * SR_TABW * sizeof(double) + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW * sizeof(double);
+  const size_t fixed = 64 + (size_t)ntab * SR_TABW * sizeof(double) +
+                       (((size_t)2 * ngrp * (NS - 1) * 3 * sr_tpw(n) + 1) & ~(size_t)1) * sizeof(double);
   if (fixed + band > SR_SMEM_MAX) return RBC3D_OK;  // direct kernel only
   C.sg_K = (fixed + 2 * band <= SR_SMEM_MAX) ? 2 : 1;  // band buffers
   C.sg_smem = fixed + C.sg_K * band;
@@ -371,11 +372,11 @@ __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned pari
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint in ns: the producer lane sleeps in hardware
       : "memory");
   return ok != 0;
 }
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
   double *s_tab = reinterpret_cast<double *>(smem_raw + 64);
   double *s_red = s_tab + (size_t)a.ntab * SR_TABW;                     // [2][consumer warp][3][tpw]
   const int tpw = a.tpw;
-  double2 *s_band = reinterpret_cast<double2 *>(s_red + (size_t)2 * (SR_NT / 32) * 3 * SR_TPW);
+  double2 *s_band = reinterpret_cast<double2 *>(s_red + (((size_t)2 * a.ngrp * (NS - 1) * 3 * tpw + 1) & ~(size_t)1));
   const int *ri = a.rowinfo + (size_t)row * SR_RI;
   const int ilo = ri[0], ni = ri[1];
   const int wpl = a.ni_max * n;                                         // double2 per plane of a band buffer (uniform)
@@ -455,7 +456,8 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
         const int buf = it % nbuf, use = it / nbuf;
         if (use > 0)  // every consumer warp has left the buffer; poll with a pause: the issue slots belong to the consumers
-          while (!mbar_test(bar_empty + buf, (unsigned)((use - 1) & 1))) __nanosleep(200);
+          while (!mbar_test(bar_empty + buf, (unsigned)((use - 1) & 1))) {
+          }
         const int cell = a.active_list[slot];
         mbar_expect_tx(bar_full + buf, band_bytes);
         for (int q = 0; q < 6; q++) {
@@ -610,19 +612,23 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
     if (MODE == SR_DL || MODE == SR_SL) {
       // fixed order: a lane's points in stream order, then the streams -- one writer per target, no atomics.  Only the NS
       // warps of a target group meet here (named barrier 1 + grp); the buffer alternates with the item's parity.
-      double *sr = s_red + ((size_t)(it & 1) * (SR_NT / 32) + warp) * 3 * SR_TPW + lane;
-      if (is_t) sr[0] = pv0, sr[SR_TPW] = pv1, sr[2 * SR_TPW] = pv2;
+      // streams 1 .. NS-1 hand their sums to stream 0 of their group: [item parity][group][stream - 1][3][tpw]
+      const size_t gsz = (size_t)(NS - 1) * 3 * tpw;
+      double *sg = s_red + ((size_t)(it & 1) * a.ngrp + grp) * gsz;
+      if (strm > 0 && is_t) {
+        double *sr = sg + (size_t)(strm - 1) * 3 * tpw + lane;
+        sr[0] = pv0, sr[tpw] = pv1, sr[2 * tpw] = pv2;
+      }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NS * 32) : "memory");
       if (strm == 0 && is_t) {
         const int tj = cell * a.npc + (jt0 + lane) * a.nlat + row;
         if (a.active[tj]) {
           const double cm = MODE == SR_DL ? a.coef * a.Bcell[cell] : a.coef;  // c2Mod, ModIntOnRbcs.F90:116
-          const double *s0 = s_red + ((size_t)(it & 1) * (SR_NT / 32) + grp * NS) * 3 * SR_TPW + lane;
+          double sum[3] = {pv0, pv1, pv2};
 #pragma unroll
           for (int d = 0; d < 3; d++) {
-            double s = 0;
-            for (int q = 0; q < NS; q++) s += s0[(size_t)q * 3 * SR_TPW + d * SR_TPW];
-            a.acc[(size_t)d * a.Np + tj] += cm * s;
+            for (int q = 0; q < NS - 1; q++) sum[d] += sg[(size_t)q * 3 * tpw + d * tpw + lane];
+            a.acc[(size_t)d * a.Np + tj] += cm * sum[d];
           }
         }
       }
