@@ -46,9 +46,10 @@ FLOPS_PATCH_EXTRA = 45.0  # kernel evaluation at a patch point
 FLOPS_PATCH_CACHED = 110.0  # cached matvec path: one 3-variable bicubic (96) + 7 FMAs per patch point
 
 
-PARTITION_TEXT = ("targets, singular/pair work, geometry caches and PME spreading by owned cell block; densities uploaded "
-                  "1/world per rank + ncclAllGather; meshes and velocities summed with ncclAllReduce; the PME chain "
-                  "overlaps the real-space kernels on a second stream (stage_ms overlap)")
+PARTITION_TEXT = ("whole cells by the z-slab of their centroid (targets, singular/pair work, geometry caches); densities "
+                  "uploaded 1/world per rank + ncclAllGather; PME by z-slabs of mesh planes (DomainDecomp): slab-local "
+                  "spreading without a mesh reduction, 2-D FFT per plane, all-to-all transpose (grouped ncclSend/Recv), "
+                  "1-D FFT in z + k-space multiplier on y-slabs, and back; velocity halo planes from their owners")
 
 
 def n_side_of(cells: int) -> int:

@@ -312,6 +312,7 @@ int rbc3d_ctx_create(rbc3d_ctx **out, const double Lb[3], double alpha, double e
   if ((rcode = upload(c->tab_dl, c->h_tab_dl.data(), (size_t)N + 1, c->stream)) != RBC3D_OK) return rcode;
   if ((rcode = upload(c->tab_mask, c->h_tab_mask.data(), (size_t)N + 1, c->stream)) != RBC3D_OK) return rcode;
   if ((rcode = pme_init(c)) != RBC3D_OK) return rcode;
+  if ((rcode = pme_slab_setup(c)) != RBC3D_OK) return rcode;
   RBC_TRY(c->cells.xvint_part.resize(3 * 296 + 8));
   CUDA_TRY(cudaMemsetAsync(c->cells.xvint_part.p, 0, sizeof(double) * (3 * 296 + 8), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -567,15 +568,18 @@ static int set_geometry_common(rbc3d_ctx *c, const double *x, const double *a3, 
   // source cell lists: real-space cells (HashTable_Build) and PME blocks
   RBC_TRY(celllist_build_realspace(c, C.cl, (int)Np, C.x.p, nullptr));
   C.geom_version++;
-  // PME sources: with several ranks every rank spreads a contiguous block of cells (comm.cu)
+  // PME sources: with several ranks every rank spreads the points whose B-spline support touches its z-slab of mesh
+  // planes (pme.cu; ModPME.F90:428-429) -- or, with the slab decomposition switched off, a contiguous block of cells
   const int *src_own = nullptr;
   if (c->prm.nranks > 1 && Np > 0) {
-    RBC_TRY(C.src_own.resize(Np));
-    const int c_lo = (int)((long long)C.ncell * c->prm.rank / c->prm.nranks);
-    const int c_hi = (int)((long long)C.ncell * (c->prm.rank + 1) / c->prm.nranks);
-    k_fill_range<<<(int)((Np + 255) / 256), 256, 0, c->stream>>>((int)Np, C.src_own.p, c_lo * C.npc, c_hi * C.npc);
-    KERNEL_CHECK();
-    src_own = C.src_own.p;
+    RBC_TRY(pme_source_ownership(c, (int)Np, C.x.p, C.src_own, &src_own));
+    if (!src_own) {
+      const int c_lo = (int)((long long)C.ncell * c->prm.rank / c->prm.nranks);
+      const int c_hi = (int)((long long)C.ncell * (c->prm.rank + 1) / c->prm.nranks);
+      k_fill_range<<<(int)((Np + 255) / 256), 256, 0, c->stream>>>((int)Np, C.src_own.p, c_lo * C.npc, c_hi * C.npc);
+      KERNEL_CHECK();
+      src_own = C.src_own.p;
+    }
   }
   RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own, c->pme.sblk, c->pme.swalk));
   if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, C.pl, C.x.p));

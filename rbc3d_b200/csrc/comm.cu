@@ -3,10 +3,14 @@
 // The reference replicates all surface state on every MPI rank, gives every rank the targets of its z-slab
 // (SetActiveFlag, ModTargetList.F90:205-233) and sums the per-rank velocity arrays with TargetList_CollectArray
 // (ModTargetList.F90:172-202 -> CollectArray, ModConf.F90:531-597: AllGatherV + scatter-add).  Here:
-//   * targets: the caller's `active` flags (by owned cell in the Python harness) select each rank's rows;
-//   * PME sources: cells are split into nranks contiguous index blocks, each rank spreads its block on a full
-//     mesh and the meshes are summed with one ncclAllReduce (the reference's slab-wise spreading + halo
-//     exchange, ModPME.F90:354-396, becomes an in-switch reduction); transforms are then rank-local;
+//   * targets: the caller's `active` flags select each rank's rows (the harness owns whole cells by the z-slab of their
+//     centroid, so a cell's splines, caches and singular integrals live on one GPU);
+//   * PME: the mesh is decomposed into z-slabs of planes as in the reference (DomainDecomp, ModConf.F90:412-437;
+//     Init_PFFTW, ModPFFTW.F90:56-89).  A rank spreads every source whose B-spline support touches its planes -- no
+//     mesh reduction (ModPME.F90:428-429) --, transforms its planes in (x, y), the spectra change hands z-slabs ->
+//     y-slabs with grouped ncclSend / ncclRecv (the MPI_Alltoallv of ModPFFTW.F90:188-316), the transform in z and the
+//     k-space multiplier run on y-slabs, and the way back mirrors it; the velocity planes a rank's targets reach into
+//     beyond its slab come from their owners (Update_Buff_Vel, ModPME.F90:354-396) -- pme.cu;
 //   * results: rbc3d_collect_array / the resident path sum the velocity rows with ncclAllReduce (rows of
 //     inactive targets are zero), which is CollectArray's MPI_SUM semantics without the index traffic.
 #include "rbc3d_internal.h"
@@ -44,6 +48,55 @@ int comm_allgather_inplace(rbc3d_ctx *c, double *buf, size_t count) {
   if (c->prm.nranks <= 1 || count == 0) return RBC3D_OK;
 #ifdef RBC3D_WITH_NCCL
   NCCL_TRY(ncclAllGather(buf + (size_t)c->prm.rank * count, buf, count, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
+int comm_allgather_ints(rbc3d_ctx *c, const int *send, int *recv, size_t count) {
+  if (c->prm.nranks <= 1) {
+    if (send != recv) CUDA_TRY(cudaMemcpyAsync(recv, send, sizeof(int) * count, cudaMemcpyDeviceToDevice, c->stream));
+    return RBC3D_OK;
+  }
+#ifdef RBC3D_WITH_NCCL
+  NCCL_TRY(ncclAllGather(send, recv, count, ncclInt32, (ncclComm_t)c->nccl_comm, c->stream));
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+
+// point-to-point pieces of the slab transposes and the velocity-mesh halo exchange: every rank issues its sends and
+// receives inside one group (ncclGroupStart / ncclGroupEnd), NCCL pairs them up and runs them concurrently over NVLink
+int comm_group_begin() {
+#ifdef RBC3D_WITH_NCCL
+  NCCL_TRY(ncclGroupStart());
+#endif
+  return RBC3D_OK;
+}
+int comm_group_end() {
+#ifdef RBC3D_WITH_NCCL
+  NCCL_TRY(ncclGroupEnd());
+#endif
+  return RBC3D_OK;
+}
+int comm_send(rbc3d_ctx *c, const void *buf, size_t bytes, int peer) {
+#ifdef RBC3D_WITH_NCCL
+  if (bytes == 0) return RBC3D_OK;
+  NCCL_TRY(ncclSend(buf, bytes / 8, ncclDouble, peer, (ncclComm_t)c->nccl_comm, c->stream));
+  return RBC3D_OK;
+#else
+  set_error("library built without NCCL");
+  return RBC3D_EINVAL;
+#endif
+}
+int comm_recv(rbc3d_ctx *c, void *buf, size_t bytes, int peer) {
+#ifdef RBC3D_WITH_NCCL
+  if (bytes == 0) return RBC3D_OK;
+  NCCL_TRY(ncclRecv(buf, bytes / 8, ncclDouble, peer, (ncclComm_t)c->nccl_comm, c->stream));
   return RBC3D_OK;
 #else
   set_error("library built without NCCL");
@@ -102,7 +155,7 @@ int rbc3d_ctx_attach_comm(rbc3d_ctx *c, int nranks, int rank, const void *id128)
   c->nccl_comm = comm;
   c->prm.nranks = nranks;
   c->prm.rank = rank;
-  return RBC3D_OK;
+  return pme_slab_setup(c);
 #else
   set_error("library built without NCCL");
   return RBC3D_EINVAL;

@@ -27,6 +27,8 @@ constexpr int SPREAD_CHUNK = 32;
 constexpr int SW_XR = 8;     // mesh cells per x run of the walking spread kernel (k_spread_walk)
 
 int pme_block_edge() { return PME_BLK; }
+static int pme_transform_slab(rbc3d_ctx *c);
+static int pme_halo_exchange(rbc3d_ctx *c, TargetList &t);
 
 void t_begin(rbc3d_ctx *c, int s) {
   cudaEventRecord(c->ev[2 * s], c->stream);
@@ -93,6 +95,12 @@ void pme_destroy(rbc3d_ctx *c) {
   for (int i = 0; i < 3; i++)
     if (pm.planF_ok[i]) cufftDestroy(pm.planF[i]);
   if (pm.planB_ok) cufftDestroy(pm.planB);
+  if (pm.plan2F_ok) cufftDestroy(pm.plan2F);
+  if (pm.plan2B_ok) cufftDestroy(pm.plan2B);
+  for (int i = 0; i < 2; i++)
+    if (pm.plan1_ok[i]) cufftDestroy(pm.plan1[i]);
+  pm.sbuf.release(), pm.rbuf.release(), pm.Tz.release(), pm.Vz.release();
+  pm.d_zoff.release(), pm.d_yoff.release(), pm.halo_tmp.release();
   pm.src.release();
   pm.srcC.release();
   pm.vvC.release();
@@ -795,8 +803,8 @@ int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_wall
     a.c2 = 0.0;
     RBC_TRY(spread_launch(c, a, true, false));
   }
-  if (c->prm.nranks > 1 && (pm.flag_sl || pm.flag_dl)) {
-    // every rank spread its block of cells: sum the meshes over the ranks (one in-switch reduction)
+  if (c->prm.nranks > 1 && !pm.slab && (pm.flag_sl || pm.flag_dl)) {
+    // (slab decomposition off) every rank spread its block of cells: sum the meshes over the ranks
     double *base = pm.src.p + (pm.flag_sl ? 0 : 3 * pm.G);
     const size_t ncomp = (pm.flag_sl ? 3 : 0) + (pm.flag_dl ? 6 : 0);
     RBC_TRY(comm_allreduce_sum(c, base, ncomp * pm.G));
@@ -817,13 +825,17 @@ struct KArgs {
   const double *bx, *by, *bz;
   int sl, dl;
   double vol;
+  // element (i, j, k) of a component sits at i*sx + (j - j0)*sy + k*sz (components M apart): [Nz][Ny][Nxh] for the
+  // single-rank transform, [y rows of the rank][Nxh][Nz] (z fastest) on the y-slabs of the decomposed transform
+  long long sx, sy, sz;
+  int j0;
 };
 
 template <bool SL, bool DL>
 __device__ __forceinline__ void kspace_mode(const KArgs &a, int i, int j, int k, double vr[3], double vi[3]) {
   vr[0] = vr[1] = vr[2] = vi[0] = vi[1] = vi[2] = 0.0;
   if (i == 0 && j == 0 && k == 0) return;
-  const size_t idx = ((size_t)k * a.Ny + j) * a.Nxh + i;
+  const size_t idx = (size_t)i * a.sx + (size_t)(j - a.j0) * a.sy + (size_t)k * a.sz;
   const double q0 = (double)i * a.prm.iLb[0];
   const double q1 = (double)(j < a.Ny / 2 ? j : j - a.Ny) * a.prm.iLb[1];
   const double q2 = (double)(k <= a.Nz / 2 ? k : k - a.Nz) * a.prm.iLb[2];
@@ -921,6 +933,7 @@ int pme_transform(rbc3d_ctx *c) {
     pm.transformed = true;
     return RBC3D_OK;
   }
+  if (pm.slab) return pme_transform_slab(c);
   t_begin(c, RBC3D_T_FFT);
   cufftHandle plan;
   if (pm.flag_sl && pm.flag_dl) {
@@ -948,6 +961,7 @@ int pme_transform(rbc3d_ctx *c) {
   a.by = pm.by.p;
   a.bz = pm.bz.p;
   a.vol = p.Lb[0] * p.Lb[1] * p.Lb[2];
+  a.sx = 1, a.sy = pm.Nxh, a.sz = (long long)pm.Ny * pm.Nxh, a.j0 = 0;
   const int grid = (int)((pm.M + 255) / 256);
   if (pm.flag_sl && pm.flag_dl)
     k_kspace<true, true><<<grid, 256, 0, c->stream>>>(a);
@@ -1194,6 +1208,7 @@ int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc) {
     set_error("PME_Add_Interp_Vel called before PME_Transform");
     return RBC3D_ESTATE;
   }
+  if (pm.slab && c->prm.nranks > 1) RBC_TRY(pme_halo_exchange(c, t));  // collective: before the empty-list return
   if (t.n == 0) return RBC3D_OK;
   CellList &pl = t.pl;
   if (pm.walk) {
@@ -1230,6 +1245,426 @@ int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc) {
   k_interp<<<a.nbx * a.nby * a.nbz, INTERP_WARPS * 32, smem, c->stream>>>(a);
   KERNEL_CHECK();
   c->launches++;
+  return RBC3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Slab-decomposed PME (several ranks): ModPFFTW.F90:56-89 (Init_PFFTW), :94-185 (transforms), :188-316 (transposes);
+// ModPME.F90:354-396 (Update_Buff_Vel), :428-429 (spreading skips planes of other ranks); ModConf.F90:412-437.
+//
+//   z-slab of rank r: planes [zoff[r], zoff[r+1]);  y-slab: rows [yoff[r], yoff[r+1]) of the half spectrum.
+//   forward :  2-D D2Z per owned plane (cuFFT, batch = planes)  ->  pack per destination [comp][z of sender][y of
+//              receiver][Nxh]  ->  grouped ncclSend/ncclRecv  ->  unpack + transpose to [comp][y][Nxh][Nz] (z fastest)
+//              ->  1-D Z2Z in z (cuFFT, contiguous)  ->  k-space multiplier on the y-slab
+//   backward:  1-D Z2Z inverse  ->  pack + transpose  ->  exchange  ->  unpack into the owned planes of the full-size
+//              spectral array  ->  Hermitian symmetrisation of the columns x = 0, Nx/2 in k_y, plane by plane (what FFTW's
+//              c2r does implicitly and the single-rank path does in (k_y, k_z) before its 3-D Z2D: no partner rank is
+//              needed)  ->  2-D Z2D per owned plane.
+// Real and spectral meshes keep their full-size single-rank layout [comp][Nz][Ny][..]; a rank only touches its planes
+// (+ the halo planes of the velocity mesh), so spreading and interpolation kernels are the single-rank ones.
+static int slab_forced() {
+  static const int v = [] {
+    const char *e = getenv("RBC3D_PME_SLAB");  // 1: run the decomposed transform on one rank too (tests)
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+int pme_slab_setup(rbc3d_ctx *c) {
+  Pme &pm = c->pme;
+  const int R = c->prm.nranks;
+  static const bool off = getenv("RBC3D_PME_ALLREDUCE") != nullptr;  // round-1 behaviour: full meshes summed with one all-reduce
+  pm.slab = (R > 1 && !off) || slab_forced() == 1;
+  pm.R = R, pm.rk = c->prm.rank;
+  pm.zoff.assign(R + 1, 0), pm.yoff.assign(R + 1, 0);
+  for (int r = 0; r <= R; r++) {
+    pm.zoff[r] = (int)((long long)pm.Nz * r / R);
+    pm.yoff[r] = (int)((long long)pm.Ny * r / R);
+  }
+  if (!pm.slab) return RBC3D_OK;
+  RBC_TRY(pm.d_zoff.resize(R + 1));
+  RBC_TRY(pm.d_yoff.resize(R + 1));
+  CUDA_TRY(cudaMemcpy(pm.d_zoff.p, pm.zoff.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(pm.d_yoff.p, pm.yoff.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice));
+  return RBC3D_OK;
+}
+
+// sources a rank spreads: every point whose B-spline support (planes cz - P + 1 .. cz) touches the rank's planes
+__global__ void k_slab_own(int n, const double *__restrict__ z, double ihz, int Nz, int z0, int nz, int P, int *__restrict__ own) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cz = imodulo((int)floor(__dmul_rn(z[i], ihz)), Nz);  // mesh cell of the point, as the spreading kernels
+  own[i] = imodulo(cz - z0, Nz) < nz + P - 1 ? 1 : 0;
+}
+
+int pme_source_ownership(rbc3d_ctx *c, int n, const double *x, dbuf<int> &own, const int **flags) {
+  Pme &pm = c->pme;
+  *flags = nullptr;
+  if (c->prm.nranks <= 1 || n == 0) return RBC3D_OK;
+  RBC_TRY(own.resize(n));
+  if (pm.slab) {
+    const int z0 = pm.zoff[pm.rk], nz = pm.zoff[pm.rk + 1] - z0;
+    k_slab_own<<<(n + 255) / 256, 256, 0, c->stream>>>(n, x + 2 * (size_t)n, c->prm.ih[2], pm.Nz, z0, nz, c->prm.P, own.p);
+    KERNEL_CHECK();
+    c->launches++;
+    *flags = own.p;
+  }
+  return RBC3D_OK;
+}
+
+struct SlabArgs {
+  int R, rk, nc, Nz, Ny, Nxh;
+  const int *zoff, *yoff;
+  size_t M;
+};
+
+__device__ __forceinline__ int slab_owner(const int *off, int R, int v) {  // rank r with off[r] <= v < off[r+1]
+  int r = 0;
+  while (r + 1 < R && v >= off[r + 1]) r++;
+  return r;
+}
+
+// element offset of the block exchanged between (z-slab owner zr, y-slab owner yr) inside the buffer of one of them:
+// blocks are ordered by the PEER rank; a block holds [comp][planes of zr][rows of yr][Nxh]
+__device__ __forceinline__ size_t slab_block_off(const SlabArgs &a, int zr, int yr, bool at_z_owner) {
+  size_t o = 0;
+  if (at_z_owner) {  // buffer of the z owner: one block per y owner
+    const size_t nz = a.zoff[zr + 1] - a.zoff[zr];
+    o = (size_t)a.nc * nz * a.yoff[yr] * a.Nxh;
+  } else {           // buffer of the y owner: one block per z owner
+    const size_t ny = a.yoff[yr + 1] - a.yoff[yr];
+    o = (size_t)a.nc * a.zoff[zr] * ny * a.Nxh;
+  }
+  return o;
+}
+
+// forward pack: the rank's planes of the 2-D spectra [comp][Nz][Ny][Nxh] -> send blocks (one thread per element, x fastest)
+__global__ void __launch_bounds__(256) k_slab_pack_fwd(SlabArgs a, const cufftDoubleComplex *__restrict__ src,
+                                                       cufftDoubleComplex *__restrict__ buf) {
+  const int z0 = a.zoff[a.rk], nz = a.zoff[a.rk + 1] - z0;
+  const size_t total = (size_t)a.nc * nz * a.Ny * a.Nxh;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(e % a.Nxh);
+    size_t r = e / a.Nxh;
+    const int y = (int)(r % a.Ny);
+    r /= a.Ny;
+    const int zl = (int)(r % nz), comp = (int)(r / nz);
+    const int s = slab_owner(a.yoff, a.R, y);
+    const int nys = a.yoff[s + 1] - a.yoff[s];
+    const size_t d = slab_block_off(a, a.rk, s, true) + (((size_t)comp * nz + zl) * nys + (y - a.yoff[s])) * a.Nxh + x;
+    buf[d] = src[(size_t)comp * a.M + ((size_t)(z0 + zl) * a.Ny + y) * a.Nxh + x];
+  }
+}
+
+// forward unpack: received blocks [z owner][comp][its planes][my rows][Nxh] -> Tz[comp][my rows][Nxh][Nz] (z fastest);
+// 32 x 32 tiles over (z, x) through shared memory, grid (x tiles, z tiles, comp * my rows)
+__global__ void __launch_bounds__(256) k_slab_unpack_fwd(SlabArgs a, const cufftDoubleComplex *__restrict__ buf,
+                                                         cufftDoubleComplex *__restrict__ Tz) {
+  __shared__ cufftDoubleComplex tile[32][33];
+  const int ny = a.yoff[a.rk + 1] - a.yoff[a.rk];
+  const int comp = blockIdx.z / ny, yl = blockIdx.z - comp * ny;
+  const int x0 = blockIdx.x * 32, zt0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int z = zt0 + r, x = x0 + threadIdx.x;
+    if (z < a.Nz && x < a.Nxh) {
+      const int s = slab_owner(a.zoff, a.R, z);
+      const int nzs = a.zoff[s + 1] - a.zoff[s];
+      tile[r][threadIdx.x] =
+          buf[slab_block_off(a, s, a.rk, false) + (((size_t)comp * nzs + (z - a.zoff[s])) * ny + yl) * a.Nxh + x];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int x = x0 + r, z = zt0 + threadIdx.x;
+    if (z < a.Nz && x < a.Nxh) Tz[(((size_t)comp * ny + yl) * a.Nxh + x) * a.Nz + z] = tile[threadIdx.x][r];
+  }
+}
+
+// backward pack: Vz[comp][my rows][Nxh][Nz] -> send blocks [z owner][comp][its planes][my rows][Nxh]
+__global__ void __launch_bounds__(256) k_slab_pack_bwd(SlabArgs a, const cufftDoubleComplex *__restrict__ Vz,
+                                                       cufftDoubleComplex *__restrict__ buf) {
+  __shared__ cufftDoubleComplex tile[32][33];
+  const int ny = a.yoff[a.rk + 1] - a.yoff[a.rk];
+  const int comp = blockIdx.z / ny, yl = blockIdx.z - comp * ny;
+  const int x0 = blockIdx.x * 32, zt0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int x = x0 + r, z = zt0 + threadIdx.x;
+    if (z < a.Nz && x < a.Nxh) tile[r][threadIdx.x] = Vz[(((size_t)comp * ny + yl) * a.Nxh + x) * a.Nz + z];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int z = zt0 + r, x = x0 + threadIdx.x;
+    if (z < a.Nz && x < a.Nxh) {
+      const int s = slab_owner(a.zoff, a.R, z);
+      const int nzs = a.zoff[s + 1] - a.zoff[s];
+      buf[slab_block_off(a, s, a.rk, false) + (((size_t)comp * nzs + (z - a.zoff[s])) * ny + yl) * a.Nxh + x] =
+          tile[threadIdx.x][r];
+    }
+  }
+}
+
+// backward unpack: received blocks [y owner][comp][my planes][its rows][Nxh] -> my planes of [comp][Nz][Ny][Nxh]
+__global__ void __launch_bounds__(256) k_slab_unpack_bwd(SlabArgs a, const cufftDoubleComplex *__restrict__ buf,
+                                                         cufftDoubleComplex *__restrict__ dst) {
+  const int z0 = a.zoff[a.rk], nz = a.zoff[a.rk + 1] - z0;
+  const size_t total = (size_t)a.nc * nz * a.Ny * a.Nxh;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(e % a.Nxh);
+    size_t r = e / a.Nxh;
+    const int y = (int)(r % a.Ny);
+    r /= a.Ny;
+    const int zl = (int)(r % nz), comp = (int)(r / nz);
+    const int s = slab_owner(a.yoff, a.R, y);
+    const int nys = a.yoff[s + 1] - a.yoff[s];
+    dst[(size_t)comp * a.M + ((size_t)(z0 + zl) * a.Ny + y) * a.Nxh + x] =
+        buf[slab_block_off(a, a.rk, s, true) + (((size_t)comp * nz + zl) * nys + (y - a.yoff[s])) * a.Nxh + x];
+  }
+}
+
+// FFTW's c2r over (x, y) uses only the real part of the x = 0 and x = Nx/2 bins after the y transform
+// (ModPFFTW.F90:139-143); with cuFFT's Z2D the same result needs those two columns Hermitian in k_y: V(j) <- (V(j) +
+// conj V(Ny - j)) / 2, plane by plane.  One thread per (comp, plane, column, j <= Ny/2).
+__global__ void k_slab_sym(SlabArgs a, int Nx, cufftDoubleComplex *__restrict__ v) {
+  const int z0 = a.zoff[a.rk], nz = a.zoff[a.rk + 1] - z0, nh = a.Ny / 2 + 1;
+  const size_t total = (size_t)a.nc * nz * 2 * nh, e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int j = (int)(e % nh);
+  size_t r = e / nh;
+  const int col = (int)(r % 2);
+  r /= 2;
+  const int zl = (int)(r % nz), comp = (int)(r / nz);
+  const int x = col == 0 ? 0 : Nx / 2;
+  if (col == 1 && (Nx & 1)) return;  // odd Nx has no Nyquist column
+  cufftDoubleComplex *pl = v + (size_t)comp * a.M + (size_t)(z0 + zl) * a.Ny * a.Nxh + x;
+  const int jm = (a.Ny - j) % a.Ny;
+  if (jm < j) return;  // the pair is handled by its smaller index
+  const cufftDoubleComplex p = pl[(size_t)j * a.Nxh], q = pl[(size_t)jm * a.Nxh];
+  const double re = 0.5 * (p.x + q.x), im = 0.5 * (p.y - q.y);
+  pl[(size_t)j * a.Nxh] = make_cuDoubleComplex(re, im);
+  pl[(size_t)jm * a.Nxh] = make_cuDoubleComplex(re, jm == j ? 0.0 : -im);
+}
+
+template <bool SL, bool DL>
+__global__ void __launch_bounds__(256) k_kspace_slab(KArgs a, int ny) {  // one thread per mode of the y-slab, z fastest
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)ny * a.Nxh * a.Nz;
+  if (idx >= total) return;
+  const int k = (int)(idx % a.Nz);
+  const int i = (int)((idx / a.Nz) % a.Nxh);
+  const int j = a.j0 + (int)(idx / ((size_t)a.Nz * a.Nxh));
+  double vr[3], vi[3];
+  kspace_mode<SL, DL>(a, i, j, k, vr, vi);
+#pragma unroll
+  for (int d = 0; d < 3; d++) a.vvC[(size_t)d * total + idx] = make_cuDoubleComplex(vr[d], vi[d]);
+}
+
+// all-to-all of blocks between z owners and y owners.  to_y: every rank sends block (me, s) of sbuf to s and receives
+// block (s, me) into rbuf; otherwise the reverse direction.  Block sizes differ when Nz or Ny is not a multiple of R.
+static int slab_exchange(rbc3d_ctx *c, int nc, bool to_y) {
+  Pme &pm = c->pme;
+  const int R = pm.R, me = pm.rk;
+  const size_t nzm = pm.zoff[me + 1] - pm.zoff[me], nym = pm.yoff[me + 1] - pm.yoff[me];
+  auto blk = [&](int zr, int yr) {
+    return (size_t)nc * (pm.zoff[zr + 1] - pm.zoff[zr]) * (pm.yoff[yr + 1] - pm.yoff[yr]) * pm.Nxh;
+  };
+  if (R > 1) RBC_TRY(comm_group_begin());
+  for (int s = 0; s < R; s++) {
+    // to_y: I am the z owner on the send side (blocks ordered by y owner), the y owner on the receive side
+    const size_t soff = to_y ? (size_t)nc * nzm * pm.yoff[s] * pm.Nxh : (size_t)nc * pm.zoff[s] * nym * pm.Nxh;
+    const size_t roff = to_y ? (size_t)nc * pm.zoff[s] * nym * pm.Nxh : (size_t)nc * nzm * pm.yoff[s] * pm.Nxh;
+    const size_t ns = to_y ? blk(me, s) : blk(s, me), nr = to_y ? blk(s, me) : blk(me, s);
+    if (s == me || R == 1) {
+      CUDA_TRY(cudaMemcpyAsync(pm.rbuf.p + roff, pm.sbuf.p + soff, ns * sizeof(cufftDoubleComplex), cudaMemcpyDeviceToDevice,
+                               c->stream));
+    } else {
+      RBC_TRY(comm_send(c, pm.sbuf.p + soff, ns * sizeof(cufftDoubleComplex), s));
+      RBC_TRY(comm_recv(c, pm.rbuf.p + roff, nr * sizeof(cufftDoubleComplex), s));
+    }
+  }
+  if (R > 1) RBC_TRY(comm_group_end());
+  return RBC3D_OK;
+}
+
+static int pme_transform_slab(rbc3d_ctx *c) {
+  Pme &pm = c->pme;
+  const Params &p = c->prm;
+  const int R = pm.R, me = pm.rk;
+  const int z0 = pm.zoff[me], nz = pm.zoff[me + 1] - z0, ny = pm.yoff[me + 1] - pm.yoff[me];
+  const int nc = (pm.flag_sl ? 3 : 0) + (pm.flag_dl ? 6 : 0), comp0 = pm.flag_sl ? 0 : 3;
+  const size_t plane_r = (size_t)pm.Ny * pm.Nx, plane_c = (size_t)pm.Ny * pm.Nxh;
+  RBC_TRY(pm.sbuf.resize((size_t)9 * nz * plane_c));
+  RBC_TRY(pm.rbuf.resize((size_t)9 * pm.Nz * ny * pm.Nxh));
+  RBC_TRY(pm.Tz.resize((size_t)9 * pm.Nz * ny * pm.Nxh));
+  RBC_TRY(pm.Vz.resize((size_t)3 * pm.Nz * ny * pm.Nxh));
+  if (!pm.plan2F_ok) {
+    int n2[2] = {pm.Ny, pm.Nx};
+    CUFFT_TRY(cufftPlanMany(&pm.plan2F, 2, n2, nullptr, 1, (int)plane_r, nullptr, 1, (int)plane_c, CUFFT_D2Z, nz));
+    CUFFT_TRY(cufftPlanMany(&pm.plan2B, 2, n2, nullptr, 1, (int)plane_c, nullptr, 1, (int)plane_r, CUFFT_Z2D, nz));
+    pm.plan2F_ok = pm.plan2B_ok = true;
+  }
+  auto plan1 = [&](int slot, int batch, cufftHandle *out) -> int {
+    if (pm.plan1_ok[slot] && pm.plan1_batch[slot] != batch) {
+      cufftDestroy(pm.plan1[slot]);
+      pm.plan1_ok[slot] = false;
+    }
+    if (!pm.plan1_ok[slot]) {
+      int n1[1] = {pm.Nz};
+      CUFFT_TRY(cufftPlanMany(&pm.plan1[slot], 1, n1, nullptr, 1, pm.Nz, nullptr, 1, pm.Nz, CUFFT_Z2Z, batch));
+      pm.plan1_ok[slot] = true;
+      pm.plan1_batch[slot] = batch;
+    }
+    *out = pm.plan1[slot];
+    CUFFT_TRY(cufftSetStream(pm.plan1[slot], c->stream));
+    return RBC3D_OK;
+  };
+  CUFFT_TRY(cufftSetStream(pm.plan2F, c->stream));
+  CUFFT_TRY(cufftSetStream(pm.plan2B, c->stream));
+  SlabArgs sa;
+  sa.R = R, sa.rk = me, sa.nc = nc, sa.Nz = pm.Nz, sa.Ny = pm.Ny, sa.Nxh = pm.Nxh;
+  sa.zoff = pm.d_zoff.p, sa.yoff = pm.d_yoff.p, sa.M = pm.M;
+  // ---- forward ----
+  t_begin(c, RBC3D_T_FFT);
+  for (int q = 0; q < nc; q++)
+    CUFFT_TRY(cufftExecD2Z(pm.plan2F, pm.src.p + (size_t)(comp0 + q) * pm.G + (size_t)z0 * plane_r,
+                           pm.srcC.p + (size_t)(comp0 + q) * pm.M + (size_t)z0 * plane_c));
+  k_slab_pack_fwd<<<c->sm_count * 8, 256, 0, c->stream>>>(sa, pm.srcC.p + (size_t)comp0 * pm.M, pm.sbuf.p);
+  KERNEL_CHECK();
+  t_end(c, RBC3D_T_FFT);
+  t_begin(c, RBC3D_T_COMM);
+  RBC_TRY(slab_exchange(c, nc, true));
+  t_end(c, RBC3D_T_COMM);
+  t_begin(c, RBC3D_T_KSPACE);
+  const dim3 tb(32, 8), tg((pm.Nxh + 31) / 32, (pm.Nz + 31) / 32, nc * ny);
+  if (ny > 0) {
+    k_slab_unpack_fwd<<<tg, tb, 0, c->stream>>>(sa, pm.rbuf.p, pm.Tz.p);
+    KERNEL_CHECK();
+    cufftHandle p1;
+    RBC_TRY(plan1(0, nc * ny * pm.Nxh, &p1));
+    CUFFT_TRY(cufftExecZ2Z(p1, pm.Tz.p, pm.Tz.p, CUFFT_FORWARD));
+    KArgs a;
+    a.prm = p;
+    a.Nx = pm.Nx, a.Ny = pm.Ny, a.Nz = pm.Nz, a.Nxh = pm.Nxh;
+    a.M = (size_t)ny * pm.Nxh * pm.Nz;                        // component stride on the y-slab
+    a.srcC = pm.Tz.p - (size_t)comp0 * a.M;                   // kspace_mode addresses components 0..2 (SL), 3..8 (DL)
+    a.vvC = pm.Vz.p;
+    a.bx = pm.bx.p, a.by = pm.by.p, a.bz = pm.bz.p;
+    a.vol = p.Lb[0] * p.Lb[1] * p.Lb[2];
+    a.sx = pm.Nz, a.sy = (long long)pm.Nxh * pm.Nz, a.sz = 1, a.j0 = pm.yoff[me];
+    const int grid = (int)((a.M + 255) / 256);
+    if (pm.flag_sl && pm.flag_dl)
+      k_kspace_slab<true, true><<<grid, 256, 0, c->stream>>>(a, ny);
+    else if (pm.flag_sl)
+      k_kspace_slab<true, false><<<grid, 256, 0, c->stream>>>(a, ny);
+    else
+      k_kspace_slab<false, true><<<grid, 256, 0, c->stream>>>(a, ny);
+    KERNEL_CHECK();
+    // ---- backward ----
+    RBC_TRY(plan1(1, 3 * ny * pm.Nxh, &p1));
+    CUFFT_TRY(cufftExecZ2Z(p1, pm.Vz.p, pm.Vz.p, CUFFT_INVERSE));
+    sa.nc = 3;
+    const dim3 tg3((pm.Nxh + 31) / 32, (pm.Nz + 31) / 32, 3 * ny);
+    k_slab_pack_bwd<<<tg3, tb, 0, c->stream>>>(sa, pm.Vz.p, pm.sbuf.p);
+    KERNEL_CHECK();
+  }
+  sa.nc = 3;
+  t_end(c, RBC3D_T_KSPACE);
+  RBC_TRY(slab_exchange(c, 3, false));
+  t_begin(c, RBC3D_T_FFT_INV);
+  k_slab_unpack_bwd<<<c->sm_count * 8, 256, 0, c->stream>>>(sa, pm.rbuf.p, pm.vvC.p);
+  {
+    const size_t tot = (size_t)3 * nz * 2 * (pm.Ny / 2 + 1);
+    if (tot) k_slab_sym<<<(int)((tot + 255) / 256), 256, 0, c->stream>>>(sa, pm.Nx, pm.vvC.p);
+  }
+  KERNEL_CHECK();
+  for (int d = 0; d < 3; d++)
+    CUFFT_TRY(cufftExecZ2D(pm.plan2B, pm.vvC.p + (size_t)d * pm.M + (size_t)z0 * plane_c,
+                           pm.vv.p + (size_t)d * pm.G + (size_t)z0 * plane_r));
+  t_end(c, RBC3D_T_FFT_INV);
+  c->launches += 8 + nc + 3;
+  pm.transformed = true;
+  return RBC3D_OK;
+}
+
+// ---- velocity-mesh halo (Update_Buff_Vel, ModPME.F90:354-396): the planes a rank's active targets interpolate from ----
+// per active target the signed plane offset of its mesh cell from the first owned plane; min / max over the list
+__global__ void k_halo_range(int n, const double *__restrict__ z, const int *__restrict__ active, double ihz, int Nz, int z0,
+                             int *__restrict__ mm) {
+  int lo = 1 << 30, hi = -(1 << 30);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (active && !active[i]) continue;
+    const int cz = imodulo((int)floor(__dmul_rn(z[i], ihz)), Nz);
+    const int d = imodulo(cz - z0 + Nz / 2, Nz) - Nz / 2;
+    lo = min(lo, d), hi = max(hi, d);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+    hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mm, lo);
+    atomicMax(mm + 1, hi);
+  }
+}
+
+static int pme_halo_exchange(rbc3d_ctx *c, TargetList &t) {
+  Pme &pm = c->pme;
+  const int R = pm.R, me = pm.rk, P = c->prm.P;
+  const int z0 = pm.zoff[me];
+  if (t.halo_version != t.version || (int)t.halo_need.size() != 2 * R) {
+    // needed planes of this list on this rank: [z0 + dmin - (P - 1), z0 + dmax], then the same of every rank
+    RBC_TRY(pm.halo_tmp.resize(2 + 2 * (size_t)R));
+    int init[2] = {1 << 30, -(1 << 30)};
+    CUDA_TRY(cudaMemcpyAsync(pm.halo_tmp.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    if (t.n > 0) {
+      k_halo_range<<<std::min(c->sm_count * 4, (t.n + 255) / 256), 256, 0, c->stream>>>(t.n, t.x.p + 2 * (size_t)t.n, t.active.p,
+                                                                                         c->prm.ih[2], pm.Nz, z0, pm.halo_tmp.p);
+      KERNEL_CHECK();
+    }
+    int mm[2];
+    CUDA_TRY(cudaMemcpyAsync(mm, pm.halo_tmp.p, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int need[2] = {0, 0};  // (first plane, count); count 0 = no active target
+    if (mm[0] <= mm[1]) {
+      const int len = std::min(pm.Nz, mm[1] - mm[0] + P);
+      need[0] = ((z0 + mm[0] - (P - 1)) % pm.Nz + pm.Nz) % pm.Nz;
+      need[1] = len;
+    }
+    CUDA_TRY(cudaMemcpyAsync(pm.halo_tmp.p, need, sizeof need, cudaMemcpyHostToDevice, c->stream));
+    RBC_TRY(comm_allgather_ints(c, pm.halo_tmp.p, pm.halo_tmp.p + 2, 2));
+    t.halo_need.assign(2 * (size_t)R, 0);
+    CUDA_TRY(cudaMemcpyAsync(t.halo_need.data(), pm.halo_tmp.p + 2, sizeof(int) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    t.halo_version = t.version;
+  }
+  // planes of owner `o` inside the needed range of rank `r`: up to two runs of the cyclic range
+  const size_t plane = (size_t)pm.Ny * pm.Nx;
+  auto runs = [&](int r, int o, int (&seg)[2][2]) {
+    int nseg = 0;
+    const int lo = t.halo_need[2 * r], len = t.halo_need[2 * r + 1];
+    if (len <= 0) return 0;
+    const int part[2][2] = {{lo, std::min(lo + len, pm.Nz)}, {0, std::max(0, lo + len - pm.Nz)}};
+    for (int k = 0; k < 2; k++) {
+      const int a = std::max(part[k][0], pm.zoff[o]), b = std::min(part[k][1], pm.zoff[o + 1]);
+      if (a < b) seg[nseg][0] = a, seg[nseg][1] = b, nseg++;
+    }
+    return nseg;
+  };
+  t_begin(c, RBC3D_T_COMM);
+  RBC_TRY(comm_group_begin());
+  for (int s = 0; s < R; s++) {
+    if (s == me) continue;
+    int seg[2][2];
+    int ns = runs(s, me, seg);  // my planes that rank s needs
+    for (int k = 0; k < ns; k++)
+      for (int d = 0; d < 3; d++)
+        RBC_TRY(comm_send(c, pm.vv.p + (size_t)d * pm.G + (size_t)seg[k][0] * plane, (size_t)(seg[k][1] - seg[k][0]) * plane * 8, s));
+    ns = runs(me, s, seg);      // planes of rank s that I need
+    for (int k = 0; k < ns; k++)
+      for (int d = 0; d < 3; d++)
+        RBC_TRY(comm_recv(c, pm.vv.p + (size_t)d * pm.G + (size_t)seg[k][0] * plane, (size_t)(seg[k][1] - seg[k][0]) * plane * 8, s));
+  }
+  RBC_TRY(comm_group_end());
+  t_end(c, RBC3D_T_COMM);
   return RBC3D_OK;
 }
 

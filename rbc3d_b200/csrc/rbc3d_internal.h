@@ -144,6 +144,9 @@ struct TargetList {
   dbuf<double> host_io; // staging for host v
   WallPairs wp;
   long long version = 0; // bumped whenever the list is rebuilt
+  // several ranks: velocity-mesh planes this rank's active targets interpolate from, of every rank (lo, count)
+  long long halo_version = -1;
+  std::vector<int> halo_need;
   // per-geometry (tile, source) pair list of the real-space sum over other surfaces (pairsum.cu)
   bool plist_valid = false;
   int plist_excl = -1, plist_n = 0;
@@ -261,6 +264,17 @@ struct Pme {
   int nsblk[3] = {0, 0, 0};
   bool swalk = false;               // P = 8: spreading by pencil walks (k_spread_walk), else source blocks
   bool walk = false;                // P = 8: register-ring column walks along z (lists keyed z-fastest)
+  // slab-decomposed transform (several ranks; ModPFFTW.F90:56-89, 188-316): z-slabs of planes for the 2-D transforms,
+  // y-slabs of pencils for the transform in z and the k-space multiplier, all-to-all transposes in between
+  bool slab = false;
+  int R = 1, rk = 0;
+  std::vector<int> zoff, yoff;      // [R + 1] first plane / first y row of every rank
+  dbuf<int> d_zoff, d_yoff;
+  dbuf<cufftDoubleComplex> sbuf, rbuf, Tz, Vz;
+  cufftHandle plan2F = 0, plan2B = 0, plan1[2] = {0, 0};
+  bool plan2F_ok = false, plan2B_ok = false, plan1_ok[2] = {false, false};
+  int plan1_batch[2] = {0, 0};
+  dbuf<int> halo_tmp;               // device scratch of the needed-plane reduction / all-gather
 };
 
 }  // namespace rbc3d
@@ -342,6 +356,8 @@ void pme_destroy(rbc3d_ctx *c);
 int pme_spread(rbc3d_ctx *c, double c1, double c2, bool use_cells, bool use_walls);
 int pme_transform(rbc3d_ctx *c);
 int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc = nullptr);  // acc: SoA(3,n) to add into (default t.acc)
+int pme_slab_setup(rbc3d_ctx *c);                                    // after the communicator is attached
+int pme_source_ownership(rbc3d_ctx *c, int n, const double *x, dbuf<int> &own, const int **flags);
 
 // ---- walls (walls.cu) ----
 int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nele, const double *x, const int *e2v,
@@ -368,6 +384,11 @@ void solver_release(rbc3d_ctx *c);
 // ---- multi-GPU (comm.cu) ----
 int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);
 int comm_allgather_inplace(rbc3d_ctx *c, double *buf, size_t count);
+int comm_allgather_ints(rbc3d_ctx *c, const int *send, int *recv, size_t count);  // device buffers, count per rank
+int comm_group_begin();
+int comm_group_end();
+int comm_send(rbc3d_ctx *c, const void *buf, size_t bytes, int peer);  // bytes: a multiple of 8
+int comm_recv(rbc3d_ctx *c, void *buf, size_t bytes, int peer);
 void comm_destroy(rbc3d_ctx *c);
 
 // timing helpers

@@ -566,13 +566,16 @@ int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nel
   RBC_TRY(celllist_build_realspace(c, W.cl, NE, W.xc.p, nullptr));
   const int *own = nullptr;
   if (c->prm.nranks > 1 && NE > 0) {
-    RBC_TRY(W.src_own.resize(NE));
-    std::vector<int> o(NE, 0);
-    const int lo = (int)((long long)NE * c->prm.rank / c->prm.nranks);
-    const int hi = (int)((long long)NE * (c->prm.rank + 1) / c->prm.nranks);
-    for (int e = lo; e < hi; e++) o[e] = 1;
-    CUDA_TRY(cudaMemcpy(W.src_own.p, o.data(), sizeof(int) * NE, cudaMemcpyHostToDevice));
-    own = W.src_own.p;
+    // element centroids whose B-spline support touches this rank's z-slab of mesh planes (pme.cu), or an index block
+    RBC_TRY(pme_source_ownership(c, NE, W.xc.p, W.src_own, &own));
+    if (!own) {
+      std::vector<int> o(NE, 0);
+      const int lo = (int)((long long)NE * c->prm.rank / c->prm.nranks);
+      const int hi = (int)((long long)NE * (c->prm.rank + 1) / c->prm.nranks);
+      for (int e = lo; e < hi; e++) o[e] = 1;
+      CUDA_TRY(cudaMemcpy(W.src_own.p, o.data(), sizeof(int) * NE, cudaMemcpyHostToDevice));
+      own = W.src_own.p;
+    }
   }
   RBC_TRY(celllist_build_pme(c, W.pl, NE, W.xc.p, own, c->pme.sblk, c->pme.swalk));
   if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, W.pl, W.xc.p));

@@ -93,9 +93,13 @@ class EwaldOperator:
         idbuf = C.create_string_buffer(unique_id, 128)
         check(self.lib.rbc3d_ctx_attach_comm(self._h, nranks, rank, idbuf), "rbc3d_ctx_attach_comm")
 
-    def ownership_mask(self, sus, nranks, rank):
+    def ownership_mask(self, sus, nranks, rank, by="zslab"):
+        """active flags of the targets this rank computes: whole cells, by the z-slab of their centroid (the slabs of the
+        PME mesh, DomainDecomp) or -- by="block" -- by contiguous blocks of cell indices"""
         from . import partition
-        return partition.ownership_mask(sus.ncell, sus.nlat * sus.nlon, nranks, rank)
+        if by == "block":
+            return partition.ownership_mask(sus.ncell, sus.nlat * sus.nlon, nranks, rank)
+        return partition.ownership_mask_zslab(sus.x, sus.nlat * sus.nlon, self.Lb, nranks, rank)
 
     def TargetList_CollectArray(self, v, tlist=TL_CELLS):
         """v <- sum over ranks (ModTargetList.F90:172-202)."""

@@ -17,11 +17,27 @@ def cell_block(ncell: int, nranks: int, rank: int) -> tuple[int, int]:
 
 
 def ownership_mask(ncell: int, npc: int, nranks: int, rank: int) -> np.ndarray:
-    """active flags (int32, one per cell point) of the targets a rank computes."""
+    """active flags (int32, one per cell point) of the targets a rank computes: contiguous blocks of cell indices."""
     lo, hi = cell_block(ncell, nranks, rank)
     act = np.zeros(ncell * npc, dtype=np.int32)
     act[lo * npc:hi * npc] = 1
     return act
+
+
+def cell_owner_zslab(x: np.ndarray, npc: int, Lb, nranks: int) -> np.ndarray:
+    """owner rank of every cell: the z-slab [r, r+1) Lb3 / nranks that holds the cell's centroid (mean of its mesh points,
+    wrapped into the box) -- DomainDecomp's slabs (ModConf.F90:421-435) applied to whole cells instead of single points
+    (SetActiveFlag, ModTargetList.F90:221-222), so that a cell's splines, caches and singular integrals live on one GPU
+    and its points reach at most a cell radius beyond the slab."""
+    zc = x[2].reshape(-1, npc).mean(axis=1)
+    zc = zc - np.floor(zc / Lb[2]) * Lb[2]
+    return np.minimum((zc * (nranks / Lb[2])).astype(np.int64), nranks - 1)
+
+
+def ownership_mask_zslab(x: np.ndarray, npc: int, Lb, nranks: int, rank: int) -> np.ndarray:
+    """active flags (int32, one per cell point): the cells whose centroid lies in this rank's z-slab."""
+    own = cell_owner_zslab(x, npc, Lb, nranks) == rank
+    return np.repeat(own.astype(np.int32), npc)
 
 
 def zslab_active(x: np.ndarray, Lb, nranks: int, rank: int) -> np.ndarray:

@@ -309,6 +309,35 @@ def test_cell_straddling_the_periodic_boundary(oracle_lib):
     op.close()
 
 
+def test_slab_decomposed_transform_on_one_rank():
+    """The slab path of the PME transform (2-D transforms per plane, pack / exchange / transpose, 1-D transform in z and
+    the multiplier on z-fastest pencils, per-plane Hermitian symmetrisation; pme.cu) forced on a single rank
+    (RBC3D_PME_SLAB=1) against the oracle: single layer, double layer and both, on a non-cubic mesh."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from oracle import oracle; from rbc3d_b200 import synth; from rbc3d_b200.ewald import EwaldOperator\n"
+        "sus = synth.make_suspension(2, L=[9.0, 10.5, 12.0])\n"
+        "op = EwaldOperator(sus.Lb); op.set_suspension(sus)\n"
+        "orc = oracle.Oracle(sus.Lb).set_cells(sus)\n"
+        "assert len(set(op.Nb)) == 3, op.Nb\n"
+        "worst = 0.0\n"
+        "for c1, c2 in ((0.0, -0.0796), (0.0796, 0.0), (0.05, 0.07)):\n"
+        "    v = op.apply(c1, c2); ref = orc.apply_cells(c1, c2, orc.cell_targets())\n"
+        "    op.PME_Distrib_Source(c1, c2); op.PME_Transform()\n"
+        "    orc.pme_distrib(c1, c2, sus.x, sus.weighted(sus.f), sus.weighted(sus.g), sus.a3, np.repeat(sus.Bcoef, sus.nlat * sus.nlon)); orc.pme_transform()\n"
+        "    worst = max(worst, np.linalg.norm(v - ref) / np.linalg.norm(ref), np.linalg.norm(op.pme_grid() - orc.pme_vv()) / np.linalg.norm(orc.pme_vv()))\n"
+        "print('SLAB_WORST %%.3e' %% worst)\n" % root)
+    env = dict(os.environ, RBC3D_PME_SLAB="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert "SLAB_WORST" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    worst = float(r.stdout.split("SLAB_WORST")[1].split()[0])
+    assert worst < 1e-10, worst
+
+
 def test_multi_gpu_parity_when_several_gpus_are_visible():
     """2-rank NCCL run of tests/run_multi_gpu.py (skipped on a single-GPU box)."""
     import subprocess
