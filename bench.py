@@ -410,23 +410,57 @@ def run_gpu(args):
         stage_ms[k] /= args.steps
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    # The call a user makes per GMRES iteration is MyMatMult (ModVelSolver.F90:523-601): packed SH coefficients in,
+    # packed SH coefficients out.  rbc3d_solver_matmult is that callback with HOST vectors: the timed region holds the
+    # host->device copy of u, Glob_Sph_Trans both ways, the density splines, operator #2 and the device->host copy of b.
+    # With several ranks every rank passes the coefficients of its own cells (sharded unknowns).  The older point-density
+    # path (g in, v out: SourceList_UpdateDensity + operator + CollectArray) is timed next to it on one rank.
     e2e_steps = 1 if args.profile else max(1, min(args.steps, args.e2e_steps))
-    for _ in range(0 if args.profile else min(2, args.warmup)):
+    solver_e2e = not args.host_splines
+    e2e_point_s = None
+    if solver_e2e:
+        op.solver_setup(sus.nlat0, sus.detj)
+        u_loc = np.random.default_rng(args.seed + rank).uniform(-1.0, 1.0, op.solver_dof)
+        b_loc = np.zeros(op.solver_dof)
+        for a in (u_loc, b_loc):
+            if a.nbytes:
+                capi.check(lib.rbc3d_host_register(a.ctypes.data, a.nbytes), "rbc3d_host_register")
+        for _ in range(0 if args.profile else min(2, args.warmup)):
+            op.solver_matmult(u_loc, out=b_loc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            op.solver_matmult(u_loc, out=b_loc)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        dof_t = torch.tensor([float(op.solver_dof)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dof_t)
+        h2d_e2e = d2h_e2e = int(dof_t[0]) * 8
+    if world == 1 or not solver_e2e:
+        for _ in range(0 if args.profile else min(2, args.warmup)):
+            op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
+            op.apply_collect(0.0, C2_MATVEC, v=v_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
+            op.apply_collect(0.0, C2_MATVEC, v=v_host)        # "v = 0" + operator + CollectArray (ModVelSolver.F90:571-584)
+        barrier()
+        e2e_point_s = (time.perf_counter() - t0) / e2e_steps
+        if not solver_e2e:
+            e2e_s = e2e_point_s
+            h2d_e2e = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0)
+            d2h_e2e = v_host.nbytes * world
+    else:   # untimed: the operator applied to g_host, for the parity checks below
         op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
         op.apply_collect(0.0, C2_MATVEC, v=v_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        op.SourceList_UpdateDensity(g=g_host, spG=spG_host)
-        op.apply_collect(0.0, C2_MATVEC, v=v_host)        # "v = 0" + operator + CollectArray (ModVelSolver.F90:571-584)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t[0])
     clocks = sampler.stop()
-    v_e2e = v_host.copy()              # operator #2 applied to g: compared with the oracle's sample below (full size)
+    v_e2e = v_host.copy()              # operator #2 applied to g: compared with the oracle below (full size)
 
     # ---- size-independent property at the full size: linearity in the density (after the timed regions) -----------
     full_size = None
@@ -482,7 +516,7 @@ def run_gpu(args):
             t_mm = float("nan")
             its, t_solve, resid = None, float("nan"), None
             if dev_geom:
-                op.solver_setup(sus.nlat0, sus.detj)
+                op.solver_setup(sus.nlat0, sus.detj)      # again: the geometry update above invalidated it
                 u = np.random.default_rng(args.seed).uniform(-1.0, 1.0, op.solver_dof)
                 op.solver_matmult(u)
                 tm = []
@@ -510,19 +544,17 @@ def run_gpu(args):
             its_used = its if its is not None else GMRES_ITS_ASSUMED
             timestep = {"geometry_splines": "device" if dev_geom else "host (uploaded)",
                         "geometry_update_ms": t_geom * 1e3, "rhs_operator_ms": t_rhs1 * 1e3,
-                        "matvec_e2e_ms": e2e_s * 1e3, "gmres_iterations": its_used,
+                        "matvec_e2e_ms": (e2e_point_s or e2e_s) * 1e3, "gmres_iterations": its_used,
                         "gmres_iterations_measured": its is not None, "gmres_relative_residual": resid,
                         "gmres_solve_ms": t_solve * 1e3 if t_solve == t_solve else None,
-                        "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its_used * e2e_s),
+                        "bi_timesteps_per_s": 1.0 / (t_geom + t_rhs1 + its_used * (e2e_point_s or e2e_s)),
                         "matmult_device_solver_ms": t_mm * 1e3,
                         "bi_timesteps_per_s_device_solver": (1.0 / (t_geom + t_rhs1 + t_solve)) if t_solve == t_solve else None,
                         "note": "boundary-integral part of one mtube step (membrane forces stay in the Fortran caller); "
                                 "device_solver: rbc3d_solver_gmres, SH transforms and Krylov vectors on the GPU"}
         except Exception as exc:  # e.g. no room left for spline(f detJ) next to the caches
             timestep = {"error": str(exc)[:200]}
-    h2d = g_host.nbytes + (spG_host.nbytes if spG_host is not None else 0)
-    d2h = v_host.nbytes * world    # whole job: every rank receives the complete v (CollectArray semantics);
-                                   # h2d stays g_host.nbytes: every rank uploads 1/world of g (replicated density)
+    h2d, d2h = h2d_e2e, d2h_e2e    # whole job, counted from the arrays copied inside the timed region
 
     if rank != 0:
         op.close()
@@ -615,7 +647,10 @@ def run_gpu(args):
                           partition=PARTITION_TEXT if world > 1 else "single GPU"),
            "clocks": clocks,
            "e2e": {"value": 1.0 / e2e_s, "unit": "matvecs/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "api": ("rbc3d_solver_matmult (MyMatMult: packed SH coefficients of the rank's cells in and out, host "
+                           "vectors)") if solver_e2e else "rbc3d_cells_set_density + rbc3d_apply_collect (g in, v out)",
+                   "point_density_path_ms": (e2e_point_s * 1e3) if e2e_point_s else None},
            "gpu_launches": int(launches),
            "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
            "roofline": roof, "kernels": rows, "timestep": timestep,

@@ -62,9 +62,15 @@ int rbc3d_ctx_create(rbc3d_ctx **ctx, const double Lb[3], double alpha, double e
                      const int Nb[3], int device);
 int rbc3d_ctx_destroy(rbc3d_ctx *ctx);
 
-/* Multi-GPU: z-slab decomposition of ModConf.F90:412-437 DomainDecomp, one context per rank; the 128-byte
- * NCCL unique id is created on rank 0 and distributed by the host program (MPI_Bcast in the Fortran driver,
- * torch.distributed in the Python harness). */
+/* Multi-GPU: one context per rank; the 128-byte NCCL unique id is created on rank 0 and distributed by the host
+ * program (MPI_Bcast in the Fortran driver, torch.distributed in the Python harness).  rbc3d_ctx_attach_comm must come
+ * BEFORE any geometry (cells, walls, raw targets) reaches the context: ownership is derived from the rank when a list
+ * is built.  Decomposition (ModConf.F90:412-437 DomainDecomp; ModPFFTW.F90:56-89): the PME mesh is split into z-slabs of
+ * planes -- a rank spreads the sources whose B-spline support touches its planes (no mesh reduction), transforms its
+ * planes in (x, y), the spectra change hands to y-slabs by an all-to-all (grouped ncclSend/ncclRecv) for the transform in
+ * z and the k-space multiplier, and back; velocity planes beyond a rank's slab that its targets interpolate from come
+ * from their owners.  Targets: the caller's `active` flags (SetActiveFlag), per point or -- as the harness does -- whole
+ * cells by the z-slab of their centroid.  Source lists stay replicated, as in the reference. */
 int rbc3d_comm_unique_id(void *id128);
 int rbc3d_ctx_attach_comm(rbc3d_ctx *ctx, int nranks, int rank, const void *id128);
 /* TargetList_CollectArray(tlist, 3, v, MPI_COMM_WORLD) (ModTargetList.F90:172-202): v <- sum over ranks of the
@@ -196,9 +202,15 @@ int rbc3d_pair_cache_info(rbc3d_ctx *ctx, int32_t *cells_cached, int64_t *rows);
  *   in Glob_Sph_Trans (ModVelSolver.F90:641-719).
  * rbc3d_solver_gmres: KSPSolve of Solve_RBC_Vel (ModVelSolver.F90:74-116) with PETSc's GMRES defaults restated
  *   (restart as given, classical Gram-Schmidt, no preconditioner, residual test rtol*||rhs||); sol: initial guess
- *   in, solution out; history (maxit+1 doubles or NULL): residual norm after every iteration. */
+ *   in, solution out; history (maxit+1 doubles or NULL): residual norm after every iteration.
+ * Several ranks: the unknowns are SHARDED.  A rank holds the coefficients of the cells it owns targets of (whole cells,
+ *   every cell active on exactly one rank; rbc3d_solver_cells lists them in vector order), so u, b, rhs and sol are
+ *   vectors of rbc3d_solver_dof = owned cells * 3 nlat0^2 doubles; inside a matvec the synthesised densities are
+ *   all-gathered over NVLink, the operator rows stay on their rank (no CollectArray, no device->host copy of v) and
+ *   the dot products of GMRES are all-reduced.  All solver calls are collective. */
 int rbc3d_solver_setup(rbc3d_ctx *ctx, int nlat0, const double *detj);
 int rbc3d_solver_dof(rbc3d_ctx *ctx, int64_t *dof);
+int rbc3d_solver_cells(rbc3d_ctx *ctx, int32_t *n, int32_t *cells, int cap);
 int rbc3d_solver_matmult(rbc3d_ctx *ctx, const double *u, double *b);
 int rbc3d_solver_gmres(rbc3d_ctx *ctx, const double *rhs, double *sol, double rtol, int restart, int maxit,
                        int *niter, double *history);

@@ -1038,7 +1038,7 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   t_begin(c, RBC3D_T_COMBINE);
   RBC_TRY(combine(c, *t, t->v.p, false, acc2));
   t_end(c, RBC3D_T_COMBINE);
-  if (c->prm.nranks > 1) {  // TargetList_CollectArray
+  if (c->prm.nranks > 1 && c->resident_collect) {  // TargetList_CollectArray
     t_begin(c, RBC3D_T_COMM);
     RBC_TRY(comm_allreduce_sum(c, t->v.p, 3 * (size_t)t->n));
     t_end(c, RBC3D_T_COMM);

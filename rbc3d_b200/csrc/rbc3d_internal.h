@@ -235,7 +235,12 @@ struct Cells {
 struct Solver {
   bool ok = false;
   int m0 = 0, dofc = 0;
-  size_t dof = 0;
+  size_t dof = 0;        // unknowns of all cells
+  size_t dof_loc = 0;    // unknowns this rank holds (= dof on one rank)
+  int nown = 0, maxown = 0;
+  dbuf<int> cells;       // [nown] cells this rank holds the unknowns of
+  dbuf<int> own_all;     // several ranks: [rank][maxown] every rank's list (-1 padded)
+  dbuf<double> gpack;    // [rank][maxown][3][npc] all-gather buffer of the synthesised density
   long long nmatvec = 0;
   dbuf<double> pb, pbw, cs, dsw, g_raw;
   dbuf<int> ka, kb;
@@ -287,6 +292,7 @@ struct rbc3d_ctx {
   // with overlap on it is issued on stream2 while singular / pair kernels run on stream (joined before combine)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int resident_collect = 1;    // rbc3d_apply_resident sums the rows over the ranks (0: the sharded solver keeps them local)
   int replicated_density = 0;  // 1: host densities are identical on all ranks -> upload 1/nranks each + all-gather
   int overlap = -1;         // -1: on with several ranks (hides the mesh all-reduce), 0 off, 1 on
   // lookup tables (device): interleaved SL (c1,c2) pairs, DL, mask

@@ -26,6 +26,7 @@ namespace rbc3d {
 
 struct ShArgs {
   int ncell, npc, nlat, nlon, m0, Np, dofc;
+  const int *cells;    // [slot] -> cell: the cells whose coefficients this rank holds (all of them on one rank)
   const double *pb;    // [m0][m0][nlat]  Pbar(m, n, i)            (synthesis)
   const double *pbw;   // [m0][m0][nlat]  Pbar w_i 2/nlon           (analysis)
   const double *cs;    // [m0][nlon][2]   cos, sin (m phi_j)
@@ -45,9 +46,9 @@ struct ShArgs {
 __global__ void __launch_bounds__(256) k_sh_synth(ShArgs a) {
   extern __shared__ double sm[];
   const int m0 = a.m0, nlat = a.nlat, nlon = a.nlon;
-  const int cell = blockIdx.x / 3, comp = blockIdx.x - 3 * cell;
+  const int slot = blockIdx.x / 3, comp = blockIdx.x - 3 * slot, cell = a.cells[slot];
   double *s_a = sm, *s_b = s_a + m0 * m0, *s_A = s_b + m0 * m0, *s_B = s_A + m0 * nlat;
-  const double *c = a.coef + (size_t)cell * a.dofc + comp;
+  const double *c = a.coef + (size_t)slot * a.dofc + comp;
   for (int e = threadIdx.x; e < m0 * m0; e += blockDim.x) {
     const int ia = a.ka[e], ib = a.kb[e];
     s_a[e] = ia >= 0 ? c[3 * ia] : 0.0;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) k_sh_synth(ShArgs a) {
 __global__ void __launch_bounds__(256) k_sh_anal(ShArgs a) {
   extern __shared__ double sm[];
   const int m0 = a.m0, nlat = a.nlat, nlon = a.nlon;
-  const int cell = blockIdx.x / 3, comp = blockIdx.x - 3 * cell;
+  const int slot = blockIdx.x / 3, comp = blockIdx.x - 3 * slot, cell = a.cells[slot];
   double *s_v = sm, *s_Fc = s_v + nlon * nlat, *s_Fs = s_Fc + m0 * nlat;
   const size_t base = (size_t)comp * a.Np + (size_t)cell * a.npc;
   const double bk = a.add_g ? 0.0 : 2.0 * a.vbkg[comp] / a.Acell[cell];  // ModVelSolver.F90:497-500
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) k_sh_anal(ShArgs a) {
     s_Fs[e] = fs;
   }
   __syncthreads();
-  double *out = a.coef_out + (size_t)cell * a.dofc + comp;
+  double *out = a.coef_out + (size_t)slot * a.dofc + comp;
   for (int e = threadIdx.x; e < m0 * m0; e += blockDim.x) {
     const int ia = a.ka[e], ib = a.kb[e];
     if (ia < 0) continue;
@@ -166,6 +167,29 @@ __global__ void k_axpy(int n, double alpha, const double *__restrict__ x, double
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   y[e] = add ? fma(alpha, x[e], y[e]) : alpha * x[e];
+}
+
+// several ranks: the double-layer density of the cells a rank owns -> [slot][3][npc] (its block of the all-gather), and
+// the other ranks' blocks back into the replicated source-list density SoA(3,Np)
+__global__ void k_dens_pack(int nown, int npc, int Np, const int *__restrict__ cells, const double *__restrict__ g,
+                            double *__restrict__ blk) {
+  const size_t total = (size_t)nown * 3 * npc;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % npc), d = (int)((e / npc) % 3), slot = (int)(e / ((size_t)3 * npc));
+    blk[e] = g[(size_t)d * Np + (size_t)cells[slot] * npc + i];
+  }
+}
+__global__ void k_dens_unpack(int R, int me, int maxown, int npc, int Np, const int *__restrict__ own_all,
+                              const double *__restrict__ all, double *__restrict__ g) {
+  const size_t per = (size_t)maxown * 3 * npc, total = (size_t)R * per;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / per);
+    if (r == me) continue;
+    const size_t q = e - (size_t)r * per;
+    const int i = (int)(q % npc), d = (int)((q / npc) % 3), slot = (int)(q / ((size_t)3 * npc));
+    const int cell = own_all[(size_t)r * maxown + slot];
+    if (cell >= 0) g[(size_t)d * Np + (size_t)cell * npc + i] = all[e];
+  }
 }
 
 static void pbar_table(int m0, int nlat, const double *th, std::vector<double> &pb) {
@@ -239,6 +263,49 @@ int solver_setup(rbc3d_ctx *c, int nlat0, const double *detj_host) {
   RBC_TRY(up(S.dsw, dsw));
   RBC_TRY(S.g_raw.resize(3 * (size_t)C.Np));
   RBC_TRY(C.g.resize(3 * (size_t)C.Np));
+  // unknowns of this rank: all cells on one rank; with several ranks the cells the rank owns targets of (whole cells:
+  // the coefficients, Krylov vectors and SH transforms of a cell live on one GPU, dot products are all-reduced)
+  const int R = c->prm.nranks;
+  std::vector<int> own;
+  if (R > 1) {
+    own.resize(C.sg_nactive);
+    if (C.sg_nactive)
+      CUDA_TRY(cudaMemcpyAsync(own.data(), C.sg_active_list.p, sizeof(int) * C.sg_nactive, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  } else {
+    own.resize(C.ncell);
+    for (int i = 0; i < C.ncell; i++) own[i] = i;
+  }
+  S.nown = (int)own.size();
+  S.dof_loc = (size_t)S.nown * S.dofc;
+  RBC_TRY(S.cells.resize(own.size() > 0 ? own.size() : 1));
+  if (!own.empty()) CUDA_TRY(cudaMemcpyAsync(S.cells.p, own.data(), sizeof(int) * own.size(), cudaMemcpyHostToDevice, c->stream));
+  S.maxown = S.nown;
+  if (R > 1) {
+    // every rank's list, padded to the largest count (-1), for the unpack side of the density all-gather
+    RBC_TRY(S.own_all.resize((size_t)R * (C.ncell + 1)));
+    int cnt = S.nown;
+    CUDA_TRY(cudaMemcpyAsync(S.own_all.p, &cnt, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RBC_TRY(comm_allgather_ints(c, S.own_all.p, S.own_all.p + 1, 1));
+    std::vector<int> counts(R);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), S.own_all.p + 1, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int mx = 0, tot = 0;
+    for (int r = 0; r < R; r++) mx = std::max(mx, counts[r]), tot += counts[r];
+    if (tot != C.ncell) {
+      set_error("rbc3d_solver_setup: the ranks own %d of %d cells -- every cell must have its targets active on exactly one rank", tot,
+                C.ncell);
+      return RBC3D_ESTATE;
+    }
+    S.maxown = mx;
+    std::vector<int> padded(std::max(mx, 1), -1);
+    std::copy(own.begin(), own.end(), padded.begin());
+    RBC_TRY(S.own_all.resize((size_t)(R + 1) * std::max(mx, 1)));
+    int *mine = S.own_all.p + (size_t)R * std::max(mx, 1);
+    CUDA_TRY(cudaMemcpyAsync(mine, padded.data(), sizeof(int) * padded.size(), cudaMemcpyHostToDevice, c->stream));
+    RBC_TRY(comm_allgather_ints(c, mine, S.own_all.p, (size_t)std::max(mx, 1)));
+    RBC_TRY(S.gpack.resize((size_t)R * std::max(mx, 1) * 3 * C.npc));
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
   S.ok = true;
   return RBC3D_OK;
@@ -249,11 +316,30 @@ static void sh_args(rbc3d_ctx *c, ShArgs &a) {
   Solver &S = c->solver;
   a.ncell = C.ncell, a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.m0 = S.m0, a.Np = C.Np, a.dofc = S.dofc;
   a.pb = S.pb.p, a.pbw = S.pbw.p, a.cs = S.cs.p, a.ka = S.ka.p, a.kb = S.kb.p, a.dsw = S.dsw.p;
+  a.cells = S.cells.p;
   a.coef = nullptr, a.coef_out = nullptr, a.g_raw = S.g_raw.p, a.g_src = C.g.p, a.v = nullptr;
   a.add_g = 1, a.vbkg[0] = a.vbkg[1] = a.vbkg[2] = 0.0, a.Acell = C.A.p;
 }
 
-// b = MyMatMult(u), device vectors of length dof (ModVelSolver.F90:523-601, c1 = 0, c2 = -1/(4 pi))
+// several ranks: every rank synthesised the density of its own cells; the source lists are replicated (every rank sums
+// over all sources within rc and spreads the sources that touch its planes), so the blocks are all-gathered over NVLink
+static int solver_share_density(rbc3d_ctx *c) {
+  Cells &C = c->cells;
+  Solver &S = c->solver;
+  const int R = c->prm.nranks;
+  if (R <= 1) return RBC3D_OK;
+  const size_t per = (size_t)std::max(S.maxown, 1) * 3 * C.npc;
+  if (S.nown > 0)
+    k_dens_pack<<<c->sm_count * 4, 256, 0, c->stream>>>(S.nown, C.npc, C.Np, S.cells.p, C.g.p, S.gpack.p + (size_t)c->prm.rank * per);
+  RBC_TRY(comm_allgather_inplace(c, S.gpack.p, per));
+  k_dens_unpack<<<c->sm_count * 8, 256, 0, c->stream>>>(R, c->prm.rank, std::max(S.maxown, 1), C.npc, C.Np, S.own_all.p, S.gpack.p,
+                                                        C.g.p);
+  KERNEL_CHECK();
+  c->launches += 2;
+  return RBC3D_OK;
+}
+
+// b = MyMatMult(u), device vectors of the rank's unknowns (ModVelSolver.F90:523-601, c1 = 0, c2 = -1/(4 pi))
 int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev) {
   Cells &C = c->cells;
   Solver &S = c->solver;
@@ -265,20 +351,31 @@ int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev) {
   ShArgs a;
   sh_args(c, a);
   a.coef = u_dev;
-  const size_t sm_s = sizeof(double) * (2 * (size_t)S.m0 * S.m0 + 2 * (size_t)S.m0 * C.nlat);
-  k_sh_synth<<<C.ncell * 3, 256, sm_s, c->stream>>>(a);  // Glob_Sph_Trans(g, u, FOUR_TO_PHYS) + SourceList_UpdateDensity
-  KERNEL_CHECK();
-  c->launches++;
+  if (S.nown > 0) {
+    const size_t sm_s = sizeof(double) * (2 * (size_t)S.m0 * S.m0 + 2 * (size_t)S.m0 * C.nlat);
+    CUDA_TRY(cudaFuncSetAttribute(k_sh_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
+    k_sh_synth<<<S.nown * 3, 256, sm_s, c->stream>>>(a);  // Glob_Sph_Trans(g, u, FOUR_TO_PHYS) + SourceList_UpdateDensity
+    KERNEL_CHECK();
+    c->launches++;
+  }
+  RBC_TRY(solver_share_density(c));
   C.g_set = true;
   C.spGi_valid = false;
-  RBC_TRY(rbc3d_apply_resident(c, 0.0, -1.0 / (4.0 * RBC_PI), 1, 0, RBC3D_TL_CELLS));  // v (summed over ranks) in t.v
+  // operator #2 on this rank's targets; with several ranks the rows stay where they are (no CollectArray: the analysis
+  // below only reads the cells this rank owns)
+  c->resident_collect = c->prm.nranks > 1 ? 0 : 1;
+  const int rc = rbc3d_apply_resident(c, 0.0, -1.0 / (4.0 * RBC_PI), 1, 0, RBC3D_TL_CELLS);
+  c->resident_collect = 1;
+  RBC_TRY(rc);
   a.v = t.v.p;
   a.coef_out = b_dev;
-  const size_t sm_a = sizeof(double) * ((size_t)C.nlon * C.nlat + 2 * (size_t)S.m0 * C.nlat);
-  CUDA_TRY(cudaFuncSetAttribute(k_sh_anal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
-  k_sh_anal<<<C.ncell * 3, 256, sm_a, c->stream>>>(a);   // v = v + g; Glob_Sph_Trans(v, b, PHYS_TO_FOUR)
-  KERNEL_CHECK();
-  c->launches++;
+  if (S.nown > 0) {
+    const size_t sm_a = sizeof(double) * ((size_t)C.nlon * C.nlat + 2 * (size_t)S.m0 * C.nlat);
+    CUDA_TRY(cudaFuncSetAttribute(k_sh_anal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+    k_sh_anal<<<S.nown * 3, 256, sm_a, c->stream>>>(a);   // v = v + g; Glob_Sph_Trans(v, b, PHYS_TO_FOUR)
+    KERNEL_CHECK();
+    c->launches++;
+  }
   S.nmatvec++;
   return RBC3D_OK;
 }
@@ -294,7 +391,11 @@ int solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs_de
     return RBC3D_ESTATE;
   }
   TargetList &t = c->tl[RBC3D_TL_CELLS];
-  RBC_TRY(rbc3d_apply_resident(c, 1.0 / (4.0 * RBC_PI), 0.0, 1, use_walls, RBC3D_TL_CELLS));
+  c->resident_collect = c->prm.nranks > 1 ? 0 : 1;
+  const int rc = rbc3d_apply_resident(c, 1.0 / (4.0 * RBC_PI), 0.0, 1, use_walls, RBC3D_TL_CELLS);
+  c->resident_collect = 1;
+  RBC_TRY(rc);
+  if (S.nown == 0) return RBC3D_OK;
   ShArgs a;
   sh_args(c, a);
   a.v = t.v.p;
@@ -303,7 +404,7 @@ int solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs_de
   for (int d = 0; d < 3; d++) a.vbkg[d] = vbkg[d];
   const size_t sm_a = sizeof(double) * ((size_t)C.nlon * C.nlat + 2 * (size_t)S.m0 * C.nlat);
   CUDA_TRY(cudaFuncSetAttribute(k_sh_anal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
-  k_sh_anal<<<C.ncell * 3, 256, sm_a, c->stream>>>(a);
+  k_sh_anal<<<S.nown * 3, 256, sm_a, c->stream>>>(a);
   KERNEL_CHECK();
   c->launches++;
   return RBC3D_OK;
@@ -311,11 +412,12 @@ int solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs_de
 
 static int dots(rbc3d_ctx *c, int k, const double *V, size_t ldv, const double *w, double *h_host) {
   Solver &S = c->solver;
-  const int n = (int)S.dof;
+  const int n = (int)S.dof_loc;
   k_dots_partial<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>(n, k, V, ldv, w, S.part.p);
   k_dots_final<<<k, 32, 0, c->stream>>>(k, S.part.p, S.h.p);
   KERNEL_CHECK();
   c->launches += 2;
+  RBC_TRY(comm_allreduce_sum(c, S.h.p, (size_t)k));  // several ranks: every rank holds the unknowns of its own cells
   CUDA_TRY(cudaMemcpyAsync(h_host, S.h.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
@@ -328,8 +430,8 @@ int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, 
   Solver &S = c->solver;
   if (!S.ok) return RBC3D_ESTATE;
   if (restart < 1 || restart > 200 || maxit < 0) return RBC3D_EINVAL;
-  const size_t n = S.dof;
-  const int nb = (int)((n + 255) / 256);
+  const size_t n = S.dof_loc;
+  const int nb = (int)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
   RBC_TRY(S.V.resize((size_t)(restart + 1) * n));
   RBC_TRY(S.w.resize(n));
   RBC_TRY(S.part.resize((size_t)(restart + 2) * DOT_BLOCKS));
@@ -370,8 +472,8 @@ int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, 
         Hm(i, k) = t;
       }
       const double d = hypot(Hm(k, k), Hm(k + 1, k));
-      cs[k] = Hm(k, k) / d;
-      sn[k] = Hm(k + 1, k) / d;
+      cs[k] = d > 0.0 ? Hm(k, k) / d : 1.0;  // exact breakdown (a zero column): identity rotation, no NaN
+      sn[k] = d > 0.0 ? Hm(k + 1, k) / d : 0.0;
       Hm(k, k) = d;
       Hm(k + 1, k) = 0.0;
       gv[k + 1] = -sn[k] * gv[k];
@@ -402,7 +504,9 @@ int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, 
 
 void solver_release(rbc3d_ctx *c) {
   Solver &S = c->solver;
-  for (dbuf<double> *b : {&S.pb, &S.pbw, &S.cs, &S.dsw, &S.g_raw, &S.V, &S.w, &S.part, &S.h, &S.u, &S.b}) b->release();
+  for (dbuf<double> *b : {&S.pb, &S.pbw, &S.cs, &S.dsw, &S.g_raw, &S.V, &S.w, &S.part, &S.h, &S.u, &S.b, &S.gpack}) b->release();
+  S.cells.release();
+  S.own_all.release();
   S.ka.release();
   S.kb.release();
   S.ok = false;
@@ -422,7 +526,16 @@ int rbc3d_solver_setup(rbc3d_ctx *c, int nlat0, const double *detj) {
 
 int rbc3d_solver_dof(rbc3d_ctx *c, int64_t *dof) {
   if (!c || !dof || !c->solver.ok) return RBC3D_ESTATE;
-  *dof = (int64_t)c->solver.dof;
+  *dof = (int64_t)c->solver.dof_loc;
+  return RBC3D_OK;
+}
+
+int rbc3d_solver_cells(rbc3d_ctx *c, int32_t *n, int32_t *cells, int cap) {
+  if (!c || !n || !c->solver.ok) return RBC3D_ESTATE;
+  CUDA_TRY(cudaSetDevice(c->device));
+  *n = c->solver.nown;
+  const int m = std::min(cap, c->solver.nown);
+  if (cells && m > 0) CUDA_TRY(cudaMemcpy(cells, c->solver.cells.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
   return RBC3D_OK;
 }
 
@@ -431,11 +544,11 @@ int rbc3d_solver_matmult(rbc3d_ctx *c, const double *u, double *b) {
   if (!c->solver.ok) return RBC3D_ESTATE;
   CUDA_TRY(cudaSetDevice(c->device));
   Solver &S = c->solver;
-  RBC_TRY(S.u.resize(S.dof));
-  RBC_TRY(S.b.resize(S.dof));
-  CUDA_TRY(cudaMemcpyAsync(S.u.p, u, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(S.u.resize(S.dof_loc));
+  RBC_TRY(S.b.resize(S.dof_loc));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, u, sizeof(double) * S.dof_loc, cudaMemcpyHostToDevice, c->stream));
   RBC_TRY(solver_matmult(c, S.u.p, S.b.p));
-  CUDA_TRY(cudaMemcpyAsync(b, S.b.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(b, S.b.p, sizeof(double) * S.dof_loc, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -445,9 +558,9 @@ int rbc3d_solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *
   if (!c->solver.ok) return RBC3D_ESTATE;
   CUDA_TRY(cudaSetDevice(c->device));
   Solver &S = c->solver;
-  RBC_TRY(S.b.resize(S.dof));
+  RBC_TRY(S.b.resize(S.dof_loc));
   RBC_TRY(solver_rhs(c, vbkg, use_walls, S.b.p));
-  CUDA_TRY(cudaMemcpyAsync(rhs, S.b.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(rhs, S.b.p, sizeof(double) * S.dof_loc, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -459,17 +572,20 @@ int rbc3d_solver_velocity(rbc3d_ctx *c, const double *sol, double *v) {
   CUDA_TRY(cudaSetDevice(c->device));
   Cells &C = c->cells;
   Solver &S = c->solver;
-  RBC_TRY(S.u.resize(S.dof));
-  RBC_TRY(S.w.resize(3 * (size_t)C.Np > S.dof ? 3 * (size_t)C.Np : S.dof));
-  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(S.u.resize(S.dof_loc));
+  RBC_TRY(S.w.resize(3 * (size_t)C.Np > S.dof ? 3 * (size_t)C.Np : S.dof_loc));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof_loc, cudaMemcpyHostToDevice, c->stream));
   ShArgs a;
   sh_args(c, a);
   a.coef = S.u.p;
   a.g_src = S.w.p;  // the weighted copy is not wanted here: scratch
   const size_t sm_s = sizeof(double) * (2 * (size_t)S.m0 * S.m0 + 2 * (size_t)S.m0 * C.nlat);
-  k_sh_synth<<<C.ncell * 3, 256, sm_s, c->stream>>>(a);
-  KERNEL_CHECK();
-  c->launches++;
+  if (S.nown > 0) {
+    CUDA_TRY(cudaFuncSetAttribute(k_sh_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
+    k_sh_synth<<<S.nown * 3, 256, sm_s, c->stream>>>(a);
+    KERNEL_CHECK();
+    c->launches++;
+  }
   CUDA_TRY(cudaMemcpyAsync(v, S.g_raw.p, sizeof(double) * 3 * C.Np, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
@@ -481,12 +597,12 @@ int rbc3d_solver_gmres(rbc3d_ctx *c, const double *rhs, double *sol, double rtol
   if (!c->solver.ok) return RBC3D_ESTATE;
   CUDA_TRY(cudaSetDevice(c->device));
   Solver &S = c->solver;
-  RBC_TRY(S.u.resize(S.dof));
-  RBC_TRY(S.b.resize(S.dof));
-  CUDA_TRY(cudaMemcpyAsync(S.b.p, rhs, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(S.u.resize(S.dof_loc));
+  RBC_TRY(S.b.resize(S.dof_loc));
+  CUDA_TRY(cudaMemcpyAsync(S.b.p, rhs, sizeof(double) * S.dof_loc, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(S.u.p, sol, sizeof(double) * S.dof_loc, cudaMemcpyHostToDevice, c->stream));
   RBC_TRY(solver_gmres(c, S.b.p, S.u.p, rtol, restart, maxit, niter, history));
-  CUDA_TRY(cudaMemcpyAsync(sol, S.u.p, sizeof(double) * S.dof, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(sol, S.u.p, sizeof(double) * S.dof_loc, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }

@@ -307,12 +307,16 @@ class EwaldOperator:
         check(self.lib.rbc3d_solver_setup(self._h, int(nlat0), dp(f64(detj))), "rbc3d_solver_setup")
         n = C.c_int64()
         check(self.lib.rbc3d_solver_dof(self._h, C.byref(n)))
-        self.solver_dof = int(n.value)
+        self.solver_dof = int(n.value)              # unknowns THIS rank holds (all of them on one rank)
+        m = C.c_int32()
+        cells = np.zeros(max(self.ncell, 1), np.int32)
+        check(self.lib.rbc3d_solver_cells(self._h, C.byref(m), ip(cells), self.ncell))
+        self.solver_cells = cells[:m.value].copy()  # ... of these cells, in vector order
 
-    def solver_matmult(self, u):
-        """MyMatMult on the device: packed SH coefficients in, packed SH coefficients out."""
+    def solver_matmult(self, u, out=None):
+        """MyMatMult on the device: packed SH coefficients in, packed SH coefficients out (of this rank's cells)."""
         u = f64(u)
-        b = np.zeros(self.solver_dof)
+        b = np.zeros(self.solver_dof) if out is None else out
         check(self.lib.rbc3d_solver_matmult(self._h, dp(u), dp(b)), "rbc3d_solver_matmult")
         return b
 
