@@ -325,7 +325,7 @@ def kernel_table(op, sus, ms, npairs, peaks, world=1):
         flops=N * npatch * FLOPS_PATCH_CACHED, bytes_=N * (sg_pts if sg_on else npatch) * 32.0, bound="hbm")
     add("near_singular", ms["nearsing"])
     add("spread(DL,6 sym comps)", ms["spread"], flops=N * P3 * (2 + 2 * 6), bytes_=80.0 * N + 2 * 6 * 8.0 * G)
-    add("mesh_allreduce+velocity_allreduce(NCCL)", ms["comm"], bound="nvlink")
+    add("slab_transposes+halo(NCCL)", ms["comm"], bound="nvlink")
     add("fft_fwd(cuFFT D2Z x6)", ms["fft"], bytes_=6 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
     add("kspace_scale", ms["kspace"], bytes_=(6 + 3) * 16.0 * M, bound="hbm")
     add("fft_inv(cuFFT Z2D x3)", ms["fft_inv"], bytes_=3 * 2 * (8.0 * G + 16.0 * M), bound="hbm")
@@ -565,7 +565,13 @@ def run_gpu(args):
     cnt, _ = op.neighbor_signature()
     npairs = float(cnt.astype(np.float64).sum())
     rows = kernel_table(op, sus, stage_ms, npairs, (hbm_peak, fp64_peak), world)
-    dom = max(rows, key=lambda r: r["ms"])
+    if world > 1:
+        # the PME chain runs on its own stream beside the real-space kernels: its per-kernel event times include waiting
+        # for SMs and are marked; the dominant kernel is taken from the real-space chain (the critical path)
+        for r in rows:
+            r["overlapped"] = r["kernel"].split("(")[0] in ("spread", "slab_transposes+halo", "fft_fwd", "fft_inv",
+                                                            "kspace_scale", "interp")
+    dom = max([r for r in rows if not r.get("overlapped")], key=lambda r: r["ms"])
     traffic = None
     try:   # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
@@ -653,6 +659,8 @@ def run_gpu(args):
                    "point_density_path_ms": (e2e_point_s * 1e3) if e2e_point_s else None},
            "gpu_launches": int(launches),
            "stage_ms": stage_ms, "fft_ms": stage_ms["fft"] + stage_ms["fft_inv"],
+           "critical_paths_ms": {"real_space_chain": stage_ms.get("real_chain"), "pme_chain": stage_ms.get("pme_chain"),
+                                 "note": "several ranks: the two chains run on two streams and join before the combine"},
            "roofline": roof, "kernels": rows, "timestep": timestep,
            "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "fp64_tflops": fp64_peak,
                      "fp64_source": "in-process DFMA micro-benchmark"},

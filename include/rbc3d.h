@@ -46,7 +46,10 @@ enum { RBC3D_TL_CELLS = 0, RBC3D_TL_RAW = 1, RBC3D_TL_WALLS = 2 };
 enum {
   RBC3D_T_PAIR = 0, RBC3D_T_SING, RBC3D_T_NEARSING, RBC3D_T_LINEAR, RBC3D_T_SPREAD, RBC3D_T_FFT,
   RBC3D_T_KSPACE, RBC3D_T_FFT_INV, RBC3D_T_INTERP, RBC3D_T_COMBINE, RBC3D_T_WALL, RBC3D_T_COMM, RBC3D_T_H2D,
-  RBC3D_T_D2H, RBC3D_T_DENSITY, RBC3D_T_TOTAL, RBC3D_T_COUNT
+  RBC3D_T_D2H, RBC3D_T_DENSITY, RBC3D_T_TOTAL,
+  /* with several ranks the PME chain (spread .. interpolate, on its own stream) overlaps the real-space chain (pair,
+   * singular, near-singular, linear): their two critical paths, each measured on its own stream */
+  RBC3D_T_PME_CHAIN, RBC3D_T_REAL_CHAIN, RBC3D_T_COUNT
 };
 
 const char *rbc3d_last_error(void);

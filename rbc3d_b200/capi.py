@@ -18,7 +18,7 @@ c_fp = C.POINTER(C.c_float)
 
 TL_CELLS, TL_RAW, TL_WALLS = 0, 1, 2
 STAGES = ["pair", "sing", "nearsing", "linear", "spread", "fft", "kspace", "fft_inv", "interp", "combine", "wall",
-          "comm", "h2d", "d2h", "density", "total"]
+          "comm", "h2d", "d2h", "density", "total", "pme_chain", "real_chain"]
 
 # name -> (restype, argtypes); every symbol declared in include/rbc3d.h
 SIGNATURES = {

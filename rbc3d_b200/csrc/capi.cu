@@ -940,12 +940,15 @@ static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int u
     int rc = cudaMemsetAsync(t.acc2.p, 0, sizeof(double) * 3 * (size_t)(t.n > 0 ? t.n : 1), c->stream) == cudaSuccess
                  ? RBC3D_OK
                  : RBC3D_ECUDA;
+    t_begin(c, RBC3D_T_PME_CHAIN);
     if (rc == RBC3D_OK) rc = pme_chain(c, t, c1, c2, use_cells, use_walls, t.acc2.p);
+    t_end(c, RBC3D_T_PME_CHAIN);
     if (rc == RBC3D_OK && cudaEventRecord(c->ev_join, c->stream) != cudaSuccess) rc = RBC3D_ECUDA;
     std::swap(c->stream, c->stream2);
     RBC_TRY(rc);
     *acc2 = t.acc2.p;
   }
+  t_begin(c, RBC3D_T_REAL_CHAIN);
   if (use_cells) RBC_TRY(realspace_cells(c, t, c1, c2));
   if (use_walls && c1 != 0) {
     t_begin(c, RBC3D_T_WALL);
@@ -955,6 +958,7 @@ static int apply_common(rbc3d_ctx *c, TargetList &t, double c1, double c2, int u
   t_begin(c, RBC3D_T_LINEAR);
   RBC_TRY(linear_term(c, t, (use_cells && !(c->skip_flags & 4)) ? c2 : 0.0));
   t_end(c, RBC3D_T_LINEAR);
+  t_end(c, RBC3D_T_REAL_CHAIN);
   if (overlap)
     CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join before combine
   else
