@@ -223,6 +223,16 @@ int rbc3d_solver_rhs(rbc3d_ctx *ctx, const double vbkg[3], int use_walls, double
 /* v = Glob_Sph_Trans(sol, FOUR_TO_PHYS): the surface velocity of a solution (ModVelSolver.F90:124), host SoA(3,Np) */
 int rbc3d_solver_velocity(rbc3d_ctx *ctx, const double *sol, double *v);
 
+/* ---- closest-neighbour queries of ModRepulsion on the GPU cell lists ----
+ * Closest_Neighbor_Cell (ModRepulsion.F90:480-546) and Closest_Neighbor_Wall (:556-613) for n points at once (the
+ * reference calls them point by point, 4x per time step over all cell points: InterCellRepulsion :270-402,
+ * LeukWallRepulsion :405-470).  x: SoA(3,n); surf_id[n]: surface the point lies on (cells 1..ncell, walls ncell+1..;
+ * elements / cells of that surface are skipped); eps_dist: the threshold below which the closest mesh point is refined
+ * by Spline_FindProjection.  Out: dist_cell[n] / dist_wall[n] (HUGE_VAL where the 27 neighbouring list cells hold
+ * no other surface), x0_cell / x0_wall SoA(3,n) the closest points.  Either output pair may be NULL. */
+int rbc3d_closest_neighbors(rbc3d_ctx *ctx, int n, const double *x, const int32_t *surf_id, double eps_dist,
+                            double *dist_cell, double *x0_cell, double *dist_wall, double *x0_wall);
+
 /* ---- introspection (tests, profiling) ---- */
 /* cell list of the cell sources: cid[Np] (0-based, i1 fastest), order[Np] (source indices sorted by cell,
  * ascending index inside a cell), start[Nc1*Nc2*Nc3+1]; any pointer may be NULL */

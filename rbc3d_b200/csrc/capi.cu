@@ -1052,6 +1052,52 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
   return RBC3D_OK;
 }
 
+// Closest_Neighbor_Cell / Closest_Neighbor_Wall (ModRepulsion.F90:480-613) for n points at once
+int rbc3d_closest_neighbors(rbc3d_ctx *c, int n, const double *x, const int32_t *surf_id, double eps_dist,
+                            double *dist_cell, double *x0_cell, double *dist_wall, double *x0_wall) {
+  if (!c || n < 0 || (n > 0 && (!x || !surf_id))) return RBC3D_EINVAL;
+  if (n == 0) return RBC3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool cells = c->cells.geom_set && c->cells.Np > 0 && dist_cell && x0_cell;
+  const bool walls = c->walls.geom_set && c->walls.NE > 0 && dist_wall && x0_wall;
+  dbuf<double> qx, out;
+  dbuf<int> sid;
+  RBC_TRY(qx.resize(3 * (size_t)n));
+  RBC_TRY(out.resize(8 * (size_t)n));
+  RBC_TRY(sid.resize(n));
+  auto done = [&](int rc) {
+    qx.release(), out.release(), sid.release();
+    return rc;
+  };
+  if (cudaMemcpyAsync(qx.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+      cudaMemcpyAsync(sid.p, surf_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+    return done(RBC3D_ECUDA);
+  double *dc = out.p, *xc = out.p + n, *dw = out.p + 4 * (size_t)n, *xw = out.p + 5 * (size_t)n;
+  int rc = RBC3D_OK;
+  if (cells) rc = closest_cells(c, n, qx.p, sid.p, eps_dist, dc, xc);
+  if (rc == RBC3D_OK && walls) rc = closest_walls(c, n, qx.p, sid.p, dw, xw);
+  if (rc != RBC3D_OK) return done(rc);
+  const double huge = HUGE_VAL;  // dist0 = huge(dist0) when there is no such surface (ModRepulsion.F90:494, 571)
+  if (dist_cell) {
+    if (cells) {
+      cudaMemcpyAsync(dist_cell, dc, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(x0_cell, xc, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream);
+    } else {
+      for (int i = 0; i < n; i++) dist_cell[i] = huge;
+    }
+  }
+  if (dist_wall) {
+    if (walls) {
+      cudaMemcpyAsync(dist_wall, dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(x0_wall, xw, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream);
+    } else {
+      for (int i = 0; i < n; i++) dist_wall[i] = huge;
+    }
+  }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return done(RBC3D_ECUDA);
+  return done(RBC3D_OK);
+}
+
 int rbc3d_get_velocity(rbc3d_ctx *c, int tlist, double *v) {
   TargetList *t;
   RBC_TRY(get_tl(c, tlist, &t));

@@ -512,4 +512,89 @@ int nearsing_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
   return RBC3D_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Closest_Neighbor_Cell (ModRepulsion.F90:480-546) on the GPU cell list.  One warp per query point:
+// the lanes scan the points of the 27 neighbouring list cells (sorted copies, coalesced), skip the query's own surface,
+// and agree on the closest mesh point (ties: the smaller point index); if it is within 2 epsDist, lane 0 refines it by
+// Spline_FindProjection on that cell's spline surface, started from the mesh point's (theta, phi).
+struct ClosestArgs {
+  Params prm;
+  int n, Np, npc, nlat, nlon;
+  const double *qx;           // query points SoA(3,n)
+  const int *surf;            // surface id of each query point (cells are 1..ncell), ModRepulsion.F90:507
+  const int *start, *order;   // cell list of the cell points
+  const double *sx;           // sorted coordinates SoA(3,Np)
+  const double *x, *spx, *th, *phi;
+  double epsDist;
+  double *dist, *x0;          // [n], SoA(3,n)
+};
+
+__global__ void __launch_bounds__(256) k_closest_cell(ClosestArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.n) return;
+  const int i = warp;
+  const double xi[3] = {a.qx[i], a.qx[(size_t)a.n + i], a.qx[2 * (size_t)a.n + i]};
+  const int *Nc = a.prm.Nc;
+  const int i1 = cell_coord(xi[0], a.prm.iLbNc[0], Nc[0]), i2 = cell_coord(xi[1], a.prm.iLbNc[1], Nc[1]),
+            i3 = cell_coord(xi[2], a.prm.iLbNc[2], Nc[2]);
+  const int sid = a.surf[i];
+  double best = INFINITY;
+  int bj = 0x7fffffff;
+  for (int d3 = -1; d3 <= 1; d3++)
+    for (int d2 = -1; d2 <= 1; d2++)
+      for (int d1 = -1; d1 <= 1; d1++) {
+        const int cj = imodulo(i1 + d1, Nc[0]) + Nc[0] * (imodulo(i2 + d2, Nc[1]) + Nc[1] * imodulo(i3 + d3, Nc[2]));
+        for (int s = a.start[cj] + lane; s < a.start[cj + 1]; s += 32) {
+          const int j = a.order[s];
+          if (j / a.npc + 1 == sid) continue;
+          const double xx = min_image(__dsub_rn(xi[0], a.sx[s]), a.prm.iLb[0], a.prm.Lb[0]);
+          const double yy = min_image(__dsub_rn(xi[1], a.sx[(size_t)a.Np + s]), a.prm.iLb[1], a.prm.Lb[1]);
+          const double zz = min_image(__dsub_rn(xi[2], a.sx[2 * (size_t)a.Np + s]), a.prm.iLb[2], a.prm.Lb[2]);
+          const double rr = sqrt(norm2_exact(xx, yy, zz));
+          if (rr < best || (rr == best && j < bj)) best = rr, bj = j;
+        }
+      }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(FULL_MASK, best, o);
+    const int oj = __shfl_xor_sync(FULL_MASK, bj, o);
+    if (ob < best || (ob == best && oj < bj)) best = ob, bj = oj;
+  }
+  if (lane != 0) return;
+  double x0[3] = {0, 0, 0}, dist0 = best;
+  if (best <= 2.0 * a.epsDist) {  // ModRepulsion.F90:525-542
+    const int jc = bj / a.npc, pt = bj - jc * a.npc, ilon0 = pt / a.nlat, ilat0 = pt - ilon0 * a.nlat;
+    double th0 = a.th[ilat0], phi0 = a.phi[ilon0], xtar[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      x0[d] = a.x[(size_t)d * a.Np + bj];
+      const double xx = min_image(__dsub_rn(xi[d], x0[d]), a.prm.iLb[d], a.prm.Lb[d]);
+      xtar[d] = x0[d] + xx;
+    }
+    const int m = 2 * a.nlat, nn = a.nlon;
+    find_projection(a.spx + (size_t)12 * m * nn * jc, m, nn, xtar, th0, phi0, x0);
+    const double e0 = xtar[0] - x0[0], e1 = xtar[1] - x0[1], e2 = xtar[2] - x0[2];
+    dist0 = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+  }
+  a.dist[i] = dist0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) a.x0[(size_t)d * a.n + i] = x0[d];
+}
+
+// device buffers in, device buffers out (capi.cu moves the host arrays)
+int closest_cells(rbc3d_ctx *c, int n, const double *qx, const int *surf, double epsDist, double *dist, double *x0) {
+  Cells &C = c->cells;
+  if (n == 0) return RBC3D_OK;
+  ClosestArgs a;
+  a.prm = c->prm;
+  a.n = n, a.Np = C.Np, a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon;
+  a.qx = qx, a.surf = surf, a.start = C.cl.start.p, a.order = C.cl.order.p, a.sx = C.sx.p;
+  a.x = C.x.p, a.spx = C.spx.p, a.th = C.th.p, a.phi = C.phi.p;
+  a.epsDist = epsDist, a.dist = dist, a.x0 = x0;
+  k_closest_cell<<<(n + 7) / 8, 256, 0, c->stream>>>(a);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
+}
+
 }  // namespace rbc3d

@@ -380,6 +380,10 @@ int walls_tri_int_batch(rbc3d_ctx *c, int n, const double *xtri, const double *f
                         const double *s0, const double *t0, double *rhs, double *lhs);
 void walls_release(rbc3d_ctx *c);
 
+// ---- closest-neighbour queries of ModRepulsion on the cell lists (nearsing.cu, walls.cu); device pointers ----
+int closest_cells(rbc3d_ctx *c, int n, const double *qx, const int *surf, double epsDist, double *dist, double *x0);
+int closest_walls(rbc3d_ctx *c, int n, const double *qx, const int *surf, double *dist, double *x0);
+
 // ---- cell velocity solve on the device (solver.cu) ----
 int solver_setup(rbc3d_ctx *c, int nlat0, const double *detj_host);
 int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev);

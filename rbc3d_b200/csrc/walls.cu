@@ -1023,4 +1023,76 @@ void walls_release(rbc3d_ctx *c) {
   for (int k = 0; k < 3; k++) c->tl[k].wp.release();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Closest_Neighbor_Wall (ModRepulsion.F90:556-613) on the wall cell list: one thread per query point,
+// every element whose centroid lies in the 27 neighbouring list cells and that is not on the query's own surface; the
+// query point is translated next to the element (:593-595), MinDistToTri gives distance and closest point (:597).
+struct ClosestWArgs {
+  Params prm;
+  WallGeom g;
+  int n, id0;                 // id0 = surface id of the first wall (walls(1)%id = nrbc + 1)
+  const double *qx;
+  const int *surf;
+  const int *wstart, *worder;
+  double *dist, *x0;
+};
+
+__global__ void __launch_bounds__(128) k_closest_wall(ClosestWArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double xi[3] = {a.qx[i], a.qx[(size_t)a.n + i], a.qx[2 * (size_t)a.n + i]};
+  const int *Nc = a.prm.Nc;
+  const int i1 = cell_coord(xi[0], a.prm.iLbNc[0], Nc[0]), i2 = cell_coord(xi[1], a.prm.iLbNc[1], Nc[1]),
+            i3 = cell_coord(xi[2], a.prm.iLbNc[2], Nc[2]);
+  const int sid = a.surf[i];
+  double best = INFINITY, bx[3] = {0, 0, 0};
+  int be = 0x7fffffff;
+  for (int d3 = -1; d3 <= 1; d3++)
+    for (int d2 = -1; d2 <= 1; d2++)
+      for (int d1 = -1; d1 <= 1; d1++) {
+        const int cj = imodulo(i1 + d1, Nc[0]) + Nc[0] * (imodulo(i2 + d2, Nc[1]) + Nc[1] * imodulo(i3 + d3, Nc[2]));
+        for (int k = a.wstart[cj]; k < a.wstart[cj + 1]; k++) {
+          const int e = a.worder[k];
+          if (a.id0 + a.g.ewall[e] == sid) continue;  // :582
+          double x[3][3], xt[3], s0, t0;
+#pragma unroll
+          for (int l = 0; l < 3; l++) {
+            const int iv = a.g.e2v[(size_t)l * a.g.NE + e];
+#pragma unroll
+            for (int d = 0; d < 3; d++) x[l][d] = a.g.x[(size_t)d * a.g.NV + iv];
+          }
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            double xx = sub_(xi[d], x[0][d]);
+            xx = sub_(xx, mul_(round(mul_(xx, a.prm.iLb[d])), a.prm.Lb[d]));
+            xt[d] = add_(x[0][d], xx);
+          }
+          const double rr = min_dist_to_tri(xt, x, s0, t0);
+          if (rr < best || (rr == best && e < be)) {
+            best = rr, be = e;
+#pragma unroll
+            for (int d = 0; d < 3; d++) bx[d] = (1.0 - s0 - t0) * x[0][d] + s0 * x[1][d] + t0 * x[2][d];  // ModIntOnWalls.F90:575
+          }
+        }
+      }
+  a.dist[i] = best;
+#pragma unroll
+  for (int d = 0; d < 3; d++) a.x0[(size_t)d * a.n + i] = bx[d];
+}
+
+int closest_walls(rbc3d_ctx *c, int n, const double *qx, const int *surf, double *dist, double *x0) {
+  Walls &W = c->walls;
+  if (n == 0) return RBC3D_OK;
+  ClosestWArgs a;
+  a.prm = c->prm;
+  a.g.NV = W.NV, a.g.NE = W.NE, a.g.x = W.x.p, a.g.e2v = W.e2v.p, a.g.ewall = W.ewall.p, a.g.epsDist = W.epsDist.p;
+  a.n = n, a.id0 = c->cells.ncell + 1;
+  a.qx = qx, a.surf = surf, a.wstart = W.cl.start.p, a.worder = W.cl.order.p;
+  a.dist = dist, a.x0 = x0;
+  k_closest_wall<<<(n + 127) / 128, 128, 0, c->stream>>>(a);
+  KERNEL_CHECK();
+  c->launches++;
+  return RBC3D_OK;
+}
+
 }  // namespace rbc3d

@@ -342,6 +342,19 @@ class EwaldOperator:
                                           dp(hist)), "rbc3d_solver_gmres")
         return sol, nit.value, hist[:nit.value + 1]
 
+    # -- ModRepulsion closest-neighbour queries on the GPU cell lists ------------------------
+    def closest_neighbors(self, x, surf_id, eps_dist):
+        """Closest_Neighbor_Cell / Closest_Neighbor_Wall for points x (3, n) on surfaces surf_id (n,) ->
+        dist_cell, x0_cell, dist_wall, x0_wall (inf where no other surface is in the 27 neighbouring list cells)."""
+        x = f64(x)
+        n = x.shape[1]
+        sid = i32(surf_id)
+        dc, dw = np.zeros(n), np.zeros(n)
+        xc, xw = np.zeros((3, n)), np.zeros((3, n))
+        check(self.lib.rbc3d_closest_neighbors(self._h, n, dp(x), ip(sid), float(eps_dist), dp(dc), dp(xc), dp(dw), dp(xw)),
+              "rbc3d_closest_neighbors")
+        return dc, xc, dw, xw
+
     def sing_cache_info(self):
         """(cached path active, patch points per target streamed from the cache)."""
         a, b = C.c_int32(), C.c_int32()

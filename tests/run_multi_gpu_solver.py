@@ -38,7 +38,8 @@ def main():
     op.solver_setup(sus.nlat0, sus.detj)
     own = op.solver_cells
     assert np.array_equal(own, np.flatnonzero(act.reshape(-1, npc)[:, 0])), own
-    dofc = op.solver_dof // max(len(own), 1)
+    dofc = 3 * sus.nlat0 ** 2                                  # unknowns per cell (ModVelSolver.F90:66)
+    assert op.solver_dof == len(own) * dofc
     # a global vector, the same on every rank; each rank passes the rows of its cells
     rng = np.random.default_rng(4)
     u_all = rng.uniform(-1, 1, (sus.ncell, dofc))

@@ -389,3 +389,69 @@ def test_edge_cases_empty_inactive_and_zero_inputs(oracle_lib):
     op.TargetList_CreateFromRaw(np.zeros((3, 0)))
     assert op.apply(C1_RHS, C2_MATVEC, TL_RAW).shape == (3, 0)
     op.close()
+
+
+def test_closest_neighbor_queries_vs_oracle(oracle_lib):
+    """Closest_Neighbor_Cell / Closest_Neighbor_Wall (ModRepulsion.F90:480-613) on the GPU cell lists
+    (rbc3d_closest_neighbors) against the oracle: a nearly touching pair of cells (projection branch, :525-542), a cell
+    close to a tube wall, wall vertices asking for their closest other surface, and the InterCellRepulsion displacement
+    (:304-325) formed from the two queries."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    EPS = 0.1
+    # (1) cells only: close pair + a third cell
+    sus = util.close_pair_suspension(gap=0.08, extra=1)
+    npc = sus.nlat * sus.nlon
+    op = EwaldOperator(sus.Lb)
+    op.set_suspension(sus)
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    sid = (np.arange(sus.npoint) // npc + 1).astype(np.int32)
+    dc, xc, dw, xw = op.closest_neighbors(sus.x, sid, EPS)
+    rdc, rxc, rdw, rxw = orc.closest_neighbors(sus.x, sid, EPS)
+    assert np.all(np.isinf(dw)) and np.all(np.isinf(rdw))
+    assert np.array_equal(np.isfinite(dc), np.isfinite(rdc))
+    fin = np.isfinite(rdc)
+    proj = fin & (rdc <= 2 * EPS)
+    assert proj.sum() > 50 and (fin & ~proj).sum() > 1000
+    assert np.abs(dc[fin & ~proj] - rdc[fin & ~proj]).max() < 1e-14     # mesh-point distances
+    assert np.abs(dc[proj] - rdc[proj]).max() < 1e-11                    # after Spline_FindProjection
+    near = fin & (rdc <= 2 * EPS)
+    assert np.abs(xc[:, near] - rxc[:, near]).max() < 1e-10
+    # InterCellRepulsion displacement from the queries (ModRepulsion.F90:304-325)
+    dx_ref, cnt_ref, _ = orc.inter_cell_repulsion(EPS)
+    push = dc < EPS
+    d = sus.x[:, push] - xc[:, push]
+    d -= np.rint(d / sus.Lb[:, None]) * sus.Lb[:, None]
+    r = np.linalg.norm(d, axis=0)
+    dx = np.zeros_like(sus.x)
+    dx[:, push] = 0.5 * d * (EPS - r) / r
+    assert push.sum() == cnt_ref and np.abs(dx - dx_ref).max() < 1e-11
+    op.close()
+    # (2) a cell close to a tube wall
+    LB = np.array([10.5, 10.5, 8.0])
+    centers = np.array([[5.25, 5.25, 2.0], [8.75, 5.6, 6.0]])
+    sus = synth.make_suspension(1, L=LB, centers=centers, seed=3)
+    W = synth.make_walls(LB, [dict(radius=4.9, ntheta=36, nz=12)])
+    op = EwaldOperator(LB)
+    op.set_suspension(sus)
+    op.set_walls(W)
+    orc = oracle_lib.Oracle(LB).set_cells(sus)
+    orc.set_walls(W)
+    sid = (np.arange(sus.npoint) // npc + 1).astype(np.int32)
+    dc, xc, dw, xw = op.closest_neighbors(sus.x, sid, EPS)
+    rdc, rxc, rdw, rxw = orc.closest_neighbors(sus.x, sid, EPS)
+    assert np.array_equal(np.isfinite(dw), np.isfinite(rdw)) and np.isfinite(rdw).sum() > 100
+    fin = np.isfinite(rdw)
+    assert np.abs(dw[fin] - rdw[fin]).max() < 1e-13 and np.abs(xw[:, fin] - rxw[:, fin]).max() < 1e-12
+    assert np.array_equal(np.isfinite(dc), np.isfinite(rdc))
+    finc = np.isfinite(rdc)
+    assert np.abs(dc[finc] - rdc[finc]).max() < 1e-11
+    # wall vertices: their own wall is skipped (:582), the closest cell is found
+    wid = np.full(W.NV, sus.ncell + 1, dtype=np.int32)
+    dcw, xcw, dww, _ = op.closest_neighbors(W.x, wid, EPS)
+    rdcw, rxcw, rdww, _ = orc.closest_neighbors(W.x, wid, EPS)
+    assert np.all(np.isinf(dww)) and np.all(np.isinf(rdww))
+    assert np.array_equal(np.isfinite(dcw), np.isfinite(rdcw)) and np.isfinite(rdcw).sum() > 10
+    f2 = np.isfinite(rdcw)
+    assert np.abs(dcw[f2] - rdcw[f2]).max() < 1e-11
+    op.close()
