@@ -270,6 +270,32 @@ def run_reference(args):
     return 0
 
 
+def minicase_config(seed):
+    """examples/minicase on the reference's own Exodus wall mesh (tests/golden/meshes/new_cyl_D6_L13_33.e, 1328 vertices /
+    2404 triangles; rbc3d_b200.cases.minicase = minit.F90 restated); the generated tube only when the fixture is missing."""
+    from rbc3d_b200 import cases, mtube
+    try:
+        sus, W, _ = cases.minicase(cases.mesh_file("new_cyl_D6_L13_33.e"), seed=seed)
+        W.f[:] = 0.0
+        return sus, W, "reference Exodus mesh new_cyl_D6_L13_33.e"
+    except Exception:
+        sus, W = mtube.minicase_like(seed=seed)
+        return sus, W, "generated tube mesh (fixture missing)"
+
+
+def carotid_walls_config(seed):
+    """the two wall meshes of examples/carotid_web (carotid.e + web.e fixtures); generated tubes when they are missing"""
+    from rbc3d_b200 import cases, synth
+    try:
+        W, Lb = cases.carotid_web_walls()
+        return W, Lb, "reference Exodus meshes carotid.e + web.e"
+    except Exception:
+        Lb = np.array([10.5, 10.5, 30.0])
+        W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02,
+                             seed=seed)
+        return W, Lb, "generated tubes (fixtures missing)"
+
+
 def cpu_mtube(args):
     """configs[0] on the CPU restatement alone: the boundary-integral work of mtube time steps (rbc3d_b200/mtube.py) on the
     oracle, all host cores (the reference's own CPU-runnable case; the GPU arm reports the same block under "mtube")."""
@@ -278,7 +304,7 @@ def cpu_mtube(args):
         from rbc3d_b200 import mtube
         oracle.build()
         nsteps = max(2, args.mtube_steps)
-        sus, W = mtube.minicase_like(seed=args.seed)
+        sus, W, _ = minicase_config(args.seed)
         from oracle import harness
         step = harness.OracleStep(oracle.Oracle(sus.Lb), sus, W)
         runs = [mtube.bi_timestep(step, advect=True) for _ in range(MTUBE_WARM_STEPS + nsteps)]
@@ -699,12 +725,12 @@ def run_mtube(args):
     from rbc3d_b200.capi import Rbc3dError
     from rbc3d_b200.ewald import EwaldOperator
     nsteps = max(2, args.mtube_steps)
-    sus, W = mtube.minicase_like(seed=args.seed)
+    sus, W, mesh_src = minicase_config(args.seed)
     try:          # no torch in this child (its import costs more than the block): the library itself refuses without a GPU
         op = EwaldOperator(sus.Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
     except Rbc3dError as exc:
         raise SystemExit("bench.py --mtube-only: no CUDA device; the product has no CPU path (%s)" % str(exc)[:160])
-    step = mtube.LibraryStep(op, sus, W)
+    step = mtube.LibraryStep(op, sus, W, device_noslip=not args.host_noslip)
     l0 = op.launch_count()
     warm = MTUBE_WARM_STEPS      # start-up transient of the wall tractions (3, 19, 60, 42 iterations), allocations, plans
     runs = [mtube.bi_timestep(step, advect=True) for _ in range(warm + nsteps)]
@@ -712,13 +738,15 @@ def run_mtube(args):
     Nb = list(op.Nb)
     op.close()
     gpu = runs[warm:]
-    out = {"workload": "examples/minicase-like: 2 RBCs (36x72 pts/cell, lambda = 1) in a periodic tube of radius 5, box "
-                       "10.5x10.5x8, generated tube mesh %d vertices / %d triangles (the reference's Exodus mesh: "
-                       "1328 / 2404), vBkg = (0,0,8), PME grid %s" % (W.NV, W.NE, "x".join(str(n) for n in Nb)),
+    out = {"workload": "examples/minicase: 2 RBCs (36x72 pts/cell, lambda = 1) in a periodic tube of radius 5, box "
+                       "10.5x10.5x8, %s, %d vertices / %d triangles, vBkg = (0,0,8), PME grid %s"
+                       % (mesh_src, W.NV, W.NE, "x".join(str(n) for n in Nb)),
            "between_steps": "cells translated by Ts = 0.0008 times their mean surface velocity (stand-in for the membrane "
                             "update, untimed); %d untimed start-up steps" % warm,
            "step": "geometry update + operator #1 (RHS, cells+wall -> cells) + NoSlipWall (operator #3 x 2 + operator #4 "
-                   "per wall-GMRES iteration, rtol = eps_Ewd = 1e-3, <= 60); host buffers through the C ABI",
+                   "per wall-GMRES iteration, rtol = eps_Ewd = 1e-3, <= 60); host buffers through the C ABI; NoSlipWall "
+                   + ("with Krylov vectors on the host around per-matvec calls" if args.host_noslip else
+                      "resident on the device (rbc3d_noslip_solve)"),
            "steps": nsteps,
            "bi_timesteps_per_s": nsteps / sum(r["seconds"]["total"] for r in gpu),
            "ms_per_step": [r["seconds"]["total"] * 1e3 for r in gpu],
@@ -729,7 +757,7 @@ def run_mtube(args):
     if not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
-        sus2, W2 = mtube.minicase_like(seed=args.seed)
+        sus2, W2, _ = minicase_config(args.seed)
         from oracle import harness
         ostep = harness.OracleStep(oracle.Oracle(sus2.Lb), sus2, W2)
         cruns = [mtube.bi_timestep(ostep, advect=True) for _ in range(warm + nsteps)]
@@ -752,7 +780,8 @@ def child_block(args, flag, key):
     """Run a side block (--mtube-only / --walls-only) in a child process, after the main operator has released the GPU,
     and return its object; a failure there becomes {"error": ...} instead of costing the headline line."""
     cmd = [sys.executable, os.path.abspath(__file__), flag, "--seed", str(args.seed), "--mtube-steps",
-           str(args.mtube_steps)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+           str(args.mtube_steps)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
+               ["--host-noslip"] if getattr(args, "host_noslip", False) else [])
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR",
                                                             "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
     try:
@@ -778,9 +807,8 @@ def run_walls(args):
     from rbc3d_b200 import synth
     from rbc3d_b200.capi import TL_WALLS, Rbc3dError
     from rbc3d_b200.ewald import EwaldOperator
-    Lb = np.array([10.5, 10.5, 30.0])
-    W = synth.make_walls(Lb, [dict(radius=4.9, ntheta=120, nz=120), dict(radius=4.0, ntheta=48, nz=60)], wobble=0.02,
-                         seed=args.seed)
+    W, Lb, mesh_src = carotid_walls_config(args.seed)
+    W.f = np.zeros_like(W.x)
     try:
         op = EwaldOperator(Lb, device=int(os.environ.get("LOCAL_RANK", "0")))
     except Rbc3dError as exc:
@@ -805,9 +833,9 @@ def run_walls(args):
     rowptr, _, _ = op.wall_matrix()
     Nb = list(op.Nb)
     op.close()
-    out = {"workload": "wall-dominated operator at the size of examples/carotid_web: %d + %d vertices, %d + %d triangles "
-                       "(generated tubes of radius 4.9 and 4.0, 0.9 < rc apart), box 10.5x10.5x30, PME grid %s"
-                       % (W.nvert[0], W.nvert[1], W.nele[0], W.nele[1], "x".join(str(n) for n in Nb)),
+    out = {"workload": "wall-dominated operator of examples/carotid_web: %s, %d + %d vertices, %d + %d triangles, box "
+                       "%.2fx%.2fx%.0f, PME grid %s" % (mesh_src, W.nvert[0], W.nvert[1], W.nele[0], W.nele[1], Lb[0], Lb[1],
+                                                        Lb[2], "x".join(str(n) for n in Nb)),
            "step": "operator #4 of the wall no-slip solve (set traction + AddIntOnWalls + PME, host buffers through the C ABI)",
            "wall_matvecs_per_s": 1.0 / t_gpu, "ms_per_matvec": t_gpu * 1e3, "matrix_blocks_3x3": int(rowptr[-1]),
            "prepare_sing_int_on_wall_ms": t_prep * 1e3, "gpu_launches": int(launches), "steps": nrep * len(fs)}
@@ -858,6 +886,7 @@ def main():
     ap.add_argument("--no-mtube", action="store_true", help="skip the minicase time-step block (configs[0])")
     ap.add_argument("--mtube-only", action="store_true", help="only the minicase time-step block, one JSON object")
     ap.add_argument("--mtube-steps", type=int, default=4)
+    ap.add_argument("--host-noslip", action="store_true", help="mtube block: wall GMRES on the host around per-matvec calls")
     ap.add_argument("--walls-only", action="store_true", help="only the wall-dominated operator block, one JSON object")
     args = ap.parse_args()
     if args.mtube_only:

@@ -223,6 +223,21 @@ int rbc3d_solver_rhs(rbc3d_ctx *ctx, const double vbkg[3], int use_walls, double
 /* v = Glob_Sph_Trans(sol, FOUR_TO_PHYS): the surface velocity of a solution (ModVelSolver.F90:124), host SoA(3,Np) */
 int rbc3d_solver_velocity(rbc3d_ctx *ctx, const double *sol, double *v);
 
+/* ---- NoSlipWall on the device (ModNoSlip.F90:44-149): the wall-traction solve every time step runs after the cell
+ * velocities.  rhs = -Compute_Wall_Residual_Vel (:153-195: operator #3, c1 = c2 = 1/4pi, cells [use_cells] + walls ->
+ * wall vertices, + vbkg), MyMatMult (:255-308: operator #4, c1 = 1/4pi, walls -> wall vertices), GMRES with PETSc's
+ * defaults restated (restart 30, classical Gram-Schmidt, no preconditioner, zero initial guess, rtol as given -- the
+ * reference passes eps_Ewd --, at most maxit iterations), wall%f = wall%f + df.  Tractions, Krylov vectors and both
+ * operators stay on the device; only the Hessenberg column crosses to the host per iteration.
+ * indx_vert_glb[NV]: indxVertGlb of ModData.F90:50-63 (1-based number of every wall vertex, periodic duplicates found
+ * by Wall_Build_V2V sharing their master's number), nindep = number of independent vertices; AssembleArray
+ * (:362-384) semantics: towards the unknown vector the last duplicate wins.  f: host SoA(3,NV), wall%f in, updated
+ * wall%f out (also left as the context's wall traction); history (maxit + 1 doubles) and slip (host SoA(3,NV): the
+ * residual wall velocity after the update, :140-146) may be NULL.  Needs rbc3d_walls_set and rbc3d_wall_prepare_sing;
+ * several ranks: collective, every rank passes the same f (the rows of v are summed over the ranks). */
+int rbc3d_noslip_solve(rbc3d_ctx *ctx, const int32_t *indx_vert_glb, int nindep, const double vbkg[3], int use_cells,
+                       double rtol, int maxit, double *f, int *niter, double *history, double *slip);
+
 /* ---- closest-neighbour queries of ModRepulsion on the GPU cell lists ----
  * Closest_Neighbor_Cell (ModRepulsion.F90:480-546) and Closest_Neighbor_Wall (:556-613) for n points at once (the
  * reference calls them point by point, 4x per time step over all cell points: InterCellRepulsion :270-402,

@@ -66,6 +66,8 @@ SIGNATURES = {
     "rbc3d_set_pair_self": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_solver_setup": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "rbc3d_solver_dof": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "rbc3d_noslip_solve": (C.c_int, [C.c_void_p, c_ip, C.c_int, c_dp, C.c_int, C.c_double, C.c_int, c_dp,
+                                    C.POINTER(C.c_int), c_dp, c_dp]),
     "rbc3d_closest_neighbors": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, C.c_double, c_dp, c_dp, c_dp, c_dp]),
     "rbc3d_solver_cells": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "rbc3d_solver_matmult": (C.c_int, [C.c_void_p, c_dp, c_dp]),

@@ -247,6 +247,13 @@ struct Solver {
   dbuf<double> V, w, part, h, u, b;
 };
 
+// device-resident wall no-slip solve (solver.cu; ModNoSlip.F90:44-149)
+struct WallSolver {
+  int nindep = 0;
+  dbuf<int> indx, last;          // [NV] 0-based independent number of a vertex; [nindep] last vertex with that number
+  dbuf<double> V, w, part, h, rhs, x, f0, fw;
+};
+
 struct Pme {
   int Nx = 0, Ny = 0, Nz = 0, Nxh = 0;
   size_t G = 0, M = 0;
@@ -303,6 +310,7 @@ struct rbc3d_ctx {
   rbc3d::Walls walls;
   rbc3d::Pme pme;
   rbc3d::Solver solver;
+  rbc3d::WallSolver wsolver;
   int skip_flags = 0;
   int pair_self_mode = 3;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel,
                             // 3 symmetric kernel streaming a per-geometry coefficient cache (double layer only)
@@ -368,7 +376,7 @@ int pme_source_ownership(rbc3d_ctx *c, int n, const double *x, dbuf<int> &own, c
 // ---- walls (walls.cu) ----
 int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nele, const double *x, const int *e2v,
                        const double *area, const double *epsDist);
-int walls_set_traction(rbc3d_ctx *c, const double *f_host);
+int walls_set_traction(rbc3d_ctx *c, const double *f, bool from_device = false);
 int walls_target_meta(rbc3d_ctx *c, TargetList &t);
 int walls_prepare_sing(rbc3d_ctx *c);
 int walls_sing_int(rbc3d_ctx *c, double c1, int iwall, double *v_dev);
@@ -390,6 +398,8 @@ int solver_matmult(rbc3d_ctx *c, const double *u_dev, double *b_dev);
 int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter,
                  double *history);
 void solver_release(rbc3d_ctx *c);
+int wall_noslip_solve(rbc3d_ctx *c, const int *indx_host, int nindep, const double vbkg[3], int use_cells, double rtol, int maxit,
+                      double *f_host, int *niter, double *history, double *slip_host);
 
 // ---- multi-GPU (comm.cu) ----
 int comm_allreduce_sum(rbc3d_ctx *c, double *buf, size_t n);

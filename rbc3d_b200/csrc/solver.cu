@@ -17,6 +17,7 @@
 //     non-zero initial guess.  Dot products are two-stage reductions in a fixed order (deterministic).
 // The host mirror of the same algorithm is rbc3d_b200/gmres.py; tests/test_gpu_gmres.py checks one against the other.
 #include <cmath>
+#include <functional>
 #include <vector>
 
 #include "device_math.cuh"
@@ -410,58 +411,66 @@ int solver_rhs(rbc3d_ctx *c, const double vbkg[3], int use_walls, double *rhs_de
   return RBC3D_OK;
 }
 
-static int dots(rbc3d_ctx *c, int k, const double *V, size_t ldv, const double *w, double *h_host) {
-  Solver &S = c->solver;
-  const int n = (int)S.dof_loc;
-  k_dots_partial<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>(n, k, V, ldv, w, S.part.p);
-  k_dots_final<<<k, 32, 0, c->stream>>>(k, S.part.p, S.h.p);
+// Krylov work space shared by the two solves (cell velocities: Solver; wall tractions: WallSolver)
+struct KrylovWork {
+  dbuf<double> &V, &w, &part, &h;
+};
+
+static int dots(rbc3d_ctx *c, KrylovWork &K, size_t n, bool reduce_ranks, int k, const double *V, size_t ldv, const double *w,
+                double *h_host) {
+  k_dots_partial<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>((int)n, k, V, ldv, w, K.part.p);
+  k_dots_final<<<k, 32, 0, c->stream>>>(k, K.part.p, K.h.p);
   KERNEL_CHECK();
   c->launches += 2;
-  RBC_TRY(comm_allreduce_sum(c, S.h.p, (size_t)k));  // several ranks: every rank holds the unknowns of its own cells
-  CUDA_TRY(cudaMemcpyAsync(h_host, S.h.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+  if (reduce_ranks) RBC_TRY(comm_allreduce_sum(c, K.h.p, (size_t)k));  // sharded unknowns: every rank holds its own cells'
+  CUDA_TRY(cudaMemcpyAsync(h_host, K.h.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
 
-// KSPGMRES, PCNONE, classical Gram-Schmidt; x_dev in: initial guess, out: solution.  history[k] = residual norm after
-// k iterations (history[0] = ||b - A x0||), at most maxit + 1 entries.
-int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter,
-                 double *history) {
-  Solver &S = c->solver;
-  if (!S.ok) return RBC3D_ESTATE;
+// KSPGMRES, PCNONE, classical Gram-Schmidt; x_dev in: initial guess (ignored and zeroed when zero_guess: PETSc then takes
+// r0 = b without a matvec), out: solution.  history[k] = residual norm after k iterations (history[0] = ||b - A x0||),
+// at most maxit + 1 entries.  Only the Hessenberg column crosses to the host per iteration.
+template <class MatVec>
+static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, bool zero_guess, MatVec &&matvec,
+                      const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter, double *history) {
   if (restart < 1 || restart > 200 || maxit < 0) return RBC3D_EINVAL;
-  const size_t n = S.dof_loc;
   const int nb = (int)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
-  RBC_TRY(S.V.resize((size_t)(restart + 1) * n));
-  RBC_TRY(S.w.resize(n));
-  RBC_TRY(S.part.resize((size_t)(restart + 2) * DOT_BLOCKS));
-  RBC_TRY(S.h.resize(restart + 2));
+  RBC_TRY(K.V.resize((size_t)(restart + 1) * (n > 0 ? n : 1)));
+  RBC_TRY(K.w.resize(n > 0 ? n : 1));
+  RBC_TRY(K.part.resize((size_t)(restart + 2) * DOT_BLOCKS));
+  RBC_TRY(K.h.resize(restart + 2));
   std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), gv(restart + 1), hcol(restart + 2);
   double bnorm2 = 0;
-  RBC_TRY(dots(c, 1, b_dev, n, b_dev, &bnorm2));
+  RBC_TRY(dots(c, K, n, reduce_ranks, 1, b_dev, n, b_dev, &bnorm2));
   const double ttol = fmax(rtol * sqrt(bnorm2), 1e-50);
   int it = 0, nh = 0;
+  if (zero_guess && n > 0) CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * n, c->stream));
   for (;;) {
-    // r = b - A x (the reference sets KSPSetInitialGuessNonzero: the initial residual needs one matvec)
-    RBC_TRY(solver_matmult(c, x_dev, S.w.p));
-    k_residual<<<nb, 256, 0, c->stream>>>((int)n, b_dev, S.w.p);
+    if (zero_guess && it == 0) {
+      CUDA_TRY(cudaMemcpyAsync(K.w.p, b_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      // r = b - A x (KSPSetInitialGuessNonzero, and every restart: the true residual of the updated solution)
+      RBC_TRY(matvec(x_dev, K.w.p));
+      k_residual<<<nb, 256, 0, c->stream>>>((int)n, b_dev, K.w.p);
+    }
     double beta2 = 0;
-    RBC_TRY(dots(c, 1, S.w.p, n, S.w.p, &beta2));
+    RBC_TRY(dots(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, &beta2));
     const double beta = sqrt(beta2);
     if (it == 0 && history) history[nh++] = beta;
     if (beta < ttol || it >= maxit) break;
-    k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / beta, S.w.p, S.V.p, 0);
+    k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / beta, K.w.p, K.V.p, 0);
     std::fill(H.begin(), H.end(), 0.0);
     std::fill(gv.begin(), gv.end(), 0.0);
     gv[0] = beta;
     int k = 0;
     double res = beta;
     while (k < restart && it < maxit) {
-      RBC_TRY(solver_matmult(c, S.V.p + (size_t)k * n, S.w.p));
-      RBC_TRY(dots(c, k + 1, S.V.p, n, S.w.p, hcol.data()));            // all projections from the same w
-      k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, S.V.p, n, S.h.p, S.w.p);
+      RBC_TRY(matvec(K.V.p + (size_t)k * n, K.w.p));
+      RBC_TRY(dots(c, K, n, reduce_ranks, k + 1, K.V.p, n, K.w.p, hcol.data()));  // all projections from the same w
+      k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, K.V.p, n, K.h.p, K.w.p);
       double hn2 = 0;
-      RBC_TRY(dots(c, 1, S.w.p, n, S.w.p, &hn2));
+      RBC_TRY(dots(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, &hn2));
       const double hn = sqrt(hn2);
       auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * restart + j]; };
       for (int i = 0; i <= k; i++) Hm(i, k) = hcol[i];
@@ -482,7 +491,7 @@ int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, 
       k++;
       res = fabs(gv[k]);
       if (history) history[nh++] = res;
-      if (hn > 0.0) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / hn, S.w.p, S.V.p + (size_t)k * n, 0);
+      if (hn > 0.0) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / hn, K.w.p, K.V.p + (size_t)k * n, 0);
       if (res < ttol || hn == 0.0) break;
     }
     // y = H^-1 g (upper triangular), x += V y
@@ -492,12 +501,113 @@ int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, 
       for (int j = i + 1; j < k; j++) s -= H[(size_t)i * restart + j] * y[j];
       y[i] = s / H[(size_t)i * restart + i];
     }
-    for (int i = 0; i < k; i++) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, y[i], S.V.p + (size_t)i * n, x_dev, 1);
+    for (int i = 0; i < k; i++) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, y[i], K.V.p + (size_t)i * n, x_dev, 1);
     KERNEL_CHECK();
     c->launches += k + 3;
     if (res < ttol || it >= maxit) break;
+    zero_guess = false;  // restart: true residual from the updated solution
   }
   if (niter) *niter = it;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RBC3D_OK;
+}
+
+int solver_gmres(rbc3d_ctx *c, const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter,
+                 double *history) {
+  Solver &S = c->solver;
+  if (!S.ok) return RBC3D_ESTATE;
+  KrylovWork K{S.V, S.w, S.part, S.h};
+  return gmres_core(c, K, S.dof_loc, c->prm.nranks > 1, false,
+                    [&](const double *in, double *out) { return solver_matmult(c, in, out); }, b_dev, x_dev, rtol, restart, maxit,
+                    niter, history);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NoSlipWall on the device (ModNoSlip.F90:44-149): the first-kind equation for the wall tractions,
+//   rhs  = -Compute_Wall_Residual_Vel   (operator #3: c1 = c2 = 1/4pi, cells + walls -> wall vertices, + vBkg; :153-195)
+//   A df = MyMatMult(df)                (operator #4: c1 = 1/4pi, walls -> wall vertices; :255-308)
+//   GMRES, no preconditioner, zero initial guess, rtol = eps_Ewd, at most 60 iterations (:70-87, 117); wall%f += df
+// with the unknowns numbered by indxVertGlb (periodic duplicates share a number; AssembleArray :362-384: going to the
+// 1-D vector the LAST duplicate wins).  Tractions, Krylov vectors and both operators stay on the device.
+__global__ void k_wall_to_1d(int nindep, int NV, const int *__restrict__ last, const double *__restrict__ v, double scale,
+                             double a0, double a1, double a2, double *__restrict__ u) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nindep) return;
+  const int iv = last[p];
+  u[3 * p + 0] = scale * (v[iv] + a0);
+  u[3 * p + 1] = scale * (v[(size_t)NV + iv] + a1);
+  u[3 * p + 2] = scale * (v[2 * (size_t)NV + iv] + a2);
+}
+__global__ void k_wall_from_1d(int NV, const int *__restrict__ indx, const double *__restrict__ u, const double *__restrict__ f0,
+                               double *__restrict__ f) {
+  const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= NV) return;
+  const int p = indx[iv];
+#pragma unroll
+  for (int d = 0; d < 3; d++) f[(size_t)d * NV + iv] = (f0 ? f0[(size_t)d * NV + iv] : 0.0) + u[3 * p + d];
+}
+
+int wall_noslip_solve(rbc3d_ctx *c, const int *indx_host, int nindep, const double vbkg[3], int use_cells, double rtol, int maxit,
+                      double *f_host, int *niter, double *history, double *slip_host) {
+  Walls &W = c->walls;
+  WallSolver &S = c->wsolver;
+  TargetList &t = c->tl[RBC3D_TL_WALLS];
+  if (!W.geom_set || !t.valid || W.NV == 0) {
+    set_error("rbc3d_noslip_solve: no walls set");
+    return RBC3D_ESTATE;
+  }
+  const int NV = W.NV;
+  const size_t n = 3 * (size_t)nindep;
+  std::vector<int> idx0(NV), last(nindep, -1);
+  for (int iv = 0; iv < NV; iv++) {
+    const int p = indx_host[iv] - 1;
+    if (p < 0 || p >= nindep) return RBC3D_EINVAL;
+    idx0[iv] = p;
+    last[p] = iv;  // vertex order: the last duplicate wins (AssembleArray, ModNoSlip.F90:373-377)
+  }
+  for (int p = 0; p < nindep; p++)
+    if (last[p] < 0) return RBC3D_EINVAL;
+  S.nindep = nindep;
+  RBC_TRY(S.indx.resize(NV));
+  RBC_TRY(S.last.resize(nindep));
+  RBC_TRY(S.rhs.resize(n));
+  RBC_TRY(S.x.resize(n));
+  RBC_TRY(S.f0.resize(3 * (size_t)NV));
+  RBC_TRY(S.fw.resize(3 * (size_t)NV));
+  CUDA_TRY(cudaMemcpyAsync(S.indx.p, idx0.data(), sizeof(int) * NV, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(S.last.p, last.data(), sizeof(int) * nindep, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(S.f0.p, f_host, sizeof(double) * 3 * NV, cudaMemcpyHostToDevice, c->stream));
+  RBC_TRY(walls_set_traction(c, S.f0.p, true));
+  const double C1W = 1.0 / (4.0 * RBC_PI);  // ModNoSlip.F90:172-173, 281
+  const int gi = (nindep + 255) / 256, gv = (NV + 255) / 256;
+  // rhs = -(operator #3 + vBkg)
+  RBC_TRY(rbc3d_apply_resident(c, C1W, C1W, use_cells, 1, RBC3D_TL_WALLS));
+  k_wall_to_1d<<<gi, 256, 0, c->stream>>>(nindep, NV, S.last.p, t.v.p, -1.0, vbkg[0], vbkg[1], vbkg[2], S.rhs.p);
+  KERNEL_CHECK();
+  auto matvec = [&](const double *in, double *out) -> int {
+    k_wall_from_1d<<<gv, 256, 0, c->stream>>>(NV, S.indx.p, in, nullptr, S.fw.p);  // wall%f = f, ModNoSlip.F90:273-278
+    KERNEL_CHECK();
+    RBC_TRY(walls_set_traction(c, S.fw.p, true));
+    RBC_TRY(rbc3d_apply_resident(c, C1W, 0.0, 0, 1, RBC3D_TL_WALLS));
+    k_wall_to_1d<<<gi, 256, 0, c->stream>>>(nindep, NV, S.last.p, t.v.p, 1.0, 0.0, 0.0, 0.0, out);
+    KERNEL_CHECK();
+    c->launches += 2;
+    return RBC3D_OK;
+  };
+  KrylovWork K{S.V, S.w, S.part, S.h};
+  RBC_TRY(gmres_core(c, K, n, false, true, matvec, S.rhs.p, S.x.p, rtol, 30, maxit, niter, history));
+  // wall%f = f0 + df (:131-137), then the residual velocity with the new tractions (:140-146)
+  k_wall_from_1d<<<gv, 256, 0, c->stream>>>(NV, S.indx.p, S.x.p, S.f0.p, S.fw.p);
+  KERNEL_CHECK();
+  RBC_TRY(walls_set_traction(c, S.fw.p, true));
+  CUDA_TRY(cudaMemcpyAsync(f_host, S.fw.p, sizeof(double) * 3 * NV, cudaMemcpyDeviceToHost, c->stream));
+  if (slip_host) {
+    RBC_TRY(rbc3d_apply_resident(c, C1W, C1W, use_cells, 1, RBC3D_TL_WALLS));
+    CUDA_TRY(cudaMemcpyAsync(slip_host, t.v.p, sizeof(double) * 3 * NV, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < 3; d++)
+      for (int iv = 0; iv < NV; iv++) slip_host[(size_t)d * NV + iv] += vbkg[d];
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
@@ -507,6 +617,10 @@ void solver_release(rbc3d_ctx *c) {
   for (dbuf<double> *b : {&S.pb, &S.pbw, &S.cs, &S.dsw, &S.g_raw, &S.V, &S.w, &S.part, &S.h, &S.u, &S.b, &S.gpack}) b->release();
   S.cells.release();
   S.own_all.release();
+  WallSolver &Ws = c->wsolver;
+  for (dbuf<double> *b : {&Ws.V, &Ws.w, &Ws.part, &Ws.h, &Ws.rhs, &Ws.x, &Ws.f0, &Ws.fw}) b->release();
+  Ws.indx.release();
+  Ws.last.release();
   S.ka.release();
   S.kb.release();
   S.ok = false;
@@ -589,6 +703,13 @@ int rbc3d_solver_velocity(rbc3d_ctx *c, const double *sol, double *v) {
   CUDA_TRY(cudaMemcpyAsync(v, S.g_raw.p, sizeof(double) * 3 * C.Np, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
+}
+
+int rbc3d_noslip_solve(rbc3d_ctx *c, const int32_t *indx_vert_glb, int nindep, const double vbkg[3], int use_cells, double rtol,
+                       int maxit, double *f, int *niter, double *history, double *slip) {
+  if (!c || !indx_vert_glb || nindep < 1 || !vbkg || !f) return RBC3D_EINVAL;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return wall_noslip_solve(c, indx_vert_glb, nindep, vbkg, use_cells, rtol, maxit, f, niter, history, slip);
 }
 
 int rbc3d_solver_gmres(rbc3d_ctx *c, const double *rhs, double *sol, double rtol, int restart, int maxit, int *niter,

@@ -583,11 +583,12 @@ int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nel
   return RBC3D_OK;
 }
 
-int walls_set_traction(rbc3d_ctx *c, const double *f_host) {
+int walls_set_traction(rbc3d_ctx *c, const double *f, bool from_device) {
   Walls &W = c->walls;
   if (!W.geom_set) return RBC3D_ESTATE;
-  if (W.NV > 0)
-    CUDA_TRY(cudaMemcpyAsync(W.f.p, f_host, sizeof(double) * 3 * W.NV, cudaMemcpyHostToDevice, c->stream));
+  if (W.NV > 0 && f != W.f.p)
+    CUDA_TRY(cudaMemcpyAsync(W.f.p, f, sizeof(double) * 3 * W.NV, from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             c->stream));
   if (W.NE > 0) {
     k_wall_pme_sources<<<(W.NE + 255) / 256, 256, 0, c->stream>>>(W.NE, W.NV, W.f.p, W.e2v.p, W.area.p, W.ft.p);
     KERNEL_CHECK();

@@ -342,6 +342,19 @@ class EwaldOperator:
                                           dp(hist)), "rbc3d_solver_gmres")
         return sol, nit.value, hist[:nit.value + 1]
 
+    # -- NoSlipWall on the device (ModNoSlip.F90:44-149) -------------------------------------------------------
+    def noslip_solve(self, f, indx, nindep, vbkg, cells=True, rtol=1e-3, maxit=60, want_slip=True):
+        """-> (f_new (3, NV), niter, residual history, residual wall velocity (3, NV) or None)."""
+        f = np.array(f, dtype=np.float64, order="C")
+        indx = i32(indx)
+        vb = f64(np.asarray(vbkg, dtype=np.float64))
+        hist = np.full(maxit + 1, np.nan)
+        slip = np.zeros_like(f) if want_slip else None
+        nit = C.c_int()
+        check(self.lib.rbc3d_noslip_solve(self._h, ip(indx), int(nindep), dp(vb), int(bool(cells)), float(rtol), int(maxit),
+                                          dp(f), C.byref(nit), dp(hist), dp(slip)), "rbc3d_noslip_solve")
+        return f, nit.value, hist[:nit.value + 1], slip
+
     # -- ModRepulsion closest-neighbour queries on the GPU cell lists (SURVEY.md 8(f)-4) ------------------------
     def closest_neighbors(self, x, surf_id, eps_dist):
         """Closest_Neighbor_Cell / Closest_Neighbor_Wall for points x (3, n) on surfaces surf_id (n,) ->

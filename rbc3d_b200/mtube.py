@@ -98,8 +98,9 @@ def advect_rigid(sus, v_cells: np.ndarray, Ts: float = TS) -> None:
 class LibraryStep:
     """The same on the CUDA library through the C ABI (rbc3d_b200.ewald.EwaldOperator)."""
 
-    def __init__(self, op, sus, W, vbkg=VBKG):
+    def __init__(self, op, sus, W, vbkg=VBKG, device_noslip=False):
         self.op, self.sus, self.W, self.vbkg = op, sus, W, np.asarray(vbkg, dtype=float)
+        self.device_noslip = device_noslip       # NoSlipWall resident on the GPU (rbc3d_noslip_solve)
         op.set_suspension(sus)
         op.set_walls(W)
         op.PrepareSingIntOnWall()
@@ -131,11 +132,16 @@ def bi_timestep(step, rtol: float = 1e-3, maxit: int = 60, advect: bool = False)
     v = step.compute_rhs()
     t["rhs"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    s = noslip.WallNoSlipSolver(step.W, step.sus.Lb, *step.noslip_backend())
-    f, niter, hist, slip = s.solve(rtol=rtol, maxit=maxit)
+    if getattr(step, "device_noslip", False):
+        f, niter, hist, slip = noslip.solve_on_device(step.op, step.W, step.sus.Lb, step.vbkg, rtol=rtol, maxit=maxit)
+        nmatvec = niter + (niter - 1) // 30      # one operator #4 per iteration + the true residual at every restart
+    else:
+        s = noslip.WallNoSlipSolver(step.W, step.sus.Lb, *step.noslip_backend())
+        f, niter, hist, slip = s.solve(rtol=rtol, maxit=maxit)
+        nmatvec = s.nmatvec
     t["noslip"] = time.perf_counter() - t0
     t["total"] = t["geometry"] + t["rhs"] + t["noslip"]
     if advect:
         advect_rigid(step.sus, v)                            # untimed: the caller's position update
     return {"v_cells": v, "f_wall": f, "wall_iterations": niter, "history": hist, "slip": slip, "seconds": t,
-            "operator_applications": 1 + 2 + s.nmatvec}
+            "operator_applications": 1 + 2 + nmatvec}

@@ -103,6 +103,17 @@ class WallNoSlipSolver:
         return f_new, niter, hist, self.residual_vel()
 
 
+def solve_on_device(op, W, Lb, vbkg, cells: bool = True, rtol: float = 1e-3, maxit: int = 60):
+    """NoSlipWall with tractions, Krylov vectors and both operators resident on the GPU (rbc3d_noslip_solve): the host
+    only supplies indxVertGlb.  Same return value as WallNoSlipSolver.solve; W.f is updated."""
+    vo = W.voff()
+    v2v = [wall_build_v2v(W.x[:, vo[w]:vo[w + 1]], np.asarray(Lb, dtype=float)) for w in range(W.nwall)]
+    indx, nindep = indx_vert_glb(v2v)
+    f_new, niter, hist, slip = op.noslip_solve(W.f, indx, nindep, vbkg, cells=cells, rtol=rtol, maxit=maxit)
+    W.f = f_new
+    return f_new, niter, list(hist), slip
+
+
 def library_backend(op, vbkg, cells: bool = True, collect: bool = False):
     """The same three callables on the CUDA library through the C ABI (rbc3d_b200.ewald.EwaldOperator with
     set_suspension / set_walls / PrepareSingIntOnWall done).  ``collect``: several ranks -- rbc3d_apply_collect sums the

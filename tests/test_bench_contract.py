@@ -144,10 +144,11 @@ def test_mtube_block_python_path_with_a_stand_in_library(monkeypatch, capsys, or
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     monkeypatch.setattr(bench, "MTUBE_WARM_STEPS", 2)
-    assert bench.run_mtube(argparse.Namespace(seed=161269, mtube_steps=2, no_cpu_baseline=False)) == 0
+    assert bench.run_mtube(argparse.Namespace(seed=161269, mtube_steps=2, no_cpu_baseline=False, host_noslip=True)) == 0
     m = json.loads(capsys.readouterr().out.strip().splitlines()[-1])["mtube"]
     assert m["steps"] == 2 and len(m["ms_per_step"]) == 2 and m["bi_timesteps_per_s"] > 0 and m["gpu_launches"] > 0
-    assert len(m["wall_gmres_iterations"]) == 4 and m["wall_gmres_iterations"][0] == 3
+    assert len(m["wall_gmres_iterations"]) == 4 and 0 < m["wall_gmres_iterations"][0] <= 60
+    assert "new_cyl_D6_L13_33.e" in m["workload"] and "1328 vertices / 2404 triangles" in m["workload"]
     cb = m["cpu_baseline"]
     assert cb["kind"] == "port" and cb["unit"] == "timesteps/s" and cb["wall_gmres_iterations"] == m["wall_gmres_iterations"]
     par = m["parity_vs_oracle"]
@@ -199,6 +200,6 @@ def test_walls_block_python_path_with_a_stand_in_library(monkeypatch, capsys, or
     assert bench.run_walls(argparse.Namespace(seed=161269, no_cpu_baseline=False)) == 0
     w = json.loads(capsys.readouterr().out.strip().splitlines()[-1])["walls"]
     assert w["wall_matvecs_per_s"] > 0 and w["steps"] == 20 and w["gpu_launches"] == 140
-    assert w["matrix_blocks_3x3"] > 1_000_000 and "17448" not in w["workload"] and "14520 + 2928" in w["workload"]
+    assert w["matrix_blocks_3x3"] > 1_000_000 and "carotid.e + web.e" in w["workload"] and "14550 + 2903" in w["workload"]
     assert w["cpu_baseline"]["kind"] == "port" and w["cpu_baseline"]["value"] > 0
     assert w["parity_vs_oracle"]["rel_l2_velocity"] < 1e-12              # the stand-in IS the oracle

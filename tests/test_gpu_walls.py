@@ -455,3 +455,32 @@ def test_closest_neighbor_queries_vs_oracle(oracle_lib):
     f2 = np.isfinite(rdcw)
     assert np.abs(dcw[f2] - rdcw[f2]).max() < 1e-11
     op.close()
+
+
+def test_device_resident_noslip_solve_matches_host_harness(one_wall):
+    """rbc3d_noslip_solve (NoSlipWall with tractions, Krylov vectors and operators #3 / #4 on the device) against the host
+    solver driving the same library through per-matvec C-ABI calls and against the oracle-driven solve: same iteration
+    count, same residual history, same tractions and slip velocity."""
+    import copy
+    from oracle import harness
+    from rbc3d_b200 import noslip
+    op, orc, _, W = one_wall
+    f_keep = W.f.copy()
+    vbkg = np.array([0.0, 0.0, 8.0])
+    Wh, Wd, Wo = copy.copy(W), copy.copy(W), copy.copy(W)
+    for w_ in (Wh, Wd, Wo):
+        w_.f = f_keep.copy()
+    f_o, it_o, h_o, slip_o = noslip.WallNoSlipSolver(Wo, LB, *harness.noslip_backend(orc, vbkg)).solve(rtol=1e-3, maxit=60)
+    f_h, it_h, h_h, slip_h = noslip.WallNoSlipSolver(Wh, LB, *noslip.library_backend(op, vbkg)).solve(rtol=1e-3, maxit=60)
+    op.set_wall_traction(f_keep)
+    f_d, it_d, h_d, slip_d = noslip.solve_on_device(op, Wd, LB, vbkg, rtol=1e-3, maxit=60)
+    assert it_d == it_h and 0 < it_d <= it_o <= 60
+    assert np.allclose(h_d, h_h, rtol=1e-8, atol=1e-12 * h_h[0])
+    assert rel_l2(f_d, f_h) < 1e-9 and np.abs(slip_d - slip_h).max() < 1e-9 * np.abs(vbkg).max()
+    if it_d == it_o:
+        assert rel_l2(f_d, f_o) < 1e-6
+    # a second solve from the converged tractions: the residual is already below the tolerance of the first
+    f2, it2, h2, _ = noslip.solve_on_device(op, Wd, LB, vbkg, rtol=1e-3, maxit=60)
+    assert h2[0] < 2e-3 * h_d[0]
+    op.set_wall_traction(f_keep)
+    orc.set_wall_traction(f_keep)
