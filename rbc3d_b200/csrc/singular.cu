@@ -412,17 +412,6 @@ __device__ __forceinline__ double2 ld_plain2(const double2 *p) {  // same, for r
   asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
   return v;
 }
-// predicated 16-byte shared-memory load: v keeps its value when the flag is zero
-__device__ __forceinline__ void lds2_if(double2 &v, unsigned addr, unsigned flag) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %3, 0;\n"
-      "@p ld.shared.v2.f64 {%0, %1}, [%2];\n"
-      "}\n"
-      : "+d"(v.x), "+d"(v.y)
-      : "r"(addr), "r"(flag));
-}
 __device__ __forceinline__ void st_stream2(double2 *p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
@@ -530,8 +519,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       }
     }
     mbar_wait(bar_full + buf, (unsigned)(use & 1));
-    const unsigned band_s = smem_u32(s_band + (size_t)buf * band_n);
-    const unsigned wpl_b = (unsigned)(wpl * sizeof(double2)), row_b = (unsigned)(n * sizeof(double2));
+    const double2 *band = s_band + (size_t)buf * band_n;
     double2 top[6], bot[6];
 #pragma unroll
     for (int q = 0; q < 6; q++) top[q] = bot[q] = make_double2(0, 0);
@@ -546,17 +534,21 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       for (int k = 0; k < SR_U; k++) {
         const int kr = k % SR_PF;
         const int code = (int)(unsigned)cw[kr];
-        {  // first point of a spline cell: theta nodes of this lane's phi column.  Predicated loads, no branch: the two
-           // points of a trip stay in one basic block and their dependency chains interleave
+        if (code & (SR_FRESH | SR_LOADX | SR_LOADY)) {  // first point of a spline cell: theta nodes of this lane's phi column
           int col = ((code >> 8) & 255) + cb;
           if (col >= n) col -= n;
-          const unsigned nb = band_s + (unsigned)(((code & 255) * n + col) * sizeof(double2));
-          const unsigned f_top = code & SR_FRESH, f_bot = code & (SR_FRESH | SR_LOADY), f_x = code & SR_LOADX;
+          const double2 *nb = band + (code & 255) * n + col;
+          if (code & SR_FRESH) {
 #pragma unroll
-          for (int q = 0; q < 6; q++) {
-            lds2_if(top[q], nb + q * wpl_b, f_top);
-            lds2_if(bot[q], nb + q * wpl_b + row_b, f_bot);
-            lds2_if(top[q], nb + q * wpl_b + row_b, f_x);  // the cell below: its lower row replaces the old upper row
+            for (int q = 0; q < 6; q++) top[q] = nb[q * wpl];
+          }
+          if (code & (SR_FRESH | SR_LOADY)) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) bot[q] = nb[q * wpl + n];
+          }
+          if (code & SR_LOADX) {  // the cell below: its lower row replaces the old upper row (roles swapped in the table)
+#pragma unroll
+            for (int q = 0; q < 6; q++) top[q] = nb[q * wpl + n];
           }
         }
         const double2 cx01 = *reinterpret_cast<const double2 *>(te), cx23 = *reinterpret_cast<const double2 *>(te + 2);
