@@ -34,6 +34,38 @@ def test_zslab_active_is_a_partition():
         assert (tot == 1).all()
 
 
+def test_cell_ownership_by_centroid_zslab():
+    """whole cells by the z-slab of their centroid (what bench.py and the multi-GPU runners hand to the library as
+    `active` flags): every cell on exactly one rank, the rank of DomainDecomp's slab (ModConf.F90:421-435) that holds the
+    centroid, cells across the periodic boundary wrapped, and the 4096-cell lattice split evenly."""
+    from rbc3d_b200 import synth
+    sus = synth.make_suspension(2)
+    npc = sus.nlat * sus.nlon
+    for nranks in (1, 2, 3, 8):
+        masks = [partition.ownership_mask_zslab(sus.x, npc, sus.Lb, nranks, r) for r in range(nranks)]
+        assert (np.sum(masks, axis=0) == 1).all()
+        own = partition.cell_owner_zslab(sus.x, npc, sus.Lb, nranks)
+        zc = sus.x[2].reshape(-1, npc).mean(axis=1)
+        assert np.array_equal(own, np.floor(zc / sus.Lb[2] * nranks).astype(int))
+        for r in range(nranks):
+            assert np.array_equal(masks[r].reshape(-1, npc)[:, 0], (own == r).astype(np.int32))
+            assert (masks[r].reshape(-1, npc).min(axis=1) == masks[r].reshape(-1, npc).max(axis=1)).all()   # whole cells
+    # a cell whose centroid lies beyond the box wraps into it
+    x = sus.x.copy()
+    x[2, :npc] += sus.Lb[2]
+    assert np.array_equal(partition.cell_owner_zslab(x, npc, sus.Lb, 4), partition.cell_owner_zslab(sus.x, npc, sus.Lb, 4))
+    # the benchmark lattice: 16 layers of 256 cells, +-0.2 jitter never crosses a slab boundary
+    rng = np.random.default_rng(1)
+    idx = np.stack(np.meshgrid(*[np.arange(16)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    L = 57.2589
+    ctr = (idx + 0.5) * (L / 16) + rng.uniform(-0.2, 0.2, size=idx.shape)
+    xz = np.zeros((3, 4096 * 4))
+    xz[2] = np.repeat(ctr[:, 2], 4)
+    for nranks in (2, 4, 8):
+        own = partition.cell_owner_zslab(xz, 4, np.array([L, L, L]), nranks)
+        assert np.array_equal(np.bincount(own, minlength=nranks), np.full(nranks, 4096 // nranks))
+
+
 def _worker(rank, world, port, mode, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
