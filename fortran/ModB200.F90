@@ -94,6 +94,36 @@ module ModB200
       integer(c_int), value :: restart, maxit
       integer(c_int) :: niter, ierr
     end function
+    ! several ranks: the cells whose unknowns this rank holds, in vector order (sharded Krylov vectors)
+    function rbc3d_solver_cells(ctx, n, cells, cap) bind(C, name="rbc3d_solver_cells") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int) :: n, cells(*)
+      integer(c_int), value :: cap
+      integer(c_int) :: ierr
+    end function
+    ! NoSlipWall's solve resident on the device (ModNoSlip.F90:44-149); f = walls(:)%f back to back, SoA(3,NV)
+    function rbc3d_noslip_solve(ctx, indx, nindep, vbkg, use_cells, rtol, maxit, f, niter, history, slip) &
+      bind(C, name="rbc3d_noslip_solve") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int) :: indx(*)
+      integer(c_int), value :: nindep, use_cells, maxit
+      real(c_double) :: vbkg(3), f(*), history(*), slip(*)
+      real(c_double), value :: rtol
+      integer(c_int) :: niter, ierr
+    end function
+    ! Closest_Neighbor_Cell / Closest_Neighbor_Wall (ModRepulsion.F90:480-613) for n points at once
+    function rbc3d_closest_neighbors(ctx, n, x, surfId, epsDist, distCell, x0Cell, distWall, x0Wall) &
+      bind(C, name="rbc3d_closest_neighbors") result(ierr)
+      import
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: n
+      real(c_double) :: x(*), distCell(*), x0Cell(*), distWall(*), x0Wall(*)
+      integer(c_int) :: surfId(*)
+      real(c_double), value :: epsDist
+      integer(c_int) :: ierr
+    end function
     function rbc3d_solver_rhs(ctx, vbkg, use_walls, rhs) bind(C, name="rbc3d_solver_rhs") result(ierr)
       import
       type(c_ptr), value :: ctx

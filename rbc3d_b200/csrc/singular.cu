@@ -573,10 +573,23 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
           }
         } else if (MODE == SR_BUILD_N) {
           const double xx = A2.x, yy = A2.y, zz = B2.x;
-          const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+          const double r2 = xx * xx + yy * yy + zz * zz;
           double w = 0.0;
-          if (rr < a.prm.rc)  // ModRbcSingInt.F90:69
-            w = ewald_dl(a.tab_dl, a.prm, rr) * te[8] * (xx * g[0] + yy * g[1] + zz * g[2]);
+          // rr < rc (ModRbcSingInt.F90:69) and EwaldCoeff_DL (ModEwaldFunc.F90:141-178: zero below r_eps and beyond the
+          // table) without divisions: 1/r from the hardware seed + one cubic step (rsqrt_pos), as the pair cache does
+          if (r2 >= a.prm.r_eps * a.prm.r_eps && !(r2 > a.prm.rc2_thr)) {
+            const double rinv = rsqrt_pos(r2), rr = r2 * rinv;
+            if (rr < a.prm.rc) {
+              const double sc = rr * a.prm.tab_scale;
+              const int i0 = (int)sc;
+              if (i0 < RBC3D_NTAB) {
+                const double t0 = __ldg(a.tab_dl + i0), t1 = __ldg(a.tab_dl + i0 + 1);
+                const double cdl = t0 * ((double)(i0 + 1) - sc) + t1 * (sc - (double)i0);
+                const double ir2 = rinv * rinv;
+                w = cdl * ir2 * ir2 * rinv * te[8] * (xx * g[0] + yy * g[1] + zz * g[2]);
+              }
+            }
+          }
           if (is_t && !(code & SR_DUMMY)) st_stream2(rp + n, make_double2(zz, w));
         } else if (MODE == SR_DL) {
           const double qd = B2.y * (A2.x * g[0] + A2.y * g[1] + B2.x * g[2]);

@@ -354,6 +354,24 @@ def test_multi_gpu_parity_when_several_gpus_are_visible():
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("runner,token", [("run_multi_gpu_walls.py", "MULTI_GPU_WALLS_OK"),
+                                          ("run_multi_gpu_solver.py", "MULTI_GPU_SOLVER_OK")])
+def test_multi_gpu_walls_and_sharded_solver_when_several_gpus_are_visible(runner, token):
+    """2-rank NCCL runs of the wall paths (operators #3 / #4, no-slip solve, point-wise z-slab wall targets) and of the
+    sharded cell velocity solve (skipped on a single-GPU box; run on 2 and 8 B200s by scripts/gpu_r2*.sh)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(root, "tests", runner)],
+                       capture_output=True, text=True, timeout=900)
+    assert token in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---- density splines built on the device (Rbc_BuildSurfaceSource on the GPU, SURVEY.md 8(f)-2) ---------------
 @pytest.fixture(scope="module")
 def dev_spline_op(sus8):
