@@ -220,7 +220,7 @@ def run_reference(args):
     from oracle import oracle
     from rbc3d_b200 import synth          # NumPy only: does not load librbc3d_b200.so
     oracle.build()
-    threads = args.ref_threads or host_threads()   # torchrun exports OMP_NUM_THREADS=1: set the team size explicitly
+    threads = host_threads()              # torchrun exports OMP_NUM_THREADS=1: set the team size explicitly
     oracle.lib().orc_set_num_threads(int(threads))
     cores = int(oracle.lib().orc_num_threads())
     n_side = n_side_of(args.cells)
@@ -877,7 +877,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-cells", type=int, default=32)
     ap.add_argument("--ref-mtube", action="store_true", help="--impl reference: also run the minicase block on the CPU")
-    ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: OpenMP threads (0 = every host thread)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-timestep", action="store_true", help="skip the geometry-update / RHS-operator timing")

@@ -364,7 +364,6 @@ int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   C.sg_st.release();
   C.spGi.release();
   C.spTi.release();
-  C.sg_cta.release();
   C.sg_cache.release();
   C.ps_warp_tgt.release();
   C.ps_maskbits.release();

@@ -205,9 +205,6 @@ struct Cells {
   size_t sg_smem = 0;
   dbuf<double> sg_st;                // (s, t) pairs
   dbuf<double> spGi;                 // spline(g detJ) as double2 planes: [cell][6][2 nlat][nlon][2] (phi fastest)
-  std::vector<double> sg_rowcost;    // cost model of a latitude row of the row kernel (per cell)
-  dbuf<int4> sg_cta;                 // [CTA] (row, replica, replicas of the row): CTAs per row follow the cost
-  int sg_cta_n = 0, sg_cta_nslot = -1;
   dbuf<double> spTi;                 // same layout, scratch: spline(x), spline(a3) at geometry time, then spline(f detJ)
   dbuf<double4> sg_cache;            // [slot][row][sorted patch point][half][nlon] x 16 B: (xx.x, xx.y) | (xx.z, w EA (xx.a3))
   // dense same-surface pair kernel (pairself.cu)

@@ -177,7 +177,6 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
   C.sg_cache_ok = false;
   C.spGi_valid = false;
   C.spFi_valid = false;
-  C.sg_cta_nslot = -1;
   const int nlat = C.nlat, nlon = C.nlon, m = 2 * nlat, n = nlon, npatch = C.nrad * C.nazm;
   const double hx = RBC_TWO_PI / (double)m, hy = RBC_TWO_PI / (double)n;
   const double ihx = 1.0 / hx, ihy = 1.0 / hy;
@@ -290,17 +289,6 @@ int singular_mesh_prepare(rbc3d_ctx *c, const double *thG, const double *phiG, c
     for (int k = 0; k < SR_PF; k++) push(npts - 1, true, 0);
     ri[2] = (int)(rt.size() / SR_TABW);
     ntab = std::max(ntab, ri[2]);
-    {  // LSU cycles of a row per cell: per point (basis, code, shuffles, record loads), per node load (4 phases each)
-      int nfresh = 0, nslide = 0;
-      for (size_t e = 0; e + SR_TABW <= rt.size(); e += SR_TABW) {
-        unsigned long long w64;
-        memcpy(&w64, &rt[e + 9], sizeof w64);
-        nfresh += ((unsigned)w64 & SR_FRESH) ? 1 : 0;
-        nslide += ((unsigned)w64 & (SR_LOADX | SR_LOADY)) ? 1 : 0;
-      }
-      C.sg_rowcost.resize(nlat);
-      C.sg_rowcost[row] = 300.0 + 15.0 * ri[2] + 48.0 * nfresh + 24.0 * nslide;
-    }
   }
   std::vector<double> tab((size_t)nlat * ntab * SR_TABW, 0.0);
   for (int row = 0; row < nlat; row++) std::copy(rowtab[row].begin(), rowtab[row].end(), tab.begin() + (size_t)row * ntab * SR_TABW);
@@ -345,8 +333,7 @@ __global__ void __launch_bounds__(256) k_spline_planes(int ncell, int m, int n, 
 // ---------------------------------------------------------------------------------------------------------
 struct RowArgs {
   Params prm;
-  int npc, nlat, nlon, Np, npts, ntab, ni_max, nslot, ngrp, NS, tpw, nbuf;
-  const int4 *cta;          // [CTA] (row, replica, replicas of the row, -)
+  int npc, nlat, nlon, Np, npts, ntab, ni_max, nslot, ngrp, NS, tpw, reps, nbuf;
   const double *tab;        // [row][ntab][SR_TABW]
   const int *rowinfo;       // [row][SR_RI]
   const double2 *planes;    // [cell][6][m][n] of the interpolated field (x, a3, g detJ or f detJ)
@@ -436,7 +423,7 @@ template <int MODE>
 __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 warps: 4 on one scheduler -> 128 registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.nlon, m = 2 * a.nlat, npts = a.npts, NS = a.NS;
-  const int row = a.cta[blockIdx.x].x, rep = a.cta[blockIdx.x].y, reps = a.cta[blockIdx.x].z;  // CTAs per row follow its cost
+  const int row = blockIdx.x % a.nlat, rep = blockIdx.x / a.nlat;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncons = a.ngrp * NS;                                        // consumer warps; warp ncons = producer
   unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem_raw);   // [2]
@@ -466,7 +453,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       const unsigned band_bytes = (unsigned)(6 * ni * n * sizeof(double2));
       const int n1 = min(ni, m - ilo);  // rows before the cyclic wrap
       int it = 0;
-      for (int slot = rep; slot < a.nslot; slot += reps, it++) {
+      for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
         const int buf = it % nbuf, use = it / nbuf;
         if (use > 0)  // every consumer warp has left the buffer; poll with a pause: the issue slots belong to the consumers
           while (!mbar_test(bar_empty + buf, (unsigned)((use - 1) & 1))) {
@@ -491,7 +478,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
   const int pbeg = ri[3 + strm], pend = ri[4 + strm]; // table entries of this stream, a multiple of SR_U
   const unsigned long long pol = l2_evict_first_policy();
   const size_t rstep = (size_t)2 * n;                 // double2 per patch point of an item
-  const size_t item_step = (size_t)reps * a.nlat * npts * rstep;
+  const size_t item_step = (size_t)a.reps * a.nlat * npts * rstep;
   // the stream's real points are contiguous in the cache: [rfirst, rfirst + rcount)
   const int rfirst = (int)(reinterpret_cast<const unsigned long long *>(s_tab + (size_t)pbeg * SR_TABW + 9)[0] >> 32);
   const int rcount = (pend > pbeg)
@@ -499,7 +486,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
                          : 0;
   const bool pf_lane = (MODE != SR_BUILD_X) && grp == 0 && lane == 0;  // group 0 prefetches whole rows (all groups' records)
   int it = 0;
-  for (int slot = rep; slot < a.nslot; slot += reps, it++) {
+  for (int slot = rep; slot < a.nslot; slot += a.reps, it++) {
     const int buf = it % nbuf, use = it / nbuf;
     const int cell = a.active_list[slot];
     double2 *item = a.cache + (((size_t)slot * a.nlat + row) * npts) * rstep;
@@ -515,7 +502,7 @@ __global__ void __launch_bounds__(SR_NT + 32, 1) k_sing_row(RowArgs a) {  // 13 
       const unsigned head = (unsigned)(min(rcount, SR_L2PF) * rstep * sizeof(double2));
       if (head) {
         if (it == 0) l2_prefetch(item + (size_t)rfirst * rstep, head);
-        if (slot + reps < a.nslot) l2_prefetch(item + item_step + (size_t)rfirst * rstep, head);
+        if (slot + a.reps < a.nslot) l2_prefetch(item + item_step + (size_t)rfirst * rstep, head);
       }
     }
     // records: SR_PF points in flight in registers
@@ -714,35 +701,7 @@ static int launch_row(rbc3d_ctx *c, TargetList &t, const double *planes, double 
   a.npc = C.npc, a.nlat = C.nlat, a.nlon = C.nlon, a.Np = C.Np;
   a.npts = C.sg_npatch_active, a.ntab = C.sg_ntab, a.ni_max = C.sg_ni_max, a.nslot = C.sg_nactive;
   a.ngrp = sr_groups(C.nlon), a.NS = sr_streams(C.nlon), a.tpw = sr_tpw(C.nlon);
-  // one persistent CTA per SM; the rows share them in proportion to their cost (polar rows touch more spline cells per
-  // patch: 1.4 x the node loads of equatorial rows), each CTA of a row takes every reps-th cell
-  if (C.sg_cta_nslot != C.sg_nactive || C.sg_cta.n == 0) {
-    const int nrow = C.nlat, ncta = std::max(nrow, std::min(c->sm_count, nrow * C.sg_nactive));
-    std::vector<int> reps(nrow, 1);
-    for (int k = nrow; k < ncta; k++) {
-      int best = -1;
-      double bv = -1.0;
-      for (int r = 0; r < nrow; r++) {
-        const double v = C.sg_rowcost[r] * ((C.sg_nactive + reps[r] - 1) / reps[r]);  // time of the row's CTAs
-        if (reps[r] < C.sg_nactive && v > bv) bv = v, best = r;
-      }
-      if (best < 0) break;
-      reps[best]++;
-    }
-    std::vector<int4> tab;
-    // CTAs of the costliest rows first: they are the ones the kernel waits for
-    std::vector<int> ord(nrow);
-    for (int r = 0; r < nrow; r++) ord[r] = r;
-    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return C.sg_rowcost[x] / reps[x] > C.sg_rowcost[y] / reps[y]; });
-    for (int r : ord)
-      for (int q = 0; q < reps[r]; q++) tab.push_back(make_int4(r, q, reps[r], 0));
-    RBC_TRY(C.sg_cta.resize(tab.size()));
-    CUDA_TRY(cudaMemcpyAsync(C.sg_cta.p, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    C.sg_cta_n = (int)tab.size();
-    C.sg_cta_nslot = C.sg_nactive;
-  }
-  a.cta = C.sg_cta.p;
+  a.reps = std::max(1, std::min(c->sm_count / C.nlat, C.sg_nactive));
   a.nbuf = C.sg_K;
   a.tab = C.sg_st.p, a.rowinfo = C.sg_idx.p;
   a.planes = reinterpret_cast<const double2 *>(planes);
@@ -753,7 +712,7 @@ static int launch_row(rbc3d_ctx *c, TargetList &t, const double *planes, double 
   a.coef = coef;
   a.acc = t.acc.p;
   CUDA_TRY(cudaFuncSetAttribute(k_sing_row<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.sg_smem));
-  k_sing_row<MODE><<<C.sg_cta_n, a.ngrp * a.NS * 32 + 32, C.sg_smem, c->stream>>>(a);
+  k_sing_row<MODE><<<C.nlat * a.reps, a.ngrp * a.NS * 32 + 32, C.sg_smem, c->stream>>>(a);
   KERNEL_CHECK();
   c->launches++;
   return RBC3D_OK;

@@ -51,7 +51,7 @@ def test_reference_arm_does_not_map_the_product_library():
             "sp = u.spec_from_file_location('b', %r); b = u.module_from_spec(sp); sp.loader.exec_module(b);"
             "import io, contextlib; buf = io.StringIO();\n"
             "with contextlib.redirect_stdout(buf):\n"
-            "    b.run_reference(argparse.Namespace(cells=8, seed=11, gpus=1, steps=1, warmup=0, ref_mtube=False, ref_threads=0))\n"
+            "    b.run_reference(argparse.Namespace(cells=8, seed=11, gpus=1, steps=1, warmup=0, ref_mtube=False))\n"
             "maps = open('/proc/self/maps').read()\n"
             "assert 'librbc3d_oracle' in maps and 'librbc3d_b200' not in maps, 'product library mapped'\n"
             "import os\n"
