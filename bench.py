@@ -600,7 +600,7 @@ def run_gpu(args):
     dom = max([r for r in rows if not r.get("overlapped")], key=lambda r: r["ms"])
     traffic = None
     try:   # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")) as fh:
             tr = json.load(fh)
         traffic = tr.get("%s@%d" % (dom["kernel"].split("(")[0], sus.ncell // world))
     except Exception:
