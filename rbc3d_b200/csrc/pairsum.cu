@@ -672,11 +672,11 @@ int cells_gather_sorted(rbc3d_ctx *c, bool geom, bool f, bool g) {
 // ---- AddLinearInt (ModIntOnRbcs.F90:162-201): xvint = -8 pi / V * sum_j B_j x_j (g_j . a3_j) with g already
 //      weighted by detJ*w; deterministic two-stage reduction ----
 constexpr int LIN_BLOCKS = 296;
-__global__ void __launch_bounds__(256) k_linear_partial(int n, int npc, const double *__restrict__ x,
+__global__ void __launch_bounds__(256) k_linear_partial(int n, int npc, int p_lo, int p_hi, const double *__restrict__ x,
                                                         const double *__restrict__ g, const double *__restrict__ a3,
                                                         const double *__restrict__ B, double *__restrict__ part) {
   double sx = 0, sy = 0, sz = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+  for (int p = p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < p_hi; p += gridDim.x * blockDim.x) {
     double vn = g[p] * a3[p] + g[(size_t)n + p] * a3[(size_t)n + p] + g[2 * (size_t)n + p] * a3[2 * (size_t)n + p];
     vn *= B[p / npc];
     sx += x[p] * vn;
@@ -717,11 +717,17 @@ int linear_term(rbc3d_ctx *c, TargetList &t, double c2) {
     return RBC3D_OK;
   }
   const Params &p = c->prm;
-  k_linear_partial<<<LIN_BLOCKS, 256, 0, c->stream>>>(C.Np, C.npc, C.x.p, C.g.p, C.a3.p, C.B.p, C.xvint_part.p);
+  // several ranks: every rank sums a contiguous block of cells (a partition whatever the target ownership is) and the
+  // three numbers are all-reduced, instead of every rank reading all N points (collective 5)
+  const int c_lo = p.nranks > 1 ? (int)((long long)C.ncell * p.rank / p.nranks) : 0;
+  const int c_hi = p.nranks > 1 ? (int)((long long)C.ncell * (p.rank + 1) / p.nranks) : C.ncell;
+  k_linear_partial<<<LIN_BLOCKS, 256, 0, c->stream>>>(C.Np, C.npc, c_lo * C.npc, c_hi * C.npc, C.x.p, C.g.p, C.a3.p, C.B.p,
+                                                      C.xvint_part.p);
   const double scale = -8.0 * RBC_PI * (p.iLb[0] * p.iLb[1] * p.iLb[2]) * c2;
   k_linear_final<<<1, 32, 0, c->stream>>>(C.xvint_part.p, scale, C.xvint_part.p + 3 * LIN_BLOCKS);
   KERNEL_CHECK();
   c->launches += 2;
+  if (p.nranks > 1) RBC_TRY(comm_allreduce_sum(c, C.xvint_part.p + 3 * LIN_BLOCKS, 3));
   return RBC3D_OK;
 }
 
