@@ -251,6 +251,29 @@ def test_singular_direct_and_cached_paths_agree(sus8, oracle_lib):
     assert rel_l2(out[0], out[1]) < 1e-12
 
 
+@pytest.mark.parametrize("nlat0,dealias", [(4, 3), (8, 3), (16, 3), (12, 2)])
+def test_singular_row_kernel_on_other_meshes(oracle_lib, nlat0, dealias):
+    """The row-walk singular kernel on meshes other than 36 x 72: 12 x 24 (one target group of 24 lanes), 24 x 48 (two
+    groups), 48 x 96 (four groups, three point streams, ONE band buffer: 129 KB bands do not fit twice), 24 x 48 with
+    dealias 2 -- double layer, single layer and both, plus the deterministic sum: two applications are bit-identical."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    sus = synth.make_suspension(1, nlat0=nlat0, dealias=dealias, L=9.0, seed=5,
+                                centers=np.array([[2.5, 4.5, 4.5], [6.3, 4.2, 4.8]]))
+    op = EwaldOperator(sus.Lb)
+    op.set_suspension(sus)
+    assert op.sing_cache_info()[0]
+    orc = oracle_lib.Oracle(sus.Lb).set_cells(sus)
+    flags = orc.FLAG_NO_PAIRS | orc.FLAG_NO_NEARSING | orc.FLAG_NO_LINEAR
+    op.set_skip_flags(2 | 4 | 8)
+    for c1, c2 in ((0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)):
+        v = op.AddIntOnRbcs(c1, c2)
+        ref = orc.add_int_on_rbcs(c1, c2, orc.cell_targets(), flags=flags)
+        assert rel_l2(v, ref) < TOL, (nlat0, c1, c2)
+        assert np.array_equal(v, op.AddIntOnRbcs(c1, c2))          # fixed summation order, no atomics
+    op.close()
+
+
 @pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)])
 def test_pair_sum_dense_self_kernel_vs_cell_list(sus8, oracle_lib, c1, c2):
     """same-surface pairs through the dense per-cell kernel (default) and through the hashed cell list."""
