@@ -193,7 +193,8 @@ int rbc3d_set_pair_self(rbc3d_ctx *ctx, int mode);
  * cell block and the blocks are all-gathered over NVLink; rbc3d_cells_set_density becomes a collective call.
  * Needs ncell divisible by the number of ranks (otherwise the full arrays are uploaded as before). */
 int rbc3d_set_replicated_density(rbc3d_ctx *ctx, int on);
-/* state of that cache after rbc3d_cells_set_geometry: cells cached (of the cells this rank owns targets of) and
+/* state of that cache (built by the first double-layer-only application after rbc3d_cells_set_geometry, so a time
+ * step without a cell solve never builds it): cells cached (of the cells this rank owns targets of) and
  * 256-byte coefficient rows held (= bytes streamed per matvec / 256); either pointer may be NULL */
 int rbc3d_pair_cache_info(rbc3d_ctx *ctx, int32_t *cells_cached, int64_t *rows);
 

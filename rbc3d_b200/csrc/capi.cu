@@ -581,8 +581,9 @@ static int set_geometry_common(rbc3d_ctx *c, const double *x, const double *a3, 
       src_own = C.src_own.p;
     }
   }
-  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own, c->pme.sblk, c->pme.swalk));
-  if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, C.pl, C.x.p));
+  pme_spread_mode(c, C.pl, (int)Np);
+  RBC_TRY(celllist_build_pme(c, C.pl, (int)Np, C.x.p, src_own, C.pl.sblk, C.pl.swalk));
+  if (C.pl.swalk) RBC_TRY(celllist_pme_weights(c, C.pl, C.x.p));
   C.geom_set = true;
   RBC_TRY(cells_gather_sorted(c, true, false, false));
   // tlist_rbc: TargetList_Update, ModTargetList.F90:95-135
@@ -607,7 +608,11 @@ static int set_geometry_common(rbc3d_ctx *c, const double *x, const double *a3, 
   RBC_TRY(cells_active_flags(c));
   RBC_TRY(pairself_geometry_prepare(c));
   RBC_TRY(singular_prepare(c));
-  RBC_TRY(pairself_cache_prepare(c));
+  // the coefficient cache of the double-layer pair sum is only read by a c1 = 0 matvec (the GMRES of lambda != 1):
+  // it is built by the first such call after this update, so that a step that never solves does not pay for it
+  C.pc_ok = false;
+  C.pc_ncached = 0;
+  C.pc_pending = true;
   // other target lists depend on the cell geometry through their near-singular entries
   for (int k = 1; k < 3; k++)
     if (c->tl[k].valid) RBC_TRY(nearsing_prepare(c, c->tl[k]));
@@ -1048,7 +1053,7 @@ int rbc3d_apply_resident(rbc3d_ctx *c, double c1, double c2, int use_cells, int 
     t_end(c, RBC3D_T_COMM);
   }
   t_end(c, RBC3D_T_TOTAL);
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (!c->quiet) CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RBC3D_OK;
 }
 

@@ -193,6 +193,11 @@ struct Self3Args {
   SelfArgs s;
   const unsigned char *needmask;  // [G][G], cell independent
   const int *cell_list;           // CTA -> cell (null: identity)
+  // Few cells: `split` CTAs share a cell and the J loop of a patch I is dealt out in `nj` interleaved parts, so the
+  // work units are (I, J = I + jc, I + jc + nj, ...) and CTA `part` of a cell draws units part, part + split, ...
+  // (every contribution leaves through an FP64 reduction, so any partition of the patch pairs is valid).  With
+  // split = nj = 1 this is one CTA per cell walking I = 0, 1, ... as before.
+  int split = 1, nj = 1;
 };
 
 template <bool SL>
@@ -205,7 +210,8 @@ __global__ void __launch_bounds__(P3_WARPS * 32, 1) k_pair_self3(Self3Args aa) {
   double *s_bs = smem + ntab;                        // [G][4] centre, radius
   double *s_rec = s_bs + 4 * ((G + 1) & ~1);         // [P3_WARPS][32][PS_REC]
   __shared__ int s_next;
-  const int cell = aa.cell_list ? aa.cell_list[blockIdx.x] : blockIdx.x;
+  const int cslot = blockIdx.x / aa.split, part = blockIdx.x - cslot * aa.split;
+  const int cell = aa.cell_list ? aa.cell_list[cslot] : cslot;
   if (!a.cell_active[cell]) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t base = (size_t)cell * a.npc, Np = a.Np;
@@ -249,11 +255,13 @@ __global__ void __launch_bounds__(P3_WARPS * 32, 1) k_pair_self3(Self3Args aa) {
   const double Bc = SL ? 1.0 : a.Bcell[cell];
   double *rec = s_rec + (size_t)warp * 32 * PS_REC;
 
+  const int nunits = G * aa.nj;
   for (;;) {
-    int I = 0;
-    if (lane == 0) I = atomicAdd(&s_next, 1);
-    I = __shfl_sync(FULL_MASK, I, 0);
-    if (I >= G) break;
+    int unit = 0;
+    if (lane == 0) unit = part + aa.split * atomicAdd(&s_next, 1);
+    unit = __shfl_sync(FULL_MASK, unit, 0);
+    if (unit >= nunits) break;
+    const int I = unit / aa.nj, jc = unit - I * aa.nj;
     const int p_i = a.warp_tgt[I * 32 + lane];
     const bool valid_i = p_i >= 0;
     double xi = 0, yi = 0, zi = 0, d0 = 0, d1 = 0, d2i = 0, n0 = 0, n1 = 0, n2 = 0;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(P3_WARPS * 32, 1) k_pair_self3(Self3Args aa) {
     }
     const double cIx = s_bs[4 * I], cIy = s_bs[4 * I + 1], cIz = s_bs[4 * I + 2], rI = s_bs[4 * I + 3];
     double ax = 0, ay = 0, az = 0;
-    for (int J = I; J < G; J++) {
+    for (int J = I + jc; J < G; J += aa.nj) {
       {
         const double ex = s_bs[4 * J] - cIx, ey = s_bs[4 * J + 1] - cIy, ez = s_bs[4 * J + 2] - cIz;
         const double reach = rc + rI + s_bs[4 * J + 3];
@@ -926,6 +934,10 @@ int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
     aa.needmask = C.ps_needmask.p;
     aa.cell_list = nullptr;
     int ncells_direct = C.ncell;
+    if (c->pair_self_mode == 3 && C.pc_pending && c1 == 0 && c2 != 0) {
+      C.pc_pending = false;
+      RBC_TRY(pairself_cache_prepare(c));
+    }
     const bool cached = c->pair_self_mode == 3 && C.pc_ok && C.pc_ncached > 0 && c1 == 0 && c2 != 0;
     if (cached) {  // double layer alone (the GMRES matvec): stream the geometry cache, direct kernel for the rest
       PcArgs pa;
@@ -942,6 +954,11 @@ int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
       ncells_direct = C.sg_nactive - C.pc_ncached;
       if (ncells_direct <= 0) return RBC3D_OK;
     }
+    // fewer cells than SMs: several CTAs per cell, about one work unit per warp (examples/minicase has 2 cells)
+    if (ncells_direct < c->sm_count) {
+      aa.split = std::min(64, (2 * c->sm_count + ncells_direct - 1) / ncells_direct);
+      aa.nj = std::max(1, std::min(8, (P3_WARPS * aa.split + C.ps_nwarps - 1) / C.ps_nwarps));
+    }
     for (int pass = 0; pass < 2; pass++) {
       const bool sl = pass == 0;
       if (sl ? (c1 == 0) : (c2 == 0)) continue;
@@ -949,10 +966,10 @@ int pairself_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
       const size_t smem = sizeof(double) * ((size_t)ntab + 4 * ((C.ps_nwarps + 1) & ~1) + (size_t)P3_WARPS * 32 * PS_REC);
       if (sl) {
         CUDA_TRY(cudaFuncSetAttribute(k_pair_self3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pair_self3<true><<<ncells_direct, P3_WARPS * 32, smem, c->stream>>>(aa);
+        k_pair_self3<true><<<ncells_direct * aa.split, P3_WARPS * 32, smem, c->stream>>>(aa);
       } else {
         CUDA_TRY(cudaFuncSetAttribute(k_pair_self3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pair_self3<false><<<ncells_direct, P3_WARPS * 32, smem, c->stream>>>(aa);
+        k_pair_self3<false><<<ncells_direct * aa.split, P3_WARPS * 32, smem, c->stream>>>(aa);
       }
       KERNEL_CHECK();
       c->launches++;

@@ -31,10 +31,28 @@ static int pme_transform_slab(rbc3d_ctx *c);
 static int pme_halo_exchange(rbc3d_ctx *c, TargetList &t);
 
 void t_begin(rbc3d_ctx *c, int s) {
+  if (c->quiet) return;
   cudaEventRecord(c->ev[2 * s], c->stream);
   c->ev_used[s] = true;
 }
-void t_end(rbc3d_ctx *c, int s) { cudaEventRecord(c->ev[2 * s + 1], c->stream); }
+void t_end(rbc3d_ctx *c, int s) {
+  if (!c->quiet) cudaEventRecord(c->ev[2 * s + 1], c->stream);
+}
+
+// P = 8 has two spreading kernels.  The pencil walk (k_spread_walk) is the fast one when every pencil has work; a
+// short list (the 2 cells or the 2404 wall triangles of examples/minicase) leaves most pencils empty and turns the
+// few occupied ones into long serial chains, where the source-block kernel (k_spread8, 9 times more work units on
+// the same sources) is several times faster.  The sort key of the list follows the choice.
+void pme_spread_mode(rbc3d_ctx *c, CellList &L, int n) {
+  const Pme &pm = c->pme;
+  const Params &p = c->prm;
+  const int sb[3] = {SPR_BX, SPR_BY, SPR_BZ};
+  L.swalk = (p.P == 8) && (pm.swalk_mode < 0 ? n >= pm.swalk_min : pm.swalk_mode == 0);
+  for (int d = 0; d < 3; d++) {
+    L.sblk[d] = (p.P == 8) ? (L.swalk ? (d == 0 ? SW_XR : 1) : sb[d]) : PME_BLK;
+    L.nsblk[d] = (p.Nb[d] + L.sblk[d] - 1) / L.sblk[d];
+  }
+}
 
 int pme_init(rbc3d_ctx *c) {
   Pme &pm = c->pme;
@@ -49,16 +67,13 @@ int pme_init(rbc3d_ctx *c) {
   pm.Nxh = pm.Nx / 2 + 1;
   pm.G = (size_t)pm.Nx * pm.Ny * pm.Nz;
   pm.M = (size_t)pm.Nxh * pm.Ny * pm.Nz;
-  const int sb[3] = {SPR_BX, SPR_BY, SPR_BZ};
-  {
-    const char *e = getenv("RBC3D_SPREAD_BLOCKS");  // 1: the 8 x 4 x 4 source-block kernel (k_spread8) instead of the walk
-    pm.swalk = (p.P == 8) && !(e && atoi(e) == 1);
-  }
+  pm.swalk_mode = -1;
+  if (const char *e = getenv("RBC3D_SPREAD_BLOCKS")) pm.swalk_mode = atoi(e) == 1 ? 1 : 0;
+  if (const char *e = getenv("RBC3D_SPREAD_WALK_MIN")) pm.swalk_min = atoi(e);
+  if (const char *e = getenv("RBC3D_INTERP_DIRECT_MAX")) pm.interp_direct_max = atoi(e);
   for (int d = 0; d < 3; d++) {
     pm.iblk[d] = (p.P == 8) ? 1 : PME_BLK;  // P = 8: targets keyed by mesh cell for the column walk (k_interp_walk)
     pm.nblk[d] = (p.Nb[d] + pm.iblk[d] - 1) / pm.iblk[d];
-    pm.sblk[d] = (p.P == 8) ? (pm.swalk ? (d == 0 ? SW_XR : 1) : sb[d]) : PME_BLK;
-    pm.nsblk[d] = (p.Nb[d] + pm.sblk[d] - 1) / pm.sblk[d];
   }
   pm.walk = (p.P == 8);
   RBC_TRY(pm.src.resize(9 * pm.G));
@@ -93,8 +108,14 @@ int pme_init(rbc3d_ctx *c) {
 void pme_destroy(rbc3d_ctx *c) {
   Pme &pm = c->pme;
   for (int i = 0; i < 3; i++)
-    if (pm.planF_ok[i]) cufftDestroy(pm.planF[i]);
-  if (pm.planB_ok) cufftDestroy(pm.planB);
+    if (pm.planF_ok[i]) {
+      alloc_epoch()++;  // plan work areas are device memory a captured graph may refer to
+      cufftDestroy(pm.planF[i]);
+    }
+  if (pm.planB_ok) {
+    alloc_epoch()++;
+    cufftDestroy(pm.planB);
+  }
   if (pm.plan2F_ok) cufftDestroy(pm.plan2F);
   if (pm.plan2B_ok) cufftDestroy(pm.plan2B);
   for (int i = 0; i < 2; i++)
@@ -674,19 +695,19 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a)
 static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
   Pme &pm = c->pme;
   struct { bool flag_sl, flag_dl; } pmf = {sl, dl};
-    a.nbx = pm.nsblk[0];
-    a.nby = pm.nsblk[1];
-    a.nbz = pm.nsblk[2];
+    const CellList &L = *a.list;
+    a.nbx = L.nsblk[0];
+    a.nby = L.nsblk[1];
+    a.nbz = L.nsblk[2];
     a.mesh = pm.src.p;
     a.G = pm.G;
     const int nblocks = a.nbx * a.nby * a.nbz;
-    if (pm.swalk) {
-      const CellList &L = *a.list;
+    if (L.swalk) {
       const int ns = L.n_sorted;
       if (ns > 0) {
         SpreadWArgs w;
         w.prm = a.prm, w.n = a.n, w.start = a.start, w.wrec = L.w.p;
-        w.nxr = pm.nsblk[0], w.mesh = pm.src.p, w.G = pm.G;
+        w.nxr = L.nsblk[0], w.mesh = pm.src.p, w.G = pm.G;
         for (int which = 0; which < 2; which++) {
           if (which == 0 ? !pmf.flag_sl : !pmf.flag_dl) continue;
           w.comp0 = which == 0 ? 0 : 3;
@@ -697,7 +718,7 @@ static int spread_launch(rbc3d_ctx *c, SpreadArgs a, bool sl, bool dl) {
           sa.f = a.f, sa.g = a.g, sa.a3 = a.a3, sa.Bcell = a.Bcell, sa.c1 = a.c1, sa.c2 = a.c2, sa.str = pm.str.p;
           k_spread_strength<<<(ns + 255) / 256, 256, 0, c->stream>>>(sa);
           w.str = pm.str.p;
-          const int ntask = pm.nsblk[0] * pm.Ny * w.npass;
+          const int ntask = L.nsblk[0] * pm.Ny * w.npass;
           k_spread_walk<<<(ntask + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, 0, c->stream>>>(w);
           c->launches += 2;
         }
@@ -1202,6 +1223,53 @@ __global__ void __launch_bounds__(IW_WARPS * 32, 3) k_interp_walk(InterpWArgs a)
   }
 }
 
+// Short target lists (the wall vertices of examples/minicase, raw point sets): one warp per target straight from the
+// mesh, no list walk.  A column walk is a serial chain per (x, y) column whatever the list length; 12 KB of L2 reads
+// per target are cheaper than that up to a few thousand targets.  Lane = two (y, z) lines of the 8 x 8 x 8 support.
+__global__ void __launch_bounds__(256) k_interp_direct(int n, const double *__restrict__ x, const int *__restrict__ active,
+                                                       Params prm, const double *__restrict__ vv, size_t G,
+                                                       double *__restrict__ acc) {
+  __shared__ double s_w[8][3][8];
+  __shared__ int s_i[8][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + warp;
+  if (p >= n || !active[p]) return;
+  if (lane < 3) {
+    int imin;
+    double ww[8];
+    bspline_func<8>(__dmul_rn(x[(size_t)lane * n + p], prm.ih[lane]), 8, imin, ww);
+#pragma unroll
+    for (int q = 0; q < 8; q++) s_w[warp][lane][q] = ww[q];
+    s_i[warp][lane] = imin;
+  }
+  __syncwarp();
+  const int Nx = prm.Nb[0], Ny = prm.Nb[1], Nz = prm.Nb[2];
+  int gx[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) gx[q] = imodulo(s_i[warp][0] + q, Nx);
+  double r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int jy = lane & 7, jz = (lane >> 3) + 4 * h;
+    const double *row = vv + ((size_t)imodulo(s_i[warp][2] + jz, Nz) * Ny + imodulo(s_i[warp][1] + jy, Ny)) * Nx;
+    const double wyz = s_w[warp][1][jy] * s_w[warp][2][jz];
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) t = fma(s_w[warp][0][q], __ldg(row + cc * G + gx[q]), t);
+      r[cc] = fma(wyz, t, r[cc]);
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 3; cc++) r[cc] = warp_sum(r[cc]);
+  if (lane == 0) {
+    acc[p] += r[0];
+    acc[(size_t)n + p] += r[1];
+    acc[2 * (size_t)n + p] += r[2];
+  }
+}
+
 int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc) {
   Pme &pm = c->pme;
   if (!pm.transformed) {
@@ -1211,6 +1279,12 @@ int pme_interp(rbc3d_ctx *c, TargetList &t, double *acc) {
   if (pm.slab && c->prm.nranks > 1) RBC_TRY(pme_halo_exchange(c, t));  // collective: before the empty-list return
   if (t.n == 0) return RBC3D_OK;
   CellList &pl = t.pl;
+  if (pm.walk && c->prm.nranks == 1 && t.n <= pm.interp_direct_max) {
+    k_interp_direct<<<(t.n + 7) / 8, 256, 0, c->stream>>>(t.n, t.x.p, t.active.p, c->prm, pm.vv.p, pm.G, acc ? acc : t.acc.p);
+    KERNEL_CHECK();
+    c->launches++;
+    return RBC3D_OK;
+  }
   if (pm.walk) {
     InterpWArgs w;
     w.prm = c->prm;

@@ -43,12 +43,20 @@ void set_error(const char *fmt, ...);
   } while (0)
 #define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
 
+// Bumped by every device (re)allocation or release: a captured CUDA graph holds raw pointers and is only replayed
+// while this has not moved since the capture.
+inline long long &alloc_epoch() {
+  static long long e = 0;
+  return e;
+}
+
 template <class T>
 struct dbuf {
   T *p = nullptr;
   size_t n = 0;
   int resize(size_t m) {  // grow-only
     if (m <= n && p) return RBC3D_OK;
+    alloc_epoch()++;
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
@@ -62,7 +70,10 @@ struct dbuf {
     return RBC3D_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      alloc_epoch()++;
+      cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
@@ -96,6 +107,10 @@ struct CellList {
   // PME lists of the P = 8 walk kernels: per SORTED point a 26-double record (B-spline weights wx[8] wy[8] wz[8],
   // mesh cell x in the low half of slot 24, pad) -- geometry-only data, computed once per list
   dbuf<double> w;
+  // spreading kernel of this source list, chosen per list by pme_spread_mode: pencil walks (long lists) or 8 x 4 x 4
+  // source blocks (short lists, where a pencil is a long serial chain and most of the GPU would idle)
+  bool swalk = false;
+  int sblk[3] = {4, 4, 4}, nsblk[3] = {0, 0, 0};
 };
 constexpr int PME_WREC = 26;
 
@@ -217,6 +232,7 @@ struct Cells {
   // geometry cache of the symmetric same-surface double-layer pair sum (pairself.cu): per active cell slot and
   // patch pair the 32-bit set of rotation steps with an in-range pair, per such step 32 coefficients (1 - mask) EA
   bool pc_ok = false;
+  bool pc_pending = false;           // geometry changed: the cache is rebuilt by the first double-layer-only pair sum
   int pc_ncached = 0;                // the first pc_ncached cells of sg_active_list are cached
   long long pc_rows = 0;
   dbuf<unsigned> pc_mask;            // [slot][G][G]
@@ -252,6 +268,13 @@ struct WallSolver {
   int nindep = 0;
   dbuf<int> indx, last;          // [NV] 0-based independent number of a vertex; [nindep] last vertex with that number
   dbuf<double> V, w, part, h, rhs, x, f0, fw;
+  // operator #4 (set traction + walls -> wall vertices) captured once and replayed while nothing it refers to changed
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  long long graph_launches = 0;
+  long long g_epoch = -1, g_geom = -1, g_mat = -1, g_tl = -1;
+  int g_flags[4] = {0, 0, 0, 0};  // NV, nindep, skip_flags, overlap
+  Params g_prm{};
 };
 
 struct Pme {
@@ -272,9 +295,9 @@ struct Pme {
   bool distributed = false, transformed = false;
   int nblk[3] = {0, 0, 0};          // PME blocks of PME_BLK^3 mesh cells (interpolation)
   int iblk[3] = {4, 4, 4};          // their edges
-  int sblk[3] = {4, 4, 4};          // edges of the source blocks of the spreading kernel
-  int nsblk[3] = {0, 0, 0};
-  bool swalk = false;               // P = 8: spreading by pencil walks (k_spread_walk), else source blocks
+  int swalk_mode = -1;              // RBC3D_SPREAD_BLOCKS: 1 = always source blocks, 0 = always pencil walks, unset = by size
+  int interp_direct_max = 16384;    // RBC3D_INTERP_DIRECT_MAX: longest target list interpolated one warp per target (k_interp_direct)
+  int swalk_min = 1 << 18;          // RBC3D_SPREAD_WALK_MIN: shortest source list that takes the pencil walk
   bool walk = false;                // P = 8: register-ring column walks along z (lists keyed z-fastest)
   // slab-decomposed transform (several ranks; ModPFFTW.F90:56-89, 188-316): z-slabs of planes for the 2-D transforms,
   // y-slabs of pencils for the transform in z and the k-space multiplier, all-to-all transposes in between
@@ -299,6 +322,7 @@ struct rbc3d_ctx {
   // with overlap on it is issued on stream2 while singular / pair kernels run on stream (joined before combine)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int quiet = 0;               // no timing events and no trailing host sync (a stream capture is in progress)
   int resident_collect = 1;    // rbc3d_apply_resident sums the rows over the ranks (0: the sharded solver keeps them local)
   int replicated_density = 0;  // 1: host densities are identical on all ranks -> upload 1/nranks each + all-gather
   int overlap = -1;         // -1: on with several ranks (hides the mesh all-reduce), 0 off, 1 on
@@ -412,6 +436,7 @@ int comm_recv(rbc3d_ctx *c, void *buf, size_t bytes, int peer);
 void comm_destroy(rbc3d_ctx *c);
 
 // timing helpers
+void pme_spread_mode(rbc3d_ctx *c, CellList &L, int n);  // before celllist_build_pme of a source list
 void t_begin(rbc3d_ctx *c, int stage);
 void t_end(rbc3d_ctx *c, int stage);
 

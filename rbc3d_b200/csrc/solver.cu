@@ -17,6 +17,7 @@
 //     non-zero initial guess.  Dot products are two-stage reductions in a fixed order (deterministic).
 // The host mirror of the same algorithm is rbc3d_b200/gmres.py; tests/test_gpu_gmres.py checks one against the other.
 #include <cmath>
+#include <cstring>
 #include <functional>
 #include <vector>
 
@@ -123,10 +124,14 @@ __global__ void __launch_bounds__(256) k_sh_anal(ShArgs a) {
 // ---- vector kernels of the Krylov solver: fixed-order two-stage reductions ----
 constexpr int DOT_BLOCKS = 256, DOT_THREADS = 256;
 
-// part[i][blk] = partial sum of V_i . w over the block's slice; i < k
-__global__ void __launch_bounds__(DOT_THREADS) k_dots_partial(int n, int k, const double *__restrict__ V, size_t ldv,
-                                                               const double *__restrict__ w, double *__restrict__ part) {
+// h[i] = V_i . w, i < gridDim.y: part[i][blk] = partial sum over the block's slice, and the block that finishes a
+// vector last (ticket) adds the DOT_BLOCKS partials in a fixed order - one launch, a result that does not depend on
+// the order the blocks ran in
+__global__ void __launch_bounds__(DOT_THREADS) k_dots(int n, const double *__restrict__ V, size_t ldv,
+                                                       const double *__restrict__ w, double *__restrict__ part,
+                                                       unsigned *__restrict__ ticket, double *__restrict__ h) {
   __shared__ double s[DOT_THREADS / 32];
+  __shared__ bool last;
   const int i = blockIdx.y;
   const double *v = V + (size_t)i * ldv;
   double acc = 0;
@@ -138,16 +143,19 @@ __global__ void __launch_bounds__(DOT_THREADS) k_dots_partial(int n, int k, cons
     double t = 0;
     for (int q = 0; q < DOT_THREADS / 32; q++) t += s[q];
     part[(size_t)i * DOT_BLOCKS + blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&ticket[i], 1u) == DOT_BLOCKS - 1;
   }
-  (void)k;
-}
-__global__ void k_dots_final(int k, const double *__restrict__ part, double *__restrict__ h) {
-  const int i = blockIdx.x;
-  if (i >= k) return;
-  double v = 0;
-  for (int q = threadIdx.x; q < DOT_BLOCKS; q += 32) v += part[(size_t)i * DOT_BLOCKS + q];
-  v = warp_sum(v);
-  if (threadIdx.x == 0) h[i] = v;
+  __syncthreads();
+  if (!last || threadIdx.x >= 32) return;
+  __threadfence();
+  double t = 0;
+  for (int q = threadIdx.x; q < DOT_BLOCKS; q += 32) t += __ldcg(part + (size_t)i * DOT_BLOCKS + q);
+  t = warp_sum(t);
+  if (threadIdx.x == 0) {
+    h[i] = t;
+    ticket[i] = 0;
+  }
 }
 // w -= sum_i h[i] V_i
 __global__ void k_gs_update(int n, int k, const double *__restrict__ V, size_t ldv, const double *__restrict__ h,
@@ -162,6 +170,24 @@ __global__ void k_gs_update(int n, int k, const double *__restrict__ V, size_t l
 __global__ void k_residual(int n, const double *__restrict__ b, double *__restrict__ w) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) w[e] = b[e] - w[e];
+}
+// y = x / sqrt(*h2) with the squared norm still on the device (nothing written for a zero norm: exact breakdown)
+__global__ void k_normalize(int n, const double *__restrict__ h2, const double *__restrict__ x, double *__restrict__ y) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double hn = sqrt(*h2);
+  if (hn > 0.0) y[e] = (1.0 / hn) * x[e];
+}
+// x += sum_i y[i] V_i, i ascending (the solution update of a restart cycle), up to 32 vectors per launch
+struct Coef32 {
+  double y[32];
+};
+__global__ void k_update_x(int n, int k, const double *__restrict__ V, size_t ldv, Coef32 y, double *__restrict__ x) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double acc = x[e];
+  for (int i = 0; i < k; i++) acc = fma(y.y[i], V[(size_t)i * ldv + e], acc);
+  x[e] = acc;
 }
 // y = alpha x (+ y if add)
 __global__ void k_axpy(int n, double alpha, const double *__restrict__ x, double *__restrict__ y, int add) {
@@ -416,21 +442,35 @@ struct KrylovWork {
   dbuf<double> &V, &w, &part, &h;
 };
 
-static int dots(rbc3d_ctx *c, KrylovWork &K, size_t n, bool reduce_ranks, int k, const double *V, size_t ldv, const double *w,
-                double *h_host) {
-  k_dots_partial<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>((int)n, k, V, ldv, w, K.part.p);
-  k_dots_final<<<k, 32, 0, c->stream>>>(k, K.part.p, K.h.p);
+// h_dev[0..k) = V_i . w on the device (summed over the ranks for sharded unknowns); nothing crosses to the host
+static int dots_dev(rbc3d_ctx *c, KrylovWork &K, size_t n, bool reduce_ranks, int k, const double *V, size_t ldv,
+                    const double *w, double *h_dev, int restart) {
+  unsigned *ticket = reinterpret_cast<unsigned *>(K.part.p + (size_t)(restart + 2) * DOT_BLOCKS);
+  k_dots<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>((int)n, V, ldv, w, K.part.p, ticket, h_dev);
   KERNEL_CHECK();
-  c->launches += 2;
-  if (reduce_ranks) RBC_TRY(comm_allreduce_sum(c, K.h.p, (size_t)k));  // sharded unknowns: every rank holds its own cells'
-  CUDA_TRY(cudaMemcpyAsync(h_host, K.h.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->launches++;
+  if (reduce_ranks) RBC_TRY(comm_allreduce_sum(c, h_dev, (size_t)k));  // sharded unknowns: every rank holds its own cells'
   return RBC3D_OK;
+}
+
+// pinned landing buffer of the Hessenberg column (one solve at a time per host thread)
+static double *krylov_host(int count) {
+  static thread_local double *buf = nullptr;
+  static thread_local int cap = 0;
+  if (count > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = 0;
+    if (cudaHostAlloc((void **)&buf, sizeof(double) * count, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    cap = count;
+  }
+  return buf;
 }
 
 // KSPGMRES, PCNONE, classical Gram-Schmidt; x_dev in: initial guess (ignored and zeroed when zero_guess: PETSc then takes
 // r0 = b without a matvec), out: solution.  history[k] = residual norm after k iterations (history[0] = ||b - A x0||),
-// at most maxit + 1 entries.  Only the Hessenberg column crosses to the host per iteration.
+// at most maxit + 1 entries.  One iteration is matvec, projections, update, norm and normalisation queued back to back
+// on the stream; only the Hessenberg column (k + 2 numbers) crosses to the host, once, at the end of the iteration.
 template <class MatVec>
 static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, bool zero_guess, MatVec &&matvec,
                       const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter, double *history) {
@@ -438,12 +478,20 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
   const int nb = (int)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
   RBC_TRY(K.V.resize((size_t)(restart + 1) * (n > 0 ? n : 1)));
   RBC_TRY(K.w.resize(n > 0 ? n : 1));
-  RBC_TRY(K.part.resize((size_t)(restart + 2) * DOT_BLOCKS));
+  RBC_TRY(K.part.resize((size_t)(restart + 2) * DOT_BLOCKS + (restart + 2)));  // partial sums, then the tickets
   RBC_TRY(K.h.resize(restart + 2));
-  std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), gv(restart + 1), hcol(restart + 2);
-  double bnorm2 = 0;
-  RBC_TRY(dots(c, K, n, reduce_ranks, 1, b_dev, n, b_dev, &bnorm2));
-  const double ttol = fmax(rtol * sqrt(bnorm2), 1e-50);
+  CUDA_TRY(cudaMemsetAsync(K.part.p + (size_t)(restart + 2) * DOT_BLOCKS, 0, sizeof(double) * (restart + 2), c->stream));
+  double *hcol = krylov_host(restart + 2);
+  if (!hcol) return RBC3D_ENOMEM;
+  auto fetch = [&](int count) -> int {  // K.h[0..count) -> hcol
+    CUDA_TRY(cudaMemcpyAsync(hcol, K.h.p, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RBC3D_OK;
+  };
+  std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), gv(restart + 1);
+  RBC_TRY(dots_dev(c, K, n, reduce_ranks, 1, b_dev, n, b_dev, K.h.p, restart));
+  RBC_TRY(fetch(1));
+  const double ttol = fmax(rtol * sqrt(hcol[0]), 1e-50);
   int it = 0, nh = 0;
   if (zero_guess && n > 0) CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * n, c->stream));
   for (;;) {
@@ -454,12 +502,12 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
       RBC_TRY(matvec(x_dev, K.w.p));
       k_residual<<<nb, 256, 0, c->stream>>>((int)n, b_dev, K.w.p);
     }
-    double beta2 = 0;
-    RBC_TRY(dots(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, &beta2));
-    const double beta = sqrt(beta2);
+    RBC_TRY(dots_dev(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, K.h.p, restart));
+    k_normalize<<<nb, 256, 0, c->stream>>>((int)n, K.h.p, K.w.p, K.V.p);
+    RBC_TRY(fetch(1));
+    const double beta = sqrt(hcol[0]);
     if (it == 0 && history) history[nh++] = beta;
     if (beta < ttol || it >= maxit) break;
-    k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / beta, K.w.p, K.V.p, 0);
     std::fill(H.begin(), H.end(), 0.0);
     std::fill(gv.begin(), gv.end(), 0.0);
     gv[0] = beta;
@@ -467,11 +515,12 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
     double res = beta;
     while (k < restart && it < maxit) {
       RBC_TRY(matvec(K.V.p + (size_t)k * n, K.w.p));
-      RBC_TRY(dots(c, K, n, reduce_ranks, k + 1, K.V.p, n, K.w.p, hcol.data()));  // all projections from the same w
+      RBC_TRY(dots_dev(c, K, n, reduce_ranks, k + 1, K.V.p, n, K.w.p, K.h.p, restart));  // all projections from the same w
       k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, K.V.p, n, K.h.p, K.w.p);
-      double hn2 = 0;
-      RBC_TRY(dots(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, &hn2));
-      const double hn = sqrt(hn2);
+      RBC_TRY(dots_dev(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, K.h.p + k + 1, restart));
+      k_normalize<<<nb, 256, 0, c->stream>>>((int)n, K.h.p + k + 1, K.w.p, K.V.p + (size_t)(k + 1) * n);
+      RBC_TRY(fetch(k + 2));
+      const double hn = sqrt(hcol[k + 1]);
       auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * restart + j]; };
       for (int i = 0; i <= k; i++) Hm(i, k) = hcol[i];
       Hm(k + 1, k) = hn;
@@ -491,7 +540,7 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
       k++;
       res = fabs(gv[k]);
       if (history) history[nh++] = res;
-      if (hn > 0.0) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, 1.0 / hn, K.w.p, K.V.p + (size_t)k * n, 0);
+      c->launches += 4;
       if (res < ttol || hn == 0.0) break;
     }
     // y = H^-1 g (upper triangular), x += V y
@@ -501,9 +550,15 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
       for (int j = i + 1; j < k; j++) s -= H[(size_t)i * restart + j] * y[j];
       y[i] = s / H[(size_t)i * restart + i];
     }
-    for (int i = 0; i < k; i++) k_axpy<<<nb, 256, 0, c->stream>>>((int)n, y[i], K.V.p + (size_t)i * n, x_dev, 1);
+    for (int i0 = 0; i0 < k; i0 += 32) {
+      Coef32 yc;
+      const int m = std::min(32, k - i0);
+      for (int i = 0; i < 32; i++) yc.y[i] = i < m ? y[i0 + i] : 0.0;
+      k_update_x<<<nb, 256, 0, c->stream>>>((int)n, m, K.V.p + (size_t)i0 * n, n, yc, x_dev);
+      c->launches++;
+    }
     KERNEL_CHECK();
-    c->launches += k + 3;
+    c->launches += 2;
     if (res < ttol || it >= maxit) break;
     zero_guess = false;  // restart: true residual from the updated solution
   }
@@ -584,11 +639,68 @@ int wall_noslip_solve(rbc3d_ctx *c, const int *indx_host, int nindep, const doub
   RBC_TRY(rbc3d_apply_resident(c, C1W, C1W, use_cells, 1, RBC3D_TL_WALLS));
   k_wall_to_1d<<<gi, 256, 0, c->stream>>>(nindep, NV, S.last.p, t.v.p, -1.0, vbkg[0], vbkg[1], vbkg[2], S.rhs.p);
   KERNEL_CHECK();
+  // The operator of one iteration is ~30 launches of microsecond kernels: it is captured into a CUDA graph (on the
+  // second matvec, after an eager one has created every lazy buffer, plan and pair list) and replayed from then on,
+  // also by later solves, for as long as nothing the graph refers to has changed.  One rank only - the collectives
+  // of several ranks stay eager.  RBC3D_NOSLIP_GRAPH=0 keeps every matvec eager.
+  bool try_graph = c->prm.nranks == 1;
+  if (const char *e = getenv("RBC3D_NOSLIP_GRAPH")) try_graph = try_graph && atoi(e) != 0;
+  const int gflags[4] = {NV, nindep, c->skip_flags, c->overlap};
+  auto graph_drop = [&]() {
+    if (S.gexec) cudaGraphExecDestroy(S.gexec);
+    if (S.graph) cudaGraphDestroy(S.graph);
+    S.gexec = nullptr;
+    S.graph = nullptr;
+  };
+  auto graph_current = [&]() {
+    return S.gexec && S.g_epoch == alloc_epoch() && S.g_geom == W.geom_version && S.g_mat == W.mat_version &&
+           S.g_tl == t.version && memcmp(S.g_flags, gflags, sizeof gflags) == 0 && memcmp(&S.g_prm, &c->prm, sizeof(Params)) == 0;
+  };
+  if (!try_graph || !graph_current()) graph_drop();
+  int ncall = 0;
+  auto body = [&]() -> int {
+    RBC_TRY(walls_set_traction(c, S.fw.p, true));
+    return rbc3d_apply_resident(c, C1W, 0.0, 0, 1, RBC3D_TL_WALLS);
+  };
+  static const bool graph_dbg = getenv("RBC3D_DEBUG_GRAPH") != nullptr;
+  if (graph_dbg)
+    fprintf(stderr, "[noslip graph] solve: cached=%d epoch=%lld (graph %lld)\n", S.gexec != nullptr, alloc_epoch(), S.g_epoch);
+  auto capture = [&]() {
+    const long long l0 = c->launches;
+    c->quiet = 1;
+    int rc = RBC3D_ECUDA;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      rc = body();
+      if (cudaStreamEndCapture(c->stream, &S.graph) != cudaSuccess || !S.graph) rc = RBC3D_ECUDA;
+    }
+    c->quiet = 0;
+    if (rc == RBC3D_OK && cudaGraphInstantiate(&S.gexec, S.graph, 0) != cudaSuccess) rc = RBC3D_ECUDA;
+    S.graph_launches = c->launches - l0;
+    c->launches = l0;
+    if (rc != RBC3D_OK) {  // not capturable here: stay eager
+      cudaGetLastError();
+      graph_drop();
+      try_graph = false;
+      return;
+    }
+    S.g_epoch = alloc_epoch();
+    S.g_geom = W.geom_version;
+    S.g_mat = W.mat_version;
+    S.g_tl = t.version;
+    memcpy(S.g_flags, gflags, sizeof gflags);
+    S.g_prm = c->prm;
+  };
   auto matvec = [&](const double *in, double *out) -> int {
     k_wall_from_1d<<<gv, 256, 0, c->stream>>>(NV, S.indx.p, in, nullptr, S.fw.p);  // wall%f = f, ModNoSlip.F90:273-278
     KERNEL_CHECK();
-    RBC_TRY(walls_set_traction(c, S.fw.p, true));
-    RBC_TRY(rbc3d_apply_resident(c, C1W, 0.0, 0, 1, RBC3D_TL_WALLS));
+    if (try_graph && !S.gexec && ncall == 1) capture();
+    if (S.gexec) {
+      CUDA_TRY(cudaGraphLaunch(S.gexec, c->stream));
+      c->launches += S.graph_launches;
+    } else {
+      RBC_TRY(body());
+    }
+    ncall++;
     k_wall_to_1d<<<gi, 256, 0, c->stream>>>(nindep, NV, S.last.p, t.v.p, 1.0, 0.0, 0.0, 0.0, out);
     KERNEL_CHECK();
     c->launches += 2;
@@ -621,6 +733,10 @@ void solver_release(rbc3d_ctx *c) {
   for (dbuf<double> *b : {&Ws.V, &Ws.w, &Ws.part, &Ws.h, &Ws.rhs, &Ws.x, &Ws.f0, &Ws.fw}) b->release();
   Ws.indx.release();
   Ws.last.release();
+  if (Ws.gexec) cudaGraphExecDestroy(Ws.gexec);
+  if (Ws.graph) cudaGraphDestroy(Ws.graph);
+  Ws.gexec = nullptr;
+  Ws.graph = nullptr;
   S.ka.release();
   S.kb.release();
   S.ok = false;

@@ -577,8 +577,9 @@ int walls_set_geometry(rbc3d_ctx *c, int nwall, const int *nvert, const int *nel
       own = W.src_own.p;
     }
   }
-  RBC_TRY(celllist_build_pme(c, W.pl, NE, W.xc.p, own, c->pme.sblk, c->pme.swalk));
-  if (c->pme.swalk) RBC_TRY(celllist_pme_weights(c, W.pl, W.xc.p));
+  pme_spread_mode(c, W.pl, NE);
+  RBC_TRY(celllist_build_pme(c, W.pl, NE, W.xc.p, own, W.pl.sblk, W.pl.swalk));
+  if (W.pl.swalk) RBC_TRY(celllist_pme_weights(c, W.pl, W.xc.p));
   W.geom_set = true;
   return RBC3D_OK;
 }

@@ -27,6 +27,27 @@ def pair8(sus8, oracle_lib):
     op.close()
 
 
+@pytest.fixture(scope="module")
+def pair8_walk(sus8, oracle_lib):
+    """the same 8 cells with the pencil-walk spreading kernel forced: a list this short takes the source-block kernel
+    by default (RBC3D_SPREAD_BLOCKS: 0 = always walk, 1 = always blocks, unset = by list length)"""
+    import os
+    from rbc3d_b200.ewald import EwaldOperator
+    old = os.environ.get("RBC3D_SPREAD_BLOCKS")
+    os.environ["RBC3D_SPREAD_BLOCKS"] = "0"
+    try:
+        op = EwaldOperator(sus8.Lb)
+        op.set_suspension(sus8)
+    finally:
+        if old is None:
+            del os.environ["RBC3D_SPREAD_BLOCKS"]
+        else:
+            os.environ["RBC3D_SPREAD_BLOCKS"] = old
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(sus8)
+    yield op, orc
+    op.close()
+
+
 def test_parameters_match(pair8):
     op, orc = pair8
     assert op.rc == orc.rc
@@ -89,10 +110,12 @@ def test_add_int_on_rbcs_full(pair8, c1, c2):
     assert rel_l2(v, ref) < TOL
 
 
+@pytest.mark.parametrize("spread", ["blocks", "walk"])
 @pytest.mark.parametrize("c1,c2", [(0.0, C2_MATVEC), (C1_RHS, 0.0), (C1_RHS, C1_RHS)])
-def test_pme_triple(pair8, sus8, c1, c2):
-    """PME_Distrib_Source -> PME_Transform -> PME_Add_Interp_Vel: mesh velocities and target velocities."""
-    op, orc = pair8
+def test_pme_triple(request, sus8, c1, c2, spread):
+    """PME_Distrib_Source -> PME_Transform -> PME_Add_Interp_Vel: mesh velocities and target velocities, with either
+    spreading kernel."""
+    op, orc = request.getfixturevalue("pair8" if spread == "blocks" else "pair8_walk")
     op.PME_Distrib_Source(c1, c2, cells=True)
     op.PME_Transform()
     v = op.PME_Add_Interp_Vel()
@@ -191,14 +214,20 @@ def test_noncubic_box_small_cells(oracle_lib):
     op.close()
 
 
+@pytest.mark.parametrize("spread", ["0", "1"])
 @pytest.mark.parametrize("Nb,P", [([44, 40, 36], 8), ([12, 20, 28], 8), ([8, 8, 8], 8), ([40, 44, 36], 6), ([20, 24, 28], 4)])
-def test_pme_odd_mesh_sizes_and_spline_orders(oracle_lib, Nb, P):
+def test_pme_odd_mesh_sizes_and_spline_orders(oracle_lib, monkeypatch, Nb, P, spread):
     """PME with meshes that are not multiples of the 8-cell x runs of the spreading walk (last run wraps on the right:
     scalar-reduction flush), narrower than 16 points, as small as the B-spline support (every ring slot aliases), and
     with P != 8 (the generic block kernels).  Accuracy of the Ewald split is irrelevant here: GPU and oracle use the
-    same mesh."""
+    same mesh.  spread = 0: pencil walks, 1: source blocks (no difference for P != 8)."""
     from rbc3d_b200 import synth
     from rbc3d_b200.ewald import EwaldOperator
+    if P != 8 and spread == "1":
+        pytest.skip("one spreading kernel for P != 8")
+    monkeypatch.setenv("RBC3D_SPREAD_BLOCKS", spread)
+    if spread == "0":
+        monkeypatch.setenv("RBC3D_INTERP_DIRECT_MAX", "0")   # and the column walk instead of one warp per target
     Lb = np.array([10.5, 9.0, 8.0])
     centers = np.array([[3.0, 3.0, 2.0], [7.0, 6.5, 5.5], [9.9, 1.0, 7.6]])   # the last cell straddles three faces
     sus = synth.make_suspension(1, nlat0=6, centers=centers, L=1.0, seed=12)

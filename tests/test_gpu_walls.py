@@ -153,6 +153,22 @@ def test_pme_wall_sources(one_wall):
     assert rel_l2(op.pme_grid(), orc.pme_vv()) < TOL
 
 
+def test_pme_wall_sources_with_the_pencil_walk_forced(one_wall, monkeypatch):
+    """a wall list this short spreads with the source-block kernel by default; the same mesh with the walk forced"""
+    from rbc3d_b200.ewald import EwaldOperator
+    _, orc, sus, W = one_wall
+    monkeypatch.setenv("RBC3D_SPREAD_BLOCKS", "0")
+    op = EwaldOperator(LB)
+    op.set_suspension(sus)
+    op.set_walls(W)
+    op.PME_Distrib_Source(C1_RHS, 0.0, cells=False, walls=True)
+    op.PME_Transform()
+    orc.pme_distrib_walls(C1_RHS)
+    orc.pme_transform()
+    assert rel_l2(op.pme_grid(), orc.pme_vv()) < TOL
+    op.close()
+
+
 @pytest.mark.parametrize("tl_name", ["cells", "walls"])
 def test_full_operator_cells_and_walls(one_wall, tl_name):
     """Compute_Rhs (cell targets, ModVelSolver.F90:465-493) and Compute_Wall_Residual_Vel (wall targets,
