@@ -297,7 +297,7 @@ struct Pme {
   int iblk[3] = {4, 4, 4};          // their edges
   int swalk_mode = -1;              // RBC3D_SPREAD_BLOCKS: 1 = always source blocks, 0 = always pencil walks, unset = by size
   int interp_direct_max = 16384;    // RBC3D_INTERP_DIRECT_MAX: longest target list interpolated one warp per target (k_interp_direct)
-  int swalk_min = 1 << 18;          // RBC3D_SPREAD_WALK_MIN: shortest source list that takes the pencil walk
+  int swalk_min = 1 << 19;          // RBC3D_SPREAD_WALK_MIN: shortest source list that takes the pencil walk (profiles/r02_spread_crossover.jsonl)
   bool walk = false;                // P = 8: register-ring column walks along z (lists keyed z-fastest)
   // slab-decomposed transform (several ranks; ModPFFTW.F90:56-89, 188-316): z-slabs of planes for the 2-D transforms,
   // y-slabs of pencils for the transform in z and the k-space multiplier, all-to-all transposes in between

@@ -144,13 +144,13 @@ __global__ void __launch_bounds__(DOT_THREADS) k_dots(int n, const double *__res
     for (int q = 0; q < DOT_THREADS / 32; q++) t += s[q];
     part[(size_t)i * DOT_BLOCKS + blockIdx.x] = t;
     __threadfence();
-    last = atomicAdd(&ticket[i], 1u) == DOT_BLOCKS - 1;
+    last = atomicAdd(&ticket[i], 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!last || threadIdx.x >= 32) return;
   __threadfence();
-  double t = 0;
-  for (int q = threadIdx.x; q < DOT_BLOCKS; q += 32) t += __ldcg(part + (size_t)i * DOT_BLOCKS + q);
+  double t = 0;  // (blocks past the end of a short vector are not launched: their partial sums would be zeros)
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += 32) t += __ldcg(part + (size_t)i * DOT_BLOCKS + q);
   t = warp_sum(t);
   if (threadIdx.x == 0) {
     h[i] = t;
@@ -446,7 +446,8 @@ struct KrylovWork {
 static int dots_dev(rbc3d_ctx *c, KrylovWork &K, size_t n, bool reduce_ranks, int k, const double *V, size_t ldv,
                     const double *w, double *h_dev, int restart) {
   unsigned *ticket = reinterpret_cast<unsigned *>(K.part.p + (size_t)(restart + 2) * DOT_BLOCKS);
-  k_dots<<<dim3(DOT_BLOCKS, k), DOT_THREADS, 0, c->stream>>>((int)n, V, ldv, w, K.part.p, ticket, h_dev);
+  const int nbx = (int)std::max<size_t>(1, std::min<size_t>(DOT_BLOCKS, (n + DOT_THREADS - 1) / DOT_THREADS));
+  k_dots<<<dim3(nbx, k), DOT_THREADS, 0, c->stream>>>((int)n, V, ldv, w, K.part.p, ticket, h_dev);
   KERNEL_CHECK();
   c->launches++;
   if (reduce_ranks) RBC_TRY(comm_allreduce_sum(c, h_dev, (size_t)k));  // sharded unknowns: every rank holds its own cells'
@@ -473,19 +474,58 @@ static double *krylov_host(int count) {
 // on the stream; only the Hessenberg column (k + 2 numbers) crosses to the host, once, at the end of the iteration.
 template <class MatVec>
 static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, bool zero_guess, MatVec &&matvec,
-                      const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter, double *history) {
+                      const double *b_dev, double *x_dev, double rtol, int restart, int maxit, int *niter, double *history,
+                      bool run_ahead = false) {
   if (restart < 1 || restart > 200 || maxit < 0) return RBC3D_EINVAL;
   const int nb = (int)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1);
   RBC_TRY(K.V.resize((size_t)(restart + 1) * (n > 0 ? n : 1)));
   RBC_TRY(K.w.resize(n > 0 ? n : 1));
   RBC_TRY(K.part.resize((size_t)(restart + 2) * DOT_BLOCKS + (restart + 2)));  // partial sums, then the tickets
-  RBC_TRY(K.h.resize(restart + 2));
+  RBC_TRY(K.h.resize(2 * (size_t)(restart + 2)));  // two columns: the one being fetched and the one being computed
   CUDA_TRY(cudaMemsetAsync(K.part.p + (size_t)(restart + 2) * DOT_BLOCKS, 0, sizeof(double) * (restart + 2), c->stream));
   double *hcol = krylov_host(restart + 2);
   if (!hcol) return RBC3D_ENOMEM;
+  // run_ahead: iteration k + 1 is queued before the column of iteration k is fetched (V_{k+1} is made on the device, so
+  // nothing of iteration k + 1 waits for the host); the fetch goes through a second stream behind an event.  The GPU
+  // then never idles across the host's per-iteration work, at the price of one discarded iteration when the solve
+  // converges.  Only for operators whose application leaves no state a caller reads afterwards (the wall solve).
+  struct Side {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~Side() {
+      for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
+      if (st) cudaStreamDestroy(st);
+    }
+  } side;
+  if (run_ahead) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&side.st, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : side.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   auto fetch = [&](int count) -> int {  // K.h[0..count) -> hcol
     CUDA_TRY(cudaMemcpyAsync(hcol, K.h.p, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RBC3D_OK;
+  };
+  // iteration k of a cycle, all on the stream: w = A V_k, the projections, the update, the norm, V_{k+1}
+  auto enqueue_iter = [&](int k) -> int {
+    double *hd = K.h.p + (size_t)(k & 1) * (restart + 2);
+    RBC_TRY(matvec(K.V.p + (size_t)k * n, K.w.p));
+    RBC_TRY(dots_dev(c, K, n, reduce_ranks, k + 1, K.V.p, n, K.w.p, hd, restart));  // all projections from the same w
+    k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, K.V.p, n, hd, K.w.p);
+    RBC_TRY(dots_dev(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, hd + k + 1, restart));
+    k_normalize<<<nb, 256, 0, c->stream>>>((int)n, hd + k + 1, K.w.p, K.V.p + (size_t)(k + 1) * n);
+    KERNEL_CHECK();
+    c->launches += 2;
+    if (run_ahead) CUDA_TRY(cudaEventRecord(side.ev[k & 1], c->stream));
+    return RBC3D_OK;
+  };
+  auto fetch_iter = [&](int k) -> int {  // column of iteration k (k + 2 numbers) -> hcol
+    const double *hd = K.h.p + (size_t)(k & 1) * (restart + 2);
+    cudaStream_t st = run_ahead ? side.st : c->stream;
+    if (run_ahead) CUDA_TRY(cudaStreamWaitEvent(side.st, side.ev[k & 1], 0));
+    CUDA_TRY(cudaMemcpyAsync(hcol, hd, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return RBC3D_OK;
   };
   std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), gv(restart + 1);
@@ -513,13 +553,11 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
     gv[0] = beta;
     int k = 0;
     double res = beta;
+    RBC_TRY(enqueue_iter(0));
     while (k < restart && it < maxit) {
-      RBC_TRY(matvec(K.V.p + (size_t)k * n, K.w.p));
-      RBC_TRY(dots_dev(c, K, n, reduce_ranks, k + 1, K.V.p, n, K.w.p, K.h.p, restart));  // all projections from the same w
-      k_gs_update<<<nb, 256, 0, c->stream>>>((int)n, k + 1, K.V.p, n, K.h.p, K.w.p);
-      RBC_TRY(dots_dev(c, K, n, reduce_ranks, 1, K.w.p, n, K.w.p, K.h.p + k + 1, restart));
-      k_normalize<<<nb, 256, 0, c->stream>>>((int)n, K.h.p + k + 1, K.w.p, K.V.p + (size_t)(k + 1) * n);
-      RBC_TRY(fetch(k + 2));
+      const bool ahead = run_ahead && k + 1 < restart && it + 1 < maxit;
+      if (ahead) RBC_TRY(enqueue_iter(k + 1));
+      RBC_TRY(fetch_iter(k));
       const double hn = sqrt(hcol[k + 1]);
       auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * restart + j]; };
       for (int i = 0; i <= k; i++) Hm(i, k) = hcol[i];
@@ -540,8 +578,8 @@ static int gmres_core(rbc3d_ctx *c, KrylovWork K, size_t n, bool reduce_ranks, b
       k++;
       res = fabs(gv[k]);
       if (history) history[nh++] = res;
-      c->launches += 4;
-      if (res < ttol || hn == 0.0) break;
+      if (res < ttol || hn == 0.0) break;  // (an iteration queued ahead is discarded: it only wrote w and V_{k+1})
+      if (!ahead && k < restart && it < maxit) RBC_TRY(enqueue_iter(k));
     }
     // y = H^-1 g (upper triangular), x += V y
     std::vector<double> y(k);
@@ -707,7 +745,9 @@ int wall_noslip_solve(rbc3d_ctx *c, const int *indx_host, int nindep, const doub
     return RBC3D_OK;
   };
   KrylovWork K{S.V, S.w, S.part, S.h};
-  RBC_TRY(gmres_core(c, K, n, false, true, matvec, S.rhs.p, S.x.p, rtol, 30, maxit, niter, history));
+  bool run_ahead = c->prm.nranks == 1;  // RBC3D_NOSLIP_RUN_AHEAD=0: fetch every column before queueing the next iteration
+  if (const char *e = getenv("RBC3D_NOSLIP_RUN_AHEAD")) run_ahead = run_ahead && atoi(e) != 0;
+  RBC_TRY(gmres_core(c, K, n, false, true, matvec, S.rhs.p, S.x.p, rtol, 30, maxit, niter, history, run_ahead));
   // wall%f = f0 + df (:131-137), then the residual velocity with the new tractions (:140-146)
   k_wall_from_1d<<<gv, 256, 0, c->stream>>>(NV, S.indx.p, S.x.p, S.f0.p, S.fw.p);
   KERNEL_CHECK();
