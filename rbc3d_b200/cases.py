@@ -56,10 +56,25 @@ def read_tube_in(path: str) -> dict:
     """Input/tube.in as ReadConfig consumes it (ModConf.F90:239-273): list-directed reads, one READ statement per
     record -- a scalar takes the first value of the next non-blank record ('!' ends the data of a line), an array of
     nCellTypes values (viscRat, refRad) takes as many values as it needs, over several records if necessary."""
+    def expand(tokens):
+        # list-directed input: 'r*c' repeats the constant c r times; a '/' ends the record's data
+        out = []
+        for tok in tokens:
+            if tok.startswith("/"):
+                break
+            head, star, tail = tok.partition("*")
+            if star and head.isdigit() and tail:
+                out += [tail] * int(head)
+            else:
+                out.append(tok.split("/")[0] if "/" in tok and not tok.startswith(("'", '"')) else tok)
+                if "/" in tok and not tok.startswith(("'", '"')):
+                    break
+        return out
+
     recs = []
     with open(path) as fh:
         for line in fh:
-            t = line.split("!")[0].replace(",", " ").split()
+            t = expand(line.split("!")[0].replace(",", " ").split())
             if t:
                 recs.append(t)
     it = iter(recs)

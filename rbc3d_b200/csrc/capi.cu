@@ -173,6 +173,7 @@ int rbc3d_set_ewald_prms(const double Lb[3], double alpha, double eps, int P, in
 }
 
 int rbc3d_ewald_coeff_sl_exact(double r, double alpha, double *A, double *B) {  // ModEwaldFunc.F90:25-52
+  if (!A || !B) return RBC3D_EINVAL;
   if (alpha <= 0) {
     *A = 1 / (r * r * r);
     *B = 1 / r;
@@ -192,6 +193,7 @@ int rbc3d_ewald_coeff_sl_exact(double r, double alpha, double *A, double *B) {  
 }
 
 int rbc3d_ewald_coeff_dl_exact(double r, double alpha, double *A) {  // ModEwaldFunc.F90:59-79
+  if (!A) return RBC3D_EINVAL;
   if (alpha <= 0) {
     *A = -6 / (r * r * r * r * r);
     return RBC3D_OK;
@@ -208,6 +210,7 @@ int rbc3d_ewald_coeff_dl_exact(double r, double alpha, double *A) {  // ModEwald
 }
 
 int rbc3d_ewald_coeff_sl(const rbc3d_ctx *c, double r, double *A, double *B) {  // ModEwaldFunc.F90:86-131
+  if (!c || !A || !B) return RBC3D_EINVAL;
   const int N = RBC3D_NTAB;
   *A = 0.;
   *B = 0.;
@@ -224,6 +227,7 @@ int rbc3d_ewald_coeff_sl(const rbc3d_ctx *c, double r, double *A, double *B) {  
 }
 
 int rbc3d_ewald_coeff_dl(const rbc3d_ctx *c, double r, double *A) {  // ModEwaldFunc.F90:141-178
+  if (!c || !A) return RBC3D_EINVAL;
   const int N = RBC3D_NTAB;
   *A = 0.;
   if (r < c->prm.r_eps) return RBC3D_OK;
@@ -236,9 +240,12 @@ int rbc3d_ewald_coeff_dl(const rbc3d_ctx *c, double r, double *A) {  // ModEwald
   return RBC3D_OK;
 }
 
+static int ctx_build(rbc3d_ctx *c, const double Lb[3], double alpha, double eps, int P, double rc, const int Nb[3]);
+
 int rbc3d_ctx_create(rbc3d_ctx **out, const double Lb[3], double alpha, double eps, int P, double rc,
                      const int Nb[3], int device) {
   if (!out || !Lb || !Nb || rc <= 0 || alpha <= 0) return RBC3D_EINVAL;
+  *out = nullptr;
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (ndev == 0) {
@@ -249,6 +256,17 @@ int rbc3d_ctx_create(rbc3d_ctx **out, const double Lb[3], double alpha, double e
   CUDA_TRY(cudaSetDevice(device));
   rbc3d_ctx *c = new rbc3d_ctx();
   c->device = device;
+  const int rc_build = ctx_build(c, Lb, alpha, eps, P, rc, Nb);
+  if (rc_build != RBC3D_OK) {  // a half-built context: release what exists (every handle starts out null)
+    rbc3d_ctx_destroy(c);
+    return rc_build;
+  }
+  *out = c;
+  return RBC3D_OK;
+}
+
+static int ctx_build(rbc3d_ctx *c, const double Lb[3], double alpha, double eps, int P, double rc, const int Nb[3]) {
+  const int device = c->device;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -317,19 +335,19 @@ int rbc3d_ctx_create(rbc3d_ctx **out, const double Lb[3], double alpha, double e
   CUDA_TRY(cudaMemsetAsync(c->cells.xvint_part.p, 0, sizeof(double) * (3 * 296 + 8), c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < 3; k++) c->tl[k].kind = k;
-  *out = c;
   return RBC3D_OK;
 }
 
 int rbc3d_ctx_destroy(rbc3d_ctx *c) {
   if (!c) return RBC3D_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   pme_destroy(c);
   comm_destroy(c);
   walls_release(c);
-  for (int i = 0; i < 2 * RBC3D_T_COUNT; i++) cudaEventDestroy(c->ev[i]);
-  cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 2 * RBC3D_T_COUNT; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -442,6 +460,7 @@ int rbc3d_pair_cache_info(rbc3d_ctx *c, int32_t *cells_cached, int64_t *rows) {
 }
 
 int rbc3d_set_skip_flags(rbc3d_ctx *c, int flags) {
+  if (!c) return RBC3D_EINVAL;
   c->skip_flags = flags;
   return RBC3D_OK;
 }
@@ -511,6 +530,17 @@ int rbc3d_cells_set_mesh(rbc3d_ctx *c, int ncell, int nlat, int nlon, const doub
   C.mesh_set = true;
   C.sb_ok = false;
   C.geom_set = C.f_set = C.g_set = false;
+  // everything sized by the old mesh goes: the cell target list, the near-singular entries of the other lists
+  // (rebuilt by the next rbc3d_cells_set_geometry), the coefficient caches and the solver tables
+  c->tl[RBC3D_TL_CELLS].valid = false;
+  c->tl[RBC3D_TL_CELLS].n = 0;
+  for (int k = 0; k < 3; k++) c->tl[k].plist_valid = false;
+  C.pc_ok = false;
+  C.pc_pending = false;
+  C.pc_ncached = 0;
+  C.sg_cache_ok = false;
+  c->solver.ok = false;
+  C.geom_version++;
   c->launches = 0;
   return RBC3D_OK;
 }

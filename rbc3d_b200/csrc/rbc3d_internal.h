@@ -339,7 +339,7 @@ struct rbc3d_ctx {
   int pair_self_mode = 3;   // same-surface pairs: 0 cell list, 1 symmetric patch-pair kernel, 2 dense per-cell kernel,
                             // 3 symmetric kernel streaming a per-geometry coefficient cache (double layer only)
   int sing_cache_mode = 1;  // 0: never cache the singular double-layer integrand, 1: when memory allows
-  cudaEvent_t ev[2 * RBC3D_T_COUNT];
+  cudaEvent_t ev[2 * RBC3D_T_COUNT] = {};
   bool ev_used[RBC3D_T_COUNT];
   float ms[RBC3D_T_COUNT];
   long long launches = 0;

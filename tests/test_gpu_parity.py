@@ -498,3 +498,22 @@ def test_apply_assign_equals_zero_then_accumulate(pair8):
     assert rel_l2(v_set, v_acc) < 1e-13    # FP64 mesh reductions are unordered: equal up to rounding
     v_col = op.apply_collect(0.0, C2_MATVEC, v=np.full_like(v_acc, -3.0))  # one rank: CollectArray is the identity
     assert rel_l2(v_col, v_acc) < 1e-13
+
+
+def test_a_second_mesh_with_a_different_cell_count_replaces_the_first(sus8, oracle_lib):
+    """rbc3d_cells_set_mesh again on a live context (another ncell, another mesh size): nothing sized by the first mesh
+    survives -- an apply before the new geometry is refused, and the operator on the new cells matches the oracle."""
+    from rbc3d_b200 import synth
+    from rbc3d_b200.ewald import EwaldOperator
+    op = EwaldOperator(sus8.Lb)
+    op.set_suspension(sus8)
+    op.AddIntOnRbcs(0.0, C2_MATVEC)
+    small = synth.make_suspension(1, nlat0=8, L=sus8.Lb, centers=np.array([[3.0, 4.0, 5.0], [7.5, 7.0, 2.0]]), seed=5)
+    op.set_mesh(small.ncell, small.nlat, small.nlon, small.th, small.phi, small.w)
+    with pytest.raises(Exception):
+        op.AddIntOnRbcs(0.0, C2_MATVEC)
+    op.set_suspension(small)
+    orc = oracle_lib.Oracle(sus8.Lb).set_cells(small)
+    for c1, c2 in [(0.0, C2_MATVEC), (C1_RHS, 0.0)]:
+        assert rel_l2(op.AddIntOnRbcs(c1, c2), orc.add_int_on_rbcs(c1, c2, orc.cell_targets())) < TOL
+    op.close()

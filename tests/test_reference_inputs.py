@@ -118,3 +118,15 @@ def test_every_shipped_tube_in_and_wall_mesh_reads():
         xe = x[:, e2v - 1]
         area = 0.5 * np.linalg.norm(np.cross((xe[:, 1] - xe[:, 0]).T, (xe[:, 2] - xe[:, 0]).T), axis=1)
         assert np.all(area > 0), m                                       # no degenerate triangles
+
+
+def test_tube_in_list_directed_repeat_counts_and_slash(tmp_path):
+    """Fortran list-directed input as ReadConfig's READ(unit, *) accepts it: 'r*c' repeat counts, ',' separators, a '/'
+    ending a record's data, D exponents; a '/' inside a quoted file name is data."""
+    from rbc3d_b200 import cases
+    p = tmp_path / "tube.in"
+    p.write_text("0.44 ! alpha\n1d-3\n8\n2\n2*1.0 / rest of the record is not read\n 2.82, 2.9\n.false.\n0.\n0.\n8.\n100\n"
+                 "0.0008\n1\n1\n1\n1\n1\n100\n'D/restart.dat'\n0.03\n10.\n4.\n.false.\n0.\n")
+    cfg = cases.read_tube_in(str(p))
+    assert cfg["viscRat"] == [1.0, 1.0] and cfg["refRad"] == [2.82, 2.9]
+    assert cfg["eps_Ewd"] == 1e-3 and cfg["restart_file"] == "D/restart.dat" and cfg["Nt"] == 100
