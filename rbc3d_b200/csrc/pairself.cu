@@ -881,7 +881,9 @@ int pairself_cache_prepare(rbc3d_ctx *c) {
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   // the buffer is grow-only: what it already holds counts as available; keep room for the density splines, the PME
   // work arrays and lists that are allocated lazily
-  const size_t reserve = (size_t)C.ncell * 12 * 2 * C.nlat * C.nlon * 8 * 2 + ((size_t)6 << 30);
+  // (built on first use, the density splines usually exist by now: only what is still to come is held back)
+  const size_t spl = (size_t)C.ncell * 12 * 2 * C.nlat * C.nlon * 8;
+  const size_t reserve = (C.spG.n ? 0 : spl) + (C.spGi.n ? 0 : spl) + ((size_t)6 << 30);
   size_t budget = free_b + C.pc_coef.n * sizeof(double);
   budget = budget > reserve ? budget - reserve : 0;
   long long max_cells = nslot;
