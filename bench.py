@@ -343,8 +343,11 @@ def kernel_table(op, sus, ms, npairs, peaks, world=1):
 
     # same-surface pairs stream (1 - mask) EA per unordered pair slot from the per-geometry cache (256-byte rows)
     pc_cells, pc_rows = op.pair_cache_info()
+    # With the cache the kernel no longer executes the algorithmic flops (the table lookup, rsqrt and mask are in the
+    # coefficient): what it moves is the coefficient stream, so the stage is rated against HBM (its nearer limit is the
+    # shared-memory pipe); frac_fp64 stays in the row as the algorithmic figure.
     add("pair_sum(DL, %d of %d cells from the coefficient cache)" % (pc_cells, max(1, sus.ncell // world)), ms["pair"],
-        flops=npairs * FLOPS_DL_PAIR, bytes_=(pc_rows * 256.0) if pc_rows else None)
+        flops=npairs * FLOPS_DL_PAIR, bytes_=(pc_rows * 256.0) if pc_rows else None, bound="hbm" if pc_rows else "fp64")
     # the cache holds (and the kernel streams) only patch points with a non-zero quadrature weight
     sg_on, sg_pts = op.sing_cache_info()
     add("singular(DL, cached geometry, %d of %d patch points)" % (sg_pts, npatch), ms["sing"],
