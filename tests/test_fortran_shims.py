@@ -160,3 +160,20 @@ def test_every_shim_creates_the_context_before_using_it():
     # Fourier-only ranks and ModPostProcess: tractions are sent by PME_Distrib_Source itself
     ds = procs["pme_distrib_source"]
     assert ds.index("call b200_syncwalltraction") < ds.index("rbc3d_pme_distrib_source")
+
+
+def test_noslip_shim_hands_the_whole_solve_to_the_library():
+    """fortran/ModNoSlip_b200.F90 keeps ModNoSlip's public procedures (ModNoSlip.F90:32-34); NoSlipWall packs wall%f and
+    indxVertGlb of all walls back to back, makes ONE library call with the reference's GMRES settings (rtol = eps_Ewd,
+    60 iterations, ModNoSlip.F90:83-87) and writes wall%f back; Compute_Wall_Residual_Vel is operator #3 + vBkg."""
+    src = open(os.path.join(ROOT, "fortran", "ModNoSlip_b200.F90")).read().lower()
+    assert re.search(r"public\s*::\s*noslipwall,\s*compute_wall_residual_vel,\s*wallbuildmat", src)
+    procs = _procedures()
+    ns = procs["noslipwall"]
+    assert ns.count("rbc3d_noslip_solve") == 1 and "rbc3d_apply" not in ns and "rbc3d_add_int" not in ns
+    assert re.search(r"rbc3d_noslip_solve\(b200_ctx, indx, nindep, vbkg, .*?, eps_ewd, maxit, f, niter, history, slip\)", ns)
+    assert "maxit = 60" in ns and "wall%indxvertglb" in ns
+    assert ns.index("= wall%f") < ns.index("rbc3d_noslip_solve") < ns.index("wall%f = f(")
+    rv = procs["compute_wall_residual_vel"]
+    assert rv.index("call b200_syncwalltraction") < rv.index("rbc3d_apply(b200_ctx, c1, c1,")
+    assert "tl_walls" in rv and "rbc3d_collect_array" in rv and "vbkg(ii)" in rv
