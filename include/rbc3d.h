@@ -171,6 +171,11 @@ int rbc3d_apply_collect(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int
 int rbc3d_apply_resident(rbc3d_ctx *ctx, double c1, double c2, int use_cells, int use_walls, int tlist);
 int rbc3d_get_velocity(rbc3d_ctx *ctx, int tlist, double *v);
 /* bit mask to skip parts of AddIntOnRbcs (testing / profiling): 1 singular, 2 near-singular, 4 linear, 8 pairs */
+/* The PME chain (spread .. interpolate) on a second stream beside the real-space kernels, joined before the combine.
+ * mode -1 (default): with several ranks, and on one rank for target lists of 100 000 points or more; 0: never (one
+ * stream: the per-stage times of rbc3d_get_timings are then each kernel's own); 1: always.  The environment variable
+ * RBC3D_OVERLAP sets the initial mode. */
+int rbc3d_set_overlap(rbc3d_ctx *ctx, int mode);
 int rbc3d_set_skip_flags(rbc3d_ctx *ctx, int flags);
 /* Singular double-layer patch integrals (RBC_SingInt, ModRbcSingInt.F90:29-90): mode 1 (default) caches the
  * density-independent factors of every patch point at geometry time (32 B per point, 8.5 MB per 36x72 cell) when

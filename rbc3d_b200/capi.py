@@ -76,6 +76,7 @@ SIGNATURES = {
     "rbc3d_solver_gmres": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), c_dp]),
     "rbc3d_sing_cache_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rbc3d_set_replicated_density": (C.c_int, [C.c_void_p, C.c_int]),
+    "rbc3d_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "rbc3d_pair_cache_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rbc3d_cell_list_get": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),
     "rbc3d_neighbor_signature": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_up]),

@@ -378,6 +378,10 @@ class EwaldOperator:
         """host densities identical on all ranks: upload 1/nranks each, all-gather over NVLink (collective)."""
         check(self.lib.rbc3d_set_replicated_density(self._h, int(bool(on))))
 
+    def set_overlap(self, mode):
+        """-1 auto, 0 one stream, 1 PME chain on its own stream beside the real-space kernels (rbc3d_set_overlap)"""
+        check(self.lib.rbc3d_set_overlap(self._h, int(mode)), "rbc3d_set_overlap")
+
     def pair_cache_info(self):
         """(cells cached, 256-byte coefficient rows) of the same-surface double-layer pair cache."""
         nc, rows = C.c_int32(), C.c_int64()
