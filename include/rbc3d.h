@@ -3,7 +3,7 @@
  * comp-physics/RBC3D.  This is the drop-in boundary: the reference has no FFI layer, its boundary is the
  * set of Fortran module procedures of ModPME, ModEwaldFunc, ModIntOnRbcs, ModIntOnWalls (+ the list modules
  * ModSourceList / ModTargetList / ModHashTable they read).  Every entry point below names the reference
- * procedure it replaces (paths relative to the reference's common/).  fortran/*.F90 holds the ISO_C_BINDING
+ * procedure it replaces (paths relative to the reference's common/).  The fortran/ directory holds the ISO_C_BINDING
  * shims that re-export the reference names; INTEGRATION.md shows how they are wired.
  *
  * Conventions

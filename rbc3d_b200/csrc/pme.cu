@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) k_spread_walk(SpreadWArgs a)
   __shared__ __align__(16) double s_rec[SW_WARPS][2][WK_ROUND * WK_REC];
   __shared__ __align__(128) double s_fl[SW_WARPS][32][SW_STG];  // flush staging, private to a lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Nx = a.prm.Nb[0], Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
+  const int Ny = a.prm.Nb[1], Nz = a.prm.Nb[2];
   const int task = blockIdx.x * SW_WARPS + warp;
   const int pencil = task / a.npass, pass = task - pencil * a.npass;
   if (pencil >= a.nxr * Ny) return;
