@@ -489,7 +489,6 @@ int nearsing_apply(rbc3d_ctx *c, TargetList &t, double c1, double c2) {
   if (ns.n == 0) return RBC3D_OK;
   const bool sl = (c1 != 0), dl = (c2 != 0);
   if (!sl && !dl) return RBC3D_OK;
-  Cells &C = c->cells;
   CellList &tcl = t.cl;
   NsArgs a;
   fill_ns(c, t, a);
