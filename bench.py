@@ -271,7 +271,7 @@ def run_reference(args):
 
 
 def minicase_config(seed):
-    """examples/minicase on the reference's own Exodus wall mesh (tests/golden/meshes/new_cyl_D6_L13_33.e, 1328 vertices /
+    """examples/minicase on the reference's own Exodus wall mesh (rbc3d_b200/data/meshes/new_cyl_D6_L13_33.e, 1328 vertices /
     2404 triangles; rbc3d_b200.cases.minicase = minit.F90 restated); the generated tube only when the fixture is missing."""
     from rbc3d_b200 import cases, mtube
     try:

@@ -10,8 +10,8 @@
 * ``case`` / ``carotid_web`` -- examples/case, case_sickles (initcond.F90, sickle_initcond.F90) and
   examples/carotid_web (carotid_initcond.F90: 72 cells in the carotid vessel with its web, two walls) restated.
 
-Nothing here is on the product path.  The wall meshes the BASELINE configs use are committed as fixtures under
-tests/golden/meshes/ (scripts/make_golden_meshes.py, SHA-256 in MANIFEST.json), so the GPU box -- where /root/reference does
+Nothing here is on the product path.  The wall meshes the BASELINE configs use are committed as input data under
+rbc3d_b200/data/meshes/ (scripts/make_golden_meshes.py, SHA-256 in MANIFEST.json), so the GPU box -- where /root/reference does
 not exist -- runs the operator on the reference's own geometries; ``mesh_file`` resolves a name to the fixture or, failing
 that, to the reference tree.
 """
@@ -25,7 +25,9 @@ from . import synth
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-MESH_DIRS = (os.path.join(os.path.dirname(_HERE), "tests", "golden", "meshes"),
+DATA_DIR = os.path.join(_HERE, "data")          # input data of the example configurations (no expected results here)
+CAROTID_CELLS = os.path.join(DATA_DIR, "carotid_web_cells.npz")
+MESH_DIRS = (os.path.join(DATA_DIR, "meshes"),
              "/root/reference/examples/minicase/Input", "/root/reference/examples/carotid_web/Input")
 
 
@@ -276,7 +278,7 @@ def carotid_web(input_dir: str | None = None, nrbc: int | None = None, visc_rati
                 hematocrit: float = 0.2, placement=None):
     """-> (suspension, walls, Lb, vBkg) of examples/carotid_web (carotid_initcond.F90): the two walls and
     nrbc = 3 * tubelen * tuber^2 * hematocrit / 4 = 72 biconcave cells (:38).  ``placement`` = (centres, rotations) as
-    returned by carotid_place_cells (the committed tests/golden/carotid_web_cells.npz holds one such draw: the sampling
+    returned by carotid_place_cells (the committed rbc3d_b200/data/carotid_web_cells.npz holds one such draw: the sampling
     takes minutes at 72 cells, as the init program's does); None = sample now."""
     from . import sphere
     W, Lb = carotid_web_walls(input_dir)

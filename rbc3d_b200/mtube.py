@@ -39,8 +39,7 @@ def minicase_like(nlat0: int = 12, dealias: int = 3, seed: int = 161269, ntheta:
     return sus, W
 
 
-GOLDEN_SICKLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                             "ref_sickle_cell.npz")
+GOLDEN_SICKLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ref_sickle_cell.npz")
 
 
 def import_read_rbc(x_file: np.ndarray, xc) -> np.ndarray:
@@ -55,7 +54,7 @@ def case_like(nrbc: int = 8, sickles: bool = True, seed: int = 161269, ntheta: i
     """examples/case (initcond.F90:42-110) and examples/case_sickles (sickle_initcond.F90:50-110) with a generated tube
     mesh: tube radius 5, length nrbc / 0.7, box 10.5 x 10.5 x length, the cells on the axis at z = (iz - 1/2) length /
     nrbc, all biconcave (case) or every second one the imported sickle cell (case_sickles; shape from the committed
-    fixture tests/golden/ref_sickle_cell.npz = the reference's SickleCell.dat).  BASELINE.json configs[1] / configs[3]."""
+    input file rbc3d_b200/data/ref_sickle_cell.npz = the reference's SickleCell.dat).  BASELINE.json configs[1] / configs[3]."""
     length = nrbc / 0.7
     Lb = np.array([10.5, 10.5, length])
     spacing = length / nrbc

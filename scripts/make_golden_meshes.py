@@ -1,4 +1,4 @@
-"""Copy the wall meshes the BASELINE.json configs use from the reference tree into tests/golden/meshes/ (input DATA of
+"""Copy the wall meshes the BASELINE.json configs use from the reference tree into rbc3d_b200/data/meshes/ (input DATA of
 the reference, not source code), with their SHA-256 in a manifest, so that the GPU box -- where /root/reference does not
 exist -- runs the operator on the reference's own geometries (tests/test_gpu_reference_configs.py).
 
@@ -10,7 +10,7 @@ import os
 import shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "tests", "golden", "meshes")
+OUT = os.path.join(ROOT, "rbc3d_b200", "data", "meshes")
 FILES = {
     "new_cyl_D6_L13_33.e": "/root/reference/examples/minicase/Input/new_cyl_D6_L13_33.e",   # minicase, case, case_sickles
     "carotid.e": "/root/reference/examples/carotid_web/Input/carotid.e",                   # carotid_web wall 1

@@ -1,4 +1,4 @@
-"""Generate tests/golden/ref_sickle_cell.npz from the reference's SickleCell.dat.
+"""Generate rbc3d_b200/data/ref_sickle_cell.npz from the reference's SickleCell.dat.
 
 SickleCell.dat (examples/case_sickles/Input, sample_files/sample_cells) is the only OUTPUT OF THE REFERENCE CODE that
 the reference tree ships: a cell surface written by ExportWriteRBC (ModIO.F90:607-629) at the end of a simulation, i.e.
@@ -33,7 +33,7 @@ def parse(path):
 def main():
     hdr, x = parse(SRC)
     digest = hashlib.sha256(open(SRC, "rb").read()).hexdigest()
-    path = os.path.join(ROOT, "tests", "golden", "ref_sickle_cell.npz")
+    path = os.path.join(ROOT, "rbc3d_b200", "data", "ref_sickle_cell.npz")
     np.savez_compressed(path, header=np.array(hdr, dtype=np.int32), x=x, sha256=np.array(digest))
     print("wrote", path, os.path.getsize(path), "bytes", hdr, digest)
 

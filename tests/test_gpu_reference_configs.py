@@ -1,7 +1,7 @@
 """The BASELINE.json example configurations on the reference's OWN wall meshes (committed fixtures under
-tests/golden/meshes/, scripts/make_golden_meshes.py) through the C ABI, against the oracle: operators #1 - #4 of a time
+rbc3d_b200/data/meshes/, scripts/make_golden_meshes.py) through the C ABI, against the oracle: operators #1 - #4 of a time
 step for examples/minicase, examples/case, examples/case_sickles and examples/carotid_web with its 72
-cells and two walls (carotid_initcond.F90:15-54; cell placement from tests/golden/carotid_web_cells.npz).
+cells and two walls (carotid_initcond.F90:15-54; cell placement from rbc3d_b200/data/carotid_web_cells.npz).
 
 Tolerance: relative L2 <= 1e-10 over all targets (north_star); cell ids bit-exact; wall GMRES with the same or fewer
 iterations.  lambda = 5 instead of the examples' 1 so that operator #2 (double layer, coefficient 1 - lambda) is not
@@ -16,7 +16,6 @@ from .util import C1_RHS, C2_MATVEC, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _operators(orc, with_matvec=True):
@@ -92,9 +91,9 @@ def test_carotid_web_72_cells_and_two_walls(oracle_lib):
     5 682), 72 cells, box 10.5 x 10.5 x 30, PME grid 48 x 48 x 136, real-space cells 8 x 8 x 25."""
     from rbc3d_b200 import cases
     from rbc3d_b200.ewald import EwaldOperator
-    if not os.path.exists(os.path.join(GOLDEN, "carotid_web_cells.npz")):
-        pytest.skip("tests/golden/carotid_web_cells.npz missing (scripts/make_golden_carotid_cells.py)")
-    pl = np.load(os.path.join(GOLDEN, "carotid_web_cells.npz"))
+    if not os.path.exists(cases.CAROTID_CELLS):
+        pytest.skip("rbc3d_b200/data/carotid_web_cells.npz missing (scripts/make_golden_carotid_cells.py)")
+    pl = np.load(cases.CAROTID_CELLS)
     sus, W, Lb, vbkg = cases.carotid_web(placement=(pl["centres"], pl["rotations"]), visc_ratio=5.0)
     assert sus.ncell == 72 and sus.npoint == 186624 and list(W.nvert) == [14550, 2903] and list(W.nele) == [28948, 5682]
     op = EwaldOperator(Lb)

@@ -241,7 +241,7 @@ def test_partial_active_rows(two_walls):
 # ---- added after round 1's GPU budget was spent (not yet run on a device), most basic first; kept at the end of the
 # ---- last GPU file so that `pytest -x` cannot hide tests that have run ------------------------------------------
 def test_device_glob_sph_trans_reproduces_the_reference_exported_cell():
-    """Golden vector FROM THE REFERENCE on the device: SickleCell.dat (tests/golden/ref_sickle_cell.npz, a cell written by
+    """Golden vector FROM THE REFERENCE on the device: SickleCell.dat (rbc3d_b200/data/ref_sickle_cell.npz, a cell written by
     the reference after its SPHEREPACK filter) is carried exactly by 3 x 12^2 packed coefficients, so
     Glob_Sph_Trans(FOUR_TO_PHYS) on the GPU (rbc3d_solver_velocity, solver.cu k_sh_synth) must give back the file's
     coordinates -- for the imported cells and the analytic biconcave ones of the case_sickles configuration alike."""
@@ -354,7 +354,7 @@ def test_mtube_time_step(oracle_lib):
 @pytest.mark.parametrize("sickles", [False, True])
 def test_case_and_case_sickles_configurations(oracle_lib, sickles):
     """BASELINE.json configs[1] / configs[3]: 8 cells on the axis of the vessel (examples/case), every second one the
-    sickle cell imported from the reference's SickleCell.dat (examples/case_sickles; tests/golden/ref_sickle_cell.npz),
+    sickle cell imported from the reference's SickleCell.dat (examples/case_sickles; rbc3d_b200/data/ref_sickle_cell.npz),
     lambda = 5 so that the matvec operator exists; operators #1 (RHS), #2 (matvec) and #3 (wall residual)."""
     from rbc3d_b200 import mtube
     from rbc3d_b200.capi import TL_CELLS, TL_WALLS

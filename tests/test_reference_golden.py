@@ -1,7 +1,7 @@
 """Golden vector FROM THE REFERENCE: SickleCell.dat, a cell surface the reference code itself exported (ExportWriteRBC,
 ModIO.F90:613-625) after its SPHEREPACK filter (FilterRbcs: shags analysis, truncation to degree < nlat0 = 12, shsgs
 synthesis on the 36 x 72 Gauss grid).  It is the only output of the reference in its tree, committed here as
-tests/golden/ref_sickle_cell.npz by scripts/make_golden_sickle.py.
+rbc3d_b200/data/ref_sickle_cell.npz by scripts/make_golden_sickle.py.
 
 What it pins of this project's restatement (CPU tests here; SURVEY.md 8(c) "parity unpinned" otherwise):
 * the Gauss colatitudes, the longitudes and the point order (ilat fastest, then ilon, then component: a1 / a2 of
