@@ -47,8 +47,9 @@ enum {
   RBC3D_T_PAIR = 0, RBC3D_T_SING, RBC3D_T_NEARSING, RBC3D_T_LINEAR, RBC3D_T_SPREAD, RBC3D_T_FFT,
   RBC3D_T_KSPACE, RBC3D_T_FFT_INV, RBC3D_T_INTERP, RBC3D_T_COMBINE, RBC3D_T_WALL, RBC3D_T_COMM, RBC3D_T_H2D,
   RBC3D_T_D2H, RBC3D_T_DENSITY, RBC3D_T_TOTAL,
-  /* with several ranks the PME chain (spread .. interpolate, on its own stream) overlaps the real-space chain (pair,
-   * singular, near-singular, linear): their two critical paths, each measured on its own stream */
+  /* where the PME chain (spread .. interpolate) runs on its own stream beside the real-space chain (pair, singular,
+   * near-singular, linear) -- several ranks, or large lists on one rank, see rbc3d_set_overlap --: their two critical
+   * paths, each measured on its own stream */
   RBC3D_T_PME_CHAIN, RBC3D_T_REAL_CHAIN, RBC3D_T_COUNT
 };
 
